@@ -1,0 +1,76 @@
+// Drop-in counterpart of reference src/Tiled-MM/mm_handle.hpp (mm_handle<Scalar>, make_context).
+// Same public surface; the object now owns a tmm_context: device panel/ring buffers, H2D / compute / D2H
+// streams, an event pool and (optionally) a host-registration cache, instead of n_streams x {A,B,C} tile
+// slabs plus one cuBLAS handle per stream (reference mm_handle.hpp:44-57, gpu_context.cpp:6-18).
+#pragma once
+#include "../tiled_mm_b200.h"
+#include "device_vector.hpp"
+
+#include <complex>
+#include <memory>
+#include <tuple>
+
+namespace gpu {
+
+template <typename Scalar> struct tmm_dtype;
+template <> struct tmm_dtype<float> { static constexpr int value = TMM_F32; };
+template <> struct tmm_dtype<double> { static constexpr int value = TMM_F64; };
+template <> struct tmm_dtype<std::complex<float>> { static constexpr int value = TMM_C32; };
+template <> struct tmm_dtype<std::complex<double>> { static constexpr int value = TMM_C64; };
+
+// What is left of the reference's gpu_context (n streams + n cuBLAS handles, gpu_context.hpp:11-40): a read-only
+// description.  Streams are owned and scheduled by the library; there are no BLAS handles.
+class gpu_context {
+public:
+    explicit gpu_context(tmm_context* ctx) : ctx_(ctx) {}
+    int get_num_streams() const { return tmm_context_get_num_streams(ctx_); }
+    tmm_context* native() const { return ctx_; }
+private:
+    tmm_context* ctx_;
+};
+
+template <typename Scalar>
+class mm_handle {
+public:
+    mm_handle(int streams, int max_tile_m, int max_tile_n, int max_tile_k);
+    ~mm_handle();
+
+    mm_handle(mm_handle&&) = delete;
+    mm_handle(const mm_handle&) = delete;
+    mm_handle& operator=(const mm_handle&& other) = delete;
+
+    void set_num_streams(int streams);
+    int get_num_streams();
+
+    gpu_context& get_gpu_context();
+
+    void set_tile_sizes(int tile_size_m, int tile_size_n, int tile_size_k);
+    void set_tile_sizes(int tile_size);
+    void set_full_sizes(int m, int n, int k);
+    std::tuple<int, int, int> optimal_tile_sizes(int m, int n, int k);
+    std::tuple<int, int, int> get_max_tile_sizes();
+
+    void set_streams_and_tiles(int streams, int tile_size_m, int tile_size_n, int tile_size_k);
+
+    // device C of the last copy_c_back=false gemm: column-major m x n, ld = m (reference README.md:102-103)
+    device_vector<Scalar>& get_full_device_buffer_c();
+
+    tmm_context* native() { return ctx_; }
+
+private:
+    tmm_context* ctx_ = nullptr;
+    gpu_context view_{nullptr};
+    device_vector<Scalar> full_c_;
+};
+
+template <typename Scalar>
+std::unique_ptr<mm_handle<Scalar>> make_context(int streams, int max_tile_m, int max_tile_n, int max_tile_k) {
+    return std::make_unique<mm_handle<Scalar>>(streams, max_tile_m, max_tile_n, max_tile_k);
+}
+
+template <typename Scalar>
+std::unique_ptr<mm_handle<Scalar>> make_context() {
+    return std::make_unique<mm_handle<Scalar>>(2, 5000, 5000, 5000);  // reference defaults, mm_handle.hpp:70-76
+}
+
+}  // namespace gpu

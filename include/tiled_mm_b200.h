@@ -1,0 +1,113 @@
+/*
+ * tiled_mm_b200 — C ABI of the B200-native out-of-core GEMM (drop-in for the eth-cscs/Tiled-MM hot path).
+ *
+ * The reference has no C ABI: its boundary is the C++ template API in namespace gpu
+ * (reference src/Tiled-MM/tiled_mm.hpp:62-80, mm_handle.hpp:11-76, util.hpp:57-118).  The C++
+ * drop-in headers under include/Tiled-MM/ are thin wrappers over the entry points below, and the
+ * same entry points are what a ctypes / cgo / JNI binding would use.
+ *
+ * Conventions: plain pointers and sizes only; dtype codes TMM_F32..TMM_C64; scalars (alpha, beta)
+ * are passed by pointer to one element of the dtype (complex = {re, im}); all matrices are
+ * column-major; every function returns TMM_OK (0) or a negative TMM_ERR_* code, and
+ * tmm_last_error() returns a thread-local message for the last failure.  Like the reference
+ * (util.hpp:13-27: message on stderr + std::runtime_error("GPU ERROR")), CUDA failures also print
+ * the CUDA error string to stderr; the C++ wrappers turn a negative code into that exception.
+ */
+#ifndef TILED_MM_B200_H
+#define TILED_MM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TMM_API __attribute__((visibility("default")))
+#else
+#define TMM_API
+#endif
+
+#define TMM_F32 0 /* float                 reference instantiation tiled_mm.cpp:626-635 */
+#define TMM_F64 1 /* double                tiled_mm.cpp:637-646 */
+#define TMM_C32 2 /* std::complex<float>   tiled_mm.cpp:648-657 */
+#define TMM_C64 3 /* std::complex<double>  tiled_mm.cpp:659-668 */
+
+#define TMM_OK 0
+#define TMM_ERR_INVALID (-1) /* bad argument (dtype, trans, negative size, ld too small) */
+#define TMM_ERR_CUDA (-2)    /* a CUDA runtime/driver call failed ("GPU ERROR" in the reference) */
+#define TMM_ERR_NOMEM (-3)   /* device or host allocation failed */
+#define TMM_ERR_NOGPU (-4)   /* no CUDA device / kernels not loadable: there is NO CPU fallback */
+
+typedef struct tmm_context tmm_context; /* opaque; replaces gpu::mm_handle<Scalar> (mm_handle.hpp:11-58) */
+
+/* gpu::make_context<Scalar>(streams, max_tile_m, max_tile_n, max_tile_k)  — mm_handle.hpp:60-76, mm_handle.cpp:10-29.
+ * Binds to the calling thread's current CUDA device (the reference never calls cudaSetDevice either,
+ * mm_handle.cpp:18-24).  n_streams / tile sizes are hints: they bound staging granularity, never results. */
+TMM_API int tmm_context_create(int dtype, int n_streams, int max_tile_m, int max_tile_n, int max_tile_k, tmm_context** out);
+/* ~mm_handle()  — mm_handle.cpp:31-34 */
+TMM_API void tmm_context_destroy(tmm_context* ctx);
+
+/* gpu::gemm<Scalar>(handle, trans_a, trans_b, m, n, k, alpha, a, ld_a, b, ld_b, beta, c, ld_c,
+ *                   pin_host_buffers, copy_c_back)  — tiled_mm.hpp:69-79, tiled_mm.cpp:492-624.
+ * a, b, c are HOST pointers.  Synchronous: returns after all device work; with copy_c_back != 0 host C
+ * holds the result, otherwise it stays in the context's device C (tmm_context_device_c), column-major
+ * with ld = m.  beta == 0 => C is never read (NaN-safe).  64-bit sizes: the reference's int offsets
+ * overflow at 2^31 elements (tiled_matrix.cpp:62-67); these do not. */
+TMM_API int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t ld_a,
+             const void* b, int64_t ld_b, const void* beta, void* c, int64_t ld_c, int pin_host_buffers, int copy_c_back);
+
+/* handle.get_full_device_buffer_c().data() / .size()  — mm_handle.cpp:162-165, device_vector.hpp:67-75.
+ * Borrowed device pointer, valid until a later call grows it or the context is destroyed. */
+TMM_API void* tmm_context_device_c(tmm_context* ctx);
+TMM_API size_t tmm_context_device_c_size(tmm_context* ctx); /* elements */
+
+/* mm_handle::optimal_tile_sizes / get_max_tile_sizes / get_num_streams / set_num_streams /
+ * set_tile_sizes / set_streams_and_tiles  — mm_handle.cpp:36-66,112-148. */
+TMM_API int tmm_context_optimal_tile_sizes(tmm_context* ctx, int m, int n, int k, int* tile_m, int* tile_n, int* tile_k);
+TMM_API int tmm_context_get_max_tile_sizes(tmm_context* ctx, int* tile_m, int* tile_n, int* tile_k);
+TMM_API int tmm_context_get_num_streams(tmm_context* ctx);
+TMM_API int tmm_context_set_streams_and_tiles(tmm_context* ctx, int n_streams, int tile_m, int tile_n, int tile_k);
+TMM_API int tmm_context_dtype(tmm_context* ctx);
+
+/* gpu::malloc_pinned<T>(N, value) minus the fill  — util.hpp:65-72 (cudaHostAlloc, flags 0). The reference
+ * has no matching free helper (its apps leak); tmm_free_pinned is cudaFreeHost. */
+TMM_API int tmm_malloc_pinned(size_t bytes, void** out);
+TMM_API int tmm_free_pinned(void* p);
+/* gpu::malloc_device / copy_to_device / copy_to_host  — util.hpp:57-63,79-88 */
+TMM_API int tmm_malloc_device(size_t bytes, void** out);
+TMM_API int tmm_free_device(void* p);
+TMM_API int tmm_copy_to_device(const void* host_from, void* device_to, size_t bytes);
+TMM_API int tmm_copy_to_host(const void* device_from, void* host_to, size_t bytes);
+
+/* The arithmetic boundary on its own: device-resident GEMM, replaces blas_api::{s,d,c,z}gemm
+ * (gpu_blas_api.hpp:194-252 as called from tiled_mm.cpp:181-268).  Device pointers; A and B must be
+ * 16-byte aligned with ld*sizeof(elem) a multiple of 16 (TMA); C: any ld >= m.  Runs on `stream`
+ * (a cudaStream_t, 0 = default stream) and does not synchronize. */
+TMM_API int tmm_device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a_dev, int64_t ld_a,
+                    const void* b_dev, int64_t ld_b, const void* beta, void* c_dev, int64_t ld_c, void* stream);
+
+/* Introspection for tests and bench.py */
+typedef struct tmm_call_stats {
+    uint64_t h2d_bytes;      /* bytes moved host->device by the last tmm_gemm */
+    uint64_t d2h_bytes;      /* bytes moved device->host by the last tmm_gemm */
+    uint64_t kernel_launches;/* kernels launched by the last tmm_gemm */
+    uint64_t h2d_copies, d2h_copies;
+    double wall_ms;          /* host wall time of the last tmm_gemm */
+    double kernel_ms;        /* summed device time of the GEMM kernels of the last call (0 unless profiling is on) */
+    int regime;              /* 0 resident (A,B,C fit in HBM), 1 streaming (k-panel ring) */
+    int c_blocks, k_chunks;
+} tmm_call_stats;
+TMM_API int tmm_context_last_stats(tmm_context* ctx, tmm_call_stats* out);
+TMM_API int tmm_context_set_profiling(tmm_context* ctx, int on);          /* time every kernel with CUDA events */
+TMM_API int tmm_context_set_device_budget(tmm_context* ctx, size_t bytes); /* cap device memory use (0 = auto); lets tests force the streaming regime */
+TMM_API uint64_t tmm_total_kernel_launches(void);
+TMM_API const char* tmm_last_error(void);
+TMM_API const char* tmm_version(void);
+TMM_API int tmm_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,43 @@
+// Device-level GEMM layer: what replaces the reference's gpu_blas_api (cuBLAS forwarders,
+// reference src/Tiled-MM/gpu_blas_api.hpp:194-252, driven from tiled_mm.cpp:181-268).
+// All operands are DEVICE pointers, column-major; op in {N,T,C}; scalars are passed by value
+// through host pointers (cuBLAS host pointer mode, as the reference uses it).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace tmm {
+
+enum DType : int { F32 = 0, F64 = 1, C32 = 2, C64 = 3 };
+
+inline size_t dtype_size(int dt) { return dt == F32 ? 4 : (dt == F64 ? 8 : (dt == C32 ? 8 : 16)); }
+
+// Alignment contract for the TMA-fed kernels: A and B base pointers 16-byte aligned and
+// lda/ldb * sizeof(elem) a multiple of 16.  The scheduler's device panels always satisfy this
+// (it chooses the device pitch); C has no alignment requirement beyond natural alignment.
+// Returns cudaSuccess or the launch error; cudaErrorInvalidValue on a contract violation.
+cudaError_t device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a,
+                        int64_t lda, const void* b, int64_t ldb, const void* beta, void* c, int64_t ldc, cudaStream_t stream);
+
+// C = beta * C over an m x n column-major block (beta == 0 writes zeros without reading C).
+cudaError_t device_scale(int dtype, int64_t m, int64_t n, const void* beta, void* c, int64_t ldc, cudaStream_t stream);
+
+// Number of kernels launched by this layer since process start (bench.py's gpu_launches).
+uint64_t launch_count();
+
+// per-dtype entry points (one translation unit each)
+cudaError_t dgemm_launch(char ta, char tb, int m, int n, int k, double alpha, const double* a, int64_t lda, const double* b, int64_t ldb,
+                         double beta, double* c, int64_t ldc, cudaStream_t stream);
+cudaError_t zgemm_launch(char ta, char tb, int m, int n, int k, const double* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
+                         const double* beta2, void* c, int64_t ldc, cudaStream_t stream);
+cudaError_t sgemm_launch(char ta, char tb, int m, int n, int k, float alpha, const float* a, int64_t lda, const float* b, int64_t ldb,
+                         float beta, float* c, int64_t ldc, cudaStream_t stream);
+cudaError_t cgemm_launch(char ta, char tb, int m, int n, int k, const float* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
+                         const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
+
+void count_launch();
+int sm_count();
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency)
+void* tensormap_encode_fn();
+
+}  // namespace tmm

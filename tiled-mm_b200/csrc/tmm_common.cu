@@ -1,0 +1,116 @@
+// Shared plumbing of the device GEMM layer: dtype dispatch, C scaling, launch accounting,
+// driver entry point lookup.
+#include "tmm_blas.h"
+
+#include <atomic>
+#include <cctype>
+#include <cuda.h>
+#include <cuComplex.h>
+
+namespace tmm {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!cached[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 1;
+    }
+    return cached[dev];
+}
+
+void* tensormap_encode_fn() {
+    static void* fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        cudaDriverEntryPointQueryResult qres;
+        void* p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = p;
+    }
+    return fn;
+}
+
+// ---- C = beta * C --------------------------------------------------------------------------
+template <typename T> struct Ops;
+template <> struct Ops<float> {
+    static __device__ float zero() { return 0.f; }
+    static __device__ float mul(float a, float b) { return a * b; }
+};
+template <> struct Ops<double> {
+    static __device__ double zero() { return 0.0; }
+    static __device__ double mul(double a, double b) { return a * b; }
+};
+template <> struct Ops<cuFloatComplex> {
+    static __device__ cuFloatComplex zero() { return make_cuFloatComplex(0.f, 0.f); }
+    static __device__ cuFloatComplex mul(cuFloatComplex a, cuFloatComplex b) { return cuCmulf(a, b); }
+};
+template <> struct Ops<cuDoubleComplex> {
+    static __device__ cuDoubleComplex zero() { return make_cuDoubleComplex(0.0, 0.0); }
+    static __device__ cuDoubleComplex mul(cuDoubleComplex a, cuDoubleComplex b) { return cuCmul(a, b); }
+};
+
+template <typename T>
+__global__ void scale_kernel(T* c, int64_t ldc, int64_t m, int64_t n, T beta, int zero) {
+    const int64_t total = m * n;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t col = idx / m, row = idx - col * m;
+        T* p = c + col * ldc + row;
+        *p = zero ? Ops<T>::zero() : Ops<T>::mul(beta, *p);
+    }
+}
+
+template <typename T>
+static cudaError_t scale_impl(int64_t m, int64_t n, T beta, bool zero, void* c, int64_t ldc, cudaStream_t st) {
+    if (m <= 0 || n <= 0) return cudaSuccess;
+    int64_t total = m * n;
+    int blocks = (int)((total + 255) / 256 < (int64_t)sm_count() * 8 ? (total + 255) / 256 : (int64_t)sm_count() * 8);
+    scale_kernel<T><<<blocks, 256, 0, st>>>(static_cast<T*>(c), ldc, m, n, beta, zero ? 1 : 0);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t device_scale(int dtype, int64_t m, int64_t n, const void* beta, void* c, int64_t ldc, cudaStream_t st) {
+    switch (dtype) {
+    case F32: { float b = *static_cast<const float*>(beta); return scale_impl<float>(m, n, b, b == 0.f, c, ldc, st); }
+    case F64: { double b = *static_cast<const double*>(beta); return scale_impl<double>(m, n, b, b == 0.0, c, ldc, st); }
+    case C32: { const float* b = static_cast<const float*>(beta); return scale_impl<cuFloatComplex>(m, n, make_cuFloatComplex(b[0], b[1]), b[0] == 0.f && b[1] == 0.f, c, ldc, st); }
+    case C64: { const double* b = static_cast<const double*>(beta); return scale_impl<cuDoubleComplex>(m, n, make_cuDoubleComplex(b[0], b[1]), b[0] == 0.0 && b[1] == 0.0, c, ldc, st); }
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t lda,
+                        const void* b, int64_t ldb, const void* beta, void* c, int64_t ldc, cudaStream_t st) {
+    char ta = (char)std::toupper((unsigned char)trans_a), tb = (char)std::toupper((unsigned char)trans_b);
+    if ((ta != 'N' && ta != 'T' && ta != 'C') || (tb != 'N' && tb != 'T' && tb != 'C')) return cudaErrorInvalidValue;
+    if (m < 0 || n < 0 || k < 0 || m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return cudaErrorInvalidValue;
+    if (m == 0 || n == 0) return cudaSuccess;
+    bool alpha_zero = false;
+    switch (dtype) {
+    case F32: alpha_zero = *static_cast<const float*>(alpha) == 0.f; break;
+    case F64: alpha_zero = *static_cast<const double*>(alpha) == 0.0; break;
+    case C32: alpha_zero = static_cast<const float*>(alpha)[0] == 0.f && static_cast<const float*>(alpha)[1] == 0.f; break;
+    case C64: alpha_zero = static_cast<const double*>(alpha)[0] == 0.0 && static_cast<const double*>(alpha)[1] == 0.0; break;
+    default: return cudaErrorInvalidValue;
+    }
+    if (k == 0 || alpha_zero) return device_scale(dtype, m, n, beta, c, ldc, st);  // BLAS convention
+    switch (dtype) {
+    case F32: return sgemm_launch(ta, tb, (int)m, (int)n, (int)k, *static_cast<const float*>(alpha), static_cast<const float*>(a), lda,
+                                  static_cast<const float*>(b), ldb, *static_cast<const float*>(beta), static_cast<float*>(c), ldc, st);
+    case F64: return dgemm_launch(ta, tb, (int)m, (int)n, (int)k, *static_cast<const double*>(alpha), static_cast<const double*>(a), lda,
+                                  static_cast<const double*>(b), ldb, *static_cast<const double*>(beta), static_cast<double*>(c), ldc, st);
+    case C32: return cgemm_launch(ta, tb, (int)m, (int)n, (int)k, static_cast<const float*>(alpha), a, lda, b, ldb, static_cast<const float*>(beta), c, ldc, st);
+    case C64: return zgemm_launch(ta, tb, (int)m, (int)n, (int)k, static_cast<const double*>(alpha), a, lda, b, ldb, static_cast<const double*>(beta), c, ldc, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tmm

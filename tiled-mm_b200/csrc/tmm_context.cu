@@ -1,0 +1,742 @@
+// Context + tile scheduler + C ABI of tiled_mm_b200.
+//
+// Replaces, for the hot path gpu::make_context -> gpu::gemm:
+//   mm_handle / gpu_context / device_buffer       (reference mm_handle.cpp, gpu_context.cpp, device_buffer.hpp)
+//   gemm front end, round_robin, round_robin_without_copy_c, copy_tile_*   (reference tiled_mm.cpp:45-123,270-624)
+//
+// It is NOT the reference's pipeline.  The reference walks C tiles, re-sends the A and B tiles of every
+// (m,n) tile and chains copy -> gemm on one stream per slot (tiled_mm.cpp:292-358).  Here:
+//   * every A/B element crosses PCIe exactly once whenever A, B and C fit in HBM ("resident" regime):
+//       phase 1: A streams in as k-chunks together with the first column block of B; each chunk is one
+//                large GEMM launch accumulating into C[:, 0:n1]   (compute starts after the first small chunk)
+//       phase 2: A is now resident; the remaining column blocks of B arrive one by one, each is multiplied
+//                with full k in one launch and its C block streams back immediately (short D2H tail)
+//   * otherwise ("streaming" regime, out-of-core): C super-blocks stay resident while k-chunks of A and B
+//     flow through a ring of device slots; the kernel epilogue accumulates across chunks (beta' = 1 after the
+//     first chunk, reference tiled_mm.cpp:309)
+//   * H2D, compute (several streams, so the tail of one launch is back-filled by the next) and D2H run on
+//     separate streams tied together by pre-allocated events; all offsets are 64-bit.
+// User tile sizes / stream counts are hints (they only cap chunk sizes / stream counts), never results.
+#include "../../include/tiled_mm_b200.h"
+#include "tmm_blas.h"
+
+#include <algorithm>
+#include <cctype>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    // reference util.hpp:13-19: print the CUDA error string to stderr, then "GPU ERROR"
+    fprintf(stderr, "error: GPU API call : %s (%s)\n", cudaGetErrorString(e), what);
+    int code = (e == cudaErrorMemoryAllocation) ? TMM_ERR_NOMEM
+               : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorNoKernelImageForDevice) ? TMM_ERR_NOGPU
+                                                                                                                       : TMM_ERR_CUDA;
+    return fail(code, "GPU ERROR: %s: %s", what, cudaGetErrorString(e));
+}
+
+#define CU(x)                                        \
+    do {                                             \
+        cudaError_t e__ = (x);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #x); \
+    } while (0)
+
+int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;  // bytes
+    cudaError_t reserve(size_t bytes, double slack = 1.0) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = (size_t)std::ceil((double)bytes * slack);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess && slack > 1.0) { want = bytes; e = cudaMalloc(&p, want); }
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) { cudaSetDevice(dev); switched = true; }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+// Throughput model used only to size chunks (not a correctness input).
+struct Rates {
+    double flops = 35e12;   // sustained FP64 tensor rate of the GEMM kernels
+    double h2d = 52e9;      // pinned H2D bytes/s
+};
+
+}  // namespace
+
+struct tmm_context {
+    int dtype = TMM_F64;
+    int n_streams = 2;
+    int max_tile_m = 5000, max_tile_n = 5000, max_tile_k = 5000;
+    int device = 0;
+    static constexpr int MAX_COMPUTE = 4;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_compute[MAX_COMPUTE] = {nullptr, nullptr, nullptr, nullptr};
+    DevBuf buf_a, buf_b, buf_c;  // panel / ring / staged-C storage (grow-only, reused across calls)
+    DevBuf full_c;               // API-visible device C (copy_c_back = false), column-major ld = m
+    size_t full_c_elems = 0;
+    std::vector<cudaEvent_t> events;
+    size_t ev_next = 0;
+    std::vector<cudaEvent_t> timing_events;
+    size_t tev_next = 0;
+    size_t budget_override = 0;
+    bool profiling = false;
+    bool pin_cache = false;
+    std::map<const void*, size_t> pinned;
+    tmm_call_stats stats{};
+
+    int n_compute() const { return std::max(1, std::min(n_streams, (int)MAX_COMPUTE)); }
+
+    cudaError_t get_event(cudaEvent_t* out) {
+        if (ev_next == events.size()) {
+            cudaEvent_t e;
+            cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            if (r != cudaSuccess) return r;
+            events.push_back(e);
+        }
+        *out = events[ev_next++];
+        return cudaSuccess;
+    }
+    cudaError_t get_timing_event(cudaEvent_t* out) {
+        if (tev_next == timing_events.size()) {
+            cudaEvent_t e;
+            cudaError_t r = cudaEventCreate(&e);
+            if (r != cudaSuccess) return r;
+            timing_events.push_back(e);
+        }
+        *out = timing_events[tev_next++];
+        return cudaSuccess;
+    }
+};
+
+namespace {
+
+struct Call {
+    tmm_context* ctx;
+    int dtype;
+    size_t es;  // element size
+    char ta, tb;
+    int64_t m, n, k;
+    const void *alpha, *beta;
+    const char *a, *b;
+    char* c;
+    int64_t lda, ldb, ldc;
+    bool copy_c_back, beta_nonzero;
+    // stored shapes (reference tiled_mm.cpp:507-514)
+    int64_t a_rows, a_cols, b_rows, b_cols;
+    unsigned char one[16];  // scalar 1 of the dtype (beta' for k-chunks > 0, tiled_mm.cpp:309)
+};
+
+void make_one(int dtype, unsigned char* out) {
+    memset(out, 0, 16);
+    if (dtype == TMM_F32 || dtype == TMM_C32) { float v = 1.f; memcpy(out, &v, 4); }
+    else { double v = 1.0; memcpy(out, &v, 8); }
+}
+
+bool scalar_is_zero(int dtype, const void* p) {
+    switch (dtype) {
+    case TMM_F32: return *(const float*)p == 0.f;
+    case TMM_F64: return *(const double*)p == 0.0;
+    case TMM_C32: return ((const float*)p)[0] == 0.f && ((const float*)p)[1] == 0.f;
+    default: return ((const double*)p)[0] == 0.0 && ((const double*)p)[1] == 0.0;
+    }
+}
+
+// ---- copy helpers (64-bit offsets throughout; reference copy_tile_* tiled_mm.cpp:45-123) -----------
+int h2d_2d(Call& cl, void* dst, int64_t dpitch_elems, const char* src, int64_t spitch_elems, int64_t rows, int64_t cols, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return TMM_OK;
+    CU(cudaMemcpy2DAsync(dst, (size_t)dpitch_elems * cl.es, src, (size_t)spitch_elems * cl.es, (size_t)rows * cl.es, (size_t)cols, cudaMemcpyHostToDevice, st));
+    cl.ctx->stats.h2d_bytes += (uint64_t)rows * cols * cl.es;
+    cl.ctx->stats.h2d_copies++;
+    return TMM_OK;
+}
+int d2h_2d(Call& cl, char* dst, int64_t dpitch_elems, const void* src, int64_t spitch_elems, int64_t rows, int64_t cols, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return TMM_OK;
+    CU(cudaMemcpy2DAsync(dst, (size_t)dpitch_elems * cl.es, src, (size_t)spitch_elems * cl.es, (size_t)rows * cl.es, (size_t)cols, cudaMemcpyDeviceToHost, st));
+    cl.ctx->stats.d2h_bytes += (uint64_t)rows * cols * cl.es;
+    cl.ctx->stats.d2h_copies++;
+    return TMM_OK;
+}
+
+// A sub-block of op(A) restricted to rows [i0,i0+mi) of op(A) and k range [p0,p0+kc): where it lives in the
+// stored (untransposed) host matrix, and its stored extent.
+struct Sub { int64_t row, col, rows, cols; };
+Sub a_sub(const Call& cl, int64_t i0, int64_t mi, int64_t p0, int64_t kc) {
+    return cl.ta == 'N' ? Sub{i0, p0, mi, kc} : Sub{p0, i0, kc, mi};
+}
+Sub b_sub(const Call& cl, int64_t p0, int64_t kc, int64_t j0, int64_t nj) {
+    return cl.tb == 'N' ? Sub{p0, j0, kc, nj} : Sub{j0, p0, nj, kc};
+}
+
+int launch_gemm(Call& cl, int64_t mi, int64_t nj, int64_t kc, const void* da, int64_t pa, const void* db, int64_t pb, const void* beta, void* dc,
+                int64_t ldc, cudaStream_t st) {
+    tmm_context* ctx = cl.ctx;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (ctx->profiling) {
+        CU(ctx->get_timing_event(&t0));
+        CU(ctx->get_timing_event(&t1));
+        CU(cudaEventRecord(t0, st));
+    }
+    cudaError_t e = tmm::device_gemm(cl.dtype, cl.ta, cl.tb, mi, nj, kc, cl.alpha, da, pa, db, pb, beta, dc, ldc, st);
+    if (e != cudaSuccess) return cuda_fail(e, "device_gemm");
+    if (ctx->profiling) CU(cudaEventRecord(t1, st));
+    return TMM_OK;
+}
+
+size_t device_budget(tmm_context* ctx) {
+    if (ctx->budget_override) return ctx->budget_override;
+    size_t fr = 0, to = 0;
+    if (cudaMemGetInfo(&fr, &to) != cudaSuccess) return (size_t)8 << 30;
+    size_t held = ctx->buf_a.cap + ctx->buf_b.cap + ctx->buf_c.cap;
+    double avail = (double)fr + (double)held;
+    return (size_t)(avail * 0.92);
+}
+
+// phase-2 / streaming block width: multiple of 64 columns near `target` that fills whole waves of CTAs
+int64_t pick_block_cols(int64_t m, int64_t target, int64_t remaining) {
+    if (remaining <= target) return remaining;
+    const int64_t tiles_m = (m + 127) / 128;
+    const int64_t slots = 2 * (int64_t)tmm::sm_count();
+    int64_t best = round_up(target, 64);
+    double best_eff = 0.0;
+    for (int64_t cols = std::max<int64_t>(64, round_up(target * 3 / 4, 64)); cols <= target * 5 / 4; cols += 64) {
+        const int64_t tiles = tiles_m * (cols / 64);
+        const double eff = (double)tiles / (double)(round_up(tiles, slots));
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = cols; }
+    }
+    return std::min(best, remaining);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Resident regime: device holds all of A, B and C.
+// ------------------------------------------------------------------------------------------------
+int run_resident(Call& cl, void* dC, int64_t ldc_dev) {
+    tmm_context* ctx = cl.ctx;
+    const size_t es = cl.es;
+    const int64_t align = 128 / (int64_t)es;
+    const int64_t pa = round_up(cl.a_rows, align), pb = round_up(cl.b_rows, align);
+    cudaError_t e;
+    if ((e = ctx->buf_a.reserve((size_t)pa * cl.a_cols * es)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(A panels)");
+    if ((e = ctx->buf_b.reserve((size_t)pb * cl.b_cols * es)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(B panels)");
+    char* dA = (char*)ctx->buf_a.p;
+    char* dB = (char*)ctx->buf_b.p;
+    const int ncs = ctx->n_compute();
+    Rates rt;
+    const double F = (cl.dtype == TMM_C32 || cl.dtype == TMM_C64) ? 8.0 : 2.0;
+
+    // --- phase-1 column block width n1: wide enough that a k-chunk's GEMM outlasts its upload
+    int64_t n1 = cl.n;
+    {
+        const double denom = F * (double)cl.m / rt.flops - 1.2 * (double)es / rt.h2d;
+        if (denom > 0) {
+            const double need = 1.2 * (double)es * (double)cl.m / rt.h2d / denom;
+            n1 = (int64_t)std::min<double>((double)cl.n, std::max(512.0, need));
+        }
+        n1 = std::min<int64_t>(cl.n, round_up(n1, 64));
+        if (cl.n - n1 < 256) n1 = cl.n;  // not worth a second phase
+    }
+    // --- phase-1 k-chunk schedule: small first chunk (short prologue), then doubling up to kc_max
+    const int64_t kc_max = std::max<int64_t>(256, std::min<int64_t>(2048, round_up(std::max(64, ctx->max_tile_k), 64)));
+    std::vector<int64_t> chunks;
+    {
+        int64_t done = 0, kc = 256;
+        while (done < cl.k) {
+            int64_t c = std::min(kc, cl.k - done);
+            if (cl.k - done - c < kc / 2) c = cl.k - done;  // fold a small remainder into this chunk
+            chunks.push_back(c);
+            done += c;
+            kc = std::min(kc * 2, kc_max);
+        }
+    }
+    ctx->stats.k_chunks = (int)chunks.size();
+
+    // C[:, 0:n1] preload when beta != 0 (host C is read only then, reference tiled_mm.cpp:325)
+    cudaEvent_t ev;
+    if (cl.beta_nonzero) {
+        int rc = h2d_2d(cl, dC, ldc_dev, cl.c, cl.ldc, cl.m, n1, ctx->s_h2d);
+        if (rc) return rc;
+    }
+    // ---- phase 1
+    int64_t p0 = 0;
+    cudaStream_t cs0 = ctx->s_compute[0];
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const int64_t kc = chunks[ci];
+        Sub sa = a_sub(cl, 0, cl.m, p0, kc);
+        Sub sb = b_sub(cl, p0, kc, 0, n1);
+        char* da = dA + ((size_t)sa.col * pa + sa.row) * es;
+        char* db = dB + ((size_t)sb.col * pb + sb.row) * es;
+        int rc = h2d_2d(cl, da, pa, cl.a + ((size_t)sa.col * cl.lda + sa.row) * es, cl.lda, sa.rows, sa.cols, ctx->s_h2d);
+        if (rc) return rc;
+        rc = h2d_2d(cl, db, pb, cl.b + ((size_t)sb.col * cl.ldb + sb.row) * es, cl.ldb, sb.rows, sb.cols, ctx->s_h2d);
+        if (rc) return rc;
+        CU(ctx->get_event(&ev));
+        CU(cudaEventRecord(ev, ctx->s_h2d));
+        CU(cudaStreamWaitEvent(cs0, ev, 0));
+        rc = launch_gemm(cl, cl.m, n1, kc, da, pa, db, pb, ci == 0 ? cl.beta : (const void*)cl.one, dC, ldc_dev, cs0);
+        if (rc) return rc;
+        p0 += kc;
+    }
+    if (cl.copy_c_back) {
+        CU(ctx->get_event(&ev));
+        CU(cudaEventRecord(ev, cs0));
+        CU(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
+        // a few pieces so the first bytes leave early and the stats stay honest
+        const int64_t piece = std::max<int64_t>(64, round_up(n1 / 4, 64));
+        for (int64_t j = 0; j < n1; j += piece) {
+            const int64_t w = std::min(piece, n1 - j);
+            int rc = d2h_2d(cl, cl.c + (size_t)j * cl.ldc * es, cl.ldc, (char*)dC + (size_t)j * ldc_dev * es, ldc_dev, cl.m, w, ctx->s_d2h);
+            if (rc) return rc;
+        }
+    }
+    // ---- phase 2: remaining column blocks with full k
+    int64_t j0 = n1;
+    int blk = 0;
+    // target block: ~1/16 of the remaining work but at least 512 columns; the last blocks shrink
+    const int64_t target = std::max<int64_t>(512, std::min<int64_t>(2048, round_up(std::max(64, ctx->max_tile_n), 64)));
+    while (j0 < cl.n) {
+        const int64_t remaining = cl.n - j0;
+        int64_t nb;
+        if (remaining <= 512) nb = remaining;
+        else if (remaining <= target + 512) nb = std::min(remaining - 256, pick_block_cols(cl.m, target, remaining));
+        else nb = pick_block_cols(cl.m, target, remaining);
+        nb = std::max<int64_t>(std::min<int64_t>(nb, remaining), std::min<int64_t>(64, remaining));
+        char* dcb = (char*)dC + (size_t)j0 * ldc_dev * es;
+        if (cl.beta_nonzero) {
+            int rc = h2d_2d(cl, dcb, ldc_dev, cl.c + (size_t)j0 * cl.ldc * es, cl.ldc, cl.m, nb, ctx->s_h2d);
+            if (rc) return rc;
+        }
+        Sub sb = b_sub(cl, 0, cl.k, j0, nb);
+        char* db = dB + ((size_t)sb.col * pb + sb.row) * es;
+        int rc = h2d_2d(cl, db, pb, cl.b + ((size_t)sb.col * cl.ldb + sb.row) * es, cl.ldb, sb.rows, sb.cols, ctx->s_h2d);
+        if (rc) return rc;
+        CU(ctx->get_event(&ev));
+        CU(cudaEventRecord(ev, ctx->s_h2d));
+        cudaStream_t cs = ctx->s_compute[(1 + blk) % ncs];
+        CU(cudaStreamWaitEvent(cs, ev, 0));
+        rc = launch_gemm(cl, cl.m, nb, cl.k, dA, pa, db, pb, cl.beta, dcb, ldc_dev, cs);
+        if (rc) return rc;
+        if (cl.copy_c_back) {
+            CU(ctx->get_event(&ev));
+            CU(cudaEventRecord(ev, cs));
+            CU(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
+            rc = d2h_2d(cl, cl.c + (size_t)j0 * cl.ldc * es, cl.ldc, dcb, ldc_dev, cl.m, nb, ctx->s_d2h);
+            if (rc) return rc;
+        }
+        j0 += nb;
+        ++blk;
+    }
+    ctx->stats.c_blocks = 1 + blk;
+    return TMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming regime (out-of-core): C super-blocks resident, k-chunks of A and B through a slot ring.
+// ------------------------------------------------------------------------------------------------
+int run_streaming(Call& cl, void* dC_full, int64_t ldc_full, size_t budget) {
+    tmm_context* ctx = cl.ctx;
+    const size_t es = cl.es;
+    const int64_t align = 128 / (int64_t)es;
+    constexpr int SLOTS = 3;
+    int64_t kc = std::max<int64_t>(256, std::min<int64_t>(2048, round_up(std::max(64, ctx->max_tile_k), 64)));
+    kc = std::min(kc, round_up(cl.k, 64));
+
+    // C super-block: whole C if it leaves >= 40% of the budget for the ring, else ~square blocks, double-buffered
+    int64_t MB = cl.m, NB = cl.n;
+    const bool c_is_full = (dC_full != nullptr);
+    auto ring_bytes = [&](int64_t mb, int64_t nb, int64_t kcc) {
+        return (size_t)SLOTS * (size_t)(round_up(mb, align) + round_up(nb, align) + 2 * align) * (size_t)round_up(kcc, align) * es;
+    };
+    if (!c_is_full) {
+        const double cbytes = (double)cl.m * cl.n * es;
+        if (cbytes > 0.6 * (double)budget) {
+            // 2 * MB * NB * es <= 0.6 budget
+            double side = std::sqrt(0.3 * (double)budget / (double)es);
+            MB = std::min<int64_t>(cl.m, std::max<int64_t>(128, (int64_t)side / 128 * 128));
+            NB = std::min<int64_t>(cl.n, std::max<int64_t>(64, (int64_t)(0.3 * (double)budget / (double)es / (double)MB) / 64 * 64));
+        }
+    }
+    const size_t c_need = c_is_full ? 0 : (size_t)((MB == cl.m && NB == cl.n) ? 1 : 2) * (size_t)round_up(MB, align) * NB * es;
+    while (kc > 64 && c_need + ring_bytes(MB, NB, kc) > budget) kc /= 2;
+    if (c_need + ring_bytes(MB, NB, kc) > budget) return fail(TMM_ERR_NOMEM, "device budget %zu B too small for streaming regime", budget);
+
+    const int64_t pa_slot = cl.ta == 'N' ? round_up(MB, align) : round_up(kc, align);  // pitch of an A slot
+    const int64_t pb_slot = cl.tb == 'N' ? round_up(kc, align) : round_up(NB, align);
+    const size_t a_slot_bytes = (size_t)pa_slot * (cl.ta == 'N' ? kc : MB) * es;
+    const size_t b_slot_bytes = (size_t)pb_slot * (cl.tb == 'N' ? NB : kc) * es;
+    cudaError_t e;
+    if ((e = ctx->buf_a.reserve(a_slot_bytes * SLOTS)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(A ring)");
+    if ((e = ctx->buf_b.reserve(b_slot_bytes * SLOTS)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(B ring)");
+    const int64_t pc_blk = round_up(MB, align);
+    const int n_cbuf = (MB == cl.m && NB == cl.n) ? 1 : 2;
+    if (!c_is_full) {
+        if ((e = ctx->buf_c.reserve((size_t)n_cbuf * pc_blk * NB * es)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(C blocks)");
+    }
+
+    cudaStream_t cs = ctx->s_compute[0];
+    cudaEvent_t slot_free[SLOTS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t cbuf_free[2] = {nullptr, nullptr};
+    int slot = 0, cbuf = 0, nblocks = 0;
+    const int64_t nchunks = (cl.k + kc - 1) / kc;
+    ctx->stats.k_chunks = (int)nchunks;
+    cudaEvent_t ev;
+
+    for (int64_t i0 = 0; i0 < cl.m; i0 += MB) {
+        const int64_t mi = std::min(MB, cl.m - i0);
+        for (int64_t j0 = 0; j0 < cl.n; j0 += NB) {
+            const int64_t nj = std::min(NB, cl.n - j0);
+            char* dcb;
+            int64_t ldcb;
+            if (c_is_full) { dcb = (char*)dC_full + ((size_t)j0 * ldc_full + i0) * es; ldcb = ldc_full; }
+            else { dcb = (char*)ctx->buf_c.p + (size_t)cbuf * pc_blk * NB * es; ldcb = pc_blk; }
+            if (!c_is_full && cbuf_free[cbuf]) {
+                // this C buffer's previous contents must have left for the host before it is overwritten
+                CU(cudaStreamWaitEvent(ctx->s_h2d, cbuf_free[cbuf], 0));
+                CU(cudaStreamWaitEvent(cs, cbuf_free[cbuf], 0));
+            }
+            if (cl.beta_nonzero) {
+                int rc = h2d_2d(cl, dcb, ldcb, cl.c + ((size_t)j0 * cl.ldc + i0) * es, cl.ldc, mi, nj, ctx->s_h2d);
+                if (rc) return rc;
+            }
+            for (int64_t ci = 0; ci < nchunks; ++ci) {
+                const int64_t p0 = ci * kc, kcc = std::min(kc, cl.k - p0);
+                if (slot_free[slot]) CU(cudaStreamWaitEvent(ctx->s_h2d, slot_free[slot], 0));
+                char* da = (char*)ctx->buf_a.p + (size_t)slot * a_slot_bytes;
+                char* db = (char*)ctx->buf_b.p + (size_t)slot * b_slot_bytes;
+                Sub sa = a_sub(cl, i0, mi, p0, kcc);
+                Sub sb = b_sub(cl, p0, kcc, j0, nj);
+                int rc = h2d_2d(cl, da, pa_slot, cl.a + ((size_t)sa.col * cl.lda + sa.row) * es, cl.lda, sa.rows, sa.cols, ctx->s_h2d);
+                if (rc) return rc;
+                rc = h2d_2d(cl, db, pb_slot, cl.b + ((size_t)sb.col * cl.ldb + sb.row) * es, cl.ldb, sb.rows, sb.cols, ctx->s_h2d);
+                if (rc) return rc;
+                CU(ctx->get_event(&ev));
+                CU(cudaEventRecord(ev, ctx->s_h2d));
+                CU(cudaStreamWaitEvent(cs, ev, 0));
+                rc = launch_gemm(cl, mi, nj, kcc, da, pa_slot, db, pb_slot, ci == 0 ? cl.beta : (const void*)cl.one, dcb, ldcb, cs);
+                if (rc) return rc;
+                CU(ctx->get_event(&slot_free[slot]));
+                CU(cudaEventRecord(slot_free[slot], cs));
+                slot = (slot + 1) % SLOTS;
+            }
+            if (cl.copy_c_back) {
+                CU(ctx->get_event(&ev));
+                CU(cudaEventRecord(ev, cs));
+                CU(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
+                int rc = d2h_2d(cl, cl.c + ((size_t)j0 * cl.ldc + i0) * es, cl.ldc, dcb, ldcb, mi, nj, ctx->s_d2h);
+                if (rc) return rc;
+                if (!c_is_full) {
+                    CU(ctx->get_event(&cbuf_free[cbuf]));
+                    CU(cudaEventRecord(cbuf_free[cbuf], ctx->s_d2h));
+                }
+            }
+            if (!c_is_full) cbuf = (cbuf + 1) % n_cbuf;
+            ++nblocks;
+        }
+    }
+    ctx->stats.c_blocks = nblocks;
+    return TMM_OK;
+}
+
+int sync_all(tmm_context* ctx) {
+    // the reference ends with a device-wide cudaDeviceSynchronize (tiled_mm.cpp:602-604); syncing our own
+    // streams gives the same guarantee for this call without stalling unrelated work on the device
+    CU(cudaStreamSynchronize(ctx->s_h2d));
+    for (int i = 0; i < tmm_context::MAX_COMPUTE; ++i) CU(cudaStreamSynchronize(ctx->s_compute[i]));
+    CU(cudaStreamSynchronize(ctx->s_d2h));
+    return TMM_OK;
+}
+
+int pin(tmm_context* ctx, const void* p, size_t bytes, std::vector<const void*>& pinned_now) {
+    if (!p || bytes == 0) return TMM_OK;
+    if (ctx->pin_cache) {
+        auto it = ctx->pinned.find(p);
+        if (it != ctx->pinned.end()) {
+            if (it->second >= bytes) return TMM_OK;
+            cudaHostUnregister(const_cast<void*>(p));
+            ctx->pinned.erase(it);
+        }
+    }
+    cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return TMM_OK; }  // already DMA-able: nothing to do, nothing to undo
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostRegister");
+    if (ctx->pin_cache) ctx->pinned[p] = bytes; else pinned_now.push_back(p);
+    return TMM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tmm_last_error(void) { return g_last_error.c_str(); }
+const char* tmm_version(void) { return "tiled_mm_b200 0.1 (sm_100a)"; }
+uint64_t tmm_total_kernel_launches(void) { return tmm::launch_count(); }
+
+int tmm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int tmm_context_create(int dtype, int n_streams, int max_tile_m, int max_tile_n, int max_tile_k, tmm_context** out) {
+    if (!out) return fail(TMM_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (dtype < TMM_F32 || dtype > TMM_C64) return fail(TMM_ERR_INVALID, "bad dtype %d", dtype);
+    if (n_streams < 1 || max_tile_m < 1 || max_tile_n < 1 || max_tile_k < 1) return fail(TMM_ERR_INVALID, "streams and tile sizes must be >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(TMM_ERR_NOGPU, "no CUDA device: tiled_mm_b200 has no CPU fallback (%s)", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    tmm_context* ctx = new tmm_context();
+    ctx->dtype = dtype; ctx->n_streams = n_streams;
+    ctx->max_tile_m = max_tile_m; ctx->max_tile_n = max_tile_n; ctx->max_tile_k = max_tile_k;
+    if ((e = cudaGetDevice(&ctx->device)) != cudaSuccess) { delete ctx; return cuda_fail(e, "cudaGetDevice"); }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) { delete ctx; return cuda_fail(e, "cudaGetDeviceProperties"); }
+    if (prop.major != 10) { delete ctx; return fail(TMM_ERR_NOGPU, "device %d is sm_%d%d; tiled_mm_b200 kernels are built for sm_100a only", ctx->device, prop.major, prop.minor); }
+    const char* pc = getenv("TMM_PIN_CACHE");
+    ctx->pin_cache = pc && pc[0] == '1';
+    cudaStream_t* all[] = {&ctx->s_h2d, &ctx->s_d2h, &ctx->s_compute[0], &ctx->s_compute[1], &ctx->s_compute[2], &ctx->s_compute[3]};
+    for (cudaStream_t* s : all)
+        if ((e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking)) != cudaSuccess) { tmm_context_destroy(ctx); return cuda_fail(e, "cudaStreamCreateWithFlags"); }
+    *out = ctx;
+    return TMM_OK;
+}
+
+void tmm_context_destroy(tmm_context* ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    for (auto& kv : ctx->pinned) cudaHostUnregister(const_cast<void*>(kv.first));
+    cudaStream_t all[] = {ctx->s_h2d, ctx->s_d2h, ctx->s_compute[0], ctx->s_compute[1], ctx->s_compute[2], ctx->s_compute[3]};
+    for (cudaStream_t s : all) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
+    ctx->buf_a.release(); ctx->buf_b.release(); ctx->buf_c.release(); ctx->full_c.release();
+    delete ctx;
+}
+
+int tmm_context_dtype(tmm_context* ctx) { return ctx ? ctx->dtype : TMM_ERR_INVALID; }
+int tmm_context_get_num_streams(tmm_context* ctx) { return ctx ? ctx->n_streams : TMM_ERR_INVALID; }
+
+int tmm_context_get_max_tile_sizes(tmm_context* ctx, int* tm, int* tn, int* tk) {
+    if (!ctx) return fail(TMM_ERR_INVALID, "null context");
+    if (tm) *tm = ctx->max_tile_m;
+    if (tn) *tn = ctx->max_tile_n;
+    if (tk) *tk = ctx->max_tile_k;
+    return TMM_OK;
+}
+
+int tmm_context_set_streams_and_tiles(tmm_context* ctx, int n_streams, int tile_m, int tile_n, int tile_k) {
+    if (!ctx) return fail(TMM_ERR_INVALID, "null context");
+    if (n_streams < 1 || tile_m < 1 || tile_n < 1 || tile_k < 1) return fail(TMM_ERR_INVALID, "streams and tile sizes must be >= 1");
+    ctx->n_streams = n_streams; ctx->max_tile_m = tile_m; ctx->max_tile_n = tile_n; ctx->max_tile_k = tile_k;
+    return TMM_OK;
+}
+
+// Same function of (dim, max) as the reference heuristic (mm_handle.cpp:89-110): dim if it fits, else the largest
+// divisor of dim that is <= max when it is at least half of max, else max.  Kept so callers that size their own
+// buffers from it see identical numbers; this library's staging granularity does not depend on it.
+static int optimal_tile(int dim, int max_tile) {
+    if (dim <= max_tile) return dim;
+    int best = 1;
+    for (int d = max_tile; d >= 1; --d) if (dim % d == 0) { best = d; break; }
+    return (max_tile - best <= max_tile / 2) ? best : max_tile;
+}
+
+int tmm_context_optimal_tile_sizes(tmm_context* ctx, int m, int n, int k, int* tm, int* tn, int* tk) {
+    if (!ctx) return fail(TMM_ERR_INVALID, "null context");
+    if (m < 1 || n < 1 || k < 1) return fail(TMM_ERR_INVALID, "dimensions must be >= 1");
+    if (tm) *tm = optimal_tile(m, ctx->max_tile_m);
+    if (tn) *tn = optimal_tile(n, ctx->max_tile_n);
+    if (tk) *tk = optimal_tile(k, ctx->max_tile_k);
+    return TMM_OK;
+}
+
+void* tmm_context_device_c(tmm_context* ctx) { return ctx ? ctx->full_c.p : nullptr; }
+size_t tmm_context_device_c_size(tmm_context* ctx) { return ctx ? ctx->full_c_elems : 0; }
+
+int tmm_context_last_stats(tmm_context* ctx, tmm_call_stats* out) {
+    if (!ctx || !out) return fail(TMM_ERR_INVALID, "null argument");
+    *out = ctx->stats;
+    return TMM_OK;
+}
+int tmm_context_set_profiling(tmm_context* ctx, int on) { if (!ctx) return TMM_ERR_INVALID; ctx->profiling = on != 0; return TMM_OK; }
+int tmm_context_set_device_budget(tmm_context* ctx, size_t bytes) { if (!ctx) return TMM_ERR_INVALID; ctx->budget_override = bytes; return TMM_OK; }
+
+int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t ld_a,
+             const void* b, int64_t ld_b, const void* beta, void* c, int64_t ld_c, int pin_host_buffers, int copy_c_back) {
+    if (!ctx) return fail(TMM_ERR_INVALID, "null context");
+    const auto t_begin = std::chrono::steady_clock::now();
+    Call cl;
+    cl.ctx = ctx; cl.dtype = ctx->dtype; cl.es = tmm::dtype_size(ctx->dtype);
+    cl.ta = (char)std::toupper((unsigned char)trans_a);  // reference tiled_mm.cpp:503-504
+    cl.tb = (char)std::toupper((unsigned char)trans_b);
+    if ((cl.ta != 'N' && cl.ta != 'T' && cl.ta != 'C') || (cl.tb != 'N' && cl.tb != 'T' && cl.tb != 'C'))
+        return fail(TMM_ERR_INVALID, "trans must be one of N, T, C (got '%c','%c')", trans_a, trans_b);
+    if (m < 0 || n < 0 || k < 0) return fail(TMM_ERR_INVALID, "negative dimension");
+    if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return fail(TMM_ERR_INVALID, "dimension exceeds 2^31-1");
+    if (!alpha || !beta) return fail(TMM_ERR_INVALID, "alpha/beta null");
+    cl.m = m; cl.n = n; cl.k = k; cl.alpha = alpha; cl.beta = beta;
+    cl.a = (const char*)a; cl.b = (const char*)b; cl.c = (char*)c;
+    cl.lda = ld_a; cl.ldb = ld_b; cl.ldc = ld_c;
+    cl.copy_c_back = copy_c_back != 0;
+    cl.beta_nonzero = !scalar_is_zero(ctx->dtype, beta);  // std::abs(beta) > 0, tiled_mm.cpp:325
+    cl.a_rows = cl.ta == 'N' ? m : k; cl.a_cols = cl.ta == 'N' ? k : m;   // tiled_mm.cpp:507-511
+    cl.b_rows = cl.tb == 'N' ? k : n; cl.b_cols = cl.tb == 'N' ? n : k;
+    make_one(ctx->dtype, cl.one);
+    // the reference builds these errors but never throws them (tiled_mm.cpp:516-527); cuBLAS would reject them
+    if (ld_a < std::max<int64_t>(1, cl.a_rows)) return fail(TMM_ERR_INVALID, "ld_a (%lld) < rows of stored A (%lld)", (long long)ld_a, (long long)cl.a_rows);
+    if (ld_b < std::max<int64_t>(1, cl.b_rows)) return fail(TMM_ERR_INVALID, "ld_b (%lld) < rows of stored B (%lld)", (long long)ld_b, (long long)cl.b_rows);
+    if (ld_c < std::max<int64_t>(1, m)) return fail(TMM_ERR_INVALID, "ld_c (%lld) < m (%lld)", (long long)ld_c, (long long)m);
+
+    ctx->stats = tmm_call_stats{};
+    ctx->ev_next = 0; ctx->tev_next = 0;
+    const uint64_t launches_before = tmm::launch_count();
+    if (m == 0 || n == 0) return TMM_OK;  // BLAS quick return (the reference divides by zero here)
+    const bool alpha_zero = scalar_is_zero(ctx->dtype, alpha);
+    const bool need_ab = k > 0 && !alpha_zero;
+    const bool c_touched = cl.copy_c_back || cl.beta_nonzero;
+    if ((need_ab && (!a || !b)) || (c_touched && !c)) return fail(TMM_ERR_INVALID, "null matrix pointer");
+
+    DeviceGuard guard(ctx->device);
+    std::vector<const void*> pinned_now;
+    int rc = TMM_OK;
+    if (pin_host_buffers) {  // reference tiled_mm.cpp:529-554
+        if (need_ab) {
+            rc = pin(ctx, a, (size_t)ld_a * cl.a_cols * cl.es, pinned_now);
+            if (!rc) rc = pin(ctx, b, (size_t)ld_b * cl.b_cols * cl.es, pinned_now);
+        }
+        if (!rc && c_touched) rc = pin(ctx, c, (size_t)ld_c * n * cl.es, pinned_now);
+    }
+
+    if (!rc) {
+        const int64_t align = 128 / (int64_t)cl.es;
+        void* dC = nullptr;
+        int64_t ldc_dev = 0;
+        cudaError_t e = cudaSuccess;
+        size_t c_bytes = 0;
+        if (!cl.copy_c_back) {
+            // device-resident C, always compact ld = m (README.md:102-103, tests/test-multiply.cpp:339)
+            e = ctx->full_c.reserve((size_t)m * n * cl.es, 1.2);  // device_vector keeps 1.2x slack (device_vector.hpp:92-107)
+            ctx->full_c_elems = (size_t)m * n;
+            dC = ctx->full_c.p; ldc_dev = m;
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(full C)");
+        } else {
+            ldc_dev = round_up(m, align);
+            c_bytes = (size_t)ldc_dev * n * cl.es;
+        }
+        const size_t budget = device_budget(ctx);  // after full C is in place
+        if (!rc) {
+            if (!need_ab) {
+                // C = beta * C
+                if (cl.copy_c_back) {
+                    if ((e = ctx->buf_c.reserve(c_bytes)) != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(C)");
+                    dC = ctx->buf_c.p;
+                }
+                if (!rc && cl.beta_nonzero) rc = h2d_2d(cl, dC, ldc_dev, cl.c, cl.ldc, m, n, ctx->s_h2d);
+                if (!rc) {
+                    cudaEvent_t ev;
+                    if ((e = ctx->get_event(&ev)) != cudaSuccess || (e = cudaEventRecord(ev, ctx->s_h2d)) != cudaSuccess ||
+                        (e = cudaStreamWaitEvent(ctx->s_compute[0], ev, 0)) != cudaSuccess ||
+                        (e = tmm::device_scale(cl.dtype, m, n, beta, dC, ldc_dev, ctx->s_compute[0])) != cudaSuccess)
+                        rc = cuda_fail(e, "scale C");
+                    if (!rc && cl.copy_c_back) {
+                        if ((e = cudaEventRecord(ev, ctx->s_compute[0])) != cudaSuccess || (e = cudaStreamWaitEvent(ctx->s_d2h, ev, 0)) != cudaSuccess) rc = cuda_fail(e, "event");
+                        if (!rc) rc = d2h_2d(cl, cl.c, cl.ldc, dC, ldc_dev, m, n, ctx->s_d2h);
+                    }
+                }
+            } else {
+                const size_t a_bytes = (size_t)round_up(cl.a_rows, align) * cl.a_cols * cl.es;
+                const size_t b_bytes = (size_t)round_up(cl.b_rows, align) * cl.b_cols * cl.es;
+                const bool resident = a_bytes + b_bytes + c_bytes <= budget;
+                ctx->stats.regime = resident ? 0 : 1;
+                if (resident) {
+                    if (cl.copy_c_back) {
+                        if ((e = ctx->buf_c.reserve(c_bytes)) != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(C)");
+                        dC = ctx->buf_c.p;
+                    }
+                    if (!rc) rc = run_resident(cl, dC, ldc_dev);
+                } else {
+                    rc = run_streaming(cl, cl.copy_c_back ? nullptr : dC, ldc_dev, budget);
+                }
+            }
+        }
+    }
+    int rc_sync = sync_all(ctx);
+    if (!rc) rc = rc_sync;
+    for (const void* p : pinned_now) cudaHostUnregister(const_cast<void*>(p));  // tiled_mm.cpp:606-618
+    if (!rc) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = cuda_fail(e, "kernel execution");
+    }
+    if (!rc && ctx->profiling) {
+        double total = 0;
+        for (size_t i = 0; i + 1 < ctx->tev_next; i += 2) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->timing_events[i], ctx->timing_events[i + 1]) == cudaSuccess) total += ms;
+        }
+        ctx->stats.kernel_ms = total;
+    }
+    ctx->stats.kernel_launches = tmm::launch_count() - launches_before;
+    ctx->stats.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return rc;
+}
+
+int tmm_malloc_pinned(size_t bytes, void** out) {
+    if (!out) return fail(TMM_ERR_INVALID, "out is null");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, 0));  // flags 0, reference util.hpp:67
+    return TMM_OK;
+}
+int tmm_free_pinned(void* p) { if (p) CU(cudaFreeHost(p)); return TMM_OK; }
+int tmm_malloc_device(size_t bytes, void** out) {
+    if (!out) return fail(TMM_ERR_INVALID, "out is null");
+    *out = nullptr;
+    CU(cudaMalloc(out, bytes ? bytes : 1));
+    return TMM_OK;
+}
+int tmm_free_device(void* p) { if (p) CU(cudaFree(p)); return TMM_OK; }
+int tmm_copy_to_device(const void* from, void* to, size_t bytes) { CU(cudaMemcpy(to, from, bytes, cudaMemcpyHostToDevice)); return TMM_OK; }
+int tmm_copy_to_host(const void* from, void* to, size_t bytes) { CU(cudaMemcpy(to, from, bytes, cudaMemcpyDeviceToHost)); return TMM_OK; }
+
+int tmm_device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t ld_a,
+                    const void* b, int64_t ld_b, const void* beta, void* c, int64_t ld_c, void* stream) {
+    if (dtype < TMM_F32 || dtype > TMM_C64) return fail(TMM_ERR_INVALID, "bad dtype %d", dtype);
+    cudaError_t e = tmm::device_gemm(dtype, trans_a, trans_b, m, n, k, alpha, a, ld_a, b, ld_b, beta, c, ld_c, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) { cudaGetLastError(); return fail(TMM_ERR_INVALID, "device_gemm: invalid argument (trans, sizes, or A/B not 16-byte aligned)"); }
+    if (e != cudaSuccess) return cuda_fail(e, "device_gemm");
+    return TMM_OK;
+}
+
+}  // extern "C"
