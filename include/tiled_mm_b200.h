@@ -102,6 +102,11 @@ typedef struct tmm_call_stats {
 TMM_API int tmm_context_last_stats(tmm_context* ctx, tmm_call_stats* out);
 TMM_API int tmm_context_set_profiling(tmm_context* ctx, int on);          /* time every kernel with CUDA events */
 TMM_API int tmm_context_set_device_budget(tmm_context* ctx, size_t bytes); /* cap device memory use (0 = auto); lets tests force the streaming regime */
+/* Pure host logic, no GPU needed: the reference's per-dimension tile heuristic (mm_handle.cpp:89-110) and this
+ * library's schedule for a call, as a JSON document (regime, phase-1 block and k-chunks, phase-2 blocks / ring geometry). */
+TMM_API int tmm_optimal_tile_size(int dim, int max_tile);
+TMM_API int tmm_plan_describe(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, int beta_nonzero, int copy_c_back, size_t budget_bytes,
+                      int n_streams, int tile_m, int tile_n, int tile_k, int sm_count, char* out, size_t out_size);
 TMM_API uint64_t tmm_total_kernel_launches(void);
 TMM_API const char* tmm_last_error(void);
 TMM_API const char* tmm_version(void);

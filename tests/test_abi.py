@@ -1,0 +1,86 @@
+"""CPU suite: the C-ABI library loads without a GPU, exports every symbol include/tiled_mm_b200.h declares, and
+refuses to compute without a device (no CPU fallback)."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(tmm):
+    lib = tmm.load_library()
+    declared = tmm.declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/tiled_mm_b200.h but not exported"
+    # and nothing is declared twice with a different spelling in the python mirror
+    for name in ("tmm_context_create", "tmm_gemm", "tmm_context_device_c", "tmm_malloc_pinned", "tmm_device_gemm"):
+        assert name in declared
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C with no torch / C++ types."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "tiled_mm_b200.h"\nint main(void){ tmm_call_stats s; (void)s; return TMM_OK; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-c", str(src), "-o", str(tmp_path / "t.o")], check=True)
+
+
+def test_cpp_dropin_symbols_exported(tmm):
+    """Same mangled names as the reference library's explicit instantiations (tiled_mm.cpp:626-668, mm_handle.cpp:167-170)."""
+    out = subprocess.run(["nm", "-D", "--defined-only", str(tmm.LIB_PATH)], check=True, capture_output=True, text=True).stdout
+    for sym in [
+        "_ZN3gpu4gemmIdEEvRNS_9mm_handleIT_EEcciiiS2_PS2_iS5_iS2_S5_ibb",
+        "_ZN3gpu4gemmIfEEvRNS_9mm_handleIT_EEcciiiS2_PS2_iS5_iS2_S5_ibb",
+        "_ZN3gpu4gemmISt7complexIdEEEvRNS_9mm_handleIT_EEcciiiS4_PS4_iS7_iS4_S7_ibb",
+        "_ZN3gpu4gemmISt7complexIfEEEvRNS_9mm_handleIT_EEcciiiS4_PS4_iS7_iS4_S7_ibb",
+        "_ZN3gpu9mm_handleIdEC1Eiiii",
+        "_ZN3gpu9mm_handleIdE24get_full_device_buffer_cEv",
+        "_ZN3gpu9mm_handleIdE18optimal_tile_sizesEiii",
+        "_ZN3gpu18get_blas_operationEc",
+    ]:
+        assert sym in out, sym
+
+
+def test_cpp_dropin_headers_compile(tmp_path):
+    """A reference-style caller (tests/test-multiply.cpp shape) compiles against include/Tiled-MM unchanged."""
+    src = tmp_path / "caller.cpp"
+    src.write_text(
+        "#include <Tiled-MM/tiled_mm.hpp>\n#include <Tiled-MM/device_vector.hpp>\n#include <Tiled-MM/util.hpp>\n"
+        "int run(int m, int n, int k) {\n"
+        "  auto a = gpu::malloc_pinned<double>(size_t(m) * k, 1); auto b = gpu::malloc_pinned<double>(size_t(k) * n, 1);\n"
+        "  auto c = gpu::malloc_pinned<double>(size_t(m) * n, 0);\n"
+        "  auto ctx = gpu::make_context<double>(2, 5000, 5000, 5000);\n"
+        "  gpu::gemm(*ctx, 'N', 'N', m, n, k, 1.0, a, m, b, k, 0.0, c, m, false, true);\n"
+        "  gpu::gemm(*ctx, 'N', 'N', m, n, k, 1.0, a, m, b, k, 0.0, c, m, false, false);\n"
+        "  gpu::copy_to_host(ctx->get_full_device_buffer_c().data(), c, size_t(m) * n);\n"
+        "  auto z = gpu::make_context<std::complex<double>>();\n"
+        "  return (int)ctx->get_num_streams() + (int)std::get<0>(ctx->optimal_tile_sizes(m, n, k)) + (gpu::get_blas_operation('T') == gpu::blas_api::operation::Transpose);\n"
+        "}\n")
+    subprocess.run(["g++", "-std=c++14", "-Wall", "-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include", "-c", str(src), "-o", str(tmp_path / "c.o")],
+                   check=True)
+
+
+def test_no_cpu_fallback_without_gpu(tmm):
+    if tmm.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tmm.make_context(np.float64)
+    with pytest.raises(ValueError):
+        tmm.make_context(np.int32)
+
+
+def test_optimal_tile_size_matches_oracle(tmm, oracle):
+    for max_tile in (4, 7, 100, 5000):
+        for dim in list(range(1, 60)) + [999, 1000, 1234, 4567, 1357, 5000, 5001, 10000, 12345, 23456, 67891]:
+            assert tmm.optimal_tile_size(dim, max_tile) == oracle.lib.oracle_optimal_tile_size(dim, max_tile), (dim, max_tile)
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through the oracle (or any CPU GEMM)."""
+    for f in list((ROOT / "tiled-mm_b200").rglob("*.py")) + list((ROOT / "tiled-mm_b200" / "csrc").glob("*.*")) + list((ROOT / "include").rglob("*.h*")):
+        text = f.read_text(errors="ignore")
+        assert not re.search(r"liboracle|oracle_gemm|oracle/|import _util", text), f

@@ -1,0 +1,331 @@
+"""tiled_mm_b200 — host-side Python mirror of the Tiled-MM public API over the C ABI.
+
+Mirrors, name for name, the reference's C++ surface for the hot path
+(reference src/Tiled-MM/tiled_mm.hpp:69-79, mm_handle.hpp:11-76, util.hpp:57-118):
+
+    ctx = make_context(np.float64, streams, tile_m, tile_n, tile_k)     # gpu::make_context<double>(...)
+    gemm(ctx, 'N', 'T', m, n, k, alpha, a, ld_a, b, ld_b, beta, c, ld_c,
+         pin_host_buffers=False, copy_c_back=True)                      # gpu::gemm(*ctx, ...)
+    a = malloc_pinned(np.float64, N, 1.0)                                # gpu::malloc_pinned<double>(N, 1)
+    dc = ctx.get_full_device_buffer_c(); dc.data(); dc.size()            # ctx->get_full_device_buffer_c()
+    copy_to_host(dc.data(), c_host, m * n)                               # gpu::copy_to_host(...)
+
+Everything numeric happens in libtiledmm_b200.so (hand-written sm_100a kernels + scheduler).
+There is NO CPU fallback: if the shared library is missing or no B200 is present, calls raise.
+Errors mirror the reference: a failing call raises RuntimeError("GPU ERROR: ...") (util.hpp:13-27).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libtiledmm_b200.so"
+HEADER_PATH = _HERE.parent / "include" / "tiled_mm_b200.h"
+
+TMM_F32, TMM_F64, TMM_C32, TMM_C64 = 0, 1, 2, 3
+TMM_OK, TMM_ERR_INVALID, TMM_ERR_CUDA, TMM_ERR_NOMEM, TMM_ERR_NOGPU = 0, -1, -2, -3, -4
+
+_DTYPES = {
+    np.dtype(np.float32): TMM_F32,
+    np.dtype(np.float64): TMM_F64,
+    np.dtype(np.complex64): TMM_C32,
+    np.dtype(np.complex128): TMM_C64,
+}
+_NP_OF = {v: k for k, v in _DTYPES.items()}
+
+
+class CallStats(ctypes.Structure):
+    _fields_ = [
+        ("h2d_bytes", ctypes.c_uint64),
+        ("d2h_bytes", ctypes.c_uint64),
+        ("kernel_launches", ctypes.c_uint64),
+        ("h2d_copies", ctypes.c_uint64),
+        ("d2h_copies", ctypes.c_uint64),
+        ("wall_ms", ctypes.c_double),
+        ("kernel_ms", ctypes.c_double),
+        ("regime", ctypes.c_int),
+        ("c_blocks", ctypes.c_int),
+        ("k_chunks", ctypes.c_int),
+    ]
+
+
+_lib = None
+
+
+def declared_symbols() -> list[str]:
+    """Every entry point include/tiled_mm_b200.h declares."""
+    text = HEADER_PATH.read_text()
+    return sorted(set(re.findall(r"TMM_API[^;(]*?\b(tmm_\w+)\s*\(", text)))
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the CUDA extension.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"tiled_mm_b200: CUDA extension {LIB_PATH} is missing - build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)"
+        )
+    lib = ctypes.CDLL(str(LIB_PATH))
+    vp, i64, ci, cc, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_char, ctypes.c_size_t
+    lib.tmm_context_create.argtypes = [ci, ci, ci, ci, ci, ctypes.POINTER(vp)]
+    lib.tmm_context_destroy.argtypes = [vp]
+    lib.tmm_context_destroy.restype = None
+    lib.tmm_gemm.argtypes = [vp, cc, cc, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, i64, ci, ci]
+    lib.tmm_context_device_c.argtypes = [vp]
+    lib.tmm_context_device_c.restype = vp
+    lib.tmm_context_device_c_size.argtypes = [vp]
+    lib.tmm_context_device_c_size.restype = sz
+    lib.tmm_context_optimal_tile_sizes.argtypes = [vp, ci, ci, ci] + [ctypes.POINTER(ci)] * 3
+    lib.tmm_context_get_max_tile_sizes.argtypes = [vp] + [ctypes.POINTER(ci)] * 3
+    lib.tmm_context_get_num_streams.argtypes = [vp]
+    lib.tmm_context_set_streams_and_tiles.argtypes = [vp, ci, ci, ci, ci]
+    lib.tmm_context_dtype.argtypes = [vp]
+    lib.tmm_malloc_pinned.argtypes = [sz, ctypes.POINTER(vp)]
+    lib.tmm_free_pinned.argtypes = [vp]
+    lib.tmm_malloc_device.argtypes = [sz, ctypes.POINTER(vp)]
+    lib.tmm_free_device.argtypes = [vp]
+    lib.tmm_copy_to_device.argtypes = [vp, vp, sz]
+    lib.tmm_copy_to_host.argtypes = [vp, vp, sz]
+    lib.tmm_device_gemm.argtypes = [ci, cc, cc, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, i64, vp]
+    lib.tmm_context_last_stats.argtypes = [vp, ctypes.POINTER(CallStats)]
+    lib.tmm_context_set_profiling.argtypes = [vp, ci]
+    lib.tmm_context_set_device_budget.argtypes = [vp, sz]
+    lib.tmm_total_kernel_launches.restype = ctypes.c_uint64
+    lib.tmm_last_error.restype = ctypes.c_char_p
+    lib.tmm_version.restype = ctypes.c_char_p
+    lib.tmm_optimal_tile_size.argtypes = [ci, ci]
+    lib.tmm_plan_describe.argtypes = [ci, cc, cc, i64, i64, i64, ci, ci, sz, ci, ci, ci, ci, ci, ctypes.c_char_p, sz]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int) -> None:
+    if rc != TMM_OK:
+        msg = load_library().tmm_last_error().decode(errors="replace")
+        if rc == TMM_ERR_INVALID:
+            raise ValueError(f"tiled_mm_b200: {msg}")
+        raise RuntimeError(f"GPU ERROR: {msg}" if not msg.startswith("GPU ERROR") else msg)
+
+
+def dtype_code(dtype) -> int:
+    try:
+        return _DTYPES[np.dtype(dtype)]
+    except KeyError:
+        raise ValueError(f"unsupported scalar type {dtype}; Tiled-MM instantiates float, double, complex<float>, complex<double>") from None
+
+
+def _ptr(x) -> ctypes.c_void_p:
+    if x is None:
+        return ctypes.c_void_p(0)
+    if isinstance(x, (int, np.integer)):
+        return ctypes.c_void_p(int(x))
+    if isinstance(x, ctypes.c_void_p):
+        return x
+    if isinstance(x, np.ndarray):
+        return ctypes.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):  # torch tensor (host, pinned)
+        return ctypes.c_void_p(x.data_ptr())
+    raise TypeError(f"cannot take a pointer from {type(x)}")
+
+
+def _scalar(dtype, v):
+    return np.array([v], dtype=dtype)
+
+
+class DeviceVector:
+    """View of the context's full device C: the object ctx->get_full_device_buffer_c() returns
+    (reference mm_handle.cpp:162-165, device_vector.hpp:67-80)."""
+
+    def __init__(self, ctx: "MMHandle"):
+        self._ctx = ctx
+
+    def data(self) -> int:
+        return load_library().tmm_context_device_c(self._ctx._h) or 0
+
+    def size(self) -> int:
+        return int(load_library().tmm_context_device_c_size(self._ctx._h))
+
+
+class MMHandle:
+    """gpu::mm_handle<Scalar> (reference mm_handle.hpp:11-58)."""
+
+    def __init__(self, dtype, streams: int = 2, max_tile_m: int = 5000, max_tile_n: int = 5000, max_tile_k: int = 5000):
+        lib = load_library()
+        self.dtype = np.dtype(dtype)
+        h = ctypes.c_void_p()
+        _check(lib.tmm_context_create(dtype_code(dtype), streams, max_tile_m, max_tile_n, max_tile_k, ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().tmm_context_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def get_num_streams(self) -> int:
+        return load_library().tmm_context_get_num_streams(self._h)
+
+    def set_num_streams(self, streams: int) -> None:
+        tm, tn, tk = self.get_max_tile_sizes()
+        self.set_streams_and_tiles(streams, tm, tn, tk)
+
+    def set_streams_and_tiles(self, streams: int, tile_m: int, tile_n: int, tile_k: int) -> None:
+        _check(load_library().tmm_context_set_streams_and_tiles(self._h, streams, tile_m, tile_n, tile_k))
+
+    def get_max_tile_sizes(self):
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _check(load_library().tmm_context_get_max_tile_sizes(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
+
+    def optimal_tile_sizes(self, m: int, n: int, k: int):
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _check(load_library().tmm_context_optimal_tile_sizes(self._h, m, n, k, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
+
+    def get_full_device_buffer_c(self) -> DeviceVector:
+        return DeviceVector(self)
+
+    # introspection (not in the reference)
+    def last_stats(self) -> CallStats:
+        st = CallStats()
+        _check(load_library().tmm_context_last_stats(self._h, ctypes.byref(st)))
+        return st
+
+    def set_profiling(self, on: bool) -> None:
+        _check(load_library().tmm_context_set_profiling(self._h, 1 if on else 0))
+
+    def set_device_budget(self, nbytes: int) -> None:
+        _check(load_library().tmm_context_set_device_budget(self._h, nbytes))
+
+
+def make_context(dtype=np.float64, streams: int = 2, max_tile_m: int = 5000, max_tile_n: int = 5000, max_tile_k: int = 5000) -> MMHandle:
+    """gpu::make_context<Scalar>(streams, max_tile_m, max_tile_n, max_tile_k); defaults 2 / 5000^3 (mm_handle.hpp:60-76)."""
+    return MMHandle(dtype, streams, max_tile_m, max_tile_n, max_tile_k)
+
+
+def gemm(handle: MMHandle, trans_a: str, trans_b: str, m: int, n: int, k: int, alpha, a, ld_a: int, b, ld_b: int, beta, c, ld_c: int,
+         pin_host_buffers: bool = True, copy_c_back: bool = True) -> None:
+    """gpu::gemm<Scalar>(handle, trans_a, trans_b, m, n, k, alpha, a, ld_a, b, ld_b, beta, c, ld_c, pin_host_buffers, copy_c_back)
+    (reference tiled_mm.hpp:69-79).  a, b, c: host buffers (numpy arrays / pinned arrays / raw addresses), column-major."""
+    lib = load_library()
+    al, be = _scalar(handle.dtype, alpha), _scalar(handle.dtype, beta)
+    for name, x in (("a", a), ("b", b), ("c", c)):
+        if isinstance(x, np.ndarray) and x.dtype != handle.dtype:
+            raise ValueError(f"{name} has dtype {x.dtype}, context is {handle.dtype}")
+    ta = ctypes.c_char(trans_a.encode()[:1])
+    tb = ctypes.c_char(trans_b.encode()[:1])
+    _check(lib.tmm_gemm(handle._h, ta, tb, m, n, k, _ptr(al), _ptr(a), ld_a, _ptr(b), ld_b, _ptr(be), _ptr(c), ld_c,
+                        1 if pin_host_buffers else 0, 1 if copy_c_back else 0))
+
+
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None:
+                _lib.tmm_free_pinned(ctypes.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+class _PinnedArray(np.ndarray):
+    """ndarray over a cudaHostAlloc block; every view keeps the block alive through `_owner`."""
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._owner = getattr(obj, "_owner", None)
+
+
+def malloc_pinned(dtype, count: int, value=0) -> np.ndarray:
+    """gpu::malloc_pinned<T>(N, value): cudaHostAlloc(flags 0) + fill (reference util.hpp:65-72).
+    Returns a 1-D numpy array over the pinned block; the block is freed when the last view is collected."""
+    lib = load_library()
+    dt = np.dtype(dtype)
+    p = ctypes.c_void_p()
+    nbytes = max(1, count) * dt.itemsize
+    _check(lib.tmm_malloc_pinned(nbytes, ctypes.byref(p)))
+    owner = _PinnedOwner(p.value)
+    buf = (ctypes.c_byte * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=count).view(_PinnedArray)
+    arr._owner = owner
+    arr.fill(value)
+    return arr
+
+
+def malloc_device(nbytes: int) -> int:
+    p = ctypes.c_void_p()
+    _check(load_library().tmm_malloc_device(nbytes, ctypes.byref(p)))
+    return p.value
+
+
+def free_device(ptr: int) -> None:
+    _check(load_library().tmm_free_device(ctypes.c_void_p(ptr)))
+
+
+def copy_to_device(host: np.ndarray, device_ptr: int, count: int | None = None) -> None:
+    """gpu::copy_to_device(from, to, n) (util.hpp:79-82); count in elements."""
+    n = host.size if count is None else count
+    _check(load_library().tmm_copy_to_device(_ptr(host), ctypes.c_void_p(device_ptr), n * host.dtype.itemsize))
+
+
+def copy_to_host(device_ptr: int, host: np.ndarray, count: int | None = None) -> None:
+    """gpu::copy_to_host(from, to, n) (util.hpp:85-88); count in elements."""
+    n = host.size if count is None else count
+    _check(load_library().tmm_copy_to_host(ctypes.c_void_p(device_ptr), _ptr(host), n * host.dtype.itemsize))
+
+
+def device_gemm(dtype, trans_a: str, trans_b: str, m: int, n: int, k: int, alpha, a_dev: int, ld_a: int, b_dev: int, ld_b: int, beta, c_dev: int,
+                ld_c: int, stream: int = 0) -> None:
+    """blas_api::{s,d,c,z}gemm replacement on device pointers (gpu_blas_api.hpp:194-252)."""
+    dt = np.dtype(dtype)
+    al, be = _scalar(dt, alpha), _scalar(dt, beta)
+    _check(load_library().tmm_device_gemm(dtype_code(dt), ctypes.c_char(trans_a.encode()[:1]), ctypes.c_char(trans_b.encode()[:1]), m, n, k,
+                                          _ptr(al), ctypes.c_void_p(a_dev), ld_a, ctypes.c_void_p(b_dev), ld_b, _ptr(be), ctypes.c_void_p(c_dev), ld_c,
+                                          ctypes.c_void_p(stream)))
+
+
+def optimal_tile_size(dim: int, max_tile: int) -> int:
+    """Pure host logic of mm_handle::optimal_tile_sizes for one dimension (reference mm_handle.cpp:89-110)."""
+    return load_library().tmm_optimal_tile_size(dim, max_tile)
+
+
+def plan_describe(dtype, trans_a: str, trans_b: str, m: int, n: int, k: int, beta_nonzero: bool, copy_c_back: bool, budget_bytes: int,
+                  streams: int = 2, tile_m: int = 5000, tile_n: int = 5000, tile_k: int = 5000, sm_count: int = 148) -> dict:
+    """The scheduler's plan for a call as JSON (pure host logic, needs no GPU)."""
+    import json
+    buf = ctypes.create_string_buffer(1 << 20)
+    rc = load_library().tmm_plan_describe(dtype_code(dtype), ctypes.c_char(trans_a.encode()[:1]), ctypes.c_char(trans_b.encode()[:1]), m, n, k,
+                                          1 if beta_nonzero else 0, 1 if copy_c_back else 0, budget_bytes, streams, tile_m, tile_n, tile_k, sm_count,
+                                          buf, len(buf))
+    _check(rc)
+    return json.loads(buf.value.decode())
+
+
+def device_count() -> int:
+    return load_library().tmm_device_count()
+
+
+def total_kernel_launches() -> int:
+    return int(load_library().tmm_total_kernel_launches())
+
+
+def version() -> str:
+    return load_library().tmm_version().decode()

@@ -19,6 +19,7 @@
 // User tile sizes / stream counts are hints (they only cap chunk sizes / stream counts), never results.
 #include "../../include/tiled_mm_b200.h"
 #include "tmm_blas.h"
+#include "tmm_plan.h"
 
 #include <algorithm>
 #include <cctype>
@@ -88,12 +89,6 @@ struct DeviceGuard {
     ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
 };
 
-// Throughput model used only to size chunks (not a correctness input).
-struct Rates {
-    double flops = 35e12;   // sustained FP64 tensor rate of the GEMM kernels
-    double h2d = 52e9;      // pinned H2D bytes/s
-};
-
 }  // namespace
 
 struct tmm_context {
@@ -113,6 +108,10 @@ struct tmm_context {
     size_t budget_override = 0;
     bool profiling = false;
     bool pin_cache = false;
+    bool trace = false;
+    struct TraceOp { std::string name; cudaEvent_t e0, e1; };
+    std::vector<TraceOp> trace_ops;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
     std::map<const void*, size_t> pinned;
     tmm_call_stats stats{};
 
@@ -210,7 +209,7 @@ int launch_gemm(Call& cl, int64_t mi, int64_t nj, int64_t kc, const void* da, in
     }
     cudaError_t e = tmm::device_gemm(cl.dtype, cl.ta, cl.tb, mi, nj, kc, cl.alpha, da, pa, db, pb, beta, dc, ldc, st);
     if (e != cudaSuccess) return cuda_fail(e, "device_gemm");
-    if (ctx->profiling) CU(cudaEventRecord(t1, st));
+    if (ctx->profiling) { CU(cudaEventRecord(t1, st)); ctx->gemm_events.push_back({t0, t1}); }
     return TMM_OK;
 }
 
@@ -223,188 +222,140 @@ size_t device_budget(tmm_context* ctx) {
     return (size_t)(avail * 0.92);
 }
 
-// phase-2 / streaming block width: multiple of 64 columns near `target` that fills whole waves of CTAs
-int64_t pick_block_cols(int64_t m, int64_t target, int64_t remaining) {
-    if (remaining <= target) return remaining;
-    const int64_t tiles_m = (m + 127) / 128;
-    const int64_t slots = 2 * (int64_t)tmm::sm_count();
-    int64_t best = round_up(target, 64);
-    double best_eff = 0.0;
-    for (int64_t cols = std::max<int64_t>(64, round_up(target * 3 / 4, 64)); cols <= target * 5 / 4; cols += 64) {
-        const int64_t tiles = tiles_m * (cols / 64);
-        const double eff = (double)tiles / (double)(round_up(tiles, slots));
-        if (eff > best_eff + 1e-9) { best_eff = eff; best = cols; }
+// ---- optional timeline (TMM_TRACE=1): every op gets a begin/end event; printed after the call ----
+struct TraceScope {
+    tmm_context* ctx; cudaStream_t st; size_t idx = (size_t)-1;
+    TraceScope(tmm_context* c, cudaStream_t s, const char* name, int64_t a = 0, int64_t b = 0, int64_t d = 0) : ctx(c), st(s) {
+        if (!ctx->trace) return;
+        cudaEvent_t e0, e1;
+        if (ctx->get_timing_event(&e0) != cudaSuccess || ctx->get_timing_event(&e1) != cudaSuccess) return;
+        cudaEventRecord(e0, st);
+        char buf[96];
+        snprintf(buf, sizeof buf, "%s(%lld,%lld,%lld)", name, (long long)a, (long long)b, (long long)d);
+        ctx->trace_ops.push_back({buf, e0, e1});
+        idx = ctx->trace_ops.size() - 1;
     }
-    return std::min(best, remaining);
-}
+    ~TraceScope() { if (idx != (size_t)-1) cudaEventRecord(ctx->trace_ops[idx].e1, st); }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Resident regime: device holds all of A, B and C.
 // ------------------------------------------------------------------------------------------------
-int run_resident(Call& cl, void* dC, int64_t ldc_dev) {
+int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
     tmm_context* ctx = cl.ctx;
     const size_t es = cl.es;
-    const int64_t align = 128 / (int64_t)es;
-    const int64_t pa = round_up(cl.a_rows, align), pb = round_up(cl.b_rows, align);
+    const int64_t pa = pl.pitch_a, pb = pl.pitch_b;
     cudaError_t e;
-    if ((e = ctx->buf_a.reserve((size_t)pa * cl.a_cols * es)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(A panels)");
-    if ((e = ctx->buf_b.reserve((size_t)pb * cl.b_cols * es)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(B panels)");
+    if ((e = ctx->buf_a.reserve(pl.bytes_a)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(A panels)");
+    if ((e = ctx->buf_b.reserve(pl.bytes_b)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(B panels)");
     char* dA = (char*)ctx->buf_a.p;
     char* dB = (char*)ctx->buf_b.p;
     const int ncs = ctx->n_compute();
-    Rates rt;
-    const double F = (cl.dtype == TMM_C32 || cl.dtype == TMM_C64) ? 8.0 : 2.0;
-
-    // --- phase-1 column block width n1: wide enough that a k-chunk's GEMM outlasts its upload
-    int64_t n1 = cl.n;
-    {
-        const double denom = F * (double)cl.m / rt.flops - 1.2 * (double)es / rt.h2d;
-        if (denom > 0) {
-            const double need = 1.2 * (double)es * (double)cl.m / rt.h2d / denom;
-            n1 = (int64_t)std::min<double>((double)cl.n, std::max(512.0, need));
-        }
-        n1 = std::min<int64_t>(cl.n, round_up(n1, 64));
-        if (cl.n - n1 < 256) n1 = cl.n;  // not worth a second phase
-    }
-    // --- phase-1 k-chunk schedule: small first chunk (short prologue), then doubling up to kc_max
-    const int64_t kc_max = std::max<int64_t>(256, std::min<int64_t>(2048, round_up(std::max(64, ctx->max_tile_k), 64)));
-    std::vector<int64_t> chunks;
-    {
-        int64_t done = 0, kc = 256;
-        while (done < cl.k) {
-            int64_t c = std::min(kc, cl.k - done);
-            if (cl.k - done - c < kc / 2) c = cl.k - done;  // fold a small remainder into this chunk
-            chunks.push_back(c);
-            done += c;
-            kc = std::min(kc * 2, kc_max);
-        }
-    }
-    ctx->stats.k_chunks = (int)chunks.size();
+    const int64_t n1 = pl.n1;
+    ctx->stats.k_chunks = (int)pl.chunks.size();
+    ctx->stats.c_blocks = 1 + (int)pl.blocks.size();
 
     // C[:, 0:n1] preload when beta != 0 (host C is read only then, reference tiled_mm.cpp:325)
     cudaEvent_t ev;
     if (cl.beta_nonzero) {
+        TraceScope ts(ctx, ctx->s_h2d, "h2dC", 0, n1);
         int rc = h2d_2d(cl, dC, ldc_dev, cl.c, cl.ldc, cl.m, n1, ctx->s_h2d);
         if (rc) return rc;
     }
-    // ---- phase 1
+    // ---- phase 1: A streams in as k-chunks with the first column block of B
     int64_t p0 = 0;
     cudaStream_t cs0 = ctx->s_compute[0];
-    for (size_t ci = 0; ci < chunks.size(); ++ci) {
-        const int64_t kc = chunks[ci];
+    for (size_t ci = 0; ci < pl.chunks.size(); ++ci) {
+        const int64_t kc = pl.chunks[ci];
         Sub sa = a_sub(cl, 0, cl.m, p0, kc);
         Sub sb = b_sub(cl, p0, kc, 0, n1);
         char* da = dA + ((size_t)sa.col * pa + sa.row) * es;
         char* db = dB + ((size_t)sb.col * pb + sb.row) * es;
-        int rc = h2d_2d(cl, da, pa, cl.a + ((size_t)sa.col * cl.lda + sa.row) * es, cl.lda, sa.rows, sa.cols, ctx->s_h2d);
-        if (rc) return rc;
-        rc = h2d_2d(cl, db, pb, cl.b + ((size_t)sb.col * cl.ldb + sb.row) * es, cl.ldb, sb.rows, sb.cols, ctx->s_h2d);
-        if (rc) return rc;
+        {
+            TraceScope ts(ctx, ctx->s_h2d, "h2dAB", p0, kc);
+            int rc = h2d_2d(cl, da, pa, cl.a + ((size_t)sa.col * cl.lda + sa.row) * es, cl.lda, sa.rows, sa.cols, ctx->s_h2d);
+            if (rc) return rc;
+            rc = h2d_2d(cl, db, pb, cl.b + ((size_t)sb.col * cl.ldb + sb.row) * es, cl.ldb, sb.rows, sb.cols, ctx->s_h2d);
+            if (rc) return rc;
+        }
         CU(ctx->get_event(&ev));
         CU(cudaEventRecord(ev, ctx->s_h2d));
         CU(cudaStreamWaitEvent(cs0, ev, 0));
-        rc = launch_gemm(cl, cl.m, n1, kc, da, pa, db, pb, ci == 0 ? cl.beta : (const void*)cl.one, dC, ldc_dev, cs0);
-        if (rc) return rc;
+        {
+            TraceScope ts(ctx, cs0, "gemm1", n1, kc);
+            int rc = launch_gemm(cl, cl.m, n1, kc, da, pa, db, pb, ci == 0 ? cl.beta : (const void*)cl.one, dC, ldc_dev, cs0);
+            if (rc) return rc;
+        }
         p0 += kc;
     }
     if (cl.copy_c_back) {
         CU(ctx->get_event(&ev));
         CU(cudaEventRecord(ev, cs0));
         CU(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
-        // a few pieces so the first bytes leave early and the stats stay honest
+        // a few pieces so the first bytes leave early
         const int64_t piece = std::max<int64_t>(64, round_up(n1 / 4, 64));
         for (int64_t j = 0; j < n1; j += piece) {
             const int64_t w = std::min(piece, n1 - j);
+            TraceScope ts(ctx, ctx->s_d2h, "d2hC", j, w);
             int rc = d2h_2d(cl, cl.c + (size_t)j * cl.ldc * es, cl.ldc, (char*)dC + (size_t)j * ldc_dev * es, ldc_dev, cl.m, w, ctx->s_d2h);
             if (rc) return rc;
         }
     }
-    // ---- phase 2: remaining column blocks with full k
+    // ---- phase 2: A resident; remaining column blocks of B, full k each, C block streams back at once
     int64_t j0 = n1;
-    int blk = 0;
-    // target block: ~1/16 of the remaining work but at least 512 columns; the last blocks shrink
-    const int64_t target = std::max<int64_t>(512, std::min<int64_t>(2048, round_up(std::max(64, ctx->max_tile_n), 64)));
-    while (j0 < cl.n) {
-        const int64_t remaining = cl.n - j0;
-        int64_t nb;
-        if (remaining <= 512) nb = remaining;
-        else if (remaining <= target + 512) nb = std::min(remaining - 256, pick_block_cols(cl.m, target, remaining));
-        else nb = pick_block_cols(cl.m, target, remaining);
-        nb = std::max<int64_t>(std::min<int64_t>(nb, remaining), std::min<int64_t>(64, remaining));
+    for (size_t blk = 0; blk < pl.blocks.size(); ++blk) {
+        const int64_t nb = pl.blocks[blk];
         char* dcb = (char*)dC + (size_t)j0 * ldc_dev * es;
         if (cl.beta_nonzero) {
+            TraceScope ts(ctx, ctx->s_h2d, "h2dC", j0, nb);
             int rc = h2d_2d(cl, dcb, ldc_dev, cl.c + (size_t)j0 * cl.ldc * es, cl.ldc, cl.m, nb, ctx->s_h2d);
             if (rc) return rc;
         }
         Sub sb = b_sub(cl, 0, cl.k, j0, nb);
         char* db = dB + ((size_t)sb.col * pb + sb.row) * es;
-        int rc = h2d_2d(cl, db, pb, cl.b + ((size_t)sb.col * cl.ldb + sb.row) * es, cl.ldb, sb.rows, sb.cols, ctx->s_h2d);
-        if (rc) return rc;
+        {
+            TraceScope ts(ctx, ctx->s_h2d, "h2dB", j0, nb);
+            int rc = h2d_2d(cl, db, pb, cl.b + ((size_t)sb.col * cl.ldb + sb.row) * es, cl.ldb, sb.rows, sb.cols, ctx->s_h2d);
+            if (rc) return rc;
+        }
         CU(ctx->get_event(&ev));
         CU(cudaEventRecord(ev, ctx->s_h2d));
         cudaStream_t cs = ctx->s_compute[(1 + blk) % ncs];
         CU(cudaStreamWaitEvent(cs, ev, 0));
-        rc = launch_gemm(cl, cl.m, nb, cl.k, dA, pa, db, pb, cl.beta, dcb, ldc_dev, cs);
-        if (rc) return rc;
+        {
+            TraceScope ts(ctx, cs, "gemm2", j0, nb);
+            int rc = launch_gemm(cl, cl.m, nb, cl.k, dA, pa, db, pb, cl.beta, dcb, ldc_dev, cs);
+            if (rc) return rc;
+        }
         if (cl.copy_c_back) {
             CU(ctx->get_event(&ev));
             CU(cudaEventRecord(ev, cs));
             CU(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
-            rc = d2h_2d(cl, cl.c + (size_t)j0 * cl.ldc * es, cl.ldc, dcb, ldc_dev, cl.m, nb, ctx->s_d2h);
+            TraceScope ts(ctx, ctx->s_d2h, "d2hC", j0, nb);
+            int rc = d2h_2d(cl, cl.c + (size_t)j0 * cl.ldc * es, cl.ldc, dcb, ldc_dev, cl.m, nb, ctx->s_d2h);
             if (rc) return rc;
         }
         j0 += nb;
-        ++blk;
     }
-    ctx->stats.c_blocks = 1 + blk;
     return TMM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Streaming regime (out-of-core): C super-blocks resident, k-chunks of A and B through a slot ring.
 // ------------------------------------------------------------------------------------------------
-int run_streaming(Call& cl, void* dC_full, int64_t ldc_full, size_t budget) {
+int run_streaming(Call& cl, const tmm::Plan& pl, void* dC_full, int64_t ldc_full) {
     tmm_context* ctx = cl.ctx;
     const size_t es = cl.es;
-    const int64_t align = 128 / (int64_t)es;
-    constexpr int SLOTS = 3;
-    int64_t kc = std::max<int64_t>(256, std::min<int64_t>(2048, round_up(std::max(64, ctx->max_tile_k), 64)));
-    kc = std::min(kc, round_up(cl.k, 64));
-
-    // C super-block: whole C if it leaves >= 40% of the budget for the ring, else ~square blocks, double-buffered
-    int64_t MB = cl.m, NB = cl.n;
-    const bool c_is_full = (dC_full != nullptr);
-    auto ring_bytes = [&](int64_t mb, int64_t nb, int64_t kcc) {
-        return (size_t)SLOTS * (size_t)(round_up(mb, align) + round_up(nb, align) + 2 * align) * (size_t)round_up(kcc, align) * es;
-    };
-    if (!c_is_full) {
-        const double cbytes = (double)cl.m * cl.n * es;
-        if (cbytes > 0.6 * (double)budget) {
-            // 2 * MB * NB * es <= 0.6 budget
-            double side = std::sqrt(0.3 * (double)budget / (double)es);
-            MB = std::min<int64_t>(cl.m, std::max<int64_t>(128, (int64_t)side / 128 * 128));
-            NB = std::min<int64_t>(cl.n, std::max<int64_t>(64, (int64_t)(0.3 * (double)budget / (double)es / (double)MB) / 64 * 64));
-        }
-    }
-    const size_t c_need = c_is_full ? 0 : (size_t)((MB == cl.m && NB == cl.n) ? 1 : 2) * (size_t)round_up(MB, align) * NB * es;
-    while (kc > 64 && c_need + ring_bytes(MB, NB, kc) > budget) kc /= 2;
-    if (c_need + ring_bytes(MB, NB, kc) > budget) return fail(TMM_ERR_NOMEM, "device budget %zu B too small for streaming regime", budget);
-
-    const int64_t pa_slot = cl.ta == 'N' ? round_up(MB, align) : round_up(kc, align);  // pitch of an A slot
-    const int64_t pb_slot = cl.tb == 'N' ? round_up(kc, align) : round_up(NB, align);
-    const size_t a_slot_bytes = (size_t)pa_slot * (cl.ta == 'N' ? kc : MB) * es;
-    const size_t b_slot_bytes = (size_t)pb_slot * (cl.tb == 'N' ? NB : kc) * es;
+    const int SLOTS = pl.slots;
+    const int64_t MB = pl.MB, NB = pl.NB, kc = pl.kc;
+    const bool c_is_full = pl.c_is_full;
     cudaError_t e;
-    if ((e = ctx->buf_a.reserve(a_slot_bytes * SLOTS)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(A ring)");
-    if ((e = ctx->buf_b.reserve(b_slot_bytes * SLOTS)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(B ring)");
-    const int64_t pc_blk = round_up(MB, align);
-    const int n_cbuf = (MB == cl.m && NB == cl.n) ? 1 : 2;
-    if (!c_is_full) {
-        if ((e = ctx->buf_c.reserve((size_t)n_cbuf * pc_blk * NB * es)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(C blocks)");
-    }
+    if ((e = ctx->buf_a.reserve(pl.bytes_a)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(A ring)");
+    if ((e = ctx->buf_b.reserve(pl.bytes_b)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(B ring)");
+    if (!c_is_full && (e = ctx->buf_c.reserve(pl.bytes_c)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(C blocks)");
 
     cudaStream_t cs = ctx->s_compute[0];
-    cudaEvent_t slot_free[SLOTS] = {nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> slot_free(SLOTS, nullptr);
     cudaEvent_t cbuf_free[2] = {nullptr, nullptr};
     int slot = 0, cbuf = 0, nblocks = 0;
     const int64_t nchunks = (cl.k + kc - 1) / kc;
@@ -418,32 +369,39 @@ int run_streaming(Call& cl, void* dC_full, int64_t ldc_full, size_t budget) {
             char* dcb;
             int64_t ldcb;
             if (c_is_full) { dcb = (char*)dC_full + ((size_t)j0 * ldc_full + i0) * es; ldcb = ldc_full; }
-            else { dcb = (char*)ctx->buf_c.p + (size_t)cbuf * pc_blk * NB * es; ldcb = pc_blk; }
+            else { dcb = (char*)ctx->buf_c.p + (size_t)cbuf * pl.pc_blk * NB * es; ldcb = pl.pc_blk; }
             if (!c_is_full && cbuf_free[cbuf]) {
                 // this C buffer's previous contents must have left for the host before it is overwritten
                 CU(cudaStreamWaitEvent(ctx->s_h2d, cbuf_free[cbuf], 0));
                 CU(cudaStreamWaitEvent(cs, cbuf_free[cbuf], 0));
             }
             if (cl.beta_nonzero) {
+                TraceScope ts(ctx, ctx->s_h2d, "h2dC", i0, j0);
                 int rc = h2d_2d(cl, dcb, ldcb, cl.c + ((size_t)j0 * cl.ldc + i0) * es, cl.ldc, mi, nj, ctx->s_h2d);
                 if (rc) return rc;
             }
             for (int64_t ci = 0; ci < nchunks; ++ci) {
                 const int64_t p0 = ci * kc, kcc = std::min(kc, cl.k - p0);
                 if (slot_free[slot]) CU(cudaStreamWaitEvent(ctx->s_h2d, slot_free[slot], 0));
-                char* da = (char*)ctx->buf_a.p + (size_t)slot * a_slot_bytes;
-                char* db = (char*)ctx->buf_b.p + (size_t)slot * b_slot_bytes;
+                char* da = (char*)ctx->buf_a.p + (size_t)slot * pl.a_slot_bytes;
+                char* db = (char*)ctx->buf_b.p + (size_t)slot * pl.b_slot_bytes;
                 Sub sa = a_sub(cl, i0, mi, p0, kcc);
                 Sub sb = b_sub(cl, p0, kcc, j0, nj);
-                int rc = h2d_2d(cl, da, pa_slot, cl.a + ((size_t)sa.col * cl.lda + sa.row) * es, cl.lda, sa.rows, sa.cols, ctx->s_h2d);
-                if (rc) return rc;
-                rc = h2d_2d(cl, db, pb_slot, cl.b + ((size_t)sb.col * cl.ldb + sb.row) * es, cl.ldb, sb.rows, sb.cols, ctx->s_h2d);
-                if (rc) return rc;
+                {
+                    TraceScope ts(ctx, ctx->s_h2d, "h2dAB", p0, kcc, slot);
+                    int rc = h2d_2d(cl, da, pl.pa_slot, cl.a + ((size_t)sa.col * cl.lda + sa.row) * es, cl.lda, sa.rows, sa.cols, ctx->s_h2d);
+                    if (rc) return rc;
+                    rc = h2d_2d(cl, db, pl.pb_slot, cl.b + ((size_t)sb.col * cl.ldb + sb.row) * es, cl.ldb, sb.rows, sb.cols, ctx->s_h2d);
+                    if (rc) return rc;
+                }
                 CU(ctx->get_event(&ev));
                 CU(cudaEventRecord(ev, ctx->s_h2d));
                 CU(cudaStreamWaitEvent(cs, ev, 0));
-                rc = launch_gemm(cl, mi, nj, kcc, da, pa_slot, db, pb_slot, ci == 0 ? cl.beta : (const void*)cl.one, dcb, ldcb, cs);
-                if (rc) return rc;
+                {
+                    TraceScope ts(ctx, cs, "gemmS", i0, j0, p0);
+                    int rc = launch_gemm(cl, mi, nj, kcc, da, pl.pa_slot, db, pl.pb_slot, ci == 0 ? cl.beta : (const void*)cl.one, dcb, ldcb, cs);
+                    if (rc) return rc;
+                }
                 CU(ctx->get_event(&slot_free[slot]));
                 CU(cudaEventRecord(slot_free[slot], cs));
                 slot = (slot + 1) % SLOTS;
@@ -452,6 +410,7 @@ int run_streaming(Call& cl, void* dC_full, int64_t ldc_full, size_t budget) {
                 CU(ctx->get_event(&ev));
                 CU(cudaEventRecord(ev, cs));
                 CU(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
+                TraceScope ts(ctx, ctx->s_d2h, "d2hC", i0, j0);
                 int rc = d2h_2d(cl, cl.c + ((size_t)j0 * cl.ldc + i0) * es, cl.ldc, dcb, ldcb, mi, nj, ctx->s_d2h);
                 if (rc) return rc;
                 if (!c_is_full) {
@@ -459,7 +418,7 @@ int run_streaming(Call& cl, void* dC_full, int64_t ldc_full, size_t budget) {
                     CU(cudaEventRecord(cbuf_free[cbuf], ctx->s_d2h));
                 }
             }
-            if (!c_is_full) cbuf = (cbuf + 1) % n_cbuf;
+            if (!c_is_full) cbuf = (cbuf + 1) % pl.n_cbuf;
             ++nblocks;
         }
     }
@@ -527,6 +486,8 @@ int tmm_context_create(int dtype, int n_streams, int max_tile_m, int max_tile_n,
     if (prop.major != 10) { delete ctx; return fail(TMM_ERR_NOGPU, "device %d is sm_%d%d; tiled_mm_b200 kernels are built for sm_100a only", ctx->device, prop.major, prop.minor); }
     const char* pc = getenv("TMM_PIN_CACHE");
     ctx->pin_cache = pc && pc[0] == '1';
+    const char* tr = getenv("TMM_TRACE");
+    ctx->trace = tr && tr[0] == '1';
     cudaStream_t* all[] = {&ctx->s_h2d, &ctx->s_d2h, &ctx->s_compute[0], &ctx->s_compute[1], &ctx->s_compute[2], &ctx->s_compute[3]};
     for (cudaStream_t* s : all)
         if ((e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking)) != cudaSuccess) { tmm_context_destroy(ctx); return cuda_fail(e, "cudaStreamCreateWithFlags"); }
@@ -564,22 +525,12 @@ int tmm_context_set_streams_and_tiles(tmm_context* ctx, int n_streams, int tile_
     return TMM_OK;
 }
 
-// Same function of (dim, max) as the reference heuristic (mm_handle.cpp:89-110): dim if it fits, else the largest
-// divisor of dim that is <= max when it is at least half of max, else max.  Kept so callers that size their own
-// buffers from it see identical numbers; this library's staging granularity does not depend on it.
-static int optimal_tile(int dim, int max_tile) {
-    if (dim <= max_tile) return dim;
-    int best = 1;
-    for (int d = max_tile; d >= 1; --d) if (dim % d == 0) { best = d; break; }
-    return (max_tile - best <= max_tile / 2) ? best : max_tile;
-}
-
 int tmm_context_optimal_tile_sizes(tmm_context* ctx, int m, int n, int k, int* tm, int* tn, int* tk) {
     if (!ctx) return fail(TMM_ERR_INVALID, "null context");
     if (m < 1 || n < 1 || k < 1) return fail(TMM_ERR_INVALID, "dimensions must be >= 1");
-    if (tm) *tm = optimal_tile(m, ctx->max_tile_m);
-    if (tn) *tn = optimal_tile(n, ctx->max_tile_n);
-    if (tk) *tk = optimal_tile(k, ctx->max_tile_k);
+    if (tm) *tm = tmm::optimal_tile_size(m, ctx->max_tile_m);
+    if (tn) *tn = tmm::optimal_tile_size(n, ctx->max_tile_n);
+    if (tk) *tk = tmm::optimal_tile_size(k, ctx->max_tile_k);
     return TMM_OK;
 }
 
@@ -621,7 +572,8 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
     if (ld_c < std::max<int64_t>(1, m)) return fail(TMM_ERR_INVALID, "ld_c (%lld) < m (%lld)", (long long)ld_c, (long long)m);
 
     ctx->stats = tmm_call_stats{};
-    ctx->ev_next = 0; ctx->tev_next = 0;
+    ctx->ev_next = 0; ctx->tev_next = 0; ctx->trace_ops.clear(); ctx->gemm_events.clear();
+    cudaEvent_t trace_t0 = nullptr;
     const uint64_t launches_before = tmm::launch_count();
     if (m == 0 || n == 0) return TMM_OK;  // BLAS quick return (the reference divides by zero here)
     const bool alpha_zero = scalar_is_zero(ctx->dtype, alpha);
@@ -630,6 +582,7 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
     if ((need_ab && (!a || !b)) || (c_touched && !c)) return fail(TMM_ERR_INVALID, "null matrix pointer");
 
     DeviceGuard guard(ctx->device);
+    if (ctx->trace && ctx->get_timing_event(&trace_t0) == cudaSuccess) cudaEventRecord(trace_t0, ctx->s_h2d);
     std::vector<const void*> pinned_now;
     int rc = TMM_OK;
     if (pin_host_buffers) {  // reference tiled_mm.cpp:529-554
@@ -677,18 +630,22 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                     }
                 }
             } else {
-                const size_t a_bytes = (size_t)round_up(cl.a_rows, align) * cl.a_cols * cl.es;
-                const size_t b_bytes = (size_t)round_up(cl.b_rows, align) * cl.b_cols * cl.es;
-                const bool resident = a_bytes + b_bytes + c_bytes <= budget;
-                ctx->stats.regime = resident ? 0 : 1;
-                if (resident) {
+                tmm::PlanInput pin_;
+                pin_.dtype = cl.dtype; pin_.ta = cl.ta; pin_.tb = cl.tb; pin_.m = m; pin_.n = n; pin_.k = k;
+                pin_.beta_nonzero = cl.beta_nonzero; pin_.copy_c_back = cl.copy_c_back; pin_.budget = budget;
+                pin_.n_streams = ctx->n_streams; pin_.tile_m = ctx->max_tile_m; pin_.tile_n = ctx->max_tile_n; pin_.tile_k = ctx->max_tile_k;
+                pin_.sm_count = tmm::sm_count();
+                const tmm::Plan pl = tmm::make_plan(pin_);
+                ctx->stats.regime = pl.regime;
+                if (!pl.error.empty()) rc = fail(TMM_ERR_NOMEM, "%s (budget %zu B)", pl.error.c_str(), budget);
+                else if (pl.regime == tmm::REGIME_RESIDENT) {
                     if (cl.copy_c_back) {
-                        if ((e = ctx->buf_c.reserve(c_bytes)) != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(C)");
+                        if ((e = ctx->buf_c.reserve(pl.bytes_c)) != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(C)");
                         dC = ctx->buf_c.p;
                     }
-                    if (!rc) rc = run_resident(cl, dC, ldc_dev);
+                    if (!rc) rc = run_resident(cl, pl, dC, pl.pitch_c);
                 } else {
-                    rc = run_streaming(cl, cl.copy_c_back ? nullptr : dC, ldc_dev, budget);
+                    rc = run_streaming(cl, pl, cl.copy_c_back ? nullptr : dC, ldc_dev);
                 }
             }
         }
@@ -700,17 +657,45 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = cuda_fail(e, "kernel execution");
     }
+    double kernel_ms_total = 0;
     if (!rc && ctx->profiling) {
-        double total = 0;
-        for (size_t i = 0; i + 1 < ctx->tev_next; i += 2) {
+        for (auto& pr : ctx->gemm_events) {
             float ms = 0;
-            if (cudaEventElapsedTime(&ms, ctx->timing_events[i], ctx->timing_events[i + 1]) == cudaSuccess) total += ms;
+            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) kernel_ms_total += ms;
         }
-        ctx->stats.kernel_ms = total;
     }
+    if (ctx->trace && trace_t0) {
+        fprintf(stderr, "[tmm trace] %-28s %10s %10s %9s\n", "op", "start_ms", "end_ms", "dur_ms");
+        for (auto& op : ctx->trace_ops) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, trace_t0, op.e0);
+            cudaEventElapsedTime(&b, trace_t0, op.e1);
+            fprintf(stderr, "[tmm trace] %-28s %10.3f %10.3f %9.3f\n", op.name.c_str(), a, b, b - a);
+        }
+    }
+    ctx->stats.kernel_ms = kernel_ms_total;
     ctx->stats.kernel_launches = tmm::launch_count() - launches_before;
     ctx->stats.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return rc;
+}
+
+int tmm_optimal_tile_size(int dim, int max_tile) {
+    if (dim < 1 || max_tile < 1) return TMM_ERR_INVALID;
+    return tmm::optimal_tile_size(dim, max_tile);
+}
+
+int tmm_plan_describe(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, int beta_nonzero, int copy_c_back, size_t budget_bytes,
+                      int n_streams, int tile_m, int tile_n, int tile_k, int sm_count, char* out, size_t out_size) {
+    if (dtype < TMM_F32 || dtype > TMM_C64 || m < 1 || n < 1 || k < 1 || !out || out_size == 0) return fail(TMM_ERR_INVALID, "plan_describe: bad argument");
+    tmm::PlanInput in;
+    in.dtype = dtype; in.ta = (char)std::toupper((unsigned char)trans_a); in.tb = (char)std::toupper((unsigned char)trans_b);
+    in.m = m; in.n = n; in.k = k; in.beta_nonzero = beta_nonzero != 0; in.copy_c_back = copy_c_back != 0; in.budget = budget_bytes;
+    in.n_streams = n_streams; in.tile_m = tile_m; in.tile_n = tile_n; in.tile_k = tile_k; in.sm_count = sm_count > 0 ? sm_count : 148;
+    const tmm::Plan pl = tmm::make_plan(in);
+    const std::string js = tmm::plan_to_json(in, pl);
+    if (js.size() + 1 > out_size) return fail(TMM_ERR_INVALID, "plan_describe: buffer too small (%zu needed)", js.size() + 1);
+    memcpy(out, js.c_str(), js.size() + 1);
+    return TMM_OK;
 }
 
 int tmm_malloc_pinned(size_t bytes, void** out) {

@@ -1,0 +1,176 @@
+#include "tmm_plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <sstream>
+
+namespace tmm {
+
+namespace {
+int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+size_t elem_size(int dt) { return dt == 0 ? 4 : (dt == 1 ? 8 : (dt == 2 ? 8 : 16)); }
+
+// Throughput model used only to size chunks (never a correctness input).  Measured on B200 (profiles/r1_probe_b200.txt):
+// FP64 DMMA GEMM 35.6 TFLOP/s, pinned H2D 55.6 GB/s (48 GB/s while D2H runs).
+constexpr double kFlops = 35e12;
+constexpr double kH2D = 52e9;
+constexpr int64_t BM = 128, BN = 64;  // CTA tile of the FP64 kernels
+
+// Column-block width: a multiple of 64 near `target` whose CTA count fills whole waves (2 CTAs per SM).
+int64_t pick_block_cols(int64_t m, int64_t target, int64_t remaining, int sm_count) {
+    if (remaining <= target) return remaining;
+    const int64_t tiles_m = (m + BM - 1) / BM;
+    const int64_t slots = 2 * (int64_t)sm_count;
+    int64_t best = std::min(remaining, round_up(target, BN));
+    double best_eff = 0.0;
+    for (int64_t cols = std::max<int64_t>(BN, round_up(target * 3 / 4, BN)); cols <= target * 5 / 4 && cols <= remaining; cols += BN) {
+        const int64_t tiles = tiles_m * (cols / BN);
+        const double eff = (double)tiles / (double)round_up(tiles, slots);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = cols; }
+    }
+    return best;
+}
+}  // namespace
+
+// Same function of (dim, max) as the reference heuristic (mm_handle.cpp:89-110): dim if it fits, else the largest
+// divisor of dim that is <= max when that divisor is at least half of max, else max.
+int optimal_tile_size(int dim, int max_tile) {
+    if (dim <= max_tile) return dim;
+    int best = 1;
+    for (int d = max_tile; d >= 1; --d)
+        if (dim % d == 0) { best = d; break; }
+    return (max_tile - best <= max_tile / 2) ? best : max_tile;
+}
+
+Plan make_plan(const PlanInput& in) {
+    Plan p;
+    p.es = elem_size(in.dtype);
+    const int64_t es = (int64_t)p.es;
+    const int64_t align = 128 / es;
+    const int64_t m = in.m, n = in.n, k = in.k;
+    p.a_rows = in.ta == 'N' ? m : k; p.a_cols = in.ta == 'N' ? k : m;
+    p.b_rows = in.tb == 'N' ? k : n; p.b_cols = in.tb == 'N' ? n : k;
+    p.pitch_a = round_up(p.a_rows, align);
+    p.pitch_b = round_up(p.b_rows, align);
+    p.pitch_c = in.copy_c_back ? round_up(m, align) : m;  // device-resident C is compact, ld = m (reference README.md:102-103)
+    const size_t full_a = (size_t)p.pitch_a * p.a_cols * es, full_b = (size_t)p.pitch_b * p.b_cols * es;
+    const size_t full_c = in.copy_c_back ? (size_t)p.pitch_c * n * es : 0;
+    const double F = (in.dtype >= 2) ? 8.0 : 2.0;
+    const int64_t kc_cap = std::max<int64_t>(256, std::min<int64_t>(2048, round_up(std::max(64, in.tile_k), 64)));
+
+    if (full_a + full_b + full_c <= in.budget) {
+        // ---------------- resident ----------------
+        p.regime = REGIME_RESIDENT;
+        p.bytes_a = full_a; p.bytes_b = full_b; p.bytes_c = full_c;
+        // phase-1 column block: wide enough that a k-chunk's GEMM outlasts its upload (with 20 % margin)
+        // (m too small for that => the call is PCIe-bound whatever we do: bring A in behind a narrow block and let
+        //  phase 2 overlap the D2H of finished C blocks with the H2D of later B blocks)
+        int64_t n1 = std::min<int64_t>(n, 1024);
+        const double denom = F * (double)m / kFlops - 1.2 * (double)es / kH2D;
+        if (denom > 0) {
+            const double need = 1.2 * (double)es * (double)m / kH2D / denom;
+            n1 = (int64_t)std::min<double>((double)n, std::max(512.0, need));
+        }
+        n1 = std::min<int64_t>(n, round_up(n1, BN));
+        if (n - n1 < 256) n1 = n;  // not worth a second phase
+        p.n1 = n1;
+        // phase-1 k-chunks: small first chunk (short prologue), doubling up to the cap
+        {
+            int64_t done = 0, kc = 256;
+            while (done < k) {
+                int64_t c = std::min(kc, k - done);
+                if (k - done - c < kc / 2) c = k - done;  // fold a small remainder into this chunk
+                p.chunks.push_back(c);
+                done += c;
+                kc = std::min(kc * 2, kc_cap);
+            }
+        }
+        // phase-2 column blocks, shrinking towards the end so the last D2H is short
+        const int64_t target = std::max<int64_t>(512, std::min<int64_t>(2048, round_up(std::max(64, in.tile_n), 64)));
+        int64_t j0 = n1;
+        while (j0 < n) {
+            const int64_t remaining = n - j0;
+            int64_t nb;
+            if (remaining <= 512) nb = remaining;
+            else if (remaining <= target + 512) nb = std::max<int64_t>(BN, std::min((remaining - 256) / BN * BN, pick_block_cols(m, target, remaining, in.sm_count)));
+            else nb = pick_block_cols(m, target, remaining, in.sm_count);
+            nb = std::min(nb, remaining);
+            p.blocks.push_back(nb);
+            j0 += nb;
+        }
+        p.launches = (int)(p.chunks.size() + p.blocks.size());
+        p.h2d_bytes = (uint64_t)es * ((uint64_t)m * k + (uint64_t)k * n + (in.beta_nonzero ? (uint64_t)m * n : 0));
+        p.d2h_bytes = in.copy_c_back ? (uint64_t)es * m * n : 0;
+        return p;
+    }
+
+    // ---------------- streaming (out-of-core) ----------------
+    p.regime = REGIME_STREAMING;
+    p.slots = 3;
+    p.c_is_full = !in.copy_c_back;
+    int64_t kc = std::min(kc_cap, round_up(std::max<int64_t>(k, 1), 64));
+    int64_t MB = m, NB = n;
+    if (!p.c_is_full) {
+        const double cbytes = (double)round_up(m, align) * (double)n * (double)es;
+        if (cbytes > 0.6 * (double)in.budget) {
+            // two C buffers of MB x NB must fit in 60 % of the budget
+            const double side = std::sqrt(0.3 * (double)in.budget / (double)es);
+            MB = std::min<int64_t>(m, std::max<int64_t>(BM, (int64_t)side / BM * BM));
+            NB = std::min<int64_t>(n, std::max<int64_t>(BN, (int64_t)(0.3 * (double)in.budget / (double)es / (double)round_up(MB, align)) / BN * BN));
+        }
+    }
+    p.n_cbuf = (MB == m && NB == n) ? 1 : 2;
+    auto c_need = [&]() { return p.c_is_full ? (size_t)0 : (size_t)p.n_cbuf * (size_t)round_up(MB, align) * (size_t)NB * (size_t)es; };
+    auto slot_a = [&](int64_t kcc) {
+        const int64_t pitch = in.ta == 'N' ? round_up(MB, align) : round_up(kcc, align);
+        return (size_t)pitch * (size_t)(in.ta == 'N' ? kcc : MB) * (size_t)es;
+    };
+    auto slot_b = [&](int64_t kcc) {
+        const int64_t pitch = in.tb == 'N' ? round_up(kcc, align) : round_up(NB, align);
+        return (size_t)pitch * (size_t)(in.tb == 'N' ? NB : kcc) * (size_t)es;
+    };
+    while (kc > 64 && c_need() + (size_t)p.slots * (slot_a(kc) + slot_b(kc)) > in.budget) kc = std::max<int64_t>(64, kc / 2 / 64 * 64);
+    while (!p.c_is_full && (MB > BM || NB > BN) && c_need() + (size_t)p.slots * (slot_a(kc) + slot_b(kc)) > in.budget) {
+        if (MB >= 2 * NB && MB > BM) MB = std::max<int64_t>(BM, MB / 2 / BM * BM);
+        else if (NB > BN) NB = std::max<int64_t>(BN, NB / 2 / BN * BN);
+        else MB = std::max<int64_t>(BM, MB / 2 / BM * BM);
+        p.n_cbuf = 2;
+    }
+    if (c_need() + (size_t)p.slots * (slot_a(kc) + slot_b(kc)) > in.budget) {
+        p.error = "device budget too small for the streaming regime";
+        return p;
+    }
+    p.MB = MB; p.NB = NB; p.kc = kc;
+    p.pa_slot = in.ta == 'N' ? round_up(MB, align) : round_up(kc, align);
+    p.pb_slot = in.tb == 'N' ? round_up(kc, align) : round_up(NB, align);
+    p.a_slot_bytes = slot_a(kc); p.b_slot_bytes = slot_b(kc);
+    p.pc_blk = round_up(MB, align);
+    p.bytes_a = p.a_slot_bytes * p.slots; p.bytes_b = p.b_slot_bytes * p.slots; p.bytes_c = c_need();
+    const int64_t bm = (m + MB - 1) / MB, bn = (n + NB - 1) / NB, nchunks = (k + kc - 1) / kc;
+    p.launches = (int)(bm * bn * nchunks);
+    // A row-panels are re-sent once per column of super-blocks, B column-panels once per row of super-blocks
+    p.h2d_bytes = (uint64_t)es * ((uint64_t)m * k * bn + (uint64_t)k * n * bm + (in.beta_nonzero ? (uint64_t)m * n : 0));
+    p.d2h_bytes = in.copy_c_back ? (uint64_t)es * m * n : 0;
+    return p;
+}
+
+std::string plan_to_json(const PlanInput& in, const Plan& p) {
+    std::ostringstream o;
+    auto vec = [&](const std::vector<int64_t>& v) {
+        o << "[";
+        for (size_t i = 0; i < v.size(); ++i) o << (i ? "," : "") << v[i];
+        o << "]";
+    };
+    o << "{\"regime\":" << p.regime << ",\"elem_size\":" << p.es << ",\"m\":" << in.m << ",\"n\":" << in.n << ",\"k\":" << in.k
+      << ",\"pitch_a\":" << p.pitch_a << ",\"pitch_b\":" << p.pitch_b << ",\"pitch_c\":" << p.pitch_c << ",\"bytes_a\":" << p.bytes_a
+      << ",\"bytes_b\":" << p.bytes_b << ",\"bytes_c\":" << p.bytes_c << ",\"n1\":" << p.n1 << ",\"chunks\":";
+    vec(p.chunks);
+    o << ",\"blocks\":";
+    vec(p.blocks);
+    o << ",\"MB\":" << p.MB << ",\"NB\":" << p.NB << ",\"kc\":" << p.kc << ",\"slots\":" << p.slots << ",\"n_cbuf\":" << p.n_cbuf
+      << ",\"c_is_full\":" << (p.c_is_full ? "true" : "false") << ",\"h2d_bytes\":" << p.h2d_bytes << ",\"d2h_bytes\":" << p.d2h_bytes
+      << ",\"launches\":" << p.launches << ",\"error\":\"" << p.error << "\"}";
+    return o.str();
+}
+
+}  // namespace tmm
