@@ -139,7 +139,21 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
     int stage = 0;
     uint32_t phase = 0;
+    // read-modify-write launches pull this warp's 64 x 32 block of C towards L2 a few k-blocks before the epilogue
+    // needs it (early enough to cover the HBM latency, late enough not to be evicted again by the A/B stream)
+    const int prefetch_kb = p.read_c ? max(0, kblocks - 12) : -1;
     for (int kb = 0; kb < kblocks; ++kb) {
+        if (kb == prefetch_kb) {
+            // lane l covers column wn + l: 64 rows = 512 B = 4 (5 when unaligned) 128-byte lines
+            const int col = tn * BN + wn + lane;
+            if (col < p.n) {
+                const char* cp = reinterpret_cast<const char*>(p.c + (int64_t)col * p.ldc + tm * BM + wm);
+                const int rows = min(WM, p.m - (tm * BM + wm));
+#pragma unroll
+                for (int o = 0; o < 5; ++o)
+                    if (o * 128 < rows * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + o * 128));
+            }
+        }
         ptx::mbar_wait(&full_bar[stage], phase);
         const double* st = reinterpret_cast<const double*>(base + stage * C::STAGE_BYTES);
         const double* as = st + a_off;
@@ -164,21 +178,37 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     // epilogue: lane (g,t) owns rows 8i+g, columns 8j+2t, 8j+2t+1 of its warp tile
     const int row0 = tm * BM + wm + g;
     const int col0 = tn * BN + wn + 2 * t;
+    if (p.read_c) {
+        // read-modify-write: all 16 loads of a column pair are issued before any is consumed
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
+        for (int j = 0; j < NJ; ++j) {
+            double old[2][MI];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int col = col0 + 8 * j + h;
-            if (col < p.n) {
-                double* cp = p.c + (int64_t)col * p.ldc;
-                if (p.read_c) {
-                    double old[MI];
+            for (int h = 0; h < 2; ++h) {
+                const int col = col0 + 8 * j + h;
+                const double* cp = p.c + (int64_t)col * p.ldc;
 #pragma unroll
-                    for (int i = 0; i < MI; ++i) old[i] = (row0 + 8 * i < p.m) ? cp[row0 + 8 * i] : 0.0;
+                for (int i = 0; i < MI; ++i) old[h][i] = (col < p.n && row0 + 8 * i < p.m) ? __ldcs(cp + row0 + 8 * i) : 0.0;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = col0 + 8 * j + h;
+                if (col < p.n) {
+                    double* cp = p.c + (int64_t)col * p.ldc;
 #pragma unroll
                     for (int i = 0; i < MI; ++i)
-                        if (row0 + 8 * i < p.m) cp[row0 + 8 * i] = p.alpha * acc[i][j][h] + p.beta * old[i];
-                } else {
+                        if (row0 + 8 * i < p.m) cp[row0 + 8 * i] = p.alpha * acc[i][j][h] + p.beta * old[h][i];
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = col0 + 8 * j + h;
+                if (col < p.n) {
+                    double* cp = p.c + (int64_t)col * p.ldc;
 #pragma unroll
                     for (int i = 0; i < MI; ++i)
                         if (row0 + 8 * i < p.m) cp[row0 + 8 * i] = p.alpha * acc[i][j][h];

@@ -106,6 +106,7 @@ struct tmm_context {
     std::vector<cudaEvent_t> timing_events;
     size_t tev_next = 0;
     size_t budget_override = 0;
+    size_t budget_cached = 0;
     bool profiling = false;
     bool pin_cache = false;
     bool trace = false;
@@ -115,7 +116,9 @@ struct tmm_context {
     std::map<const void*, size_t> pinned;
     tmm_call_stats stats{};
 
-    int n_compute() const { return std::max(1, std::min(n_streams, (int)MAX_COMPUTE)); }
+    // compute streams: [0] carries the phase-1 / streaming chain at the highest priority, the others (lower priorities)
+    // carry independent column blocks, whose CTAs then only back-fill SM slots the chain leaves free
+    int n_compute() const { return std::max(3, std::min(n_streams + 1, (int)MAX_COMPUTE)); }
 
     cudaError_t get_event(cudaEvent_t* out) {
         if (ev_next == events.size()) {
@@ -215,11 +218,13 @@ int launch_gemm(Call& cl, int64_t mi, int64_t nj, int64_t kc, const void* da, in
 
 size_t device_budget(tmm_context* ctx) {
     if (ctx->budget_override) return ctx->budget_override;
+    if (ctx->budget_cached) return ctx->budget_cached;  // refreshed whenever an allocation fails or the context grows full C
     size_t fr = 0, to = 0;
     if (cudaMemGetInfo(&fr, &to) != cudaSuccess) return (size_t)8 << 30;
     size_t held = ctx->buf_a.cap + ctx->buf_b.cap + ctx->buf_c.cap;
     double avail = (double)fr + (double)held;
-    return (size_t)(avail * 0.92);
+    ctx->budget_cached = (size_t)(avail * 0.92);
+    return ctx->budget_cached;
 }
 
 // ---- optional timeline (TMM_TRACE=1): every op gets a begin/end event; printed after the call ----
@@ -320,7 +325,7 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
         }
         CU(ctx->get_event(&ev));
         CU(cudaEventRecord(ev, ctx->s_h2d));
-        cudaStream_t cs = ctx->s_compute[(1 + blk) % ncs];
+        cudaStream_t cs = ctx->s_compute[1 + blk % (ncs - 1)];
         CU(cudaStreamWaitEvent(cs, ev, 0));
         {
             TraceScope ts(ctx, cs, "gemm2", j0, nb);
@@ -488,9 +493,15 @@ int tmm_context_create(int dtype, int n_streams, int max_tile_m, int max_tile_n,
     ctx->pin_cache = pc && pc[0] == '1';
     const char* tr = getenv("TMM_TRACE");
     ctx->trace = tr && tr[0] == '1';
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);  // numerically lower = higher priority
     cudaStream_t* all[] = {&ctx->s_h2d, &ctx->s_d2h, &ctx->s_compute[0], &ctx->s_compute[1], &ctx->s_compute[2], &ctx->s_compute[3]};
-    for (cudaStream_t* s : all)
-        if ((e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking)) != cudaSuccess) { tmm_context_destroy(ctx); return cuda_fail(e, "cudaStreamCreateWithFlags"); }
+    // phase-2 streams share ONE lower priority: among equal priorities the block scheduler drains kernels in launch
+    // order, so column blocks finish in order (their D2H copies queue in that order) while still back-filling tails
+    const int low = std::min(prio_least, prio_greatest + 1);
+    const int prio[] = {prio_greatest, prio_greatest, prio_greatest, low, low, low};
+    for (int i = 0; i < 6; ++i)
+        if ((e = cudaStreamCreateWithPriority(all[i], cudaStreamNonBlocking, prio[i])) != cudaSuccess) { tmm_context_destroy(ctx); return cuda_fail(e, "cudaStreamCreateWithPriority"); }
     *out = ctx;
     return TMM_OK;
 }
@@ -601,6 +612,7 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
         size_t c_bytes = 0;
         if (!cl.copy_c_back) {
             // device-resident C, always compact ld = m (README.md:102-103, tests/test-multiply.cpp:339)
+            if ((size_t)m * n * cl.es > ctx->full_c.cap) ctx->budget_cached = 0;
             e = ctx->full_c.reserve((size_t)m * n * cl.es, 1.2);  // device_vector keeps 1.2x slack (device_vector.hpp:92-107)
             ctx->full_c_elems = (size_t)m * n;
             dC = ctx->full_c.p; ldc_dev = m;
@@ -650,6 +662,7 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
             }
         }
     }
+    const double t_enqueued = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     int rc_sync = sync_all(ctx);
     if (!rc) rc = rc_sync;
     for (const void* p : pinned_now) cudaHostUnregister(const_cast<void*>(p));  // tiled_mm.cpp:606-618
@@ -665,6 +678,8 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
         }
     }
     if (ctx->trace && trace_t0) {
+        fprintf(stderr, "[tmm trace] host: enqueue done at %.3f ms, all streams idle at %.3f ms after entry\n", t_enqueued,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
         fprintf(stderr, "[tmm trace] %-28s %10s %10s %9s\n", "op", "start_ms", "end_ms", "dur_ms");
         for (auto& op : ctx->trace_ops) {
             float a = 0, b = 0;
@@ -673,6 +688,7 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
             fprintf(stderr, "[tmm trace] %-28s %10.3f %10.3f %9.3f\n", op.name.c_str(), a, b, b - a);
         }
     }
+    if (rc == TMM_ERR_NOMEM) ctx->budget_cached = 0;  // free memory changed under us: re-query next time
     ctx->stats.kernel_ms = kernel_ms_total;
     ctx->stats.kernel_launches = tmm::launch_count() - launches_before;
     ctx->stats.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();

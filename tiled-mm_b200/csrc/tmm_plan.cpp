@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <sstream>
 
 namespace tmm {
@@ -15,6 +16,18 @@ size_t elem_size(int dt) { return dt == 0 ? 4 : (dt == 1 ? 8 : (dt == 2 ? 8 : 16
 constexpr double kFlops = 35e12;
 constexpr double kH2D = 52e9;
 constexpr int64_t BM = 128, BN = 64;  // CTA tile of the FP64 kernels
+
+// developer knobs for schedule experiments (never needed for correctness)
+double env_or(const char* name, double dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atof(v) : dflt;
+}
+
+// fraction of the last wave of CTAs that is filled (2 CTAs per SM resident)
+double wave_fill(int64_t tiles, int sm_count) {
+    const int64_t slots = 2 * (int64_t)sm_count;
+    return (double)tiles / (double)round_up(tiles, slots);
+}
 
 // Column-block width: a multiple of 64 near `target` whose CTA count fills whole waves (2 CTAs per SM).
 int64_t pick_block_cols(int64_t m, int64_t target, int64_t remaining, int sm_count) {
@@ -65,28 +78,45 @@ Plan make_plan(const PlanInput& in) {
         // phase-1 column block: wide enough that a k-chunk's GEMM outlasts its upload (with 20 % margin)
         // (m too small for that => the call is PCIe-bound whatever we do: bring A in behind a narrow block and let
         //  phase 2 overlap the D2H of finished C blocks with the H2D of later B blocks)
+        const double margin = env_or("TMM_PLAN_MARGIN", 1.3);
         int64_t n1 = std::min<int64_t>(n, 1024);
-        const double denom = F * (double)m / kFlops - 1.2 * (double)es / kH2D;
+        const double denom = F * (double)m / kFlops - margin * (double)es / kH2D;
         if (denom > 0) {
-            const double need = 1.2 * (double)es * (double)m / kH2D / denom;
+            const double need = margin * (double)es * (double)m / kH2D / denom;
             n1 = (int64_t)std::min<double>((double)n, std::max(512.0, need));
         }
         n1 = std::min<int64_t>(n, round_up(n1, BN));
+        if (n1 < n) {
+            // nudge n1 upwards (at most 12 %) to the width whose CTA count fills whole waves best
+            const int64_t tiles_m = (m + BM - 1) / BM;
+            int64_t best = n1;
+            double best_fill = wave_fill(tiles_m * (n1 / BN), in.sm_count);
+            for (int64_t c = n1 + BN; c <= std::min<int64_t>(n, n1 + n1 / 8); c += BN) {
+                const double f = wave_fill(tiles_m * (c / BN), in.sm_count);
+                if (f > best_fill + 0.01) { best_fill = f; best = c; }
+            }
+            n1 = best;
+        }
         if (n - n1 < 256) n1 = n;  // not worth a second phase
         p.n1 = n1;
-        // phase-1 k-chunks: small first chunk (short prologue), doubling up to the cap
+        // phase-1 k-chunks: small first chunk (short prologue); a chunk may grow only as fast as the previous chunk's
+        // GEMM can hide its upload (ratio r of GEMM time to upload time per unit of k), up to the cap
         {
-            int64_t done = 0, kc = 256;
+            const double r = (F * (double)m * (double)n1 / kFlops) / ((double)es * (double)(m + n1) / kH2D);
+            const double growth = env_or("TMM_PLAN_GROWTH", std::max(1.25, std::min(2.0, 0.95 * r)));
+            int64_t done = 0;
+            int64_t kc = (int64_t)env_or("TMM_PLAN_KC0", 256);
+            const int64_t cap = (int64_t)env_or("TMM_PLAN_KCMAX", (double)kc_cap);
             while (done < k) {
                 int64_t c = std::min(kc, k - done);
                 if (k - done - c < kc / 2) c = k - done;  // fold a small remainder into this chunk
                 p.chunks.push_back(c);
                 done += c;
-                kc = std::min(kc * 2, kc_cap);
+                kc = std::min<int64_t>(cap, std::max<int64_t>(kc + 64, (int64_t)((double)kc * growth) / 64 * 64));
             }
         }
         // phase-2 column blocks, shrinking towards the end so the last D2H is short
-        const int64_t target = std::max<int64_t>(512, std::min<int64_t>(2048, round_up(std::max(64, in.tile_n), 64)));
+        const int64_t target = std::max<int64_t>(512, std::min<int64_t>((int64_t)env_or("TMM_PLAN_NB", 2048), round_up(std::max(64, in.tile_n), 64)));
         int64_t j0 = n1;
         while (j0 < n) {
             const int64_t remaining = n - j0;

@@ -136,6 +136,14 @@ int main(int argc, char** argv) {
         bench_dev(h, 'N', 'N', 10000, 512, 10000, 0.0);
         bench_dev(h, 'N', 'N', 8192, 8192, 8192, 0.0);
     }
+    if (mode == "hostone") {  // hostone ta tb m n k beta copy_back streams reps
+        host_gemm(h, argv[2][0], argv[3][0], atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atof(argv[7]), atoi(argv[9]) > 0 ? atoi(argv[10]) : 3, atoi(argv[8]), atoi(argv[9]));
+        return 0;
+    }
+    if (mode == "benchone") {  // benchone ta tb m n k beta
+        bench_dev(h, argv[2][0], argv[3][0], atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atof(argv[7]));
+        return 0;
+    }
     if (mode == "all" || mode == "host") {
         host_gemm(h, 'N', 'N', 1000, 1000, 1000, 1.0, 2, 1);
         host_gemm(h, 'N', 'N', 10000, 10000, 10000, 0.0, 4, 1);
