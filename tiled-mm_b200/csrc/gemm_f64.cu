@@ -7,9 +7,12 @@
 //     (first TMA round trip) or epilogue (C read-modify-write), the other owns the FP64 pipe;
 //     the hardware block scheduler balances tiles dynamically and back-fills the tail of one
 //     launch with the next launch from another stream.  Column-group raster for L2 reuse.
-//   * 1 producer warp: TMA (cp.async.bulk.tensor.2d) fills a 3-4 stage shared-memory ring,
-//     completion on mbarriers; 4 math warps (2 x 2), each owning a 64 x 32 block of the
-//     CTA tile = 8 x 4 DMMA tiles = 128 accumulator registers per lane
+//   * two warpgroups per CTA.  Warpgroup 1 is the producer: it gives its registers back (setmaxnreg.dec 24) and one
+//     lane drives TMA (cp.async.bulk.tensor.2d) into a 4-6 stage shared-memory ring, completion on mbarriers.
+//     Warpgroup 0 = 4 math warps (2 x 2) that take those registers (setmaxnreg.inc 232): each owns a 64 x 32 block of
+//     the CTA tile = 8 x 4 DMMA tiles = 128 accumulator registers per lane, with room left for fragments, the C
+//     prefetch and the read-modify-write epilogue without a single spill (168 registers, the 2-CTA/SM cap without
+//     the split, spilled inside the main loop: ncu long_scoreboard stalls, -3.7 % - profiles/r1_ncu_dgemm.md)
 //   * operands are NEVER transposed or repacked: the TMA box is taken straight from the
 //     column-major device panel in whichever orientation it is stored (N: m-/n-contiguous,
 //     T/C: k-contiguous).  The box's contiguous extent is over-fetched by PAD = 4 doubles, which
@@ -28,7 +31,8 @@ namespace tmm {
 namespace f64 {
 
 constexpr int BM = 128, BN = 64, BK = 16, PAD = 4;
-constexpr int MATH_WARPS = 4, THREADS = (MATH_WARPS + 1) * 32;
+constexpr int MATH_WARPS = 4, THREADS = 2 * MATH_WARPS * 32;  // warpgroup 0 = math, warpgroup 1 = TMA producer (one active lane)
+constexpr int MATH_REGS = 232, PRODUCER_REGS = 24;            // setmaxnreg split of the 2 x 128-register launch allocation
 constexpr int SMEM_BUDGET = 113 * 1024;  // two CTAs per SM
 constexpr int WM = 64, WN = 32;           // warp tile
 constexpr int MI = WM / 8, NJ = WN / 8;   // DMMA tiles per warp
@@ -97,9 +101,10 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     tile_coords(blockIdx.x, p.tiles_m, p.tiles_n, tm, tn);
     const int kblocks = (p.k + BK - 1) / BK;
 
-    if (warp == MATH_WARPS) {
-        // ===== producer warp: one lane drives TMA =====
-        if (lane == 0) {
+    if (warp >= MATH_WARPS) {
+        // ===== producer warpgroup: hands its registers to the math warpgroup, then one lane drives TMA =====
+        ptx::setmaxnreg_dec<PRODUCER_REGS>();
+        if (warp == MATH_WARPS && lane == 0) {
             ptx::prefetch_tensormap(&tmap_a);
             ptx::prefetch_tensormap(&tmap_b);
             int stage = 0;
@@ -120,6 +125,7 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
 
     // ===== math warps (2 x 2) =====
+    ptx::setmaxnreg_inc<MATH_REGS>();
     const int g = lane >> 2, t = lane & 3;
     const int wm = (warp >> 1) * WM;  // 0 or 64
     const int wn = (warp & 1) * WN;   // 0 or 32

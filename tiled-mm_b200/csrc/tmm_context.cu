@@ -450,6 +450,11 @@ int pin(tmm_context* ctx, const void* p, size_t bytes, std::vector<const void*>&
             ctx->pinned.erase(it);
         }
     }
+    // memory that is already page-locked (cudaHostAlloc / gpu::malloc_pinned, or registered by the caller) needs nothing:
+    // the reference would fail in cudaHostRegister here (tiled_mm.cpp:532-549); accepting it is a superset
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) { if (attr.type == cudaMemoryTypeHost) return TMM_OK; }
+    else cudaGetLastError();
     cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
     if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return TMM_OK; }  // already DMA-able: nothing to do, nothing to undo
     if (e != cudaSuccess) return cuda_fail(e, "cudaHostRegister");

@@ -54,6 +54,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
+// Warpgroup register reallocation (all 4 warps of a warpgroup must execute it).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // D(8x8) += A(8x4) * B(4x8), FP64.  Lane l = 4*g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1].
 // SASS: one DMMA.8x8x4.
 __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
