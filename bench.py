@@ -268,9 +268,13 @@ def main():
         tmm.gemm(ctx, "N", "N", m, n, k, 1.0, a, m, b, k, 0.0, c, m, pin_host_buffers=False, copy_c_back=True)
 
     if world > 1:
+        # rank (gi, gj) owns C block (gi, gj) of the global (pr*m) x (pc*n) x k product: `a` is its A row-panel, `b` its B column-panel.
+        # It uploads 1/pc of a and 1/pr of b over its own PCIe link; NCCL all-gathers the shares over NVLink (csrc/tmm_dist.cu).
         from tiled_mm_b200 import multi_gpu
-        dg = multi_gpu.DistributedGemm(ctx, dist, pr, pc, m, n, k, a, b, c)
-        e2e_step = dg.step  # noqa: F811
+        grid = multi_gpu.GridGemm(ctx, dist)
+
+        def e2e_step():  # noqa: F811
+            grid.gemm("N", "N", m, n, k, 1.0, a, m, b, k, 0.0, c, m, pin_host_buffers=False, copy_c_back=True)
     for _ in range(args.warmup):
         e2e_step()
     barrier()
@@ -284,13 +288,14 @@ def main():
     e2e_ms = max_over_ranks(e2e_ms)
     launches = tmm.total_kernel_launches() - launches0
     e2e_tf = world * flops / (e2e_ms * 1e-3) * 1e-12
-    if world > 1:
-        h2d, d2h = dg.h2d_bytes_per_step, dg.d2h_bytes_per_step
-    else:
-        stt = ctx.last_stats()
-        h2d, d2h = int(stt.h2d_bytes), int(stt.d2h_bytes)
+    stt = ctx.last_stats()
+    h2d, d2h, peer = int(stt.h2d_bytes), int(stt.d2h_bytes), int(stt.peer_bytes)
+    if world > 1:  # whole-job bytes per step, summed over ranks
+        t = torch.tensor([h2d, d2h, peer], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        h2d, d2h, peer = (int(x) for x in t.tolist())
     # sanity: the timed result is a real product (C x = A (B x) on rank 0 at N = 1)
-    if world == 1:
+    if True:  # every rank checks its own block (its A row-panel and B column-panel are local)
         x = np.random.default_rng(5).random(n) - 0.5
         lhs = np.asarray(c).reshape(n, m).T @ x
         rhs = np.asarray(a).reshape(k, m).T @ (np.asarray(b).reshape(n, k).T @ x)
@@ -302,10 +307,10 @@ def main():
 
     if rank == 0:
         # rooflines for the host-to-host call: min(FP64 peak, AI x PCIe) and the full-duplex variant
-        pcie_bytes = 8.0 * (m * k + k * n + m * n)
+        pcie_bytes = 8.0 * (m * k / pc + k * n / pr + m * n)  # per GPU: its upload shares of the shared panels + its C block
         ai = flops / pcie_bytes
         roof_simple = min(FP64_PEAK_TFLOPS, ai * PCIE_H2D_GBS * 1e-3)
-        t_duplex = max(flops / (FP64_PEAK_TFLOPS * 1e12), 8.0 * (m * k + k * n) / (PCIE_H2D_GBS * 1e9), 8.0 * m * n / (PCIE_D2H_GBS * 1e9))
+        t_duplex = max(flops / (FP64_PEAK_TFLOPS * 1e12), 8.0 * (m * k / pc + k * n / pr) / (PCIE_H2D_GBS * 1e9), 8.0 * m * n / (PCIE_D2H_GBS * 1e9))
         clocks = cs_e2e.summary()
         out = {
             "metric": "host-to-host dgemm TFLOP/s", "value": round(value_tf, 3), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -315,7 +320,7 @@ def main():
                                    f"{args.streams} streams" + (f"; weak-scaled over a {pr}x{pc} C-block grid, global {pr*m}x{pc*n}x{k}, A/B panel slices all-gathered over NVLink" if world > 1 else ""),
                        "l2": "inputs (A, B = 800 MB each) larger than the 126 MB L2; no flush needed",
                        "value_is": "device-resident DGEMM (tmm_device_gemm, operands in HBM)", "e2e_is": "tmm_gemm with host pointers (H2D + GEMM + D2H)"},
-            "e2e": {"value": round(e2e_tf, 3), "unit": "TFLOP/s", "ms_per_step": round(e2e_ms, 3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": round(e2e_tf, 3), "unit": "TFLOP/s", "ms_per_step": round(e2e_ms, 3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "nvlink_bytes_per_step": peer,
                     "frac_of_host_roofline": round(e2e_tf / world / roof_simple, 4),
                     "host_roofline": {"formula": "min(FP64 peak, AI x PCIe H2D BW)", "tflops": round(roof_simple, 2), "ai_flop_per_byte": round(ai, 1),
                                       "duplex_tflops": round(flops / t_duplex * 1e-12, 2), "active_bound": "fp64" if roof_simple >= FP64_PEAK_TFLOPS - 1e-9 else "pcie",

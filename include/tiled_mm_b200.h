@@ -88,6 +88,30 @@ TMM_API int tmm_copy_to_host(const void* device_from, void* host_to, size_t byte
 TMM_API int tmm_device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a_dev, int64_t ld_a,
                     const void* b_dev, int64_t ld_b, const void* beta, void* c_dev, int64_t ld_c, void* stream);
 
+/* ---- Multi-GPU: C tile-blocks over a p_r x p_c grid of the box's GPUs (no counterpart in the reference, which drives one
+ * device; north_star: "partitioned across the 8 B200s of one box by assigning C tile-blocks to GPUs").  GPUs of a grid row
+ * share the A row-panel, GPUs of a grid column the B column-panel; every GPU uploads a distinct share of each shared panel
+ * over its own PCIe link and the shares are all-gathered over NVLink (NCCL, loaded at run time).  k is never split.
+ *
+ * (1) One process, many GPUs - the drop-in path: after tmm_context_set_devices(ctx, n, ids) every tmm_gemm(ctx, ...) with
+ *     copy_c_back != 0 splits C over n child contexts (one host thread each).  ids == NULL means devices 0..n-1.
+ * (2) One process per GPU (torchrun / MPI): each rank creates a context on its device and joins the grid with
+ *     tmm_context_attach_grid(); tmm_gemm(ctx, ...) then computes THIS RANK's C block: m, n are the block's extents, a points
+ *     at the rank's rows of op(A) (its A row-panel, full k), b at its columns of op(B), c at its block (ld_c = host ld).
+ *     All ranks call tmm_gemm collectively with the same trans / k / beta==0-ness / copy_c_back.  The 128-byte NCCL ids
+ *     come from tmm_dist_unique_id() on one rank of each grid row / column and are distributed by the caller. */
+TMM_API int tmm_grid_shape(int n_gpus, int* grid_rows, int* grid_cols);                 /* 1->1x1, 2->1x2, 4->2x2, 8->2x4 */
+TMM_API int tmm_share_range(int64_t extent, int parts, int index, int64_t* lo, int64_t* hi); /* balanced split used for blocks and upload shares */
+TMM_API int tmm_dist_unique_id(void* out128);
+TMM_API int tmm_context_attach_grid(tmm_context* ctx, int grid_rows, int grid_cols, int my_row, int my_col, const void* row_id128, const void* col_id128);
+TMM_API int tmm_context_grid(tmm_context* ctx, int* grid_rows, int* grid_cols, int* my_row, int* my_col);
+TMM_API int tmm_context_set_devices(tmm_context* ctx, int n_devices, const int* device_ids);
+TMM_API int tmm_context_num_devices(tmm_context* ctx);
+TMM_API tmm_context* tmm_context_child(tmm_context* ctx, int index);
+/* cudaMemcpy2DAsync with plain arguments (kind: 1 H2D, 2 D2H, 3 D2D) - what copy_tile_to_device_async / copy_tile_to_host_async
+ * (tiled_mm.cpp:45-123) reduce to; lets a binding stage strided panels without a CUDA runtime binding of its own. */
+TMM_API int tmm_memcpy_2d_async(void* dst, size_t dpitch_bytes, const void* src, size_t spitch_bytes, size_t width_bytes, size_t height, int kind, void* stream);
+
 /* Introspection for tests and bench.py */
 typedef struct tmm_call_stats {
     uint64_t h2d_bytes;      /* bytes moved host->device by the last tmm_gemm */
@@ -98,6 +122,7 @@ typedef struct tmm_call_stats {
     double kernel_ms;        /* summed device time of the GEMM kernels of the last call (0 unless profiling is on) */
     int regime;              /* 0 resident (A,B,C fit in HBM), 1 streaming (k-panel ring) */
     int c_blocks, k_chunks;
+    uint64_t peer_bytes;     /* bytes this GPU received from peer GPUs over NVLink (GPU grid only) */
 } tmm_call_stats;
 TMM_API int tmm_context_last_stats(tmm_context* ctx, tmm_call_stats* out);
 TMM_API int tmm_context_set_profiling(tmm_context* ctx, int on);          /* time every kernel with CUDA events */

@@ -51,6 +51,7 @@ class CallStats(ctypes.Structure):
         ("regime", ctypes.c_int),
         ("c_blocks", ctypes.c_int),
         ("k_chunks", ctypes.c_int),
+        ("peer_bytes", ctypes.c_uint64),
     ]
 
 
@@ -103,6 +104,16 @@ def load_library() -> ctypes.CDLL:
     lib.tmm_version.restype = ctypes.c_char_p
     lib.tmm_optimal_tile_size.argtypes = [ci, ci]
     lib.tmm_plan_describe.argtypes = [ci, cc, cc, i64, i64, i64, ci, ci, sz, ci, ci, ci, ci, ci, ctypes.c_char_p, sz]
+    lib.tmm_grid_shape.argtypes = [ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.tmm_share_range.argtypes = [i64, ci, ci, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.tmm_dist_unique_id.argtypes = [vp]
+    lib.tmm_context_attach_grid.argtypes = [vp, ci, ci, ci, ci, vp, vp]
+    lib.tmm_context_grid.argtypes = [vp] + [ctypes.POINTER(ci)] * 4
+    lib.tmm_context_set_devices.argtypes = [vp, ci, ctypes.POINTER(ci)]
+    lib.tmm_context_num_devices.argtypes = [vp]
+    lib.tmm_context_child.argtypes = [vp, ci]
+    lib.tmm_context_child.restype = vp
+    lib.tmm_memcpy_2d_async.argtypes = [vp, sz, vp, sz, sz, sz, ci, vp]
     _lib = lib
     return lib
 
@@ -199,6 +210,28 @@ class MMHandle:
 
     def get_full_device_buffer_c(self) -> DeviceVector:
         return DeviceVector(self)
+
+    # multi-GPU (not in the reference, which drives one device)
+    def set_devices(self, n_devices: int, device_ids=None) -> None:
+        """One process, many GPUs: every later gemm(copy_c_back=True) splits C over `n_devices` child contexts."""
+        ids = (ctypes.c_int * n_devices)(*device_ids) if device_ids is not None else None
+        _check(load_library().tmm_context_set_devices(self._h, n_devices, ids))
+
+    def num_devices(self) -> int:
+        return load_library().tmm_context_num_devices(self._h)
+
+    def attach_grid(self, grid_rows: int, grid_cols: int, my_row: int, my_col: int, row_id: bytes | None, col_id: bytes | None) -> None:
+        """One process per GPU: join a grid_rows x grid_cols grid; gemm() then computes this rank's C block (see multi_gpu.py)."""
+        rb = ctypes.create_string_buffer(row_id, 128) if row_id is not None else None
+        cb = ctypes.create_string_buffer(col_id, 128) if col_id is not None else None
+        _check(load_library().tmm_context_attach_grid(self._h, grid_rows, grid_cols, my_row, my_col,
+                                                      ctypes.cast(rb, ctypes.c_void_p) if rb is not None else None,
+                                                      ctypes.cast(cb, ctypes.c_void_p) if cb is not None else None))
+
+    def grid(self):
+        v = [ctypes.c_int() for _ in range(4)]
+        _check(load_library().tmm_context_grid(self._h, *(ctypes.byref(x) for x in v)))
+        return tuple(x.value for x in v)
 
     # introspection (not in the reference)
     def last_stats(self) -> CallStats:
@@ -317,6 +350,26 @@ def plan_describe(dtype, trans_a: str, trans_b: str, m: int, n: int, k: int, bet
                                           buf, len(buf))
     _check(rc)
     return json.loads(buf.value.decode())
+
+
+def grid_shape(n_gpus: int):
+    """(grid_rows, grid_cols) of the C-block grid for n GPUs: 1->1x1, 2->1x2, 4->2x2, 8->2x4."""
+    a, b = ctypes.c_int(), ctypes.c_int()
+    _check(load_library().tmm_grid_shape(n_gpus, ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
+
+
+def share_range(extent: int, parts: int, index: int):
+    """[lo, hi) of share `index` of a balanced split of `extent` into `parts` (C blocks and panel upload shares)."""
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    _check(load_library().tmm_share_range(extent, parts, index, ctypes.byref(lo), ctypes.byref(hi)))
+    return lo.value, hi.value
+
+
+def dist_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    _check(load_library().tmm_dist_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+    return buf.raw
 
 
 def device_count() -> int:

@@ -17,25 +17,18 @@
 //   * H2D, compute (several streams, so the tail of one launch is back-filled by the next) and D2H run on
 //     separate streams tied together by pre-allocated events; all offsets are 64-bit.
 // User tile sizes / stream counts are hints (they only cap chunk sizes / stream counts), never results.
-#include "../../include/tiled_mm_b200.h"
-#include "tmm_blas.h"
-#include "tmm_plan.h"
+#include "tmm_internal.h"
 
 #include <algorithm>
 #include <cctype>
 #include <chrono>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <map>
-#include <string>
-#include <vector>
 
-namespace {
+namespace tmm {
 
-thread_local std::string g_last_error;
+static thread_local std::string g_last_error;
+const char* last_error_cstr() { return g_last_error.c_str(); }
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -56,91 +49,24 @@ int cuda_fail(cudaError_t e, const char* what) {
     return fail(code, "GPU ERROR: %s: %s", what, cudaGetErrorString(e));
 }
 
-#define CU(x)                                        \
-    do {                                             \
-        cudaError_t e__ = (x);                       \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #x); \
-    } while (0)
+int nccl_fail(int rc, const char* what) {
+    const nccl::Api& n = nccl::api();
+    const char* msg = (n.ok && n.GetErrorString) ? n.GetErrorString(rc) : "NCCL unavailable";
+    fprintf(stderr, "error: NCCL call : %s (%s)\n", msg, what);
+    return fail(TMM_ERR_CUDA, "GPU ERROR: %s: %s", what, msg);
+}
 
+}  // namespace tmm
+
+using tmm::fail;
+using tmm::cuda_fail;
+using tmm::DevBuf;
+using tmm::DeviceGuard;
+#define CU(x) TMM_CU(x)
+
+namespace {
 int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;  // bytes
-    cudaError_t reserve(size_t bytes, double slack = 1.0) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        size_t want = (size_t)std::ceil((double)bytes * slack);
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess && slack > 1.0) { want = bytes; e = cudaMalloc(&p, want); }
-        if (e != cudaSuccess) { p = nullptr; return e; }
-        cap = want;
-        return cudaSuccess;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct DeviceGuard {
-    int prev = -1;
-    bool switched = false;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) { cudaSetDevice(dev); switched = true; }
-    }
-    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
-};
-
 }  // namespace
-
-struct tmm_context {
-    int dtype = TMM_F64;
-    int n_streams = 2;
-    int max_tile_m = 5000, max_tile_n = 5000, max_tile_k = 5000;
-    int device = 0;
-    static constexpr int MAX_COMPUTE = 4;
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_compute[MAX_COMPUTE] = {nullptr, nullptr, nullptr, nullptr};
-    DevBuf buf_a, buf_b, buf_c;  // panel / ring / staged-C storage (grow-only, reused across calls)
-    DevBuf full_c;               // API-visible device C (copy_c_back = false), column-major ld = m
-    size_t full_c_elems = 0;
-    std::vector<cudaEvent_t> events;
-    size_t ev_next = 0;
-    std::vector<cudaEvent_t> timing_events;
-    size_t tev_next = 0;
-    size_t budget_override = 0;
-    size_t budget_cached = 0;
-    bool profiling = false;
-    bool pin_cache = false;
-    bool trace = false;
-    struct TraceOp { std::string name; cudaEvent_t e0, e1; };
-    std::vector<TraceOp> trace_ops;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
-    std::map<const void*, size_t> pinned;
-    tmm_call_stats stats{};
-
-    // compute streams: [0] carries the phase-1 / streaming chain at the highest priority, the others (lower priorities)
-    // carry independent column blocks, whose CTAs then only back-fill SM slots the chain leaves free
-    int n_compute() const { return std::max(3, std::min(n_streams + 1, (int)MAX_COMPUTE)); }
-
-    cudaError_t get_event(cudaEvent_t* out) {
-        if (ev_next == events.size()) {
-            cudaEvent_t e;
-            cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-            if (r != cudaSuccess) return r;
-            events.push_back(e);
-        }
-        *out = events[ev_next++];
-        return cudaSuccess;
-    }
-    cudaError_t get_timing_event(cudaEvent_t* out) {
-        if (tev_next == timing_events.size()) {
-            cudaEvent_t e;
-            cudaError_t r = cudaEventCreate(&e);
-            if (r != cudaSuccess) return r;
-            timing_events.push_back(e);
-        }
-        *out = timing_events[tev_next++];
-        return cudaSuccess;
-    }
-};
 
 namespace {
 
@@ -158,6 +84,8 @@ struct Call {
     // stored shapes (reference tiled_mm.cpp:507-514)
     int64_t a_rows, a_cols, b_rows, b_cols;
     unsigned char one[16];  // scalar 1 of the dtype (beta' for k-chunks > 0, tiled_mm.cpp:309)
+    int64_t m_plan, n_plan;  // dims the schedule was planned for: == m, n on one GPU; the grid-wide maximum block dims on a GPU
+                             // grid, where every rank must walk the same schedule so that the panel exchanges line up
 };
 
 void make_one(int dtype, unsigned char* out) {
@@ -199,6 +127,36 @@ Sub a_sub(const Call& cl, int64_t i0, int64_t mi, int64_t p0, int64_t kc) {
 }
 Sub b_sub(const Call& cl, int64_t p0, int64_t kc, int64_t j0, int64_t nj) {
     return cl.tb == 'N' ? Sub{p0, j0, kc, nj} : Sub{j0, p0, nj, kc};
+}
+
+// Bring the stored sub-block `s` of A (or B) to its device position.  One GPU: a single 2-D H2D copy on s_h2d.  On a GPU grid
+// the sub-block is shared by the grid row (A) / grid column (B): this rank uploads only its 1/p share and the shares are
+// all-gathered over NVLink on s_comm (tmm_dist.cu).  Callers order consumers after BOTH streams (panels_ready).
+int fetch_a(Call& cl, char* dst, int64_t dpitch, const Sub& s) {
+    const tmm::Grid& g = cl.ctx->grid;
+    const char* src = cl.a + ((size_t)s.col * cl.lda + s.row) * cl.es;
+    if (g.pc > 1) return tmm::dist_exchange(cl.ctx, g.row_comm, g.pc, g.col, cl.es, src, cl.lda, s.rows, s.cols, dst, dpitch);
+    return h2d_2d(cl, dst, dpitch, src, cl.lda, s.rows, s.cols, cl.ctx->s_h2d);
+}
+int fetch_b(Call& cl, char* dst, int64_t dpitch, const Sub& s) {
+    const tmm::Grid& g = cl.ctx->grid;
+    const char* src = cl.b + ((size_t)s.col * cl.ldb + s.row) * cl.es;
+    if (g.pr > 1) return tmm::dist_exchange(cl.ctx, g.col_comm, g.pr, g.row, cl.es, src, cl.ldb, s.rows, s.cols, dst, dpitch);
+    return h2d_2d(cl, dst, dpitch, src, cl.ldb, s.rows, s.cols, cl.ctx->s_h2d);
+}
+// make `consumer` wait for everything fetched so far
+int panels_ready(Call& cl, cudaStream_t consumer) {
+    tmm_context* ctx = cl.ctx;
+    cudaEvent_t ev;
+    CU(ctx->get_event(&ev));
+    CU(cudaEventRecord(ev, ctx->s_h2d));
+    CU(cudaStreamWaitEvent(consumer, ev, 0));
+    if (ctx->grid.active()) {
+        CU(ctx->get_event(&ev));
+        CU(cudaEventRecord(ev, ctx->s_comm));
+        CU(cudaStreamWaitEvent(consumer, ev, 0));
+    }
+    return TMM_OK;
 }
 
 int launch_gemm(Call& cl, int64_t mi, int64_t nj, int64_t kc, const void* da, int64_t pa, const void* db, int64_t pb, const void* beta, void* dc,
@@ -256,7 +214,7 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
     char* dA = (char*)ctx->buf_a.p;
     char* dB = (char*)ctx->buf_b.p;
     const int ncs = ctx->n_compute();
-    const int64_t n1 = pl.n1;
+    const int64_t n1 = std::min<int64_t>(pl.n1, cl.n);  // the plan is for (m_plan, n_plan) >= (m, n): clamp to this rank's block
     ctx->stats.k_chunks = (int)pl.chunks.size();
     ctx->stats.c_blocks = 1 + (int)pl.blocks.size();
 
@@ -278,14 +236,15 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
         char* db = dB + ((size_t)sb.col * pb + sb.row) * es;
         {
             TraceScope ts(ctx, ctx->s_h2d, "h2dAB", p0, kc);
-            int rc = h2d_2d(cl, da, pa, cl.a + ((size_t)sa.col * cl.lda + sa.row) * es, cl.lda, sa.rows, sa.cols, ctx->s_h2d);
+            int rc = fetch_a(cl, da, pa, sa);
             if (rc) return rc;
-            rc = h2d_2d(cl, db, pb, cl.b + ((size_t)sb.col * cl.ldb + sb.row) * es, cl.ldb, sb.rows, sb.cols, ctx->s_h2d);
+            rc = fetch_b(cl, db, pb, sb);
             if (rc) return rc;
         }
-        CU(ctx->get_event(&ev));
-        CU(cudaEventRecord(ev, ctx->s_h2d));
-        CU(cudaStreamWaitEvent(cs0, ev, 0));
+        {
+            int rc = panels_ready(cl, cs0);
+            if (rc) return rc;
+        }
         {
             TraceScope ts(ctx, cs0, "gemm1", n1, kc);
             int rc = launch_gemm(cl, cl.m, n1, kc, da, pa, db, pb, ci == 0 ? cl.beta : (const void*)cl.one, dC, ldc_dev, cs0);
@@ -307,9 +266,10 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
         }
     }
     // ---- phase 2: A resident; remaining column blocks of B, full k each, C block streams back at once
-    int64_t j0 = n1;
+    int64_t j0 = pl.n1;
     for (size_t blk = 0; blk < pl.blocks.size(); ++blk) {
-        const int64_t nb = pl.blocks[blk];
+        const int64_t nb = std::min<int64_t>(pl.blocks[blk], cl.n - j0);
+        if (nb <= 0) break;  // this rank's block is narrower than the planned one (same for its whole grid column)
         char* dcb = (char*)dC + (size_t)j0 * ldc_dev * es;
         if (cl.beta_nonzero) {
             TraceScope ts(ctx, ctx->s_h2d, "h2dC", j0, nb);
@@ -320,13 +280,14 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
         char* db = dB + ((size_t)sb.col * pb + sb.row) * es;
         {
             TraceScope ts(ctx, ctx->s_h2d, "h2dB", j0, nb);
-            int rc = h2d_2d(cl, db, pb, cl.b + ((size_t)sb.col * cl.ldb + sb.row) * es, cl.ldb, sb.rows, sb.cols, ctx->s_h2d);
+            int rc = fetch_b(cl, db, pb, sb);
             if (rc) return rc;
         }
-        CU(ctx->get_event(&ev));
-        CU(cudaEventRecord(ev, ctx->s_h2d));
         cudaStream_t cs = ctx->s_compute[1 + blk % (ncs - 1)];
-        CU(cudaStreamWaitEvent(cs, ev, 0));
+        {
+            int rc = panels_ready(cl, cs);
+            if (rc) return rc;
+        }
         {
             TraceScope ts(ctx, cs, "gemm2", j0, nb);
             int rc = launch_gemm(cl, cl.m, nb, cl.k, dA, pa, db, pb, cl.beta, dcb, ldc_dev, cs);
@@ -367,42 +328,51 @@ int run_streaming(Call& cl, const tmm::Plan& pl, void* dC_full, int64_t ldc_full
     ctx->stats.k_chunks = (int)nchunks;
     cudaEvent_t ev;
 
-    for (int64_t i0 = 0; i0 < cl.m; i0 += MB) {
-        const int64_t mi = std::min(MB, cl.m - i0);
-        for (int64_t j0 = 0; j0 < cl.n; j0 += NB) {
-            const int64_t nj = std::min(NB, cl.n - j0);
-            char* dcb;
-            int64_t ldcb;
-            if (c_is_full) { dcb = (char*)dC_full + ((size_t)j0 * ldc_full + i0) * es; ldcb = ldc_full; }
-            else { dcb = (char*)ctx->buf_c.p + (size_t)cbuf * pl.pc_blk * NB * es; ldcb = pl.pc_blk; }
-            if (!c_is_full && cbuf_free[cbuf]) {
-                // this C buffer's previous contents must have left for the host before it is overwritten
-                CU(cudaStreamWaitEvent(ctx->s_h2d, cbuf_free[cbuf], 0));
-                CU(cudaStreamWaitEvent(cs, cbuf_free[cbuf], 0));
-            }
-            if (cl.beta_nonzero) {
-                TraceScope ts(ctx, ctx->s_h2d, "h2dC", i0, j0);
-                int rc = h2d_2d(cl, dcb, ldcb, cl.c + ((size_t)j0 * cl.ldc + i0) * es, cl.ldc, mi, nj, ctx->s_h2d);
-                if (rc) return rc;
+    // The loop nest walks the PLANNED extents (m_plan, n_plan >= m, n): on a GPU grid every rank issues the same sequence of
+    // panel exchanges; a rank whose own block ends earlier still contributes its upload share, and only skips the GEMM / C part.
+    for (int64_t i0 = 0; i0 < cl.m_plan; i0 += MB) {
+        const int64_t mi = std::max<int64_t>(0, std::min(MB, cl.m - i0));
+        for (int64_t j0 = 0; j0 < cl.n_plan; j0 += NB) {
+            const int64_t nj = std::max<int64_t>(0, std::min(NB, cl.n - j0));
+            const bool mine = mi > 0 && nj > 0;
+            char* dcb = nullptr;
+            int64_t ldcb = 0;
+            if (mine) {
+                if (c_is_full) { dcb = (char*)dC_full + ((size_t)j0 * ldc_full + i0) * es; ldcb = ldc_full; }
+                else { dcb = (char*)ctx->buf_c.p + (size_t)cbuf * pl.pc_blk * NB * es; ldcb = pl.pc_blk; }
+                if (!c_is_full && cbuf_free[cbuf]) {
+                    // this C buffer's previous contents must have left for the host before it is overwritten
+                    CU(cudaStreamWaitEvent(ctx->s_h2d, cbuf_free[cbuf], 0));
+                    CU(cudaStreamWaitEvent(cs, cbuf_free[cbuf], 0));
+                }
+                if (cl.beta_nonzero) {
+                    TraceScope ts(ctx, ctx->s_h2d, "h2dC", i0, j0);
+                    int rc = h2d_2d(cl, dcb, ldcb, cl.c + ((size_t)j0 * cl.ldc + i0) * es, cl.ldc, mi, nj, ctx->s_h2d);
+                    if (rc) return rc;
+                }
             }
             for (int64_t ci = 0; ci < nchunks; ++ci) {
                 const int64_t p0 = ci * kc, kcc = std::min(kc, cl.k - p0);
-                if (slot_free[slot]) CU(cudaStreamWaitEvent(ctx->s_h2d, slot_free[slot], 0));
+                if (slot_free[slot]) {
+                    CU(cudaStreamWaitEvent(ctx->s_h2d, slot_free[slot], 0));
+                    if (ctx->grid.active()) CU(cudaStreamWaitEvent(ctx->s_comm, slot_free[slot], 0));
+                }
                 char* da = (char*)ctx->buf_a.p + (size_t)slot * pl.a_slot_bytes;
                 char* db = (char*)ctx->buf_b.p + (size_t)slot * pl.b_slot_bytes;
                 Sub sa = a_sub(cl, i0, mi, p0, kcc);
                 Sub sb = b_sub(cl, p0, kcc, j0, nj);
                 {
                     TraceScope ts(ctx, ctx->s_h2d, "h2dAB", p0, kcc, slot);
-                    int rc = h2d_2d(cl, da, pl.pa_slot, cl.a + ((size_t)sa.col * cl.lda + sa.row) * es, cl.lda, sa.rows, sa.cols, ctx->s_h2d);
+                    int rc = mi > 0 ? fetch_a(cl, da, pl.pa_slot, sa) : TMM_OK;
                     if (rc) return rc;
-                    rc = h2d_2d(cl, db, pl.pb_slot, cl.b + ((size_t)sb.col * cl.ldb + sb.row) * es, cl.ldb, sb.rows, sb.cols, ctx->s_h2d);
+                    rc = nj > 0 ? fetch_b(cl, db, pl.pb_slot, sb) : TMM_OK;
                     if (rc) return rc;
                 }
-                CU(ctx->get_event(&ev));
-                CU(cudaEventRecord(ev, ctx->s_h2d));
-                CU(cudaStreamWaitEvent(cs, ev, 0));
                 {
+                    int rc = panels_ready(cl, cs);
+                    if (rc) return rc;
+                }
+                if (mine) {
                     TraceScope ts(ctx, cs, "gemmS", i0, j0, p0);
                     int rc = launch_gemm(cl, mi, nj, kcc, da, pl.pa_slot, db, pl.pb_slot, ci == 0 ? cl.beta : (const void*)cl.one, dcb, ldcb, cs);
                     if (rc) return rc;
@@ -411,6 +381,7 @@ int run_streaming(Call& cl, const tmm::Plan& pl, void* dC_full, int64_t ldc_full
                 CU(cudaEventRecord(slot_free[slot], cs));
                 slot = (slot + 1) % SLOTS;
             }
+            if (!mine) continue;
             if (cl.copy_c_back) {
                 CU(ctx->get_event(&ev));
                 CU(cudaEventRecord(ev, cs));
@@ -435,6 +406,7 @@ int sync_all(tmm_context* ctx) {
     // the reference ends with a device-wide cudaDeviceSynchronize (tiled_mm.cpp:602-604); syncing our own
     // streams gives the same guarantee for this call without stalling unrelated work on the device
     CU(cudaStreamSynchronize(ctx->s_h2d));
+    CU(cudaStreamSynchronize(ctx->s_comm));
     for (int i = 0; i < tmm_context::MAX_COMPUTE; ++i) CU(cudaStreamSynchronize(ctx->s_compute[i]));
     CU(cudaStreamSynchronize(ctx->s_d2h));
     return TMM_OK;
@@ -466,7 +438,7 @@ int pin(tmm_context* ctx, const void* p, size_t bytes, std::vector<const void*>&
 
 extern "C" {
 
-const char* tmm_last_error(void) { return g_last_error.c_str(); }
+const char* tmm_last_error(void) { return tmm::last_error_cstr(); }
 const char* tmm_version(void) { return "tiled_mm_b200 0.1 (sm_100a)"; }
 uint64_t tmm_total_kernel_launches(void) { return tmm::launch_count(); }
 
@@ -500,12 +472,12 @@ int tmm_context_create(int dtype, int n_streams, int max_tile_m, int max_tile_n,
     ctx->trace = tr && tr[0] == '1';
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);  // numerically lower = higher priority
-    cudaStream_t* all[] = {&ctx->s_h2d, &ctx->s_d2h, &ctx->s_compute[0], &ctx->s_compute[1], &ctx->s_compute[2], &ctx->s_compute[3]};
+    cudaStream_t* all[] = {&ctx->s_h2d, &ctx->s_d2h, &ctx->s_compute[0], &ctx->s_compute[1], &ctx->s_compute[2], &ctx->s_compute[3], &ctx->s_comm};
     // phase-2 streams share ONE lower priority: among equal priorities the block scheduler drains kernels in launch
     // order, so column blocks finish in order (their D2H copies queue in that order) while still back-filling tails
     const int low = std::min(prio_least, prio_greatest + 1);
-    const int prio[] = {prio_greatest, prio_greatest, prio_greatest, low, low, low};
-    for (int i = 0; i < 6; ++i)
+    const int prio[] = {prio_greatest, prio_greatest, prio_greatest, low, low, low, prio_greatest};
+    for (int i = 0; i < 7; ++i)
         if ((e = cudaStreamCreateWithPriority(all[i], cudaStreamNonBlocking, prio[i])) != cudaSuccess) { tmm_context_destroy(ctx); return cuda_fail(e, "cudaStreamCreateWithPriority"); }
     *out = ctx;
     return TMM_OK;
@@ -515,8 +487,13 @@ void tmm_context_destroy(tmm_context* ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
     for (auto& kv : ctx->pinned) cudaHostUnregister(const_cast<void*>(kv.first));
-    cudaStream_t all[] = {ctx->s_h2d, ctx->s_d2h, ctx->s_compute[0], ctx->s_compute[1], ctx->s_compute[2], ctx->s_compute[3]};
-    for (cudaStream_t s : all) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    for (tmm_context* ch : ctx->children) tmm_context_destroy(ch);
+    ctx->children.clear();
+    if (ctx->solo) { tmm_context_destroy(ctx->solo); ctx->solo = nullptr; }
+    cudaStream_t all[] = {ctx->s_h2d, ctx->s_d2h, ctx->s_compute[0], ctx->s_compute[1], ctx->s_compute[2], ctx->s_compute[3], ctx->s_comm};
+    for (cudaStream_t s : all) if (s) cudaStreamSynchronize(s);
+    tmm::dist_release(ctx);
+    for (cudaStream_t s : all) if (s) cudaStreamDestroy(s);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
     ctx->buf_a.release(); ctx->buf_b.release(); ctx->buf_c.release(); ctx->full_c.release();
@@ -564,6 +541,8 @@ int tmm_context_set_device_budget(tmm_context* ctx, size_t bytes) { if (!ctx) re
 int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t ld_a,
              const void* b, int64_t ld_b, const void* beta, void* c, int64_t ld_c, int pin_host_buffers, int copy_c_back) {
     if (!ctx) return fail(TMM_ERR_INVALID, "null context");
+    if (!ctx->children.empty())  // single-process multi-GPU: C blocks over the child contexts, one host thread each
+        return tmm::multi_gemm(ctx, trans_a, trans_b, m, n, k, alpha, a, ld_a, b, ld_b, beta, c, ld_c, pin_host_buffers, copy_c_back);
     const auto t_begin = std::chrono::steady_clock::now();
     Call cl;
     cl.ctx = ctx; cl.dtype = ctx->dtype; cl.es = tmm::dtype_size(ctx->dtype);
@@ -591,6 +570,7 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
     ctx->ev_next = 0; ctx->tev_next = 0; ctx->trace_ops.clear(); ctx->gemm_events.clear();
     cudaEvent_t trace_t0 = nullptr;
     const uint64_t launches_before = tmm::launch_count();
+    if ((m == 0 || n == 0) && ctx->grid.active()) return fail(TMM_ERR_INVALID, "on a GPU grid every rank must own a non-empty block of C");
     if (m == 0 || n == 0) return TMM_OK;  // BLAS quick return (the reference divides by zero here)
     const bool alpha_zero = scalar_is_zero(ctx->dtype, alpha);
     const bool need_ab = k > 0 && !alpha_zero;
@@ -647,20 +627,59 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                     }
                 }
             } else {
+                // on a GPU grid all ranks plan for the same (largest) block and the smallest budget, so the exchanges line up
+                int64_t m_plan = m, n_plan = n;
+                size_t plan_budget = budget;
+                const tmm::Grid& gr = ctx->grid;
+                if (gr.active()) {
+                    const int flags = (cl.ta << 16) | (cl.tb << 8) | (cl.beta_nonzero ? 2 : 0) | (cl.copy_c_back ? 1 : 0);
+                    rc = tmm::dist_agree(ctx, m, n, k, flags, budget, &m_plan, &n_plan, &plan_budget);
+                    if (!rc) {
+                        // staging rings for the all-gathers: shares of at most one k-chunk of A / one column block of B
+                        const int64_t kcap = std::min<int64_t>(k, 2048), ncap = std::min<int64_t>(n_plan, 8192);
+                        size_t share = 0;
+                        if (gr.pc > 1) share = std::max(share, (size_t)(cl.ta == 'N' ? m_plan * ((kcap + gr.pc - 1) / gr.pc) : kcap * ((m_plan + gr.pc - 1) / gr.pc)) * cl.es);
+                        if (gr.pr > 1) share = std::max(share, (size_t)(cl.tb == 'N' ? k * ((ncap + gr.pr - 1) / gr.pr) : ncap * ((k + gr.pr - 1) / gr.pr)) * cl.es);
+                        const size_t stage = tmm::dist_stage_bytes(share, std::max(gr.pr, gr.pc));
+                        const size_t held = ctx->stage_send.cap + ctx->stage_recv.cap;  // already counted as used by cudaMemGetInfo
+                        const size_t extra = stage > held ? stage - held : 0;
+                        if (!ctx->budget_override) plan_budget = plan_budget > extra ? plan_budget - extra : 0;  // an explicit budget bounds panel storage only
+                    }
+                }
+                cl.m_plan = m_plan; cl.n_plan = n_plan;
                 tmm::PlanInput pin_;
-                pin_.dtype = cl.dtype; pin_.ta = cl.ta; pin_.tb = cl.tb; pin_.m = m; pin_.n = n; pin_.k = k;
-                pin_.beta_nonzero = cl.beta_nonzero; pin_.copy_c_back = cl.copy_c_back; pin_.budget = budget;
+                pin_.dtype = cl.dtype; pin_.ta = cl.ta; pin_.tb = cl.tb; pin_.m = m_plan; pin_.n = n_plan; pin_.k = k;
+                pin_.beta_nonzero = cl.beta_nonzero; pin_.copy_c_back = cl.copy_c_back; pin_.budget = plan_budget;
                 pin_.n_streams = ctx->n_streams; pin_.tile_m = ctx->max_tile_m; pin_.tile_n = ctx->max_tile_n; pin_.tile_k = ctx->max_tile_k;
                 pin_.sm_count = tmm::sm_count();
-                const tmm::Plan pl = tmm::make_plan(pin_);
+                pin_.parts_a = gr.pc; pin_.parts_b = gr.pr;
+                tmm::Plan pl;
+                if (!rc) pl = tmm::make_plan(pin_);
                 ctx->stats.regime = pl.regime;
-                if (!pl.error.empty()) rc = fail(TMM_ERR_NOMEM, "%s (budget %zu B)", pl.error.c_str(), budget);
+                if (!rc && gr.active()) {
+                    // exact staging need of this plan
+                    size_t share = 0;
+                    auto upd = [&](int64_t rows, int64_t cols, int parts) { if (parts > 1) share = std::max(share, (size_t)rows * (size_t)((cols + parts - 1) / parts) * cl.es); };
+                    if (pl.regime == tmm::REGIME_RESIDENT) {
+                        for (int64_t kc : pl.chunks) {
+                            Sub sa = a_sub(cl, 0, m, 0, kc), sb = b_sub(cl, 0, kc, 0, std::min(pl.n1, n));
+                            upd(sa.rows, sa.cols, gr.pc); upd(sb.rows, sb.cols, gr.pr);
+                        }
+                        for (int64_t nb : pl.blocks) { Sub sb = b_sub(cl, 0, k, 0, std::min(nb, n)); upd(sb.rows, sb.cols, gr.pr); }
+                    } else if (pl.error.empty()) {
+                        Sub sa = a_sub(cl, 0, std::min(pl.MB, m), 0, std::min(pl.kc, k)), sb = b_sub(cl, 0, std::min(pl.kc, k), 0, std::min(pl.NB, n));
+                        upd(sa.rows, sa.cols, gr.pc); upd(sb.rows, sb.cols, gr.pr);
+                    }
+                    rc = tmm::dist_reserve_stage(ctx, share, std::max(gr.pr, gr.pc));
+                }
+                if (rc) {}
+                else if (!pl.error.empty()) rc = fail(TMM_ERR_NOMEM, "%s (budget %zu B)", pl.error.c_str(), plan_budget);
                 else if (pl.regime == tmm::REGIME_RESIDENT) {
                     if (cl.copy_c_back) {
                         if ((e = ctx->buf_c.reserve(pl.bytes_c)) != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(C)");
                         dC = ctx->buf_c.p;
                     }
-                    if (!rc) rc = run_resident(cl, pl, dC, pl.pitch_c);
+                    if (!rc) rc = run_resident(cl, pl, dC, cl.copy_c_back ? pl.pitch_c : ldc_dev);
                 } else {
                     rc = run_streaming(cl, pl, cl.copy_c_back ? nullptr : dC, ldc_dev);
                 }
@@ -668,7 +687,9 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
         }
     }
     const double t_enqueued = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    TMM_DBG("dev %d enqueued rc %d regime %d, syncing", ctx->device, rc, ctx->stats.regime);
     int rc_sync = sync_all(ctx);
+    TMM_DBG("dev %d synced rc %d", ctx->device, rc_sync);
     if (!rc) rc = rc_sync;
     for (const void* p : pinned_now) cudaHostUnregister(const_cast<void*>(p));  // tiled_mm.cpp:606-618
     if (!rc) {

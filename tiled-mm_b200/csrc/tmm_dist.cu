@@ -1,0 +1,367 @@
+// Multi-GPU layer: C tile-blocks are assigned to the GPUs of one box as a p_r x p_c grid (the reference is
+// single-GPU, tiled_mm.cpp never selects a device).  Nothing is reduced across GPUs: k is never split, so the
+// summation structure of every C element is the one-GPU one.  The only exchange is of read-only panels:
+//   * the p_c GPUs of a grid row need the same A row-panel, the p_r GPUs of a grid column the same B column-panel;
+//   * each GPU uploads a distinct 1/p share of every shared panel chunk over its OWN PCIe link (so aggregate host-link
+//     bandwidth scales with the GPU count) and the shares are all-gathered over NVLink 5 / NVSwitch with NCCL,
+//     chunk by chunk, on a dedicated high-priority stream that overlaps the DMMA kernels of the previous chunk.
+// Two ways in:
+//   (1) one process per GPU (torchrun): tmm_context_attach_grid() on each rank's context; tmm_gemm() then means "my block";
+//   (2) one process, many GPUs: tmm_context_set_devices() turns a context into a parent whose tmm_gemm() partitions C
+//       over child contexts, one host thread per GPU - the drop-in gpu::gemm then uses the whole box unchanged.
+#include "tmm_internal.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cctype>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+namespace tmm {
+const char* last_error_cstr();
+bool debug_on() {
+    static const bool on = [] { const char* v = getenv("TMM_DEBUG"); return v && v[0] == '1'; }();
+    return on;
+}
+
+namespace nccl {
+
+const Api& api() {
+    static Api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = nullptr;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) { a.why = "libnccl.so.2 not found (dlopen)"; return; }
+        auto sym = [&](const char* n) { return dlsym(h, n); };
+        a.GetUniqueId = reinterpret_cast<int (*)(UniqueId*)>(sym("ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<int (*)(Comm*, int, UniqueId, int)>(sym("ncclCommInitRank"));
+        a.CommDestroy = reinterpret_cast<int (*)(Comm)>(sym("ncclCommDestroy"));
+        a.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, Comm, cudaStream_t)>(sym("ncclAllGather"));
+        a.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, Comm, cudaStream_t)>(sym("ncclAllReduce"));
+        a.GroupStart = reinterpret_cast<int (*)()>(sym("ncclGroupStart"));
+        a.GroupEnd = reinterpret_cast<int (*)()>(sym("ncclGroupEnd"));
+        a.GetErrorString = reinterpret_cast<const char* (*)(int)>(sym("ncclGetErrorString"));
+        a.GetVersion = reinterpret_cast<int (*)(int*)>(sym("ncclGetVersion"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce && a.GetErrorString;
+        if (!a.ok) a.why = "libnccl.so.2 lacks a required entry point";
+    });
+    return a;
+}
+
+}  // namespace nccl
+
+#define NC(x)                                        \
+    do {                                             \
+        int r__ = (x);                               \
+        if (r__ != 0) return nccl_fail(r__, #x);     \
+    } while (0)
+
+size_t dist_stage_bytes(size_t share_bytes, int parts) {
+    const size_t slot = (size_t)round_up64((int64_t)share_bytes, 512);
+    return (size_t)STAGE_SLOTS * slot * (size_t)(1 + parts);
+}
+
+int dist_reserve_stage(tmm_context* ctx, size_t share_bytes, int parts) {
+    const size_t slot = (size_t)round_up64((int64_t)std::max<size_t>(share_bytes, 512), 512);
+    cudaError_t e;
+    if ((e = ctx->stage_send.reserve((size_t)STAGE_SLOTS * slot)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(all-gather send ring)");
+    if ((e = ctx->stage_recv.reserve((size_t)STAGE_SLOTS * slot * parts)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(all-gather recv ring)");
+    ctx->stage_slot_bytes = slot;
+    ctx->stage_next = 0;
+    for (auto& ev : ctx->stage_send_free) ev = nullptr;  // events are per call (ctx->get_event pool)
+    return TMM_OK;
+}
+
+int dist_agree(tmm_context* ctx, int64_t m, int64_t n, int64_t k, int flags, size_t budget, int64_t* m_plan, int64_t* n_plan, size_t* budget_min) {
+    const nccl::Api& nc = nccl::api();
+    if (!nc.ok) return fail(TMM_ERR_CUDA, "GPU ERROR: NCCL unavailable: %s", nc.why);
+    cudaError_t e;
+    if ((e = ctx->dist_scratch.reserve(256)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(dist scratch)");
+    // max-reduce {m, n, k, -k, flags, -flags, -budget}: maxima give the planning block and the smallest budget, and the
+    // +/- pairs show (on every rank alike, so all ranks fail together instead of hanging) whether k and the flags agree
+    int64_t v[8] = {m, n, k, -k, (int64_t)flags, -(int64_t)flags, -(int64_t)std::min<size_t>(budget, (size_t)INT64_MAX), 0};
+    int64_t* d = static_cast<int64_t*>(ctx->dist_scratch.p);
+    TMM_DBG("dev %d agree: m %lld n %lld k %lld", ctx->device, (long long)m, (long long)n, (long long)k);
+    TMM_CU(cudaMemcpyAsync(d, v, sizeof v, cudaMemcpyHostToDevice, ctx->s_comm));
+    if (ctx->grid.pr > 1) NC(nc.AllReduce(d, d, 8, nccl::Int64, nccl::Max, ctx->grid.col_comm, ctx->s_comm));
+    if (ctx->grid.pc > 1) NC(nc.AllReduce(d, d, 8, nccl::Int64, nccl::Max, ctx->grid.row_comm, ctx->s_comm));
+    TMM_CU(cudaMemcpyAsync(v, d, sizeof v, cudaMemcpyDeviceToHost, ctx->s_comm));
+    TMM_CU(cudaStreamSynchronize(ctx->s_comm));
+    if (v[2] != -v[3]) return fail(TMM_ERR_INVALID, "GPU grid: ranks disagree on k (%lld vs %lld)", (long long)v[2], (long long)-v[3]);
+    if (v[4] != -v[5]) return fail(TMM_ERR_INVALID, "GPU grid: ranks disagree on trans / beta==0 / copy_c_back");
+    *m_plan = v[0]; *n_plan = v[1]; *budget_min = (size_t)(-v[6]);
+    TMM_DBG("dev %d agreed: m_plan %lld n_plan %lld budget %zu", ctx->device, (long long)*m_plan, (long long)*n_plan, *budget_min);
+    return TMM_OK;
+}
+
+int dist_exchange(tmm_context* ctx, nccl::Comm comm, int parts, int me, size_t es, const char* src, int64_t spitch, int64_t rows, int64_t cols,
+                  char* dst, int64_t dpitch) {
+    if (rows <= 0 || cols <= 0) return TMM_OK;
+    const nccl::Api& nc = nccl::api();
+    const int64_t max_cols = (cols + parts - 1) / parts;
+    const size_t share_bytes = (size_t)rows * (size_t)max_cols * es;
+    if (share_bytes > ctx->stage_slot_bytes) return fail(TMM_ERR_INVALID, "internal: all-gather share %zu B exceeds the staging slot %zu B", share_bytes, ctx->stage_slot_bytes);
+    const int slot = ctx->stage_next;
+    TMM_DBG("dev %d exchange: %lld x %lld over %d ranks (me %d), share %zu B, slot %d", ctx->device, (long long)rows, (long long)cols, parts, me, share_bytes, slot);
+    ctx->stage_next = (slot + 1) % STAGE_SLOTS;
+    char* send = static_cast<char*>(ctx->stage_send.p) + (size_t)slot * ctx->stage_slot_bytes;
+    char* recv = static_cast<char*>(ctx->stage_recv.p) + (size_t)slot * ctx->stage_slot_bytes * parts;
+    // 1. my share (a range of stored columns: long contiguous runs for the DMA engine) -> send slot, compact
+    int64_t lo, hi;
+    share_range(cols, parts, me, &lo, &hi);
+    if (ctx->stage_send_free[slot]) TMM_CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->stage_send_free[slot], 0));
+    if (hi > lo) {
+        TMM_CU(cudaMemcpy2DAsync(send, (size_t)rows * es, src + (size_t)lo * spitch * es, (size_t)spitch * es, (size_t)rows * es, (size_t)(hi - lo),
+                                 cudaMemcpyHostToDevice, ctx->s_h2d));
+        ctx->stats.h2d_bytes += (uint64_t)rows * (hi - lo) * es;
+        ctx->stats.h2d_copies++;
+    }
+    cudaEvent_t up;
+    TMM_CU(ctx->get_event(&up));
+    TMM_CU(cudaEventRecord(up, ctx->s_h2d));
+    TMM_CU(cudaStreamWaitEvent(ctx->s_comm, up, 0));
+    // 2. all-gather the shares over NVLink (equal counts: the largest share; shorter shares carry padding that is never unpacked)
+    NC(nc.AllGather(send, recv, share_bytes, nccl::Int8, comm, ctx->s_comm));
+    TMM_CU(ctx->get_event(&ctx->stage_send_free[slot]));
+    TMM_CU(cudaEventRecord(ctx->stage_send_free[slot], ctx->s_comm));
+    // 3. unpack into the panel (device-to-device 2-D copies re-pitch for free; stream order protects the recv slot)
+    for (int g = 0; g < parts; ++g) {
+        share_range(cols, parts, g, &lo, &hi);
+        if (hi <= lo) continue;
+        TMM_CU(cudaMemcpy2DAsync(dst + (size_t)lo * dpitch * es, (size_t)dpitch * es, recv + (size_t)g * share_bytes, (size_t)rows * es, (size_t)rows * es,
+                                 (size_t)(hi - lo), cudaMemcpyDeviceToDevice, ctx->s_comm));
+        if (g != me) ctx->stats.peer_bytes += (uint64_t)rows * (hi - lo) * es;
+    }
+    return TMM_OK;
+}
+
+void dist_release(tmm_context* ctx) {
+    const nccl::Api& nc = nccl::api();
+    if (ctx->grid.row_comm && nc.ok) nc.CommDestroy(ctx->grid.row_comm);
+    if (ctx->grid.col_comm && nc.ok) nc.CommDestroy(ctx->grid.col_comm);
+    ctx->grid = Grid{};
+    ctx->stage_send.release(); ctx->stage_recv.release(); ctx->dist_scratch.release();
+}
+
+static int attach(tmm_context* ctx, int pr, int pc, int row, int col, const nccl::UniqueId* row_id, const nccl::UniqueId* col_id) {
+    const nccl::Api& nc = nccl::api();
+    if (!nc.ok) return fail(TMM_ERR_CUDA, "GPU ERROR: NCCL unavailable: %s", nc.why);
+    DeviceGuard guard(ctx->device);
+    dist_release(ctx);
+    Grid g;
+    g.pr = pr; g.pc = pc; g.row = row; g.col = col;
+    TMM_DBG("dev %d attach %dx%d at (%d,%d)", ctx->device, pr, pc, row, col);
+    if (pc > 1) NC(nc.CommInitRank(&g.row_comm, pc, *row_id, col));
+    if (pr > 1) NC(nc.CommInitRank(&g.col_comm, pr, *col_id, row));
+    ctx->grid = g;
+    ctx->budget_cached = 0;
+    TMM_DBG("dev %d attached", ctx->device);
+    return TMM_OK;
+}
+
+// ---- single process, many GPUs -------------------------------------------------------------------------------------
+int multi_gemm(tmm_context* parent, char ta, char tb, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t lda, const void* b,
+               int64_t ldb, const void* beta, void* c, int64_t ldc, int pin, int copy_c_back) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    const int nd = (int)parent->children.size();
+    const Grid& g0 = parent->children[0]->grid;
+    const int pr = g0.pr, pc = g0.pc;
+    const size_t es = dtype_size(parent->dtype);
+    const char TA = (char)std::toupper((unsigned char)ta), TB = (char)std::toupper((unsigned char)tb);
+    parent->stats = tmm_call_stats{};
+    if (!copy_c_back) return fail(TMM_ERR_INVALID, "copy_c_back=false on a multi-GPU context: C blocks live on different devices; call tmm_gemm on tmm_context_child(ctx, i)");
+    if (m < 0 || n < 0 || k < 0) return fail(TMM_ERR_INVALID, "negative dimension");
+    if (m == 0 || n == 0) return TMM_OK;
+    if ((TA != 'N' && TA != 'T' && TA != 'C') || (TB != 'N' && TB != 'T' && TB != 'C')) return fail(TMM_ERR_INVALID, "trans must be one of N, T, C (got '%c','%c')", ta, tb);
+    if (m < pr || n < pc) {  // fewer rows / columns than grid rows / columns: not worth a grid, run on the first device
+        return tmm_gemm(parent->children[0]->grid.active() ? parent->solo : parent->children[0], ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, pin, copy_c_back);
+    }
+    // page-lock once for all devices (portable), not once per child
+    std::vector<void*> pinned;
+    if (pin) {
+        const int64_t a_cols = TA == 'N' ? k : m, b_cols = TB == 'N' ? n : k;
+        struct { const void* p; size_t bytes; } regs[3] = {{a, (size_t)lda * a_cols * es}, {b, (size_t)ldb * b_cols * es}, {c, (size_t)ldc * n * es}};
+        for (auto& r : regs) {
+            if (!r.p || !r.bytes) continue;
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, r.p) == cudaSuccess && attr.type == cudaMemoryTypeHost) continue;
+            cudaGetLastError();
+            cudaError_t e = cudaHostRegister(const_cast<void*>(r.p), r.bytes, cudaHostRegisterPortable);
+            if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); continue; }
+            if (e != cudaSuccess) { for (void* q : pinned) cudaHostUnregister(q); return cuda_fail(e, "cudaHostRegister"); }
+            pinned.push_back(const_cast<void*>(r.p));
+        }
+    }
+    std::vector<int> rcs(nd, TMM_OK);
+    std::vector<std::string> errs(nd);
+    std::vector<std::thread> threads;
+    for (int d = 0; d < nd; ++d) {
+        threads.emplace_back([&, d] {
+            tmm_context* ch = parent->children[d];
+            cudaSetDevice(ch->device);
+            int64_t i0, i1, j0, j1;
+            share_range(m, pr, ch->grid.row, &i0, &i1);
+            share_range(n, pc, ch->grid.col, &j0, &j1);
+            const char* ap = static_cast<const char*>(a) + (TA == 'N' ? (size_t)i0 : (size_t)i0 * lda) * es;
+            const char* bp = static_cast<const char*>(b) + (TB == 'N' ? (size_t)j0 * ldb : (size_t)j0) * es;
+            char* cp = static_cast<char*>(c) + ((size_t)j0 * ldc + i0) * es;
+            TMM_DBG("dev %d child gemm block rows [%lld,%lld) cols [%lld,%lld)", ch->device, (long long)i0, (long long)i1, (long long)j0, (long long)j1);
+            rcs[d] = tmm_gemm(ch, ta, tb, i1 - i0, j1 - j0, k, alpha, ap, lda, bp, ldb, beta, cp, ldc, 0, 1);
+            TMM_DBG("dev %d child gemm done rc %d", ch->device, rcs[d]);
+            if (rcs[d]) errs[d] = last_error_cstr();
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (void* q : pinned) cudaHostUnregister(q);
+    int rc = TMM_OK;
+    for (int d = 0; d < nd; ++d) {
+        const tmm_call_stats& s = parent->children[d]->stats;
+        parent->stats.h2d_bytes += s.h2d_bytes; parent->stats.d2h_bytes += s.d2h_bytes; parent->stats.peer_bytes += s.peer_bytes;
+        parent->stats.kernel_launches += s.kernel_launches; parent->stats.h2d_copies += s.h2d_copies; parent->stats.d2h_copies += s.d2h_copies;
+        parent->stats.kernel_ms = std::max(parent->stats.kernel_ms, s.kernel_ms);
+        parent->stats.regime = s.regime; parent->stats.c_blocks += s.c_blocks; parent->stats.k_chunks = s.k_chunks;
+        if (rcs[d] && !rc) { rc = rcs[d]; fail(rc, "device %d: %s", parent->children[d]->device, errs[d].c_str()); }
+    }
+    parent->stats.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return rc;
+}
+
+}  // namespace tmm
+
+extern "C" {
+
+int tmm_grid_shape(int n_gpus, int* grid_rows, int* grid_cols) {
+    if (n_gpus < 1 || !grid_rows || !grid_cols) return tmm::fail(TMM_ERR_INVALID, "grid_shape: bad argument");
+    int pr = 1;
+    for (int d = 1; d * d <= n_gpus; ++d)
+        if (n_gpus % d == 0) pr = d;  // the most square factorisation with p_r <= p_c: 1->1x1, 2->1x2, 4->2x2, 8->2x4
+    *grid_rows = pr; *grid_cols = n_gpus / pr;
+    return TMM_OK;
+}
+
+int tmm_share_range(int64_t extent, int parts, int index, int64_t* lo, int64_t* hi) {
+    if (extent < 0 || parts < 1 || index < 0 || index >= parts || !lo || !hi) return tmm::fail(TMM_ERR_INVALID, "share_range: bad argument");
+    tmm::share_range(extent, parts, index, lo, hi);
+    return TMM_OK;
+}
+
+int tmm_dist_unique_id(void* out128) {
+    if (!out128) return tmm::fail(TMM_ERR_INVALID, "out is null");
+    const tmm::nccl::Api& nc = tmm::nccl::api();
+    if (!nc.ok) return tmm::fail(TMM_ERR_CUDA, "GPU ERROR: NCCL unavailable: %s", nc.why);
+    tmm::nccl::UniqueId id;
+    int r = nc.GetUniqueId(&id);
+    if (r) return tmm::nccl_fail(r, "ncclGetUniqueId");
+    memcpy(out128, &id, sizeof id);
+    return TMM_OK;
+}
+
+int tmm_context_attach_grid(tmm_context* ctx, int grid_rows, int grid_cols, int my_row, int my_col, const void* row_id128, const void* col_id128) {
+    if (!ctx) return tmm::fail(TMM_ERR_INVALID, "null context");
+    if (grid_rows < 1 || grid_cols < 1 || my_row < 0 || my_row >= grid_rows || my_col < 0 || my_col >= grid_cols)
+        return tmm::fail(TMM_ERR_INVALID, "attach_grid: bad grid position (%d,%d) in %dx%d", my_row, my_col, grid_rows, grid_cols);
+    if ((grid_cols > 1 && !row_id128) || (grid_rows > 1 && !col_id128)) return tmm::fail(TMM_ERR_INVALID, "attach_grid: missing NCCL unique id");
+    if (!ctx->children.empty()) return tmm::fail(TMM_ERR_INVALID, "attach_grid: context already drives several devices");
+    tmm::nccl::UniqueId rid{}, cid{};
+    if (row_id128) memcpy(&rid, row_id128, sizeof rid);
+    if (col_id128) memcpy(&cid, col_id128, sizeof cid);
+    return tmm::attach(ctx, grid_rows, grid_cols, my_row, my_col, &rid, &cid);
+}
+
+int tmm_context_grid(tmm_context* ctx, int* grid_rows, int* grid_cols, int* my_row, int* my_col) {
+    if (!ctx) return tmm::fail(TMM_ERR_INVALID, "null context");
+    const tmm::Grid& g = ctx->children.empty() ? ctx->grid : ctx->children[0]->grid;
+    if (grid_rows) *grid_rows = g.pr;
+    if (grid_cols) *grid_cols = g.pc;
+    if (my_row) *my_row = ctx->children.empty() ? g.row : -1;
+    if (my_col) *my_col = ctx->children.empty() ? g.col : -1;
+    return TMM_OK;
+}
+
+int tmm_context_set_devices(tmm_context* ctx, int n_devices, const int* device_ids) {
+    if (!ctx) return tmm::fail(TMM_ERR_INVALID, "null context");
+    if (n_devices < 1) return tmm::fail(TMM_ERR_INVALID, "set_devices: n_devices must be >= 1");
+    int ndev = 0;
+    TMM_CU(cudaGetDeviceCount(&ndev));
+    std::vector<int> ids(n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        ids[i] = device_ids ? device_ids[i] : i;
+        if (ids[i] < 0 || ids[i] >= ndev) return tmm::fail(TMM_ERR_INVALID, "set_devices: device %d not present (%d devices)", ids[i], ndev);
+        for (int j = 0; j < i; ++j)
+            if (ids[j] == ids[i]) return tmm::fail(TMM_ERR_INVALID, "set_devices: device %d listed twice", ids[i]);
+    }
+    for (tmm_context* ch : ctx->children) tmm_context_destroy(ch);
+    ctx->children.clear();
+    if (ctx->solo) { tmm_context_destroy(ctx->solo); ctx->solo = nullptr; }
+    if (n_devices == 1 && ids[0] == ctx->device) return TMM_OK;  // back to the plain single-GPU context
+    int pr, pc;
+    tmm_grid_shape(n_devices, &pr, &pc);
+    const tmm::nccl::Api& nc = tmm::nccl::api();
+    if (n_devices > 1 && !nc.ok) return tmm::fail(TMM_ERR_CUDA, "GPU ERROR: NCCL unavailable: %s", nc.why);
+    std::vector<tmm::nccl::UniqueId> row_ids(pr), col_ids(pc);
+    if (n_devices > 1) {
+        for (auto& id : row_ids) { int r = nc.GetUniqueId(&id); if (r) return tmm::nccl_fail(r, "ncclGetUniqueId"); }
+        for (auto& id : col_ids) { int r = nc.GetUniqueId(&id); if (r) return tmm::nccl_fail(r, "ncclGetUniqueId"); }
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = TMM_OK;
+    for (int i = 0; i < n_devices && !rc; ++i) {
+        cudaSetDevice(ids[i]);
+        tmm_context* ch = nullptr;
+        rc = tmm_context_create(ctx->dtype, ctx->n_streams, ctx->max_tile_m, ctx->max_tile_n, ctx->max_tile_k, &ch);
+        if (!rc) { ch->budget_override = ctx->budget_override; ch->profiling = ctx->profiling; ctx->children.push_back(ch); }
+    }
+    if (!rc && n_devices > 1) {
+        // ncclCommInitRank blocks until every rank of the communicator has called it: one thread per device
+        std::vector<int> rcs(n_devices, TMM_OK);
+        std::vector<std::string> errs(n_devices);
+        std::vector<std::thread> threads;
+        for (int i = 0; i < n_devices; ++i)
+            threads.emplace_back([&, i] {
+                cudaSetDevice(ids[i]);
+                const int row = i / pc, col = i % pc;
+                rcs[i] = tmm::attach(ctx->children[i], pr, pc, row, col, &row_ids[row], &col_ids[col]);
+                if (rcs[i]) errs[i] = tmm::last_error_cstr();
+            });
+        for (auto& t : threads) t.join();
+        for (int i = 0; i < n_devices; ++i)
+            if (rcs[i] && !rc) rc = tmm::fail(rcs[i], "device %d: %s", ids[i], errs[i].c_str());
+        if (!rc) {  // shapes too small for the grid fall back to one plain context on the first device
+            cudaSetDevice(ids[0]);
+            rc = tmm_context_create(ctx->dtype, ctx->n_streams, ctx->max_tile_m, ctx->max_tile_n, ctx->max_tile_k, &ctx->solo);
+        }
+    }
+    cudaSetDevice(prev);
+    if (rc) {
+        for (tmm_context* ch : ctx->children) tmm_context_destroy(ch);
+        ctx->children.clear();
+    }
+    return rc;
+}
+
+int tmm_context_num_devices(tmm_context* ctx) { return ctx ? (ctx->children.empty() ? 1 : (int)ctx->children.size()) : TMM_ERR_INVALID; }
+
+tmm_context* tmm_context_child(tmm_context* ctx, int index) {
+    if (!ctx || index < 0 || index >= (int)ctx->children.size()) return nullptr;
+    return ctx->children[index];
+}
+
+int tmm_memcpy_2d_async(void* dst, size_t dpitch_bytes, const void* src, size_t spitch_bytes, size_t width_bytes, size_t height, int kind, void* stream) {
+    // kind: 1 host->device, 2 device->host, 3 device->device (cudaMemcpyKind values); the copy_tile_* helpers of the
+    // reference (tiled_mm.cpp:45-123) are cudaMemcpy2DAsync with exactly these arguments
+    if (kind < 1 || kind > 3) return tmm::fail(TMM_ERR_INVALID, "memcpy_2d: bad kind %d", kind);
+    if (width_bytes == 0 || height == 0) return TMM_OK;
+    TMM_CU(cudaMemcpy2DAsync(dst, dpitch_bytes, src, spitch_bytes, width_bytes, height, (cudaMemcpyKind)kind, (cudaStream_t)stream));
+    return TMM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+// Internal definitions shared by the scheduler (tmm_context.cu) and the multi-GPU layer (tmm_dist.cu).
+#pragma once
+#include "../../include/tiled_mm_b200.h"
+#include "tmm_blas.h"
+#include "tmm_nccl.h"
+#include "tmm_plan.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace tmm {
+
+// error plumbing: every failure sets the thread-local message returned by tmm_last_error()
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);  // also prints the CUDA error string to stderr (reference util.hpp:13-19)
+int nccl_fail(int rc, const char* what);
+
+#define TMM_CU(x)                                                \
+    do {                                                         \
+        cudaError_t e__ = (x);                                   \
+        if (e__ != cudaSuccess) return ::tmm::cuda_fail(e__, #x); \
+    } while (0)
+
+// developer tracing of the multi-GPU path: TMM_DEBUG=1 prints one line per step to stderr
+bool debug_on();
+#define TMM_DBG(...)                                  \
+    do {                                              \
+        if (::tmm::debug_on()) { fprintf(stderr, "[tmm dbg] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } \
+    } while (0)
+
+inline int64_t round_up64(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;  // bytes
+    cudaError_t reserve(size_t bytes, double slack = 1.0) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = (size_t)std::ceil((double)bytes * slack);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess && slack > 1.0) { want = bytes; e = cudaMalloc(&p, want); }
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) { cudaSetDevice(dev); switched = true; }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+// Position of a context in a p_r x p_c grid of GPUs over the C blocks.  The grid row shares the A
+// row-panel, the grid column shares the B column-panel; each member uploads a distinct 1/p share of a shared
+// panel over its own PCIe link and the shares are all-gathered over NVLink (NCCL) - no k split, no reduction.
+struct Grid {
+    int pr = 1, pc = 1, row = 0, col = 0;
+    nccl::Comm row_comm = nullptr;  // the p_c ranks of my grid row    (my rank = col): exchanges A
+    nccl::Comm col_comm = nullptr;  // the p_r ranks of my grid column (my rank = row): exchanges B
+    bool active() const { return pr * pc > 1; }
+};
+
+constexpr int STAGE_SLOTS = 3;
+
+}  // namespace tmm
+
+struct tmm_context {
+    int dtype = TMM_F64;
+    int n_streams = 2;
+    int max_tile_m = 5000, max_tile_n = 5000, max_tile_k = 5000;
+    int device = 0;
+    static constexpr int MAX_COMPUTE = 4;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comm = nullptr, s_compute[MAX_COMPUTE] = {nullptr, nullptr, nullptr, nullptr};
+    tmm::DevBuf buf_a, buf_b, buf_c;  // panel / ring / staged-C storage (grow-only, reused across calls)
+    tmm::DevBuf full_c;               // API-visible device C (copy_c_back = false), column-major ld = m
+    size_t full_c_elems = 0;
+    std::vector<cudaEvent_t> events;
+    size_t ev_next = 0;
+    std::vector<cudaEvent_t> timing_events;
+    size_t tev_next = 0;
+    size_t budget_override = 0;
+    size_t budget_cached = 0;
+    bool profiling = false;
+    bool pin_cache = false;
+    bool trace = false;
+    struct TraceOp { std::string name; cudaEvent_t e0, e1; };
+    std::vector<TraceOp> trace_ops;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
+    std::map<const void*, size_t> pinned;
+    tmm_call_stats stats{};
+
+    // ---- multi-GPU (tmm_dist.cu) ----
+    tmm::Grid grid;                         // this context's place in a GPU grid (per-process or child of a parent)
+    tmm::DevBuf stage_send, stage_recv, dist_scratch;  // all-gather staging rings (STAGE_SLOTS slots each)
+    size_t stage_slot_bytes = 0;            // bytes of one share (send slot); a recv slot holds `parts` of them
+    int stage_next = 0;
+    cudaEvent_t stage_send_free[tmm::STAGE_SLOTS] = {nullptr, nullptr, nullptr};
+    std::vector<tmm_context*> children;     // single-process multi-GPU: one child context per device, driven by host threads
+    tmm_context* solo = nullptr;            // plain context on the first device for shapes too small to split
+
+    // compute streams: [0] carries the phase-1 / streaming chain at the highest priority, the others (lower priorities)
+    // carry independent column blocks, whose CTAs then only back-fill SM slots the chain leaves free
+    int n_compute() const { int v = n_streams + 1; if (v > MAX_COMPUTE) v = MAX_COMPUTE; return v < 3 ? 3 : v; }
+
+    cudaError_t get_event(cudaEvent_t* out) {
+        if (ev_next == events.size()) {
+            cudaEvent_t e;
+            cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            if (r != cudaSuccess) return r;
+            events.push_back(e);
+        }
+        *out = events[ev_next++];
+        return cudaSuccess;
+    }
+    cudaError_t get_timing_event(cudaEvent_t* out) {
+        if (tev_next == timing_events.size()) {
+            cudaEvent_t e;
+            cudaError_t r = cudaEventCreate(&e);
+            if (r != cudaSuccess) return r;
+            timing_events.push_back(e);
+        }
+        *out = timing_events[tev_next++];
+        return cudaSuccess;
+    }
+};
+
+namespace tmm {
+
+// ---- multi-GPU layer (tmm_dist.cu) ----
+// Agree on the planning inputs across the grid (max block dims, min budget) and check that k / flags match everywhere.
+int dist_agree(tmm_context* ctx, int64_t m, int64_t n, int64_t k, int flags, size_t budget, int64_t* m_plan, int64_t* n_plan, size_t* budget_min);
+// Device bytes the staging rings need for shares of at most `share_bytes` gathered from up to `parts` ranks.
+size_t dist_stage_bytes(size_t share_bytes, int parts);
+int dist_reserve_stage(tmm_context* ctx, size_t share_bytes, int parts);
+// All-gather a stored rows x cols sub-block (host src, leading dimension spitch elements) into dst (device, pitch dpitch
+// elements): this rank uploads columns [lo, hi) of it (its share) on s_h2d, the shares are gathered on s_comm over `comm`
+// and unpacked into place.  On return the tail of s_comm marks "dst complete".
+int dist_exchange(tmm_context* ctx, nccl::Comm comm, int parts, int me, size_t es, const char* src, int64_t spitch, int64_t rows, int64_t cols,
+                  char* dst, int64_t dpitch);
+void dist_release(tmm_context* ctx);
+// share g of `parts` over an extent: balanced split, [lo, hi)
+inline void share_range(int64_t extent, int parts, int g, int64_t* lo, int64_t* hi) {
+    const int64_t base = extent / parts, rem = extent % parts;
+    *lo = g * base + (g < rem ? g : rem);
+    *hi = *lo + base + (g < rem ? 1 : 0);
+}
+// single-process multi-GPU: run one call over the children of a parent context
+int multi_gemm(tmm_context* parent, char ta, char tb, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t lda, const void* b,
+               int64_t ldb, const void* beta, void* c, int64_t ldc, int pin, int copy_c_back);
+
+}  // namespace tmm

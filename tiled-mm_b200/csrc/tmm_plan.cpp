@@ -80,9 +80,10 @@ Plan make_plan(const PlanInput& in) {
         //  phase 2 overlap the D2H of finished C blocks with the H2D of later B blocks)
         const double margin = env_or("TMM_PLAN_MARGIN", 1.3);
         int64_t n1 = std::min<int64_t>(n, 1024);
-        const double denom = F * (double)m / kFlops - margin * (double)es / kH2D;
+        const double sa = 1.0 / std::max(1, in.parts_a), sb = 1.0 / std::max(1, in.parts_b);  // upload shares on a GPU grid
+        const double denom = F * (double)m / kFlops - margin * (double)es * sb / kH2D;
         if (denom > 0) {
-            const double need = margin * (double)es * (double)m / kH2D / denom;
+            const double need = margin * (double)es * sa * (double)m / kH2D / denom;
             n1 = (int64_t)std::min<double>((double)n, std::max(512.0, need));
         }
         n1 = std::min<int64_t>(n, round_up(n1, BN));
@@ -102,7 +103,7 @@ Plan make_plan(const PlanInput& in) {
         // phase-1 k-chunks: small first chunk (short prologue); a chunk may grow only as fast as the previous chunk's
         // GEMM can hide its upload (ratio r of GEMM time to upload time per unit of k), up to the cap
         {
-            const double r = (F * (double)m * (double)n1 / kFlops) / ((double)es * (double)(m + n1) / kH2D);
+            const double r = (F * (double)m * (double)n1 / kFlops) / ((double)es * (sa * (double)m + sb * (double)n1) / kH2D);
             const double growth = env_or("TMM_PLAN_GROWTH", std::max(1.25, std::min(2.0, 0.95 * r)));
             int64_t done = 0;
             int64_t kc = (int64_t)env_or("TMM_PLAN_KC0", 256);
