@@ -318,4 +318,4 @@ def test_full_size_10000_cubed_linearity(gpu_tmm):
     lhs, rhs = C @ x, A @ (B @ x)
     # |C x - A B x| <= k * eps-level * |A||B||x| ; allow 1e-15 * k per product entry as in north_star, times sum |x|
     assert np.max(np.abs(lhs - rhs)) <= 1e-15 * n * np.abs(x).sum() + 1e-9
-    assert st.h2d_bytes == 2 * 8 * n * n and st.d2h_bytes == 8 * n * n and st.kernel_launches <= 16
+    assert st.h2d_bytes == 2 * 8 * n * n and st.d2h_bytes == 8 * n * n and st.kernel_launches <= 64

@@ -145,19 +145,20 @@ int fetch_b(Call& cl, char* dst, int64_t dpitch, const Sub& s) {
     return h2d_2d(cl, dst, dpitch, src, cl.ldb, s.rows, s.cols, cl.ctx->s_h2d);
 }
 // make `consumer` wait for everything fetched so far
-int panels_ready(Call& cl, cudaStream_t consumer) {
+int panels_ready(Call& cl, const cudaStream_t* consumers, int n_consumers) {
     tmm_context* ctx = cl.ctx;
     cudaEvent_t ev;
     CU(ctx->get_event(&ev));
     CU(cudaEventRecord(ev, ctx->s_h2d));
-    CU(cudaStreamWaitEvent(consumer, ev, 0));
+    for (int i = 0; i < n_consumers; ++i) CU(cudaStreamWaitEvent(consumers[i], ev, 0));
     if (ctx->grid.active()) {
         CU(ctx->get_event(&ev));
         CU(cudaEventRecord(ev, ctx->s_comm));
-        CU(cudaStreamWaitEvent(consumer, ev, 0));
+        for (int i = 0; i < n_consumers; ++i) CU(cudaStreamWaitEvent(consumers[i], ev, 0));
     }
     return TMM_OK;
 }
+int panels_ready(Call& cl, cudaStream_t consumer) { return panels_ready(cl, &consumer, 1); }
 
 int launch_gemm(Call& cl, int64_t mi, int64_t nj, int64_t kc, const void* da, int64_t pa, const void* db, int64_t pb, const void* beta, void* dc,
                 int64_t ldc, cudaStream_t st) {
@@ -225,9 +226,18 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
         int rc = h2d_2d(cl, dC, ldc_dev, cl.c, cl.ldc, cl.m, n1, ctx->s_h2d);
         if (rc) return rc;
     }
-    // ---- phase 1: A streams in as k-chunks with the first column block of B
+    // ---- phase 1: A streams in as k-chunks with the first column block of B.  The block is cut into P1 column stripes, each a
+    // chain of accumulating launches on its own high-priority stream: a chain is serial (chunk c+1 reads what chunk c wrote),
+    // so a single chain drains the SMs at every launch boundary; with two or more staggered chains the block scheduler always
+    // has CTAs of another stripe to dispatch while one stripe's launch drains.
+    int P1 = (int)std::min<int64_t>(tmm_context::MAX_P1, std::max<int64_t>(1, n1 / 1024));
+    {
+        const char* v = getenv("TMM_PLAN_P1SPLIT");
+        if (v && *v) P1 = std::max(1, std::min<int>(std::min<int64_t>(tmm_context::MAX_P1, (n1 + 63) / 64), atoi(v)));
+    }
+    int64_t s_off[tmm_context::MAX_P1 + 1];
+    for (int s = 0; s <= P1; ++s) s_off[s] = s == P1 ? n1 : std::min<int64_t>(n1, round_up(n1 * s / P1, 64));
     int64_t p0 = 0;
-    cudaStream_t cs0 = ctx->s_compute[0];
     for (size_t ci = 0; ci < pl.chunks.size(); ++ci) {
         const int64_t kc = pl.chunks[ci];
         Sub sa = a_sub(cl, 0, cl.m, p0, kc);
@@ -242,27 +252,35 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
             if (rc) return rc;
         }
         {
-            int rc = panels_ready(cl, cs0);
+            int rc = panels_ready(cl, ctx->s_p1, P1);
             if (rc) return rc;
         }
-        {
-            TraceScope ts(ctx, cs0, "gemm1", n1, kc);
-            int rc = launch_gemm(cl, cl.m, n1, kc, da, pa, db, pb, ci == 0 ? cl.beta : (const void*)cl.one, dC, ldc_dev, cs0);
+        for (int s = 0; s < P1; ++s) {
+            const int64_t js = s_off[s], ws = s_off[s + 1] - js;
+            if (ws <= 0) continue;
+            Sub sbs = b_sub(cl, p0, kc, js, ws);
+            TraceScope ts(ctx, ctx->s_p1[s], "gemm1", js, ws, kc);
+            int rc = launch_gemm(cl, cl.m, ws, kc, da, pa, dB + ((size_t)sbs.col * pb + sbs.row) * es, pb, ci == 0 ? cl.beta : (const void*)cl.one,
+                                 (char*)dC + (size_t)js * ldc_dev * es, ldc_dev, ctx->s_p1[s]);
             if (rc) return rc;
         }
         p0 += kc;
     }
     if (cl.copy_c_back) {
-        CU(ctx->get_event(&ev));
-        CU(cudaEventRecord(ev, cs0));
-        CU(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
-        // a few pieces so the first bytes leave early
-        const int64_t piece = std::max<int64_t>(64, round_up(n1 / 4, 64));
-        for (int64_t j = 0; j < n1; j += piece) {
-            const int64_t w = std::min(piece, n1 - j);
-            TraceScope ts(ctx, ctx->s_d2h, "d2hC", j, w);
-            int rc = d2h_2d(cl, cl.c + (size_t)j * cl.ldc * es, cl.ldc, (char*)dC + (size_t)j * ldc_dev * es, ldc_dev, cl.m, w, ctx->s_d2h);
-            if (rc) return rc;
+        // stripes finish in order; each leaves for the host as soon as its chain is done
+        for (int s = 0; s < P1; ++s) {
+            const int64_t js = s_off[s], ws = s_off[s + 1] - js;
+            if (ws <= 0) continue;
+            CU(ctx->get_event(&ev));
+            CU(cudaEventRecord(ev, ctx->s_p1[s]));
+            CU(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
+            const int64_t piece = std::max<int64_t>(64, round_up(ws / 2, 64));
+            for (int64_t j = js; j < js + ws; j += piece) {
+                const int64_t w = std::min(piece, js + ws - j);
+                TraceScope ts(ctx, ctx->s_d2h, "d2hC", j, w);
+                int rc = d2h_2d(cl, cl.c + (size_t)j * cl.ldc * es, cl.ldc, (char*)dC + (size_t)j * ldc_dev * es, ldc_dev, cl.m, w, ctx->s_d2h);
+                if (rc) return rc;
+            }
         }
     }
     // ---- phase 2: A resident; remaining column blocks of B, full k each, C block streams back at once
@@ -408,6 +426,7 @@ int sync_all(tmm_context* ctx) {
     CU(cudaStreamSynchronize(ctx->s_h2d));
     CU(cudaStreamSynchronize(ctx->s_comm));
     for (int i = 0; i < tmm_context::MAX_COMPUTE; ++i) CU(cudaStreamSynchronize(ctx->s_compute[i]));
+    for (int i = 1; i < tmm_context::MAX_P1; ++i) CU(cudaStreamSynchronize(ctx->s_p1[i]));
     CU(cudaStreamSynchronize(ctx->s_d2h));
     return TMM_OK;
 }
@@ -479,6 +498,9 @@ int tmm_context_create(int dtype, int n_streams, int max_tile_m, int max_tile_n,
     const int prio[] = {prio_greatest, prio_greatest, prio_greatest, low, low, low, prio_greatest};
     for (int i = 0; i < 7; ++i)
         if ((e = cudaStreamCreateWithPriority(all[i], cudaStreamNonBlocking, prio[i])) != cudaSuccess) { tmm_context_destroy(ctx); return cuda_fail(e, "cudaStreamCreateWithPriority"); }
+    ctx->s_p1[0] = ctx->s_compute[0];  // phase-1 stripe chains: [0] is the main high-priority compute stream
+    for (int i = 1; i < tmm_context::MAX_P1; ++i)
+        if ((e = cudaStreamCreateWithPriority(&ctx->s_p1[i], cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) { tmm_context_destroy(ctx); return cuda_fail(e, "cudaStreamCreateWithPriority"); }
     *out = ctx;
     return TMM_OK;
 }
@@ -492,6 +514,7 @@ void tmm_context_destroy(tmm_context* ctx) {
     if (ctx->solo) { tmm_context_destroy(ctx->solo); ctx->solo = nullptr; }
     cudaStream_t all[] = {ctx->s_h2d, ctx->s_d2h, ctx->s_compute[0], ctx->s_compute[1], ctx->s_compute[2], ctx->s_compute[3], ctx->s_comm};
     for (cudaStream_t s : all) if (s) cudaStreamSynchronize(s);
+    for (int i = 1; i < tmm_context::MAX_P1; ++i) if (ctx->s_p1[i]) { cudaStreamSynchronize(ctx->s_p1[i]); cudaStreamDestroy(ctx->s_p1[i]); }
     tmm::dist_release(ctx);
     for (cudaStream_t s : all) if (s) cudaStreamDestroy(s);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);

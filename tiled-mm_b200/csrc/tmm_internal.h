@@ -79,7 +79,8 @@ struct tmm_context {
     int n_streams = 2;
     int max_tile_m = 5000, max_tile_n = 5000, max_tile_k = 5000;
     int device = 0;
-    static constexpr int MAX_COMPUTE = 4;
+    static constexpr int MAX_COMPUTE = 4, MAX_P1 = 4;
+    cudaStream_t s_p1[MAX_P1] = {nullptr, nullptr, nullptr, nullptr};  // phase-1 stripe chains ([0] aliases s_compute[0])
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comm = nullptr, s_compute[MAX_COMPUTE] = {nullptr, nullptr, nullptr, nullptr};
     tmm::DevBuf buf_a, buf_b, buf_c;  // panel / ring / staged-C storage (grow-only, reused across calls)
     tmm::DevBuf full_c;               // API-visible device C (copy_c_back = false), column-major ld = m
