@@ -49,6 +49,8 @@ if __name__ == "__main__":
         bench(np.float64, "NN", 10000, 4800, 512, beta=1.0)
         bench(np.float64, "NN", 10000, 4800, 2048, beta=1.0)
         bench(np.float64, "NN", 10000, 2048, 10000)
+    if which == "z1":
+        bench(np.complex128, "NN", 6000, 6000, 6000, reps=2)
     if which in ("all", "z"):
         for tt in ("NN", "CN", "NC", "TT"):
             bench(np.complex128, tt, 6000, 6000, 6000)
