@@ -3,6 +3,7 @@
 #include "tmm_blas.h"
 
 #include <atomic>
+#include <mutex>
 #include <cctype>
 #include <cuda.h>
 #include <cuComplex.h>
@@ -27,14 +28,14 @@ int sm_count() {
 }
 
 void* tensormap_encode_fn() {
+    // resolved once, thread-safe: the multi-GPU path launches from one host thread per device
     static void* fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         cudaDriverEntryPointQueryResult qres;
         void* p = nullptr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = p;
-    }
+    });
     return fn;
 }
 

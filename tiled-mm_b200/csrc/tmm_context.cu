@@ -24,6 +24,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace tmm {
 
@@ -132,16 +133,16 @@ Sub b_sub(const Call& cl, int64_t p0, int64_t kc, int64_t j0, int64_t nj) {
 // Bring the stored sub-block `s` of A (or B) to its device position.  One GPU: a single 2-D H2D copy on s_h2d.  On a GPU grid
 // the sub-block is shared by the grid row (A) / grid column (B): this rank uploads only its 1/p share and the shares are
 // all-gathered over NVLink on s_comm (tmm_dist.cu).  Callers order consumers after BOTH streams (panels_ready).
-int fetch_a(Call& cl, char* dst, int64_t dpitch, const Sub& s) {
+int fetch_a(Call& cl, char* dst, int64_t dpitch, const Sub& s, int ring_slot = -1) {
     const tmm::Grid& g = cl.ctx->grid;
     const char* src = cl.a + ((size_t)s.col * cl.lda + s.row) * cl.es;
-    if (g.pc > 1) return tmm::dist_exchange(cl.ctx, g.row_comm, g.pc, g.col, cl.es, src, cl.lda, s.rows, s.cols, dst, dpitch);
+    if (g.pc > 1) return tmm::dist_exchange(cl.ctx, cl.ctx->grid.rowl, cl.es, src, cl.lda, s.rows, s.cols, dst, dpitch, ring_slot);
     return h2d_2d(cl, dst, dpitch, src, cl.lda, s.rows, s.cols, cl.ctx->s_h2d);
 }
-int fetch_b(Call& cl, char* dst, int64_t dpitch, const Sub& s) {
+int fetch_b(Call& cl, char* dst, int64_t dpitch, const Sub& s, int ring_slot = -1) {
     const tmm::Grid& g = cl.ctx->grid;
     const char* src = cl.b + ((size_t)s.col * cl.ldb + s.row) * cl.es;
-    if (g.pr > 1) return tmm::dist_exchange(cl.ctx, g.col_comm, g.pr, g.row, cl.es, src, cl.ldb, s.rows, s.cols, dst, dpitch);
+    if (g.pr > 1) return tmm::dist_exchange(cl.ctx, cl.ctx->grid.coll, cl.es, src, cl.ldb, s.rows, s.cols, dst, dpitch, ring_slot);
     return h2d_2d(cl, dst, dpitch, src, cl.ldb, s.rows, s.cols, cl.ctx->s_h2d);
 }
 // make `consumer` wait for everything fetched so far
@@ -152,9 +153,18 @@ int panels_ready(Call& cl, const cudaStream_t* consumers, int n_consumers) {
     CU(cudaEventRecord(ev, ctx->s_h2d));
     for (int i = 0; i < n_consumers; ++i) CU(cudaStreamWaitEvent(consumers[i], ev, 0));
     if (ctx->grid.active()) {
-        CU(ctx->get_event(&ev));
-        CU(cudaEventRecord(ev, ctx->s_comm));
-        for (int i = 0; i < n_consumers; ++i) CU(cudaStreamWaitEvent(consumers[i], ev, 0));
+        // NCCL-staged links complete on s_comm; DMA-pushed links complete when the peers' arrival counters say so
+        tmm::Grid& g = ctx->grid;
+        if ((g.rowl.active() && !g.rowl.direct) || (g.coll.active() && !g.coll.direct)) {
+            CU(ctx->get_event(&ev));
+            CU(cudaEventRecord(ev, ctx->s_comm));
+            for (int i = 0; i < n_consumers; ++i) CU(cudaStreamWaitEvent(consumers[i], ev, 0));
+        }
+        for (int i = 0; i < n_consumers; ++i) {
+            int rc = tmm::link_wait(ctx, g.rowl, consumers[i]);
+            if (!rc) rc = tmm::link_wait(ctx, g.coll, consumers[i]);
+            if (rc) return rc;
+        }
     }
     return TMM_OK;
 }
@@ -186,21 +196,7 @@ size_t device_budget(tmm_context* ctx) {
     return ctx->budget_cached;
 }
 
-// ---- optional timeline (TMM_TRACE=1): every op gets a begin/end event; printed after the call ----
-struct TraceScope {
-    tmm_context* ctx; cudaStream_t st; size_t idx = (size_t)-1;
-    TraceScope(tmm_context* c, cudaStream_t s, const char* name, int64_t a = 0, int64_t b = 0, int64_t d = 0) : ctx(c), st(s) {
-        if (!ctx->trace) return;
-        cudaEvent_t e0, e1;
-        if (ctx->get_timing_event(&e0) != cudaSuccess || ctx->get_timing_event(&e1) != cudaSuccess) return;
-        cudaEventRecord(e0, st);
-        char buf[96];
-        snprintf(buf, sizeof buf, "%s(%lld,%lld,%lld)", name, (long long)a, (long long)b, (long long)d);
-        ctx->trace_ops.push_back({buf, e0, e1});
-        idx = ctx->trace_ops.size() - 1;
-    }
-    ~TraceScope() { if (idx != (size_t)-1) cudaEventRecord(ctx->trace_ops[idx].e1, st); }
-};
+using tmm::TraceScope;
 
 // ------------------------------------------------------------------------------------------------
 // Resident regime: device holds all of A, B and C.
@@ -212,6 +208,11 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
     cudaError_t e;
     if ((e = ctx->buf_a.reserve(pl.bytes_a)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(A panels)");
     if ((e = ctx->buf_b.reserve(pl.bytes_b)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(B panels)");
+    if (ctx->grid.active()) {
+        int rc = tmm::link_bind(ctx, ctx->grid.rowl, ctx->buf_a);
+        if (!rc) rc = tmm::link_bind(ctx, ctx->grid.coll, ctx->buf_b);
+        if (rc) return rc;
+    }
     char* dA = (char*)ctx->buf_a.p;
     char* dB = (char*)ctx->buf_b.p;
     const int ncs = ctx->n_compute();
@@ -338,6 +339,11 @@ int run_streaming(Call& cl, const tmm::Plan& pl, void* dC_full, int64_t ldc_full
     if ((e = ctx->buf_b.reserve(pl.bytes_b)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(B ring)");
     if (!c_is_full && (e = ctx->buf_c.reserve(pl.bytes_c)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(C blocks)");
 
+    if (ctx->grid.active()) {
+        int rc = tmm::link_bind(ctx, ctx->grid.rowl, ctx->buf_a);
+        if (!rc) rc = tmm::link_bind(ctx, ctx->grid.coll, ctx->buf_b);
+        if (rc) return rc;
+    }
     cudaStream_t cs = ctx->s_compute[0];
     std::vector<cudaEvent_t> slot_free(SLOTS, nullptr);
     cudaEvent_t cbuf_free[2] = {nullptr, nullptr};
@@ -381,9 +387,9 @@ int run_streaming(Call& cl, const tmm::Plan& pl, void* dC_full, int64_t ldc_full
                 Sub sb = b_sub(cl, p0, kcc, j0, nj);
                 {
                     TraceScope ts(ctx, ctx->s_h2d, "h2dAB", p0, kcc, slot);
-                    int rc = mi > 0 ? fetch_a(cl, da, pl.pa_slot, sa) : TMM_OK;
+                    int rc = mi > 0 ? fetch_a(cl, da, pl.pa_slot, sa, slot) : TMM_OK;
                     if (rc) return rc;
-                    rc = nj > 0 ? fetch_b(cl, db, pl.pb_slot, sb) : TMM_OK;
+                    rc = nj > 0 ? fetch_b(cl, db, pl.pb_slot, sb, slot) : TMM_OK;
                     if (rc) return rc;
                 }
                 {
@@ -397,6 +403,11 @@ int run_streaming(Call& cl, const tmm::Plan& pl, void* dC_full, int64_t ldc_full
                 }
                 CU(ctx->get_event(&slot_free[slot]));
                 CU(cudaEventRecord(slot_free[slot], cs));
+                if (ctx->grid.active()) {  // the peers that push into this ring slot may overwrite it from here on
+                    int rc = mi > 0 ? tmm::link_ack(ctx, ctx->grid.rowl, cs) : TMM_OK;
+                    if (!rc && nj > 0) rc = tmm::link_ack(ctx, ctx->grid.coll, cs);
+                    if (rc) return rc;
+                }
                 slot = (slot + 1) % SLOTS;
             }
             if (!mine) continue;
@@ -423,11 +434,27 @@ int run_streaming(Call& cl, const tmm::Plan& pl, void* dC_full, int64_t ldc_full
 int sync_all(tmm_context* ctx) {
     // the reference ends with a device-wide cudaDeviceSynchronize (tiled_mm.cpp:602-604); syncing our own
     // streams gives the same guarantee for this call without stalling unrelated work on the device
-    CU(cudaStreamSynchronize(ctx->s_h2d));
-    CU(cudaStreamSynchronize(ctx->s_comm));
-    for (int i = 0; i < tmm_context::MAX_COMPUTE; ++i) CU(cudaStreamSynchronize(ctx->s_compute[i]));
-    for (int i = 1; i < tmm_context::MAX_P1; ++i) CU(cudaStreamSynchronize(ctx->s_p1[i]));
-    CU(cudaStreamSynchronize(ctx->s_d2h));
+    std::vector<cudaStream_t> all = {ctx->s_h2d, ctx->s_comm, ctx->s_d2h};
+    for (int i = 0; i < tmm_context::MAX_COMPUTE; ++i) all.push_back(ctx->s_compute[i]);
+    for (int i = 1; i < tmm_context::MAX_P1; ++i) all.push_back(ctx->s_p1[i]);
+    if (ctx->grid.active()) {
+        // on a GPU grid a stream may be waiting for a peer that failed: poll with a deadline instead of blocking forever
+        const char* v = getenv("TMM_DIST_TIMEOUT_S");
+        const double limit_s = (v && *v) ? atof(v) : 600.0;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (cudaStream_t s : all) {
+            for (;;) {
+                cudaError_t e = cudaStreamQuery(s);
+                if (e == cudaSuccess) break;
+                if (e != cudaErrorNotReady) return cuda_fail(e, "cudaStreamQuery");
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit_s)
+                    return fail(TMM_ERR_CUDA, "GPU ERROR: GPU grid call did not finish within %.0f s (a peer rank failed?); the context is unusable", limit_s);
+                std::this_thread::yield();
+            }
+        }
+        return TMM_OK;
+    }
+    for (cudaStream_t s : all) CU(cudaStreamSynchronize(s));
     return TMM_OK;
 }
 
@@ -654,10 +681,12 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                 int64_t m_plan = m, n_plan = n;
                 size_t plan_budget = budget;
                 const tmm::Grid& gr = ctx->grid;
+                bool need_stage = false;  // only links that could not map peer memory stage their shares through NCCL
                 if (gr.active()) {
                     const int flags = (cl.ta << 16) | (cl.tb << 8) | (cl.beta_nonzero ? 2 : 0) | (cl.copy_c_back ? 1 : 0);
                     rc = tmm::dist_agree(ctx, m, n, k, flags, budget, &m_plan, &n_plan, &plan_budget);
-                    if (!rc) {
+                    need_stage = (gr.rowl.active() && !gr.rowl.direct) || (gr.coll.active() && !gr.coll.direct);
+                    if (!rc && need_stage) {
                         // staging rings for the all-gathers: shares of at most one k-chunk of A / one column block of B
                         const int64_t kcap = std::min<int64_t>(k, 2048), ncap = std::min<int64_t>(n_plan, 8192);
                         size_t share = 0;
@@ -679,7 +708,7 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                 tmm::Plan pl;
                 if (!rc) pl = tmm::make_plan(pin_);
                 ctx->stats.regime = pl.regime;
-                if (!rc && gr.active()) {
+                if (!rc && need_stage) {
                     // exact staging need of this plan
                     size_t share = 0;
                     auto upd = [&](int64_t rows, int64_t cols, int parts) { if (parts > 1) share = std::max(share, (size_t)rows * (size_t)((cols + parts - 1) / parts) * cl.es); };

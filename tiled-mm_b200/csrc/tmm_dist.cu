@@ -12,6 +12,7 @@
 #include "tmm_internal.h"
 
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cctype>
@@ -26,6 +27,11 @@ const char* last_error_cstr();
 bool debug_on() {
     static const bool on = [] { const char* v = getenv("TMM_DEBUG"); return v && v[0] == '1'; }();
     return on;
+}
+
+double debug_ms() {
+    static const auto t0 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
 namespace nccl {
@@ -80,19 +86,206 @@ int dist_reserve_stage(tmm_context* ctx, size_t share_bytes, int parts) {
     return TMM_OK;
 }
 
+// ---- stream memory operations (driver API, resolved at run time) -----------------------------------------------------
+namespace {
+typedef int (*StreamMemOpFn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+struct MemOps { StreamMemOpFn wait = nullptr, write = nullptr; bool ok = false; };
+const MemOps& memops() {
+    static MemOps m;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaDriverEntryPointQueryResult q;
+        void* p = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) m.wait = (StreamMemOpFn)p;
+        p = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) m.write = (StreamMemOpFn)p;
+        m.ok = m.wait && m.write;
+    });
+    return m;
+}
+int wait_geq(cudaStream_t st, const uint32_t* addr, uint32_t value) {
+    int r = memops().wait(st, (unsigned long long)(uintptr_t)addr, value, 0 /* CU_STREAM_WAIT_VALUE_GEQ: (int32)(*addr - value) >= 0 */);
+    return r ? fail(TMM_ERR_CUDA, "GPU ERROR: cuStreamWaitValue32 failed (%d)", r) : TMM_OK;
+}
+int write_value(cudaStream_t st, uint32_t* addr, uint32_t value) {
+    int r = memops().write(st, (unsigned long long)(uintptr_t)addr, value, 0);
+    return r ? fail(TMM_ERR_CUDA, "GPU ERROR: cuStreamWriteValue32 failed (%d)", r) : TMM_OK;
+}
+
+// what one rank tells the others about a buffer it owns
+struct BufMsg {
+    int64_t pid;
+    int32_t dev, ok;
+    uint64_t ptr, bytes;
+    cudaIpcMemHandle_t handle;  // 64 bytes
+};
+static_assert(sizeof(BufMsg) == 96, "BufMsg layout");
+
+// all-gather one BufMsg per rank over the link (tiny NCCL collective + host sync)
+int gather_msgs(tmm_context* ctx, Link& link, const BufMsg& mine, std::vector<BufMsg>& all) {
+    const nccl::Api& nc = nccl::api();
+    cudaError_t e;
+    if ((e = ctx->dist_scratch.reserve(4096)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(dist scratch)");
+    if ((size_t)(link.parts + 1) * sizeof(BufMsg) + 256 > ctx->dist_scratch.cap) return fail(TMM_ERR_INVALID, "grid link too wide");
+    char* d = static_cast<char*>(ctx->dist_scratch.p) + 256;
+    TMM_CU(cudaMemcpyAsync(d, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->s_comm));
+    NC(nc.AllGather(d, d + sizeof(BufMsg), sizeof(BufMsg), nccl::Int8, link.comm, ctx->s_comm));
+    all.resize(link.parts);
+    TMM_CU(cudaMemcpyAsync(all.data(), d + sizeof(BufMsg), sizeof(BufMsg) * link.parts, cudaMemcpyDeviceToHost, ctx->s_comm));
+    TMM_CU(cudaStreamSynchronize(ctx->s_comm));
+    return TMM_OK;
+}
+
+BufMsg describe(tmm_context* ctx, void* p, size_t bytes) {
+    BufMsg m;
+    memset(&m, 0, sizeof m);
+    m.pid = (int64_t)getpid(); m.dev = ctx->device; m.ptr = (uint64_t)(uintptr_t)p; m.bytes = bytes; m.ok = 1;
+    if (p && cudaIpcGetMemHandle(&m.handle, p) != cudaSuccess) { cudaGetLastError(); m.ok = 0; }
+    return m;
+}
+
+// map a peer's buffer into this process / device; returns nullptr on failure
+void* map_peer(tmm_context* ctx, const BufMsg& msg, bool* via_ipc) {
+    *via_ipc = false;
+    if (!msg.ptr) return nullptr;
+    if (msg.pid == (int64_t)getpid()) {  // same process: peer access is enough
+        if (msg.dev != ctx->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(msg.dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return nullptr; }
+            cudaGetLastError();
+        }
+        return (void*)(uintptr_t)msg.ptr;
+    }
+    if (!msg.ok) return nullptr;
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, msg.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *via_ipc = true;
+    return p;
+}
+
+std::string key_of(const BufMsg& m) { return std::string(reinterpret_cast<const char*>(&m), sizeof m); }
+
+// do all ranks of the link agree that a step worked?  (min-reduce of a flag; keeps the ranks on the same path)
+int all_ok(tmm_context* ctx, Link& link, bool mine, bool* everyone) {
+    const nccl::Api& nc = nccl::api();
+    int32_t v = mine ? 1 : 0;
+    int32_t* d = static_cast<int32_t*>(ctx->dist_scratch.p);
+    TMM_CU(cudaMemcpyAsync(d, &v, sizeof v, cudaMemcpyHostToDevice, ctx->s_comm));
+    NC(nc.AllReduce(d, d, 1, nccl::Int32, nccl::Min, link.comm, ctx->s_comm));
+    TMM_CU(cudaMemcpyAsync(&v, d, sizeof v, cudaMemcpyDeviceToHost, ctx->s_comm));
+    TMM_CU(cudaStreamSynchronize(ctx->s_comm));
+    *everyone = v == 1;
+    return TMM_OK;
+}
+
+void link_unmap(Link& link) {
+    for (size_t g = 0; g < link.peer_base.size(); ++g)
+        if (link.peer_ipc[g] && link.peer_base[g]) cudaIpcCloseMemHandle(link.peer_base[g]);
+    link.peer_base.clear(); link.peer_key.clear(); link.peer_ipc.clear();
+}
+
+// at attach: my flag block, the peers' flag blocks, and the decision DMA push vs NCCL staging
+int link_setup(tmm_context* ctx, Link& link) {
+    if (!link.active()) return TMM_OK;
+    cudaError_t e;
+    if ((e = ctx->dist_scratch.reserve(4096)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(dist scratch)");
+    const char* force = getenv("TMM_DIST_NCCL");
+    bool ok = memops().ok && !(force && force[0] == '1');
+    void* fl = nullptr;
+    if ((e = cudaMalloc(&fl, 1024)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(flags)");
+    TMM_CU(cudaMemset(fl, 0, 1024));
+    link.flags = static_cast<uint32_t*>(fl);
+    std::vector<BufMsg> all;
+    int rc = gather_msgs(ctx, link, describe(ctx, fl, 1024), all);
+    if (rc) return rc;
+    link.peer_flags.assign(link.parts, nullptr);
+    std::vector<bool> ipc(link.parts, false);
+    for (int g = 0; g < link.parts && ok; ++g) {
+        if (g == link.me) { link.peer_flags[g] = link.flags; continue; }
+        bool via = false;
+        link.peer_flags[g] = static_cast<uint32_t*>(map_peer(ctx, all[g], &via));
+        ipc[g] = via;
+        if (!link.peer_flags[g]) ok = false;
+    }
+    bool everyone = false;
+    if ((rc = all_ok(ctx, link, ok, &everyone))) return rc;
+    link.direct = everyone;
+    TMM_DBG("dev %d link of %d ranks (me %d): %s", ctx->device, link.parts, link.me, link.direct ? "DMA push over mapped peer memory" : "NCCL all-gather staging");
+    link.peer_base.assign(link.parts, nullptr); link.peer_key.assign(link.parts, std::string()); link.peer_ipc.assign(link.parts, false);
+    return TMM_OK;
+}
+
+void link_teardown(Link& link) {
+    const nccl::Api& nc = nccl::api();
+    link_unmap(link);
+    // mapped peer flag blocks opened through IPC are released with the process; the local block is freed here
+    if (link.flags) cudaFree(link.flags);
+    if (link.comm && nc.ok) nc.CommDestroy(link.comm);
+    link = Link{};
+}
+}  // namespace
+
+int link_bind(tmm_context* ctx, Link& link, DevBuf& buf) {
+    if (!link.active() || !link.direct) return TMM_OK;
+    std::vector<BufMsg> all;
+    int rc = gather_msgs(ctx, link, describe(ctx, buf.p, buf.cap), all);
+    if (rc) return rc;
+    bool ok = true;
+    for (int g = 0; g < link.parts; ++g) {
+        if (g == link.me) { link.peer_base[g] = static_cast<char*>(buf.p); continue; }
+        const std::string key = key_of(all[g]);
+        if (key == link.peer_key[g] && link.peer_base[g]) continue;  // same allocation as last call: mapping still valid
+        if (link.peer_ipc[g] && link.peer_base[g]) cudaIpcCloseMemHandle(link.peer_base[g]);
+        bool via = false;
+        link.peer_base[g] = static_cast<char*>(map_peer(ctx, all[g], &via));
+        link.peer_ipc[g] = via; link.peer_key[g] = key;
+        if (!link.peer_base[g]) ok = false;
+    }
+    link.local_base = static_cast<char*>(buf.p);
+    bool everyone = false;
+    if ((rc = all_ok(ctx, link, ok, &everyone))) return rc;
+    if (!everyone) return fail(TMM_ERR_CUDA, "GPU ERROR: could not map a peer GPU's panel buffer (CUDA IPC / peer access); set TMM_DIST_NCCL=1 to use NCCL staging");
+    return TMM_OK;
+}
+
+int link_wait(tmm_context* ctx, Link& link, cudaStream_t stream) {
+    if (!link.active() || !link.direct || link.sent == 0) return TMM_OK;
+    for (int g = 0; g < link.parts; ++g) {
+        if (g == link.me) continue;
+        int rc = wait_geq(stream, link.flags + g, link.sent);
+        if (rc) return rc;
+    }
+    return TMM_OK;
+}
+
+int link_ack(tmm_context* ctx, Link& link, cudaStream_t stream) {
+    if (!link.active() || !link.direct) return TMM_OK;
+    ++link.acked;
+    uint32_t* word = link.flags + 2 * link.parts + 1;
+    int rc = write_value(stream, word, link.acked);
+    if (rc) return rc;
+    for (int g = 0; g < link.parts; ++g) {
+        if (g == link.me) continue;
+        TMM_CU(cudaMemcpyAsync(link.peer_flags[g] + link.parts + link.me, word, 4, cudaMemcpyDeviceToDevice, stream));
+    }
+    return TMM_OK;
+}
+
 int dist_agree(tmm_context* ctx, int64_t m, int64_t n, int64_t k, int flags, size_t budget, int64_t* m_plan, int64_t* n_plan, size_t* budget_min) {
     const nccl::Api& nc = nccl::api();
     if (!nc.ok) return fail(TMM_ERR_CUDA, "GPU ERROR: NCCL unavailable: %s", nc.why);
     cudaError_t e;
-    if ((e = ctx->dist_scratch.reserve(256)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(dist scratch)");
+    if ((e = ctx->dist_scratch.reserve(4096)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(dist scratch)");
     // max-reduce {m, n, k, -k, flags, -flags, -budget}: maxima give the planning block and the smallest budget, and the
-    // +/- pairs show (on every rank alike, so all ranks fail together instead of hanging) whether k and the flags agree
+    // +/- pairs show (on every rank alike, so all ranks fail together instead of hanging) whether k and the flags agree.
+    // Being a blocking collective it is also the barrier that keeps a fast rank from pushing panels of the next call into
+    // a peer that is still computing the previous one.
     int64_t v[8] = {m, n, k, -k, (int64_t)flags, -(int64_t)flags, -(int64_t)std::min<size_t>(budget, (size_t)INT64_MAX), 0};
     int64_t* d = static_cast<int64_t*>(ctx->dist_scratch.p);
     TMM_DBG("dev %d agree: m %lld n %lld k %lld", ctx->device, (long long)m, (long long)n, (long long)k);
     TMM_CU(cudaMemcpyAsync(d, v, sizeof v, cudaMemcpyHostToDevice, ctx->s_comm));
-    if (ctx->grid.pr > 1) NC(nc.AllReduce(d, d, 8, nccl::Int64, nccl::Max, ctx->grid.col_comm, ctx->s_comm));
-    if (ctx->grid.pc > 1) NC(nc.AllReduce(d, d, 8, nccl::Int64, nccl::Max, ctx->grid.row_comm, ctx->s_comm));
+    if (ctx->grid.pr > 1) NC(nc.AllReduce(d, d, 8, nccl::Int64, nccl::Max, ctx->grid.coll.comm, ctx->s_comm));
+    if (ctx->grid.pc > 1) NC(nc.AllReduce(d, d, 8, nccl::Int64, nccl::Max, ctx->grid.rowl.comm, ctx->s_comm));
     TMM_CU(cudaMemcpyAsync(v, d, sizeof v, cudaMemcpyDeviceToHost, ctx->s_comm));
     TMM_CU(cudaStreamSynchronize(ctx->s_comm));
     if (v[2] != -v[3]) return fail(TMM_ERR_INVALID, "GPU grid: ranks disagree on k (%lld vs %lld)", (long long)v[2], (long long)-v[3]);
@@ -102,10 +295,61 @@ int dist_agree(tmm_context* ctx, int64_t m, int64_t n, int64_t k, int flags, siz
     return TMM_OK;
 }
 
-int dist_exchange(tmm_context* ctx, nccl::Comm comm, int parts, int me, size_t es, const char* src, int64_t spitch, int64_t rows, int64_t cols,
-                  char* dst, int64_t dpitch) {
+// DMA push: my share goes host -> my panel (in place), then panel -> the same place in every peer's panel over NVLink.
+static int dist_push(tmm_context* ctx, Link& link, size_t es, const char* src, int64_t spitch, int64_t rows, int64_t cols, char* dst, int64_t dpitch,
+                     int ring_slot) {
+    const int parts = link.parts, me = link.me;
+    int64_t lo, hi;
+    share_range(cols, parts, me, &lo, &hi);
+    if (ring_slot >= 0) {
+        // the peers must have consumed the exchange that last filled this ring slot before it is overwritten
+        const uint32_t last = link.slot_last[ring_slot & 7];
+        if (last)
+            for (int g = 0; g < parts; ++g)
+                if (g != me) { int rc = wait_geq(ctx->s_comm, link.flags + parts + g, last); if (rc) return rc; }
+        link.slot_last[ring_slot & 7] = ++link.ring_sent;
+    }
+    const uint32_t x = ++link.sent;
+    TMM_DBG("dev %d push #%u: %lld x %lld, my columns [%lld,%lld), %d peers, slot %d", ctx->device, x, (long long)rows, (long long)cols, (long long)lo, (long long)hi, parts - 1, ring_slot);
+    char* mine = dst + (size_t)lo * dpitch * es;
+    if (hi > lo) {
+        TMM_CU(cudaMemcpy2DAsync(mine, (size_t)dpitch * es, src + (size_t)lo * spitch * es, (size_t)spitch * es, (size_t)rows * es, (size_t)(hi - lo),
+                                 cudaMemcpyHostToDevice, ctx->s_h2d));
+        ctx->stats.h2d_bytes += (uint64_t)rows * (hi - lo) * es;
+        ctx->stats.h2d_copies++;
+    }
+    cudaEvent_t up;
+    TMM_CU(ctx->get_event(&up));
+    TMM_CU(cudaEventRecord(up, ctx->s_h2d));
+    TMM_CU(cudaStreamWaitEvent(ctx->s_comm, up, 0));
+    const size_t off = (size_t)(mine - link.local_base);
+    uint32_t* word = link.flags + 2 * parts;
+    {
+        TraceScope ts(ctx, ctx->s_comm, "push", rows, hi - lo, parts - 1);
+        for (int g = 0; g < parts; ++g) {
+            if (g == me) continue;
+            if (hi > lo) {
+                char* pd = link.peer_base[g] + off;
+                if (rows == dpitch) TMM_CU(cudaMemcpyAsync(pd, mine, (size_t)rows * (hi - lo) * es, cudaMemcpyDeviceToDevice, ctx->s_comm));
+                else TMM_CU(cudaMemcpy2DAsync(pd, (size_t)dpitch * es, mine, (size_t)dpitch * es, (size_t)rows * es, (size_t)(hi - lo), cudaMemcpyDeviceToDevice, ctx->s_comm));
+                ctx->stats.peer_bytes += (uint64_t)rows * (hi - lo) * es;
+            }
+        }
+        // arrival counter: raised in every peer after the data (stream order on s_comm)
+        int rc = write_value(ctx->s_comm, word, x);
+        if (rc) return rc;
+        for (int g = 0; g < parts; ++g)
+            if (g != me) TMM_CU(cudaMemcpyAsync(link.peer_flags[g] + me, word, 4, cudaMemcpyDeviceToDevice, ctx->s_comm));
+    }
+    return TMM_OK;
+}
+
+int dist_exchange(tmm_context* ctx, Link& link, size_t es, const char* src, int64_t spitch, int64_t rows, int64_t cols, char* dst, int64_t dpitch,
+                  int ring_slot) {
     if (rows <= 0 || cols <= 0) return TMM_OK;
+    if (link.direct) return dist_push(ctx, link, es, src, spitch, rows, cols, dst, dpitch, ring_slot);
     const nccl::Api& nc = nccl::api();
+    const int parts = link.parts, me = link.me;
     const int64_t max_cols = (cols + parts - 1) / parts;
     const size_t share_bytes = (size_t)rows * (size_t)max_cols * es;
     if (share_bytes > ctx->stage_slot_bytes) return fail(TMM_ERR_INVALID, "internal: all-gather share %zu B exceeds the staging slot %zu B", share_bytes, ctx->stage_slot_bytes);
@@ -129,10 +373,14 @@ int dist_exchange(tmm_context* ctx, nccl::Comm comm, int parts, int me, size_t e
     TMM_CU(cudaEventRecord(up, ctx->s_h2d));
     TMM_CU(cudaStreamWaitEvent(ctx->s_comm, up, 0));
     // 2. all-gather the shares over NVLink (equal counts: the largest share; shorter shares carry padding that is never unpacked)
-    NC(nc.AllGather(send, recv, share_bytes, nccl::Int8, comm, ctx->s_comm));
+    {
+        TraceScope ts(ctx, ctx->s_comm, "allgather", rows, cols, parts);
+        NC(nc.AllGather(send, recv, share_bytes, nccl::Int8, link.comm, ctx->s_comm));
+    }
     TMM_CU(ctx->get_event(&ctx->stage_send_free[slot]));
     TMM_CU(cudaEventRecord(ctx->stage_send_free[slot], ctx->s_comm));
     // 3. unpack into the panel (device-to-device 2-D copies re-pitch for free; stream order protects the recv slot)
+    TraceScope ts_unpack(ctx, ctx->s_comm, "unpack", rows, cols, parts);
     for (int g = 0; g < parts; ++g) {
         share_range(cols, parts, g, &lo, &hi);
         if (hi <= lo) continue;
@@ -144,9 +392,8 @@ int dist_exchange(tmm_context* ctx, nccl::Comm comm, int parts, int me, size_t e
 }
 
 void dist_release(tmm_context* ctx) {
-    const nccl::Api& nc = nccl::api();
-    if (ctx->grid.row_comm && nc.ok) nc.CommDestroy(ctx->grid.row_comm);
-    if (ctx->grid.col_comm && nc.ok) nc.CommDestroy(ctx->grid.col_comm);
+    link_teardown(ctx->grid.rowl);
+    link_teardown(ctx->grid.coll);
     ctx->grid = Grid{};
     ctx->stage_send.release(); ctx->stage_recv.release(); ctx->dist_scratch.release();
 }
@@ -156,15 +403,18 @@ static int attach(tmm_context* ctx, int pr, int pc, int row, int col, const nccl
     if (!nc.ok) return fail(TMM_ERR_CUDA, "GPU ERROR: NCCL unavailable: %s", nc.why);
     DeviceGuard guard(ctx->device);
     dist_release(ctx);
-    Grid g;
+    Grid& g = ctx->grid;
     g.pr = pr; g.pc = pc; g.row = row; g.col = col;
+    g.rowl.parts = pc; g.rowl.me = col;
+    g.coll.parts = pr; g.coll.me = row;
     TMM_DBG("dev %d attach %dx%d at (%d,%d)", ctx->device, pr, pc, row, col);
-    if (pc > 1) NC(nc.CommInitRank(&g.row_comm, pc, *row_id, col));
-    if (pr > 1) NC(nc.CommInitRank(&g.col_comm, pr, *col_id, row));
-    ctx->grid = g;
+    if (pc > 1) NC(nc.CommInitRank(&g.rowl.comm, pc, *row_id, col));
+    if (pr > 1) NC(nc.CommInitRank(&g.coll.comm, pr, *col_id, row));
+    int rc = link_setup(ctx, g.rowl);
+    if (!rc) rc = link_setup(ctx, g.coll);
     ctx->budget_cached = 0;
-    TMM_DBG("dev %d attached", ctx->device);
-    return TMM_OK;
+    TMM_DBG("dev %d attached rc %d", ctx->device, rc);
+    return rc;
 }
 
 // ---- single process, many GPUs -------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <map>
 #include <string>
+#include <array>
 #include <vector>
 
 namespace tmm {
@@ -28,9 +29,10 @@ int nccl_fail(int rc, const char* what);
 
 // developer tracing of the multi-GPU path: TMM_DEBUG=1 prints one line per step to stderr
 bool debug_on();
+double debug_ms();
 #define TMM_DBG(...)                                  \
     do {                                              \
-        if (::tmm::debug_on()) { fprintf(stderr, "[tmm dbg] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } \
+        if (::tmm::debug_on()) { fprintf(stderr, "[tmm dbg %9.3f] ", ::tmm::debug_ms()); fprintf(stderr, __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } \
     } while (0)
 
 inline int64_t round_up64(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
@@ -63,10 +65,32 @@ struct DeviceGuard {
 // Position of a context in a p_r x p_c grid of GPUs over the C blocks.  The grid row shares the A
 // row-panel, the grid column shares the B column-panel; each member uploads a distinct 1/p share of a shared
 // panel over its own PCIe link and the shares are all-gathered over NVLink (NCCL) - no k split, no reduction.
+// One communicator of the grid: my grid row (shares the A row-panel) or my grid column (shares the B column-panel).
+// Control plane: NCCL (agreement, handle exchange).  Data plane, when the peers' buffers can be mapped (same process, or
+// CUDA IPC across processes): every rank DMA-pushes its upload share straight into the peers' panels with the copy engines
+// (no SMs, no staging) and raises a per-peer arrival counter that consumers wait on with stream memory operations.
+// If mapping fails the shares are all-gathered by NCCL through a staging ring instead (needs SMs).
+struct Link {
+    nccl::Comm comm = nullptr;
+    int parts = 1, me = 0;
+    bool direct = false;
+    uint32_t* flags = nullptr;             // my flag block (device): arrive[parts] | ack[parts] | word[2]
+    std::vector<uint32_t*> peer_flags;     // the peers' flag blocks, mapped
+    std::vector<char*> peer_base;          // the peers' panel buffers for the current call, mapped ([me] = mine)
+    std::vector<std::string> peer_key;     // what peer_base[g] was mapped from (pid, pointer, IPC handle)
+    std::vector<bool> peer_ipc;            // peer_base[g] came from cudaIpcOpenMemHandle (close when replaced)
+    char* local_base = nullptr;
+    uint32_t sent = 0;                     // exchanges issued on this link since attach (the same number on all its ranks)
+    uint32_t ring_sent = 0, acked = 0;     // streaming ring: exchanges into ring slots / exchanges consumed here
+    uint32_t slot_last[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ring exchange number that last filled each ring slot
+    bool active() const { return parts > 1; }
+};
+
+// Position of a context in a p_r x p_c grid of GPUs over the C blocks.  No k split, no reduction.
 struct Grid {
     int pr = 1, pc = 1, row = 0, col = 0;
-    nccl::Comm row_comm = nullptr;  // the p_c ranks of my grid row    (my rank = col): exchanges A
-    nccl::Comm col_comm = nullptr;  // the p_r ranks of my grid column (my rank = row): exchanges B
+    Link rowl;  // the p_c ranks of my grid row    (my rank = col): exchanges A
+    Link coll;  // the p_r ranks of my grid column (my rank = row): exchanges B
     bool active() const { return pr * pc > 1; }
 };
 
@@ -137,6 +161,23 @@ struct tmm_context {
 
 namespace tmm {
 
+// ---- optional timeline (TMM_TRACE=1): every op gets a begin/end event; printed after the call ----
+struct TraceScope {
+    tmm_context* ctx; cudaStream_t st; size_t idx = (size_t)-1;
+    TraceScope(tmm_context* c, cudaStream_t s, const char* name, int64_t a = 0, int64_t b = 0, int64_t d = 0) : ctx(c), st(s) {
+        if (!ctx->trace) return;
+        cudaEvent_t e0, e1;
+        if (ctx->get_timing_event(&e0) != cudaSuccess || ctx->get_timing_event(&e1) != cudaSuccess) return;
+        cudaEventRecord(e0, st);
+        char buf[96];
+        snprintf(buf, sizeof buf, "%s(%lld,%lld,%lld)", name, (long long)a, (long long)b, (long long)d);
+        ctx->trace_ops.push_back({buf, e0, e1});
+        idx = ctx->trace_ops.size() - 1;
+    }
+    ~TraceScope() { if (idx != (size_t)-1) cudaEventRecord(ctx->trace_ops[idx].e1, st); }
+};
+
+
 // ---- multi-GPU layer (tmm_dist.cu) ----
 // Agree on the planning inputs across the grid (max block dims, min budget) and check that k / flags match everywhere.
 int dist_agree(tmm_context* ctx, int64_t m, int64_t n, int64_t k, int flags, size_t budget, int64_t* m_plan, int64_t* n_plan, size_t* budget_min);
@@ -146,8 +187,15 @@ int dist_reserve_stage(tmm_context* ctx, size_t share_bytes, int parts);
 // All-gather a stored rows x cols sub-block (host src, leading dimension spitch elements) into dst (device, pitch dpitch
 // elements): this rank uploads columns [lo, hi) of it (its share) on s_h2d, the shares are gathered on s_comm over `comm`
 // and unpacked into place.  On return the tail of s_comm marks "dst complete".
-int dist_exchange(tmm_context* ctx, nccl::Comm comm, int parts, int me, size_t es, const char* src, int64_t spitch, int64_t rows, int64_t cols,
-                  char* dst, int64_t dpitch);
+int dist_exchange(tmm_context* ctx, Link& link, size_t es, const char* src, int64_t spitch, int64_t rows, int64_t cols, char* dst, int64_t dpitch,
+                  int ring_slot = -1);
+// Per call, after the panel buffer of this link is allocated: (re)map the peers' buffers (collective over the link).
+int link_bind(tmm_context* ctx, Link& link, DevBuf& buf);
+// Make `stream` wait until every peer's share of all exchanges issued so far on the link has arrived (direct links only).
+int link_wait(tmm_context* ctx, Link& link, cudaStream_t stream);
+// Streaming ring: tell the peers (after the work queued on `stream`) that one more ring exchange has been consumed here;
+// dist_exchange(ring_slot >= 0) waits for the peers' acknowledgement of the exchange that last filled that slot.
+int link_ack(tmm_context* ctx, Link& link, cudaStream_t stream);
 void dist_release(tmm_context* ctx);
 // share g of `parts` over an extent: balanced split, [lo, hi)
 inline void share_range(int64_t extent, int parts, int g, int64_t* lo, int64_t* hi) {
