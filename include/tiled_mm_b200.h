@@ -88,6 +88,17 @@ TMM_API int tmm_copy_to_host(const void* device_from, void* host_to, size_t byte
 TMM_API int tmm_device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a_dev, int64_t ld_a,
                     const void* b_dev, int64_t ld_b, const void* beta, void* c_dev, int64_t ld_c, void* stream);
 
+/* Math mode of the float (TMM_F32) GEMM, process-wide; the counterpart of cublasSetMathMode, which the reference never calls
+ * (gpu_blas_handle.hpp:11-17 -> cuBLAS default math = FP32-accurate results).  TMM_MATH_FP32 (default) keeps that accuracy on
+ * the tcgen05 tensor cores by splitting every operand into two TF32 numbers (3 MMAs per product, FP32 accumulation in TMEM);
+ * TMM_MATH_TF32 is the opt-in fast mode (one TF32 MMA, ~1e-3 relative); TMM_MATH_SIMT forces the FFMA kernel.
+ * Also settable with the environment variable TMM_F32_MATH = fp32 | tf32 | simt. */
+#define TMM_MATH_SIMT 0
+#define TMM_MATH_TF32 1
+#define TMM_MATH_FP32 3
+TMM_API int tmm_set_f32_math(int mode);
+TMM_API int tmm_get_f32_math(void);
+
 /* ---- Multi-GPU: C tile-blocks over a p_r x p_c grid of the box's GPUs (no counterpart in the reference, which drives one
  * device; north_star: "partitioned across the 8 B200s of one box by assigning C tile-blocks to GPUs").  GPUs of a grid row
  * share the A row-panel, GPUs of a grid column the B column-panel; every GPU uploads a distinct share of each shared panel

@@ -1,0 +1,358 @@
+// SGEMM for sm_100a on the 5th-generation tensor cores:  C = alpha * op(A) * op(B) + beta * C, column-major, device operands.
+// Replaces blas_api::sgemm (reference gpu_blas_api.hpp:194-211, called from tiled_mm.cpp:181-198).
+//
+// The reference runs cuBLAS in its default math mode (gpu_blas_handle.hpp:11-17 never enables TF32), i.e. FP32-accurate
+// results.  tcgen05 has no FP32 kind, so every FP32 operand element x is split into two TF32 numbers
+//     hi = tf32(x)   (round to nearest, 11 significant bits)          lo = tf32(x - hi)   (x - hi is exact)
+// and each product is evaluated as  lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  by three kind::tf32 MMAs that accumulate in FP32
+// in tensor memory ("3xTF32": the dropped lo*lo term and the rounding of lo are both ~2^-24 relative, the size of an
+// FP32 rounding error).  Small integers are exact in TF32 (lo = 0), so integer-valued parity tests stay bit-exact.
+// mode = 1 issues only hi_a*hi_b on the raw FP32 bits (plain TF32, ~3x faster, 2^-11 relative error) - opt-in.
+//
+// Structure - one persistent CTA per SM, 16 warps with fixed roles, everything hand-written (TMA, mbarrier, tcgen05):
+//   warp 0      TMA producer: raw FP32 operand tiles straight from the column-major panels in their stored orientation
+//               (never transposed or repacked in global memory), 128B-swizzled, into a 3-stage ring
+//   warps 8-15  split stage: each 16-byte chunk of the landed tile is rewritten in place as `hi` and its `lo` twin is
+//               written at the same offset of a second buffer.  The pass is purely element-wise, so it is independent of
+//               the operand's orientation and swizzle; fence.proxy.async publishes it to the tensor core
+//   warp 1      MMA issuer: one lane issues 12 tcgen05.mma (4 k-steps x 3 terms, 128x128x8 each) per stage, operands
+//               described in place: k-contiguous tiles (A^T, B) as K-major SWIZZLE_128B, m/n-contiguous tiles (A, B^T)
+//               as MN-major "128B swizzle, 32B atoms" (the only MN-major layout the TF32 kind accepts) - so all four
+//               transpose combinations run the same kernel with different descriptors.  tcgen05.commit releases the
+//               stage to the producer and, after the last k-block, hands the accumulator to the epilogue
+//   warps 4-7   epilogue: tcgen05.ld of the 128x128 FP32 accumulator (TMEM lane = row, column = column), alpha/beta,
+//               plain coalesced global stores (any ldc; the device-resident C of copy_c_back=false has ld = m, reference
+//               tiled_mm.cpp:446).  Two accumulators (2 x 128 TMEM columns) are alternated, so the epilogue of one tile
+//               overlaps the main loop of the next
+//   warp 2      TMEM allocation / release
+// All m / n / k edges are handled by TMA zero fill plus masked stores.
+#include "tmm_blas.h"
+#include "tmm_tc.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+
+namespace tmm {
+namespace f32tc {
+
+constexpr int BM = 128, BN = 128, BK = 32, UMMA_K = 8;
+constexpr int STAGES = 3;
+constexpr int OPERAND_BYTES = BM * BK * 4;      // one 128 x 32 FP32 tile (BM == BN)
+constexpr int STAGE_BYTES = 4 * OPERAND_BYTES;  // A hi | A lo | B hi | B lo
+constexpr int ATOM_MN = 32;                     // floats per 128-byte swizzle row of an MN-major tile
+constexpr int MN_BOX_BYTES = ATOM_MN * BK * 4;  // one [32 (m|n) x BK] TMA box of an MN-major tile
+constexpr int TMEM_COLS = 2 * BN;               // two accumulators
+constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_TMEM = 2, WARP_EPI0 = 4, WARP_SPLIT0 = 8, SPLIT_WARPS = 8;
+constexpr int THREADS = (WARP_SPLIT0 + SPLIT_WARPS) * 32;
+constexpr int GROUP_COLS = 16;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+static_assert(BM == BN, "operand tiles share one size");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+struct Params {
+    float* c;
+    int64_t ldc;
+    int m, n, k;
+    float alpha, beta;
+    int read_c;  // 0: C = alpha*acc (C never read, NaN-safe, reference tiled_mm.cpp:325); 1: += beta*C
+    int tiles_m, tiles_n;
+    int a_mn_major, b_mn_major;  // operand orientation in shared memory (A: op N, B: op T/C)
+    uint64_t desc_a, desc_b;     // shared-memory descriptor templates (everything but the address)
+    uint32_t kstep_a, kstep_b;   // bytes between consecutive UMMA_K slices of a tile
+    uint32_t idesc;
+    int terms;  // 3: FP32-accurate 3xTF32;  1: plain TF32 on the raw bits
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+    const int per_group = GROUP_COLS * tiles_m;
+    const int group = tile / per_group;
+    const int r = tile - group * per_group;
+    const int first = group * GROUP_COLS;
+    const int width = min(GROUP_COLS, tiles_n - first);
+    tm = r / width;
+    tn = first + (r - tm * width);
+}
+
+// x -> (hi, lo): hi = x rounded to TF32 (nearest, ties away), lo = (x - hi) rounded to TF32; Inf/NaN keep lo = 0
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    const uint32_t u = __float_as_uint(x);
+    uint32_t h = (u + 0x1000u) & 0xFFFFE000u;
+    float r = x - __uint_as_float(h);
+    if ((u & 0x7F800000u) == 0x7F800000u) { h = (u & 0x007FFFFFu) ? 0x7FC00000u : u; r = 0.f; }
+    else if ((h & 0x7F800000u) == 0x7F800000u) r = 0.f;  // rounded up to Inf
+    hi = __uint_as_float(h);
+    lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    // swizzled tiles need 1024-byte alignment: [stage: A hi | A lo | B hi | B lo] x STAGES, then the barriers
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);  // TMA landed          -> split warps
+    uint64_t* ready_bar = full_bar + STAGES;                                         // hi/lo written       -> MMA issuer
+    uint64_t* empty_bar = ready_bar + STAGES;                                        // MMAs retired        -> TMA producer
+    uint64_t* acc_full_bar = empty_bar + STAGES;                                     // accumulator final   -> epilogue
+    uint64_t* acc_empty_bar = acc_full_bar + 2;                                      // accumulator drained -> MMA issuer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&ready_bar[s], SPLIT_WARPS);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(&acc_full_bar[b], 1);
+            ptx::mbar_init(&acc_empty_bar[b], 4);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == WARP_TMEM) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.tiles_m * p.tiles_n;
+    const int kblocks = (p.k + BK - 1) / BK;
+
+    if (warp == WARP_TMA) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            ptx::prefetch_tensormap(&tmap_a);
+            ptx::prefetch_tensormap(&tmap_b);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int tm, tn;
+                tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    tc::mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * OPERAND_BYTES);
+                    unsigned char* sa = base + stage * STAGE_BYTES;
+                    unsigned char* sb = sa + 2 * OPERAND_BYTES;
+                    if (p.a_mn_major) {
+#pragma unroll
+                        for (int j = 0; j < BM / ATOM_MN; ++j) ptx::tma_load_2d(sa + j * MN_BOX_BYTES, &tmap_a, &full_bar[stage], tm * BM + j * ATOM_MN, kb * BK);
+                    } else {
+                        ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, tm * BM);
+                    }
+                    if (p.b_mn_major) {
+#pragma unroll
+                        for (int j = 0; j < BN / ATOM_MN; ++j) ptx::tma_load_2d(sb + j * MN_BOX_BYTES, &tmap_b, &full_bar[stage], tn * BN + j * ATOM_MN, kb * BK);
+                    } else {
+                        ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, tn * BN);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == WARP_MMA) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            const bool split = p.terms == 3;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                tc::mbar_wait_guarded(&acc_empty_bar[acc], acc_phase ^ 1);
+                tc::fence_after_thread_sync();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    tc::mbar_wait_guarded(split ? &ready_bar[stage] : &full_bar[stage], phase);
+                    tc::fence_after_thread_sync();
+                    const uint32_t a_hi = ptx::smem_u32(base + stage * STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + OPERAND_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * OPERAND_BYTES;
+                    const uint32_t b_lo = b_hi + OPERAND_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                        const uint32_t oa = ks * p.kstep_a, ob = ks * p.kstep_b;
+                        const uint32_t first = (kb | ks) ? 1u : 0u;
+                        const uint64_t da_hi = tc::smem_desc(p.desc_a, a_hi + oa), db_hi = tc::smem_desc(p.desc_b, b_hi + ob);
+                        if (split) {
+                            const uint64_t da_lo = tc::smem_desc(p.desc_a, a_lo + oa), db_lo = tc::smem_desc(p.desc_b, b_lo + ob);
+                            tc::mma_tf32(d_tmem, da_lo, db_hi, p.idesc, first);  // small terms first
+                            tc::mma_tf32(d_tmem, da_hi, db_lo, p.idesc, 1u);
+                            tc::mma_tf32(d_tmem, da_hi, db_hi, p.idesc, 1u);
+                        } else {
+                            tc::mma_tf32(d_tmem, da_hi, db_hi, p.idesc, first);
+                        }
+                    }
+                    tc::mma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc::mma_commit(&acc_full_bar[acc]);  // accumulator complete
+                if ((acc ^= 1) == 0) acc_phase ^= 1;
+            }
+        }
+        __syncwarp();
+    } else if (warp >= WARP_EPI0 && warp < WARP_EPI0 + 4) {
+        // ===== epilogue: warp q owns TMEM lanes 32q .. 32q+31 = rows 32q + lane of the tile =====
+        const int q = warp - WARP_EPI0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int tm, tn;
+            tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+            tc::mbar_wait_guarded(&acc_full_bar[acc], acc_phase);
+            tc::fence_after_thread_sync();
+            const int row = tm * BM + q * 32 + lane;
+            const bool row_ok = row < p.m;
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cb * 32, v);
+                tc::tmem_ld_wait();
+                if (cb == BN / 32 - 1) {  // accumulator fully read: hand it back before the global stores
+                    tc::fence_before_thread_sync();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&acc_empty_bar[acc]);
+                }
+                const int col0 = tn * BN + cb * 32;
+                float* cp = p.c + (int64_t)col0 * p.ldc + row;
+                if (p.read_c) {
+                    float old[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) old[j] = (row_ok && col0 + j < p.n) ? __ldcs(cp + (int64_t)j * p.ldc) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (row_ok && col0 + j < p.n) cp[(int64_t)j * p.ldc] = p.alpha * __uint_as_float(v[j]) + p.beta * old[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (row_ok && col0 + j < p.n) cp[(int64_t)j * p.ldc] = p.alpha * __uint_as_float(v[j]);
+                }
+            }
+            if ((acc ^= 1) == 0) acc_phase ^= 1;
+        }
+    } else if (warp >= WARP_SPLIT0 && p.terms == 3) {
+        // ===== split stage: raw FP32 -> (hi in place, lo in the twin buffer), 16 bytes per access =====
+        const int t = threadIdx.x - WARP_SPLIT0 * 32;
+        constexpr int CHUNKS = 2 * OPERAND_BYTES / 16;  // A and B raw tiles
+        constexpr int PER_THREAD = CHUNKS / (SPLIT_WARPS * 32);
+        static_assert(CHUNKS % (SPLIT_WARPS * 32) == 0, "chunk split");
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                tc::mbar_wait_guarded(&full_bar[stage], phase);
+                unsigned char* st = base + stage * STAGE_BYTES;
+                float4 x[PER_THREAD];
+#pragma unroll
+                for (int i = 0; i < PER_THREAD; ++i) {
+                    const int idx = t + i * (SPLIT_WARPS * 32);
+                    const int off = idx * 16 + (idx >= OPERAND_BYTES / 16 ? OPERAND_BYTES : 0);  // skip over A lo
+                    x[i] = *reinterpret_cast<const float4*>(st + off);
+                }
+#pragma unroll
+                for (int i = 0; i < PER_THREAD; ++i) {
+                    const int idx = t + i * (SPLIT_WARPS * 32);
+                    const int off = idx * 16 + (idx >= OPERAND_BYTES / 16 ? OPERAND_BYTES : 0);
+                    float4 hi, lo;
+                    split_tf32(x[i].x, hi.x, lo.x);
+                    split_tf32(x[i].y, hi.y, lo.y);
+                    split_tf32(x[i].z, hi.z, lo.z);
+                    split_tf32(x[i].w, hi.w, lo.w);
+                    *reinterpret_cast<float4*>(st + off) = hi;
+                    *reinterpret_cast<float4*>(st + off + OPERAND_BYTES) = lo;
+                }
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&ready_bar[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == WARP_TMEM) {
+        tc::fence_after_thread_sync();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+static CUresult make_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, uint64_t ld_elems, uint32_t box0, uint32_t box1,
+                         CUtensorMapSwizzle swizzle) {
+    auto encode = reinterpret_cast<CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill)>(tensormap_encode_fn());
+    if (!encode) return CUDA_ERROR_NOT_SUPPORTED;
+    cuuint64_t dims[2] = {dim0, dim1};
+    cuuint64_t strides[1] = {ld_elems * 4};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+// developer override of the MN-major descriptor fields (tools/tc_test.cu sweeps them on a new driver / chip)
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    return v && *v ? (uint32_t)strtoul(v, nullptr, 0) : dflt;
+}
+
+}  // namespace f32tc
+
+bool sgemm_tc_eligible(const void* a, int64_t lda, const void* b, int64_t ldb) {
+    return !((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (lda & 3) || (ldb & 3));
+}
+
+cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, const float* a, int64_t lda, const float* b, int64_t ldb, float beta,
+                            float* c, int64_t ldc, cudaStream_t stream, int terms) {
+    using namespace f32tc;
+    if (m <= 0 || n <= 0) return cudaSuccess;
+    if (!sgemm_tc_eligible(a, lda, b, ldb)) return cudaErrorInvalidValue;
+    const bool a_mn = (ta == 'N'), b_mn = (tb != 'N');
+    CUtensorMap map_a, map_b;
+    CUresult r;
+    const CUtensorMapSwizzle swz_k = CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle swz_mn = (CUtensorMapSwizzle)env_u32("TMM_TC_MN_SWIZZLE", (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    // A: op(A) is m x k.  N: stored m x k (m contiguous) -> boxes [32 m x BK];  T/C: stored k x m (k contiguous) -> one box [BK x BM]
+    r = a_mn ? make_map(&map_a, a, (uint64_t)m, (uint64_t)k, (uint64_t)lda, ATOM_MN, BK, swz_mn) : make_map(&map_a, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, BK, BM, swz_k);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "[tiled-mm_b200] cuTensorMapEncodeTiled(A, f32) failed: %d\n", (int)r); return cudaErrorInvalidValue; }
+    // B: op(B) is k x n.  N: stored k x n (k contiguous) -> one box [BK x BN];  T/C: stored n x k (n contiguous) -> boxes [32 n x BK]
+    r = b_mn ? make_map(&map_b, b, (uint64_t)n, (uint64_t)k, (uint64_t)ldb, ATOM_MN, BK, swz_mn) : make_map(&map_b, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, BK, BN, swz_k);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "[tiled-mm_b200] cuTensorMapEncodeTiled(B, f32) failed: %d\n", (int)r); return cudaErrorInvalidValue; }
+
+    Params p;
+    p.c = c; p.ldc = ldc; p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta;
+    p.read_c = (beta != 0.f);
+    p.tiles_m = (m + BM - 1) / BM; p.tiles_n = (n + BN - 1) / BN;
+    p.a_mn_major = a_mn; p.b_mn_major = b_mn;
+    // K-major tile: rows of 128 B (BK floats), 8-row swizzle atoms 1024 B apart; the next UMMA_K slice is 32 B further along the row.
+    const uint64_t desc_k = tc::smem_desc_template(16, 8 * BK * 4, tc::LAYOUT_SW128);
+    // MN-major tile: per k one 128-B row of 32 floats; 4-row atoms 512 B apart (stride offset), the next 32 rows/columns of
+    // the tile in the next TMA box (leading offset); a UMMA_K slice is 8 k-rows = 1024 B.
+    const uint64_t desc_mn = tc::smem_desc_template(env_u32("TMM_TC_MN_LBO", MN_BOX_BYTES), env_u32("TMM_TC_MN_SBO", 4 * ATOM_MN * 4),
+                                                    env_u32("TMM_TC_MN_LAYOUT", tc::LAYOUT_SW128_ATOM32B));
+    const uint32_t kstep_mn = env_u32("TMM_TC_MN_KSTEP", UMMA_K * ATOM_MN * 4);
+    p.desc_a = a_mn ? desc_mn : desc_k; p.kstep_a = a_mn ? kstep_mn : UMMA_K * 4;
+    p.desc_b = b_mn ? desc_mn : desc_k; p.kstep_b = b_mn ? kstep_mn : UMMA_K * 4;
+    p.idesc = tc::instr_desc(tc::FMT_TF32, BM, BN, a_mn, b_mn);
+    p.terms = terms == 1 ? 1 : 3;
+
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(sgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+    if (tiles > INT32_MAX) return cudaErrorInvalidValue;
+    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    sgemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(map_a, map_b, p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace tmm

@@ -1,8 +1,8 @@
 // Generic shared-memory-tiled SIMT GEMM (FFMA / complex FMA), all dtypes, N/T/C, any ld.
-// First correct CUDA path for float / complex<float> (reference blas_api::sgemm / cgemm,
-// gpu_blas_api.hpp:194-211,233-251): true FP32 arithmetic like cuBLAS' default math mode
-// (the reference never sets a TF32 math mode, gpu_blas_handle.hpp:11-17).
-// The tcgen05/TMEM (3xTF32) kernels replace this file's float paths; see DESIGN.md.
+// complex<float> path (reference blas_api::cgemm, gpu_blas_api.hpp:233-251) and the float path for operands that do
+// not meet the TMA alignment contract or when TMM_F32_MATH=simt is selected: true FP32 FFMA arithmetic like cuBLAS'
+// default math mode (the reference never sets a TF32 math mode, gpu_blas_handle.hpp:11-17).
+// Aligned float operands run on tcgen05/TMEM (gemm_f32_tc.cu, 3xTF32); see DESIGN.md.
 #include "tmm_blas.h"
 
 #include <cuComplex.h>
@@ -115,8 +115,8 @@ static cudaError_t launch(char ta, char tb, int m, int n, int k, T alpha, const 
 
 }  // namespace simt
 
-cudaError_t sgemm_launch(char ta, char tb, int m, int n, int k, float alpha, const float* a, int64_t lda, const float* b, int64_t ldb, float beta,
-                         float* c, int64_t ldc, cudaStream_t st) {
+cudaError_t sgemm_simt_launch(char ta, char tb, int m, int n, int k, float alpha, const float* a, int64_t lda, const float* b, int64_t ldb, float beta,
+                              float* c, int64_t ldc, cudaStream_t st) {
     return simt::launch<float>(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, beta != 0.f, c, ldc, st);
 }
 cudaError_t cgemm_launch(char ta, char tb, int m, int n, int k, const float* al, const void* a, int64_t lda, const void* b, int64_t ldb,

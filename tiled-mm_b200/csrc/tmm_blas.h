@@ -32,6 +32,15 @@ cudaError_t zgemm_launch(char ta, char tb, int m, int n, int k, const double* al
                          const double* beta2, void* c, int64_t ldc, cudaStream_t stream);
 cudaError_t sgemm_launch(char ta, char tb, int m, int n, int k, float alpha, const float* a, int64_t lda, const float* b, int64_t ldb,
                          float beta, float* c, int64_t ldc, cudaStream_t stream);
+// float back ends: tcgen05/TMEM tensor-core kernel (terms = 3: FP32-accurate 3xTF32, 1: plain TF32) and the SIMT FFMA kernel
+bool sgemm_tc_eligible(const void* a, int64_t lda, const void* b, int64_t ldb);
+cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, const float* a, int64_t lda, const float* b, int64_t ldb,
+                            float beta, float* c, int64_t ldc, cudaStream_t stream, int terms);
+cudaError_t sgemm_simt_launch(char ta, char tb, int m, int n, int k, float alpha, const float* a, int64_t lda, const float* b, int64_t ldb,
+                              float beta, float* c, int64_t ldc, cudaStream_t stream);
+// process-wide math mode of the float GEMM: 3 = FP32-accurate on tensor cores (default), 1 = TF32, 0 = SIMT FFMA
+int f32_math_mode();
+void set_f32_math_mode(int mode);
 cudaError_t cgemm_launch(char ta, char tb, int m, int n, int k, const float* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
                          const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
 

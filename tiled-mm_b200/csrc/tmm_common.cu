@@ -5,6 +5,8 @@
 #include <atomic>
 #include <mutex>
 #include <cctype>
+#include <cstdlib>
+#include <cstring>
 #include <cuda.h>
 #include <cuComplex.h>
 
@@ -37,6 +39,28 @@ void* tensormap_encode_fn() {
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = p;
     });
     return fn;
+}
+
+// ---- float GEMM math mode and dispatch ---------------------------------------------------------
+static std::atomic<int> g_f32_mode{-1};
+int f32_math_mode() {
+    int v = g_f32_mode.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("TMM_F32_MATH");  // "fp32" (default) | "tf32" | "simt"
+        v = 3;
+        if (e && (!strcmp(e, "tf32") || !strcmp(e, "TF32"))) v = 1;
+        else if (e && (!strcmp(e, "simt") || !strcmp(e, "SIMT"))) v = 0;
+        g_f32_mode.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+void set_f32_math_mode(int mode) { g_f32_mode.store(mode == 1 ? 1 : (mode == 0 ? 0 : 3), std::memory_order_relaxed); }
+
+cudaError_t sgemm_launch(char ta, char tb, int m, int n, int k, float alpha, const float* a, int64_t lda, const float* b, int64_t ldb, float beta,
+                         float* c, int64_t ldc, cudaStream_t st) {
+    const int mode = f32_math_mode();
+    if (mode != 0 && sgemm_tc_eligible(a, lda, b, ldb)) return sgemm_tc_launch(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, st, mode);
+    return sgemm_simt_launch(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, st);
 }
 
 // ---- C = beta * C --------------------------------------------------------------------------

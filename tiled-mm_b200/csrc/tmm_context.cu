@@ -487,6 +487,12 @@ extern "C" {
 const char* tmm_last_error(void) { return tmm::last_error_cstr(); }
 const char* tmm_version(void) { return "tiled_mm_b200 0.1 (sm_100a)"; }
 uint64_t tmm_total_kernel_launches(void) { return tmm::launch_count(); }
+int tmm_set_f32_math(int mode) {
+    if (mode != TMM_MATH_FP32 && mode != TMM_MATH_TF32 && mode != TMM_MATH_SIMT) return tmm::fail(TMM_ERR_INVALID, "tmm_set_f32_math: unknown mode %d", mode);
+    tmm::set_f32_math_mode(mode);
+    return TMM_OK;
+}
+int tmm_get_f32_math(void) { return tmm::f32_math_mode(); }
 
 int tmm_device_count(void) {
     int n = 0;
