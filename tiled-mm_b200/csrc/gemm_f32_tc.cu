@@ -20,10 +20,15 @@
 //               as MN-major "128B swizzle, 32B atoms" (the only MN-major layout the TF32 kind accepts) - so all four
 //               transpose combinations run the same kernel with different descriptors.  tcgen05.commit releases the
 //               stage to the producer and, after the last k-block, hands the accumulator to the epilogue
-//   warps 4-7   epilogue: tcgen05.ld of the 128x128 FP32 accumulator (TMEM lane = row, column = column), alpha/beta,
-//               plain coalesced global stores (any ldc; the device-resident C of copy_c_back=false has ld = m, reference
-//               tiled_mm.cpp:446).  Two accumulators (2 x 128 TMEM columns) are alternated, so the epilogue of one tile
-//               overlaps the main loop of the next
+//   warps 4-7   accumulate + epilogue.  The tensor core adds into its FP32 accumulator with truncation (measured: the error
+//               of a plain TMEM accumulation grows like k^1.5, 30x the error of an FFMA chain at k = 4096), so TMEM only
+//               ever holds the partial sum of a short k-window (default 4 k-blocks = 128): after each window these warps
+//               drain it with tcgen05.ld (TMEM lane = row, column = column) and add it - round to nearest - into 128 FP32
+//               registers per thread (setmaxnreg gives this warpgroup 232 registers, taken from the other roles).  Four
+//               window accumulators (4 x 128 columns = all of TMEM) rotate, so draining and the tile's global-memory
+//               epilogue overlap the MMAs of the next windows / the next tile.
+//               Tile end: alpha/beta and plain coalesced global stores (any ldc; the device-resident C of
+//               copy_c_back=false has ld = m, reference tiled_mm.cpp:446)
 //   warp 2      TMEM allocation / release
 // All m / n / k edges are handled by TMA zero fill plus masked stores.
 #include "tmm_blas.h"
@@ -41,10 +46,13 @@ constexpr int OPERAND_BYTES = BM * BK * 4;      // one 128 x 32 FP32 tile (BM ==
 constexpr int STAGE_BYTES = 4 * OPERAND_BYTES;  // A hi | A lo | B hi | B lo
 constexpr int ATOM_MN = 32;                     // floats per 128-byte swizzle row of an MN-major tile
 constexpr int MN_BOX_BYTES = ATOM_MN * BK * 4;  // one [32 (m|n) x BK] TMA box of an MN-major tile
-constexpr int TMEM_COLS = 2 * BN;               // two accumulators
+constexpr int ACC_BUFS = 4;                     // window accumulators in TMEM (4 x 128 columns = all of it)
+constexpr int TMEM_COLS = ACC_BUFS * BN;
 constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_TMEM = 2, WARP_EPI0 = 4, WARP_SPLIT0 = 8, SPLIT_WARPS = 8;
 constexpr int THREADS = (WARP_SPLIT0 + SPLIT_WARPS) * 32;
 constexpr int GROUP_COLS = 16;
+constexpr int REGS_CONTROL = 40, REGS_SPLIT = 88, REGS_EPILOGUE = 232;  // setmaxnreg split of the 512 x 128 launch allocation
+constexpr int WINDOW_KBLOCKS = 4;  // k-blocks summed in TMEM before promotion to the FP32 register accumulators
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 static_assert(BM == BN, "operand tiles share one size");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -60,7 +68,8 @@ struct Params {
     uint64_t desc_a, desc_b;     // shared-memory descriptor templates (everything but the address)
     uint32_t kstep_a, kstep_b;   // bytes between consecutive UMMA_K slices of a tile
     uint32_t idesc;
-    int terms;  // 3: FP32-accurate 3xTF32;  1: plain TF32 on the raw bits
+    int terms;   // 3: FP32-accurate 3xTF32;  1: plain TF32 on the raw bits
+    int window;  // k-blocks per TMEM accumulation window
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
@@ -93,8 +102,8 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint64_t* ready_bar = full_bar + STAGES;                                         // hi/lo written       -> MMA issuer
     uint64_t* empty_bar = ready_bar + STAGES;                                        // MMAs retired        -> TMA producer
     uint64_t* acc_full_bar = empty_bar + STAGES;                                     // accumulator final   -> epilogue
-    uint64_t* acc_empty_bar = acc_full_bar + 2;                                      // accumulator drained -> MMA issuer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
+    uint64_t* acc_empty_bar = acc_full_bar + ACC_BUFS;                               // accumulator drained -> MMA issuer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + ACC_BUFS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -107,7 +116,7 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             ptx::mbar_init(&empty_bar[s], 1);
         }
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < ACC_BUFS; ++b) {
             ptx::mbar_init(&acc_full_bar[b], 1);
             ptx::mbar_init(&acc_empty_bar[b], 4);
         }
@@ -122,8 +131,11 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int total_tiles = p.tiles_m * p.tiles_n;
     const int kblocks = (p.k + BK - 1) / BK;
 
+    // Every role starts with its share of the warpgroup-wide register reallocation (setmaxnreg): the control and split
+    // warpgroups hand registers to the accumulate/epilogue warpgroup.
     if (warp == WARP_TMA) {
         // ===== TMA producer =====
+        ptx::setmaxnreg_dec<REGS_CONTROL>();
         if (lane == 0) {
             ptx::prefetch_tensormap(&tmap_a);
             ptx::prefetch_tensormap(&tmap_b);
@@ -156,15 +168,19 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         __syncwarp();
     } else if (warp == WARP_MMA) {
         // ===== MMA issuer =====
+        ptx::setmaxnreg_dec<REGS_CONTROL>();
         if (lane == 0) {
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             const bool split = p.terms == 3;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                tc::mbar_wait_guarded(&acc_empty_bar[acc], acc_phase ^ 1);
-                tc::fence_after_thread_sync();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < kblocks; ++kb) {
+                uint32_t d_tmem = 0;
+                for (int kb = 0, wk = 0; kb < kblocks; ++kb) {
+                    if (wk == 0) {  // open a window: its TMEM accumulator must have been drained
+                        tc::mbar_wait_guarded(&acc_empty_bar[acc], acc_phase ^ 1);
+                        tc::fence_after_thread_sync();
+                        d_tmem = tmem_base + acc * BN;
+                    }
                     tc::mbar_wait_guarded(split ? &ready_bar[stage] : &full_bar[stage], phase);
                     tc::fence_after_thread_sync();
                     const uint32_t a_hi = ptx::smem_u32(base + stage * STAGE_BYTES);
@@ -174,7 +190,7 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ++ks) {
                         const uint32_t oa = ks * p.kstep_a, ob = ks * p.kstep_b;
-                        const uint32_t first = (kb | ks) ? 1u : 0u;
+                        const uint32_t first = (wk | ks) ? 1u : 0u;  // the first MMA of a window overwrites
                         const uint64_t da_hi = tc::smem_desc(p.desc_a, a_hi + oa), db_hi = tc::smem_desc(p.desc_b, b_hi + ob);
                         if (split) {
                             const uint64_t da_lo = tc::smem_desc(p.desc_a, a_lo + oa), db_lo = tc::smem_desc(p.desc_b, b_lo + ob);
@@ -187,53 +203,78 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     }
                     tc::mma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++wk == p.window || kb == kblocks - 1) {  // close the window: hand its partial sum to the accumulate warps
+                        tc::mma_commit(&acc_full_bar[acc]);
+                        if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+                        wk = 0;
+                    }
                 }
-                tc::mma_commit(&acc_full_bar[acc]);  // accumulator complete
-                if ((acc ^= 1) == 0) acc_phase ^= 1;
             }
         }
         __syncwarp();
     } else if (warp >= WARP_EPI0 && warp < WARP_EPI0 + 4) {
-        // ===== epilogue: warp q owns TMEM lanes 32q .. 32q+31 = rows 32q + lane of the tile =====
+        // ===== accumulate + epilogue: warp q owns TMEM lanes 32q .. 32q+31 = rows 32q + lane of the tile =====
+        ptx::setmaxnreg_inc<REGS_EPILOGUE>();
         const int q = warp - WARP_EPI0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        const int windows = (kblocks + p.window - 1) / p.window;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int tm, tn;
             tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-            tc::mbar_wait_guarded(&acc_full_bar[acc], acc_phase);
-            tc::fence_after_thread_sync();
+            float sum[BN];
+#pragma unroll
+            for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+            for (int w = 0; w < windows; ++w) {
+                tc::mbar_wait_guarded(&acc_full_bar[acc], acc_phase);
+                tc::fence_after_thread_sync();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll
+                for (int h = 0; h < BN / 64; ++h) {
+                    uint32_t v0[32], v1[32];
+                    tc::tmem_ld_32x32b_x32(taddr + h * 64, v0);
+                    tc::tmem_ld_32x32b_x32(taddr + h * 64 + 32, v1);
+                    tc::tmem_ld_wait();
+                    if (h == BN / 64 - 1) {  // window accumulator fully read: hand it back to the MMA issuer
+                        tc::fence_before_thread_sync();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&acc_empty_bar[acc]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        sum[h * 64 + j] += __uint_as_float(v0[j]);
+                        sum[h * 64 + 32 + j] += __uint_as_float(v1[j]);
+                    }
+                }
+                if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+            }
             const int row = tm * BM + q * 32 + lane;
             const bool row_ok = row < p.m;
-#pragma unroll 1
-            for (int cb = 0; cb < BN / 32; ++cb) {
-                uint32_t v[32];
-                tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cb * 32, v);
-                tc::tmem_ld_wait();
-                if (cb == BN / 32 - 1) {  // accumulator fully read: hand it back before the global stores
-                    tc::fence_before_thread_sync();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&acc_empty_bar[acc]);
-                }
-                const int col0 = tn * BN + cb * 32;
-                float* cp = p.c + (int64_t)col0 * p.ldc + row;
-                if (p.read_c) {
+            const int col0 = tn * BN;
+            float* cp = p.c + (int64_t)col0 * p.ldc + row;
+            if (p.read_c) {
+#pragma unroll
+                for (int cb = 0; cb < BN / 32; ++cb) {
                     float old[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) old[j] = (row_ok && col0 + j < p.n) ? __ldcs(cp + (int64_t)j * p.ldc) : 0.f;
+                    for (int j = 0; j < 32; ++j) old[j] = (row_ok && col0 + cb * 32 + j < p.n) ? __ldcs(cp + (int64_t)(cb * 32 + j) * p.ldc) : 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (row_ok && col0 + j < p.n) cp[(int64_t)j * p.ldc] = p.alpha * __uint_as_float(v[j]) + p.beta * old[j];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (row_ok && col0 + j < p.n) cp[(int64_t)j * p.ldc] = p.alpha * __uint_as_float(v[j]);
+                        if (row_ok && col0 + cb * 32 + j < p.n) cp[(int64_t)(cb * 32 + j) * p.ldc] = p.alpha * sum[cb * 32 + j] + p.beta * old[j];
                 }
+            } else {
+#pragma unroll
+                for (int j = 0; j < BN; ++j)
+                    if (row_ok && col0 + j < p.n) cp[(int64_t)j * p.ldc] = p.alpha * sum[j];
             }
-            if ((acc ^= 1) == 0) acc_phase ^= 1;
         }
-    } else if (warp >= WARP_SPLIT0 && p.terms == 3) {
+    } else if (warp < WARP_EPI0) {
+        ptx::setmaxnreg_dec<REGS_CONTROL>();  // TMEM warp and the spare warp of the control warpgroup
+    } else if (p.terms != 3) {
+        ptx::setmaxnreg_dec<REGS_SPLIT>();    // plain TF32: the tensor core reads the raw tiles, nothing to split
+    } else {
         // ===== split stage: raw FP32 -> (hi in place, lo in the twin buffer), 16 bytes per access =====
+        ptx::setmaxnreg_dec<REGS_SPLIT>();
         const int t = threadIdx.x - WARP_SPLIT0 * 32;
         constexpr int CHUNKS = 2 * OPERAND_BYTES / 16;  // A and B raw tiles
         constexpr int PER_THREAD = CHUNKS / (SPLIT_WARPS * 32);
@@ -338,6 +379,8 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
     p.desc_b = b_mn ? desc_mn : desc_k; p.kstep_b = b_mn ? kstep_mn : UMMA_K * 4;
     p.idesc = tc::instr_desc(tc::FMT_TF32, BM, BN, a_mn, b_mn);
     p.terms = terms == 1 ? 1 : 3;
+    p.window = (int)env_u32("TMM_TC_WINDOW", WINDOW_KBLOCKS);
+    if (p.window < 1) p.window = 1;
 
     static bool configured[64] = {false};
     int dev = 0;

@@ -125,6 +125,58 @@ static int probe(char ta, char tb, bool probe_a) {
     return wrong;
 }
 
+// Accuracy against an exact (double) reference with well-mixed inputs: ours at the current TMM_TC_WINDOW vs cuBLAS FP32 (pedantic)
+static inline float hrand(uint64_t i, uint64_t seed, bool positive) {
+    uint64_t z = (i + seed * 0x9E3779B97F4A7C15ull) + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    double u = (double)(z >> 11) / 9007199254740992.0;
+    return (float)(positive ? u : 2.0 * u - 1.0);
+}
+static void precision(cublasHandle_t h, char ta, char tb, int m, int n, int k, bool positive) {
+    int ar = ta == 'N' ? m : k, ac = ta == 'N' ? k : m, br = tb == 'N' ? k : n, bc = tb == 'N' ? n : k;
+    int lda = ar, ldb = br, ldc = m;
+    std::vector<float> A((size_t)lda * ac), B((size_t)ldb * bc);
+    for (size_t i = 0; i < A.size(); ++i) A[i] = hrand(i, 1, positive);
+    for (size_t i = 0; i < B.size(); ++i) B[i] = hrand(i, 2, positive);
+    std::vector<double> R((size_t)m * n);
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < m; ++i) {
+            double s = 0;
+            for (int kk = 0; kk < k; ++kk) s += (double)geta(A, ta, lda, i, kk) * (double)getb(B, tb, ldb, kk, j);
+            R[(size_t)j * m + i] = s;
+        }
+    float *dA, *dB, *dC;
+    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dC, (size_t)m * n * 4));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    float alpha = 1.f, beta = 0.f;
+    std::vector<float> O((size_t)m * n);
+    double cmax = 0; for (double r : R) cmax = std::max(cmax, std::fabs(r));
+    auto report = [&](const char* who) {
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(O.data(), dC, O.size() * 4, cudaMemcpyDeviceToHost));
+        double emax = 0, e2 = 0;
+        for (size_t i = 0; i < O.size(); ++i) { double d = std::fabs((double)O[i] - R[i]); emax = std::max(emax, d); e2 += d * d; }
+        printf("  %-22s max|err|=%.3e  rms=%.3e  max/(k)=%.2e  max/max|C|=%.2e\n", who, emax, std::sqrt(e2 / O.size()), emax / k, emax / cmax);
+    };
+    const char* w = getenv("TMM_TC_WINDOW");
+    printf("precision %c%c m=%d n=%d k=%d %s window=%s max|C|=%.1f\n", ta, tb, m, n, k, positive ? "uniform(0,1)" : "uniform(-1,1)", w ? w : "default", cmax);
+    cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
+    cublasSgemm(h, op(ta), op(tb), m, n, k, &alpha, dA, lda, dB, ldb, &beta, dC, ldc); report("cuBLAS fp32 pedantic");
+    cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
+    cublasSgemm(h, op(ta), op(tb), m, n, k, &alpha, dA, lda, dB, ldb, &beta, dC, ldc); report("cuBLAS fp32 default");
+    tmm_set_f32_math(TMM_MATH_FP32);
+    if (tmm_device_gemm(TMM_F32, ta, tb, m, n, k, &alpha, dA, lda, dB, ldb, &beta, dC, ldc, nullptr)) { printf("rc!=0 %s\n", tmm_last_error()); exit(2); }
+    report("tmm fp32 (3xTF32)");
+    tmm_set_f32_math(TMM_MATH_SIMT);
+    tmm_device_gemm(TMM_F32, ta, tb, m, n, k, &alpha, dA, lda, dB, ldb, &beta, dC, ldc, nullptr); report("tmm simt ffma");
+    tmm_set_f32_math(TMM_MATH_TF32);
+    tmm_device_gemm(TMM_F32, ta, tb, m, n, k, &alpha, dA, lda, dB, ldb, &beta, dC, ldc, nullptr); report("tmm tf32");
+    tmm_set_f32_math(TMM_MATH_FP32);
+    fflush(stdout);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+}
+
 static void bench(cublasHandle_t h, char ta, char tb, int m, int n, int k, float beta) {
     int ar = ta == 'N' ? m : k, ac = ta == 'N' ? k : m, br = tb == 'N' ? k : n, bc = tb == 'N' ? n : k;
     int lda = (ar + 31) & ~31, ldb = (br + 31) & ~31, ldc = m;
@@ -230,6 +282,14 @@ int main(int argc, char** argv) {
         tmm_set_f32_math(TMM_MATH_FP32);
         printf("check %c%c: %d failing\n", ta, tb, bad);
         return bad ? 3 : 0;
+    }
+    if (mode == "precision") {  // precision [k...]
+        precision(h, 'N', 'N', 512, 512, 256, false);
+        precision(h, 'N', 'N', 512, 512, 4096, false);
+        precision(h, 'N', 'T', 512, 512, 4096, false);
+        precision(h, 'N', 'N', 512, 512, 4096, true);
+        precision(h, 'T', 'N', 384, 384, 32768, false);
+        return 0;
     }
     if (mode == "bench") {
         bench(h, 'N', 'N', 8192, 8192, 8192, 0.f);
