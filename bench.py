@@ -134,6 +134,39 @@ def cpu_baseline_dgemm(size: int) -> dict:
             "sample": f"host BLAS dgemm (numpy/OpenBLAS, all {host_cores()} hardware threads) on the full workload {m}x{n}x{k}, mean of {runs} runs, {total:.1f} s of CPU work"}
 
 
+class NumaLocal:
+    """While active, this process runs on the CPUs NVML reports as local to GPU `index`, so that the pinned host buffers
+    allocated (and first touched) inside land on that GPU's NUMA node: with 8 ranks streaming over 8 PCIe links, buffers on
+    the remote socket would halve the achievable host-link bandwidth.  The previous mask is restored on exit (pages stay put)."""
+
+    def __init__(self, index: int):
+        self.index, self.prev, self.bound = index, None, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+            self.prev = os.sched_getaffinity(0)
+            want = local & self.prev
+            if want and want != self.prev:
+                os.sched_setaffinity(0, want)
+                self.bound = len(want)
+        except Exception:
+            self.prev = None
+        return self
+
+    def __exit__(self, *a):
+        if self.prev is not None and self.bound is not None:
+            try:
+                os.sched_setaffinity(0, self.prev)
+            except Exception:
+                pass
+
+
 def grid_shape(n: int):
     return {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}.get(n, (1, n))
 
@@ -152,8 +185,10 @@ def run_reference(args, rank: int, world: int) -> None:
     try:
         import tiled_mm_b200 as tmm
         ref = _util.Reference(cpu=False)
-        a = tmm.malloc_pinned(np.float64, size * size); b = tmm.malloc_pinned(np.float64, size * size); c = tmm.malloc_pinned(np.float64, size * size)
-        fill_uniform(a, 1); fill_uniform(b, 2)
+        with NumaLocal(0):  # same placement policy as our arm
+            a = tmm.malloc_pinned(np.float64, size * size); b = tmm.malloc_pinned(np.float64, size * size); c = tmm.malloc_pinned(np.float64, size * size)
+            fill_uniform(a, 1); fill_uniform(b, 2)
+            np.asarray(c)[:] = 0.0
         ctx = ref.context(np.float64, 2, 5000, 5000, 5000)
         for _ in range(args.warmup):
             ctx.gemm("N", "N", size, size, size, 1.0, a, size, b, size, 0.0, c, size, pin=False, copy_c_back=True)
@@ -225,8 +260,10 @@ def main():
     # ------------------------------------------------------------------ host buffers (pinned, like gpu::malloc_pinned)
     pr, pc = grid_shape(world)
     gi, gj = rank // pc, rank % pc
-    a = tmm.malloc_pinned(np.float64, m * k); b = tmm.malloc_pinned(np.float64, k * n); c = tmm.malloc_pinned(np.float64, m * n)
-    fill_uniform(a, 100 + gi); fill_uniform(b, 200 + gj)
+    with NumaLocal(local_rank) as numa:  # pinned pages on the NUMA node of this rank's GPU
+        a = tmm.malloc_pinned(np.float64, m * k); b = tmm.malloc_pinned(np.float64, k * n); c = tmm.malloc_pinned(np.float64, m * n)
+        fill_uniform(a, 100 + gi); fill_uniform(b, 200 + gj)
+        np.asarray(c)[:] = 0.0
     ctx = tmm.make_context(np.float64, args.streams, 5000, 5000, 5000)
 
     # ------------------------------------------------------------------ (1) device-resident kernel throughput -> value, roofline
@@ -323,6 +360,7 @@ def main():
             "config": {"workload": f"README miniapp (BASELINE configs[1]): dgemm m=n=k={size} NN alpha=1 beta=0, pinned host buffers, tile hints 5000^3, "
                                    f"{args.streams} streams" + (f"; weak-scaled over a {pr}x{pc} C-block grid, global {pr*m}x{pc*n}x{k}, A/B panel slices all-gathered over NVLink" if world > 1 else ""),
                        "l2": "inputs (A, B = 800 MB each) larger than the 126 MB L2; no flush needed",
+                       "host_buffers": f"cudaHostAlloc, first touched on the GPU-local NUMA node ({numa.bound} CPUs)" if numa.bound else "cudaHostAlloc (no NUMA binding applied)",
                        "value_is": "device-resident DGEMM (tmm_device_gemm, operands in HBM)", "e2e_is": "tmm_gemm with host pointers (H2D + GEMM + D2H)"},
             "e2e": {"value": round(e2e_tf, 3), "unit": "TFLOP/s", "ms_per_step": round(e2e_ms, 3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "nvlink_bytes_per_step": peer,
                     "frac_of_host_roofline": round(e2e_tf / world / roof_simple, 4),

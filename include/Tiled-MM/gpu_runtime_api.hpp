@@ -41,6 +41,14 @@ template <typename... A> inline StatusType get_device(A... a) { return cudaGetDe
 template <typename... A> inline StatusType set_device(A... a) { return cudaSetDevice(std::forward<A>(a)...); }
 template <typename... A> inline StatusType mem_get_info(A... a) { return cudaMemGetInfo(std::forward<A>(a)...); }
 template <typename... A> inline StatusType stream_synchronize(A... a) { return cudaStreamSynchronize(std::forward<A>(a)...); }
+template <typename... A> inline StatusType stream_create_with_flags(A... a) { return cudaStreamCreateWithFlags(std::forward<A>(a)...); }
+template <typename... A> inline StatusType stream_destroy(A... a) { return cudaStreamDestroy(std::forward<A>(a)...); }
+template <typename... A> inline StatusType stream_wait_event(A... a) { return cudaStreamWaitEvent(std::forward<A>(a)...); }
+template <typename... A> inline StatusType event_create_with_flags(A... a) { return cudaEventCreateWithFlags(std::forward<A>(a)...); }
+template <typename... A> inline StatusType event_destroy(A... a) { return cudaEventDestroy(std::forward<A>(a)...); }
+template <typename... A> inline StatusType event_record(A... a) { return cudaEventRecord(std::forward<A>(a)...); }
+template <typename... A> inline StatusType event_synchronize(A... a) { return cudaEventSynchronize(std::forward<A>(a)...); }
+template <typename... A> inline StatusType event_elapsed_time(A... a) { return cudaEventElapsedTime(std::forward<A>(a)...); }
 inline const char* get_error_string(StatusType s) { return cudaGetErrorString(s); }
 inline StatusType get_last_error() { return cudaGetLastError(); }
 inline StatusType device_synchronize() { return cudaDeviceSynchronize(); }

@@ -4,7 +4,10 @@
 // slabs plus one cuBLAS handle per stream (reference mm_handle.hpp:44-57, gpu_context.cpp:6-18).
 #pragma once
 #include "../tiled_mm_b200.h"
+#include "device_buffer.hpp"
 #include "device_vector.hpp"
+#include "gpu_context.hpp"
+#include "gpu_runtime_api.hpp"
 
 #include <complex>
 #include <memory>
@@ -17,17 +20,6 @@ template <> struct tmm_dtype<float> { static constexpr int value = TMM_F32; };
 template <> struct tmm_dtype<double> { static constexpr int value = TMM_F64; };
 template <> struct tmm_dtype<std::complex<float>> { static constexpr int value = TMM_C32; };
 template <> struct tmm_dtype<std::complex<double>> { static constexpr int value = TMM_C64; };
-
-// What is left of the reference's gpu_context (n streams + n cuBLAS handles, gpu_context.hpp:11-40): a read-only
-// description.  Streams are owned and scheduled by the library; there are no BLAS handles.
-class gpu_context {
-public:
-    explicit gpu_context(tmm_context* ctx) : ctx_(ctx) {}
-    int get_num_streams() const { return tmm_context_get_num_streams(ctx_); }
-    tmm_context* native() const { return ctx_; }
-private:
-    tmm_context* ctx_;
-};
 
 template <typename Scalar>
 class mm_handle {
@@ -52,6 +44,11 @@ public:
 
     void set_streams_and_tiles(int streams, int tile_size_m, int tile_size_n, int tile_size_k);
 
+    // per-stream tile slabs (n_streams x tile): caller-visible device scratch, allocated on first use; the scheduler itself
+    // stages through context-owned panels / rings instead (csrc/tmm_context.cu)
+    device_buffer<Scalar>& get_device_buffer_a();
+    device_buffer<Scalar>& get_device_buffer_b();
+    device_buffer<Scalar>& get_device_buffer_c();
     // device C of the last copy_c_back=false gemm: column-major m x n, ld = m (reference README.md:102-103)
     device_vector<Scalar>& get_full_device_buffer_c();
 
@@ -60,6 +57,8 @@ public:
 private:
     tmm_context* ctx_ = nullptr;
     gpu_context view_{nullptr};
+    int max_tile_m_ = 5000, max_tile_n_ = 5000, max_tile_k_ = 5000;  // fixed at construction (mm_handle.cpp:10-16)
+    device_buffer<Scalar> a_buff_, b_buff_, c_buff_;
     device_vector<Scalar> full_c_;
 };
 

@@ -62,6 +62,17 @@ TMM_API int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, in
  * Borrowed device pointer, valid until a later call grows it or the context is destroyed. */
 TMM_API void* tmm_context_device_c(tmm_context* ctx);
 TMM_API size_t tmm_context_device_c_size(tmm_context* ctx); /* elements */
+/* mm_handle::set_full_sizes(m, n, k)  — mm_handle.cpp:73-80: make the context's device C hold m x n elements now (grow-only,
+ * 1.2x slack, contents discarded on growth like device_vector::resize, device_vector.hpp:92-107).  tmm_gemm with
+ * copy_c_back == 0 does this itself; the call exists for callers that size the buffer up front. */
+TMM_API int tmm_context_reserve_device_c(tmm_context* ctx, int64_t m, int64_t n);
+/* gpu_context::get_stream(i) / get_result_stream()  — gpu_context.cpp:20-57.  The context's own streams as cudaStream_t, for
+ * callers that order their device work against the library's: kind TMM_STREAM_COMPUTE (index 0 = the high-priority chain,
+ * 1.. = column-block streams), TMM_STREAM_H2D, TMM_STREAM_D2H (the reference's "result stream").  NULL if out of range. */
+#define TMM_STREAM_COMPUTE 0
+#define TMM_STREAM_H2D 1
+#define TMM_STREAM_D2H 2
+TMM_API void* tmm_context_stream(tmm_context* ctx, int kind, int index);
 
 /* mm_handle::optimal_tile_sizes / get_max_tile_sizes / get_num_streams / set_num_streams /
  * set_tile_sizes / set_streams_and_tiles  — mm_handle.cpp:36-66,112-148. */

@@ -41,6 +41,10 @@ def test_cpp_dropin_symbols_exported(tmm):
         "_ZN3gpu9mm_handleIdE24get_full_device_buffer_cEv",
         "_ZN3gpu9mm_handleIdE18optimal_tile_sizesEiii",
         "_ZN3gpu18get_blas_operationEc",
+        "_ZN3gpu9mm_handleIdE19get_device_buffer_aEv",
+        "_ZN3gpu9mm_handleIfE19get_device_buffer_cEv",
+        "_ZN3gpu9mm_handleISt7complexIdEE21set_streams_and_tilesEiiii",
+        "_ZN3gpu9mm_handleIdE14set_full_sizesEiii",
     ]:
         assert sym in out, sym
 
@@ -49,7 +53,8 @@ def test_cpp_dropin_headers_compile(tmp_path):
     """A reference-style caller (tests/test-multiply.cpp shape) compiles against include/Tiled-MM unchanged."""
     src = tmp_path / "caller.cpp"
     src.write_text(
-        "#include <Tiled-MM/tiled_mm.hpp>\n#include <Tiled-MM/device_vector.hpp>\n#include <Tiled-MM/util.hpp>\n"
+        "#include <Tiled-MM/tiled_mm.hpp>\n#include <Tiled-MM/device_vector.hpp>\n#include <Tiled-MM/util.hpp>\n#include <Tiled-MM/gpu_blas_handle.hpp>\n"
+        "#include <Tiled-MM/gpu_blas_api.hpp>\n#include <Tiled-MM/gpu_runtime_api.hpp>\n#include <Tiled-MM/device_buffer.hpp>\n#include <Tiled-MM/gpu_context.hpp>\n"
         "int run(int m, int n, int k) {\n"
         "  auto a = gpu::malloc_pinned<double>(size_t(m) * k, 1); auto b = gpu::malloc_pinned<double>(size_t(k) * n, 1);\n"
         "  auto c = gpu::malloc_pinned<double>(size_t(m) * n, 0);\n"
@@ -58,7 +63,14 @@ def test_cpp_dropin_headers_compile(tmp_path):
         "  gpu::gemm(*ctx, 'N', 'N', m, n, k, 1.0, a, m, b, k, 0.0, c, m, false, false);\n"
         "  gpu::copy_to_host(ctx->get_full_device_buffer_c().data(), c, size_t(m) * n);\n"
         "  auto z = gpu::make_context<std::complex<double>>();\n"
-        "  return (int)ctx->get_num_streams() + (int)std::get<0>(ctx->optimal_tile_sizes(m, n, k)) + (gpu::get_blas_operation('T') == gpu::blas_api::operation::Transpose);\n"
+        "  // the rest of the handle surface (mm_handle.hpp:22-42): slabs, full C sizing, streams\n"
+        "  ctx->set_num_streams(3); ctx->set_tile_sizes(100, 200, 300); ctx->set_tile_sizes(64); ctx->set_streams_and_tiles(2, 10, 20, 30);\n"
+        "  ctx->set_full_sizes(m, n, k);\n"
+        "  gpu::device_buffer<double>& ab = ctx->get_device_buffer_a(); gpu::tile_dim td = ab.get_tile_sizes();\n"
+        "  double* slab1 = ctx->get_device_buffer_c().stream_buffer(1); double* base = ctx->get_device_buffer_b().data(); (void)slab1; (void)base;\n"
+        "  gpu::gpu_context& gc = ctx->get_gpu_context(); cudaStream_t s0 = gc.get_stream(0); cudaStream_t rs = gc.get_result_stream().stream(); gpu::device_stream& ds = gc.get_device_stream(1); (void)s0; (void)rs; (void)ds;\n"
+        "  int t0 = td.rows() + td.cols() + td.size() + std::get<2>(ctx->get_max_tile_sizes()) + gc.get_num_streams();\n"
+        "  return (int)ctx->get_num_streams() + (int)std::get<0>(ctx->optimal_tile_sizes(m, n, k)) + (gpu::get_blas_operation('T') == gpu::blas_api::operation::Transpose) + t0;\n"
         "}\n")
     subprocess.run(["g++", "-std=c++14", "-Wall", "-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include", "-c", str(src), "-o", str(tmp_path / "c.o")],
                    check=True)

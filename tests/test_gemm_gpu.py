@@ -237,8 +237,16 @@ def test_device_gemm_boundary(gpu_tmm, oracle):
     out = np.empty_like(c0)
     tmm.copy_to_host(dc, out)
     assert np.array_equal(out, expect)
+    # operands outside the TMA contract (odd ld, base at 8 mod 16) are accepted like cuBLAS accepts them: the copy engine re-pitches
+    # them into stream-ordered scratch and the same DMMA kernel runs (reference tests/test-multiply.cpp:44 passes ld_b = k = 1357)
+    for tt, oa, lda, ob, ldb in [("NN", 1, 304, 0, 104), ("NN", 0, 301, 0, 103), ("TT", 1, 101, 1, 201), ("TN", 0, 101, 1, 101)]:
+        expect = oracle.gemm(tt[0], tt[1], m, n, k, 2.0, a0[oa:], lda, b0[ob:], ldb, -1.0, c0.copy(), m)
+        tmm.copy_to_device(c0, dc)
+        tmm.device_gemm(np.float64, tt[0], tt[1], m, n, k, 2.0, da + 8 * oa, lda, db + 8 * ob, ldb, -1.0, dc, m)
+        tmm.copy_to_host(dc, out)
+        assert np.array_equal(out, expect), (tt, oa, lda, ob, ldb)
     with pytest.raises(ValueError):
-        tmm.device_gemm(np.float64, "N", "N", m, n, k, 1.0, da + 8, 304, db, 104, 1.0, dc, m)  # misaligned A violates the TMA contract
+        tmm.device_gemm(np.float64, "Q", "N", m, n, k, 1.0, da, 304, db, 104, 1.0, dc, m)
     for p in (da, db, dc):
         tmm.free_device(p)
 

@@ -84,6 +84,9 @@ def load_library() -> ctypes.CDLL:
     lib.tmm_context_device_c.restype = vp
     lib.tmm_context_device_c_size.argtypes = [vp]
     lib.tmm_context_device_c_size.restype = sz
+    lib.tmm_context_reserve_device_c.argtypes = [vp, i64, i64]
+    lib.tmm_context_stream.argtypes = [vp, ci, ci]
+    lib.tmm_context_stream.restype = vp
     lib.tmm_context_optimal_tile_sizes.argtypes = [vp, ci, ci, ci] + [ctypes.POINTER(ci)] * 3
     lib.tmm_context_get_max_tile_sizes.argtypes = [vp] + [ctypes.POINTER(ci)] * 3
     lib.tmm_context_get_num_streams.argtypes = [vp]
@@ -211,6 +214,14 @@ class MMHandle:
 
     def get_full_device_buffer_c(self) -> DeviceVector:
         return DeviceVector(self)
+
+    def set_full_sizes(self, m: int, n: int, k: int = 1) -> None:
+        """mm_handle::set_full_sizes (mm_handle.cpp:73-80): size the full device C to m x n elements now."""
+        _check(load_library().tmm_context_reserve_device_c(self._h, m, n))
+
+    def stream(self, kind: int = 0, index: int = 0) -> int:
+        """The context's own CUDA streams (gpu_context::get_stream / get_result_stream): kind STREAM_COMPUTE / STREAM_H2D / STREAM_D2H."""
+        return load_library().tmm_context_stream(self._h, kind, index) or 0
 
     # multi-GPU (not in the reference, which drives one device)
     def set_devices(self, n_devices: int, device_ids=None) -> None:
@@ -382,6 +393,7 @@ def total_kernel_launches() -> int:
 
 
 MATH_SIMT, MATH_TF32, MATH_FP32 = 0, 1, 3
+STREAM_COMPUTE, STREAM_H2D, STREAM_D2H = 0, 1, 2
 
 
 def set_f32_math(mode: int) -> None:

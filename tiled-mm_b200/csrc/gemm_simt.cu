@@ -18,6 +18,13 @@ template <> struct Num<float> {
     static __device__ __forceinline__ float add(float a, float b) { return a + b; }
     static __device__ __forceinline__ float conj(float a) { return a; }
 };
+template <> struct Num<double> {
+    static __device__ __forceinline__ double zero() { return 0.0; }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
+    static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
+    static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+    static __device__ __forceinline__ double conj(double a) { return a; }
+};
 template <> struct Num<cuFloatComplex> {
     using T = cuFloatComplex;
     static __device__ __forceinline__ T zero() { return make_cuFloatComplex(0.f, 0.f); }
@@ -123,6 +130,15 @@ cudaError_t cgemm_launch(char ta, char tb, int m, int n, int k, const float* al,
                          const float* be, void* c, int64_t ldc, cudaStream_t st) {
     return simt::launch<cuFloatComplex>(ta, tb, m, n, k, make_cuFloatComplex(al[0], al[1]), a, lda, b, ldb, make_cuFloatComplex(be[0], be[1]),
                                         be[0] != 0.f || be[1] != 0.f, c, ldc, st);
+}
+cudaError_t dgemm_simt_launch(char ta, char tb, int m, int n, int k, double alpha, const double* a, int64_t lda, const double* b, int64_t ldb, double beta,
+                              double* c, int64_t ldc, cudaStream_t st) {
+    return simt::launch<double>(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, beta != 0.0, c, ldc, st);
+}
+cudaError_t zgemm_simt_launch(char ta, char tb, int m, int n, int k, const double* al, const void* a, int64_t lda, const void* b, int64_t ldb,
+                              const double* be, void* c, int64_t ldc, cudaStream_t st) {
+    return simt::launch<cuDoubleComplex>(ta, tb, m, n, k, make_cuDoubleComplex(al[0], al[1]), a, lda, b, ldb, make_cuDoubleComplex(be[0], be[1]),
+                                         be[0] != 0.0 || be[1] != 0.0, c, ldc, st);
 }
 #ifndef TMM_HAVE_ZGEMM_DMMA
 cudaError_t zgemm_launch(char ta, char tb, int m, int n, int k, const double* al, const void* a, int64_t lda, const void* b, int64_t ldb,

@@ -12,10 +12,11 @@ enum DType : int { F32 = 0, F64 = 1, C32 = 2, C64 = 3 };
 
 inline size_t dtype_size(int dt) { return dt == F32 ? 4 : (dt == F64 ? 8 : (dt == C32 ? 8 : 16)); }
 
-// Alignment contract for the TMA-fed kernels: A and B base pointers 16-byte aligned and
-// lda/ldb * sizeof(elem) a multiple of 16.  The scheduler's device panels always satisfy this
-// (it chooses the device pitch); C has no alignment requirement beyond natural alignment.
-// Returns cudaSuccess or the launch error; cudaErrorInvalidValue on a contract violation.
+// The TMA-fed kernels want A and B base pointers 16-byte aligned and lda/ldb * sizeof(elem) a multiple of 16.  The
+// scheduler's device panels always satisfy this (it chooses the device pitch).  Other callers may pass anything cuBLAS
+// accepts: an operand outside the contract is re-pitched once by the copy engine (FP64 types) or handled by the SIMT
+// kernel (float types).  C has no alignment requirement beyond natural alignment.
+// Returns cudaSuccess or the launch error; cudaErrorInvalidValue for bad trans / sizes.
 cudaError_t device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a,
                         int64_t lda, const void* b, int64_t ldb, const void* beta, void* c, int64_t ldc, cudaStream_t stream);
 
@@ -43,6 +44,12 @@ int f32_math_mode();
 void set_f32_math_mode(int mode);
 cudaError_t cgemm_launch(char ta, char tb, int m, int n, int k, const float* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
                          const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
+
+// true-FP64 SIMT kernels: last resort for FP64 operands outside the TMA contract when no scratch can be allocated
+cudaError_t dgemm_simt_launch(char ta, char tb, int m, int n, int k, double alpha, const double* a, int64_t lda, const double* b, int64_t ldb,
+                              double beta, double* c, int64_t ldc, cudaStream_t stream);
+cudaError_t zgemm_simt_launch(char ta, char tb, int m, int n, int k, const double* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
+                              const double* beta2, void* c, int64_t ldc, cudaStream_t stream);
 
 void count_launch();
 int sm_count();

@@ -112,6 +112,53 @@ cudaError_t device_scale(int dtype, int64_t m, int64_t n, const void* beta, void
     return cudaErrorInvalidValue;
 }
 
+// ---- operands that do not meet the TMA contract (FP64 paths) --------------------------------------------------------
+// cuBLAS takes any pointer / leading dimension; the TMA-fed DMMA kernels need a 16-byte aligned base and a pitch that is a
+// multiple of 16 bytes.  The scheduler's own panels always qualify (it picks the device pitch), but blas_api::dgemm is also a
+// public entry point (reference tests/test-multiply.cpp:44 calls it with ld = k = 1357).  Such an operand is re-pitched once
+// by the copy engine into a stream-ordered scratch block (cudaMallocAsync -> 2-D D2D copy -> kernel -> cudaFreeAsync), so the
+// arithmetic stays on the tensor pipe; if the pool allocation fails the FP64 SIMT kernel takes the call.
+namespace {
+struct Operand {
+    const void* p;
+    int64_t ld;
+    void* scratch = nullptr;
+};
+bool tma_ok(const void* p, int64_t ld, size_t es) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (((size_t)ld * es) & 15) == 0; }
+cudaError_t repitch(Operand& op, int64_t rows, int64_t cols, size_t es, cudaStream_t st) {
+    if (tma_ok(op.p, op.ld, es) || rows <= 0 || cols <= 0) return cudaSuccess;
+    const int64_t q = 128 / (int64_t)es, pitch = (rows + q - 1) / q * q;
+    void* buf = nullptr;
+    cudaError_t e = cudaMallocAsync(&buf, (size_t)pitch * (size_t)cols * es, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy2DAsync(buf, (size_t)pitch * es, op.p, (size_t)op.ld * es, (size_t)rows * es, (size_t)cols, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { cudaFreeAsync(buf, st); return e; }
+    op.p = buf; op.ld = pitch; op.scratch = buf;
+    return cudaSuccess;
+}
+}  // namespace
+
+static cudaError_t fp64_gemm(int dtype, char ta, char tb, int m, int n, int k, const void* alpha, const void* a, int64_t lda, const void* b, int64_t ldb,
+                             const void* beta, void* c, int64_t ldc, cudaStream_t st) {
+    const size_t es = dtype_size(dtype);
+    Operand A{a, lda}, B{b, ldb};
+    cudaError_t e = repitch(A, ta == 'N' ? m : k, ta == 'N' ? k : m, es, st);
+    if (e == cudaSuccess) e = repitch(B, tb == 'N' ? k : n, tb == 'N' ? n : k, es, st);
+    if (e == cudaSuccess) {
+        e = dtype == F64 ? dgemm_launch(ta, tb, m, n, k, *static_cast<const double*>(alpha), static_cast<const double*>(A.p), A.ld,
+                                        static_cast<const double*>(B.p), B.ld, *static_cast<const double*>(beta), static_cast<double*>(c), ldc, st)
+                         : zgemm_launch(ta, tb, m, n, k, static_cast<const double*>(alpha), A.p, A.ld, B.p, B.ld, static_cast<const double*>(beta), c, ldc, st);
+    } else {
+        cudaGetLastError();  // no scratch: true-FP64 SIMT kernel on the operands as they are
+        e = dtype == F64 ? dgemm_simt_launch(ta, tb, m, n, k, *static_cast<const double*>(alpha), static_cast<const double*>(a), lda,
+                                             static_cast<const double*>(b), ldb, *static_cast<const double*>(beta), static_cast<double*>(c), ldc, st)
+                         : zgemm_simt_launch(ta, tb, m, n, k, static_cast<const double*>(alpha), a, lda, b, ldb, static_cast<const double*>(beta), c, ldc, st);
+    }
+    if (A.scratch) cudaFreeAsync(A.scratch, st);
+    if (B.scratch) cudaFreeAsync(B.scratch, st);
+    return e;
+}
+
 cudaError_t device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t lda,
                         const void* b, int64_t ldb, const void* beta, void* c, int64_t ldc, cudaStream_t st) {
     char ta = (char)std::toupper((unsigned char)trans_a), tb = (char)std::toupper((unsigned char)trans_b);
@@ -130,10 +177,9 @@ cudaError_t device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_
     switch (dtype) {
     case F32: return sgemm_launch(ta, tb, (int)m, (int)n, (int)k, *static_cast<const float*>(alpha), static_cast<const float*>(a), lda,
                                   static_cast<const float*>(b), ldb, *static_cast<const float*>(beta), static_cast<float*>(c), ldc, st);
-    case F64: return dgemm_launch(ta, tb, (int)m, (int)n, (int)k, *static_cast<const double*>(alpha), static_cast<const double*>(a), lda,
-                                  static_cast<const double*>(b), ldb, *static_cast<const double*>(beta), static_cast<double*>(c), ldc, st);
+    case F64: return fp64_gemm(F64, ta, tb, (int)m, (int)n, (int)k, alpha, a, lda, b, ldb, beta, c, ldc, st);
     case C32: return cgemm_launch(ta, tb, (int)m, (int)n, (int)k, static_cast<const float*>(alpha), a, lda, b, ldb, static_cast<const float*>(beta), c, ldc, st);
-    case C64: return zgemm_launch(ta, tb, (int)m, (int)n, (int)k, static_cast<const double*>(alpha), a, lda, b, ldb, static_cast<const double*>(beta), c, ldc, st);
+    case C64: return fp64_gemm(C64, ta, tb, (int)m, (int)n, (int)k, alpha, a, lda, b, ldb, beta, c, ldc, st);
     }
     return cudaErrorInvalidValue;
 }

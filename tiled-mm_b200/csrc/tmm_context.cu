@@ -586,6 +586,28 @@ int tmm_context_optimal_tile_sizes(tmm_context* ctx, int m, int n, int k, int* t
 void* tmm_context_device_c(tmm_context* ctx) { return ctx ? ctx->full_c.p : nullptr; }
 size_t tmm_context_device_c_size(tmm_context* ctx) { return ctx ? ctx->full_c_elems : 0; }
 
+int tmm_context_reserve_device_c(tmm_context* ctx, int64_t m, int64_t n) {
+    if (!ctx) return fail(TMM_ERR_INVALID, "null context");
+    if (m < 1 || n < 1) return fail(TMM_ERR_INVALID, "set_full_sizes: dimensions must be >= 1");  // asserts in the reference, mm_handle.cpp:75-77
+    DeviceGuard guard(ctx->device);
+    const size_t bytes = (size_t)m * (size_t)n * tmm::dtype_size(ctx->dtype);
+    if (bytes > ctx->full_c.cap) ctx->budget_cached = 0;
+    cudaError_t e = ctx->full_c.reserve(bytes, 1.2);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(full C)");
+    ctx->full_c_elems = (size_t)m * (size_t)n;
+    return TMM_OK;
+}
+
+void* tmm_context_stream(tmm_context* ctx, int kind, int index) {
+    if (!ctx) return nullptr;
+    switch (kind) {
+    case TMM_STREAM_COMPUTE: return (index >= 0 && index < ctx->n_compute()) ? (void*)ctx->s_compute[index] : nullptr;
+    case TMM_STREAM_H2D: return index == 0 ? (void*)ctx->s_h2d : nullptr;
+    case TMM_STREAM_D2H: return index == 0 ? (void*)ctx->s_d2h : nullptr;
+    default: return nullptr;
+    }
+}
+
 int tmm_context_last_stats(tmm_context* ctx, tmm_call_stats* out) {
     if (!ctx || !out) return fail(TMM_ERR_INVALID, "null argument");
     *out = ctx->stats;
