@@ -223,6 +223,17 @@ def test_error_behaviour(gpu_tmm):
         tmm.gemm(ctx, "n", "t", 2, 2, 2, 1.0, a, 2, a, 2, 0.0, a, 2, False, True)          # lower case accepted (tiled_mm.cpp:503-504)
         assert ctx.optimal_tile_sizes(12345, 23456, 67891) == (4115, 2932, 5000)
         assert ctx.get_max_tile_sizes() == (5000, 5000, 5000) and ctx.get_num_streams() == 2
+        # the rest of the handle (mm_handle.cpp:36-80): stream / tile hints never move the construction-time maxima
+        ctx.set_streams_and_tiles(3, 100, 200, 300)
+        assert ctx.get_num_streams() == 3 and ctx.get_max_tile_sizes() == (5000, 5000, 5000)
+        ctx.set_tile_sizes(64)
+        ctx.set_num_streams(2)
+        assert ctx.get_num_streams() == 2 and ctx.optimal_tile_sizes(12345, 23456, 67891) == (4115, 2932, 5000)
+        ctx.set_full_sizes(10, 20, 30)                                                       # full device C sized up front
+        assert ctx.get_full_device_buffer_c().size() == 200 and ctx.get_full_device_buffer_c().data() != 0
+        assert ctx.stream(tmm.STREAM_COMPUTE, 0) != 0 and ctx.stream(tmm.STREAM_D2H) != 0 and ctx.stream(tmm.STREAM_COMPUTE, 99) == 0
+        with pytest.raises(ValueError):
+            ctx.set_full_sizes(0, 5)
 
 
 def test_device_gemm_boundary(gpu_tmm, oracle):

@@ -202,6 +202,12 @@ class MMHandle:
     def set_streams_and_tiles(self, streams: int, tile_m: int, tile_n: int, tile_k: int) -> None:
         _check(load_library().tmm_context_set_streams_and_tiles(self._h, streams, tile_m, tile_n, tile_k))
 
+    def set_tile_sizes(self, tile_m: int, tile_n: int | None = None, tile_k: int | None = None) -> None:
+        """mm_handle::set_tile_sizes(m, n, k) / set_tile_sizes(size) (mm_handle.cpp:57-71): staging hints, clamped to the maxima."""
+        tn = tile_m if tile_n is None else tile_n
+        tk = tile_m if tile_k is None else tile_k
+        self.set_streams_and_tiles(self.get_num_streams(), tile_m, tn, tk)
+
     def get_max_tile_sizes(self):
         a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         _check(load_library().tmm_context_get_max_tile_sizes(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))

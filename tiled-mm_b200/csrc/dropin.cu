@@ -30,9 +30,9 @@ mm_handle<Scalar>::~mm_handle() { tmm_context_destroy(ctx_); }
 template <typename Scalar>
 void mm_handle<Scalar>::set_num_streams(int streams) {
     // reference mm_handle.cpp:36-45: the stream count of the context and of the three slab buffers
-    int tm, tn, tk;
-    check_tmm_status(tmm_context_get_max_tile_sizes(ctx_, &tm, &tn, &tk));
-    check_tmm_status(tmm_context_set_streams_and_tiles(ctx_, streams, tm, tn, tk));
+    const tile_dim a = a_buff_.get_tile_sizes(), c = c_buff_.get_tile_sizes();  // keep the current tile hints (0 x 0 before the first set)
+    check_tmm_status(tmm_context_set_streams_and_tiles(ctx_, streams, c.rows() > 0 ? c.rows() : max_tile_m_, c.cols() > 0 ? c.cols() : max_tile_n_,
+                                                       a.cols() > 0 ? a.cols() : max_tile_k_));
     a_buff_.set_num_streams(streams);
     b_buff_.set_num_streams(streams);
     c_buff_.set_num_streams(streams);

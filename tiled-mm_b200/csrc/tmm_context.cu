@@ -514,6 +514,7 @@ int tmm_context_create(int dtype, int n_streams, int max_tile_m, int max_tile_n,
     tmm_context* ctx = new tmm_context();
     ctx->dtype = dtype; ctx->n_streams = n_streams;
     ctx->max_tile_m = max_tile_m; ctx->max_tile_n = max_tile_n; ctx->max_tile_k = max_tile_k;
+    ctx->tile_m = max_tile_m; ctx->tile_n = max_tile_n; ctx->tile_k = max_tile_k;
     if ((e = cudaGetDevice(&ctx->device)) != cudaSuccess) { delete ctx; return cuda_fail(e, "cudaGetDevice"); }
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) { delete ctx; return cuda_fail(e, "cudaGetDeviceProperties"); }
@@ -570,7 +571,11 @@ int tmm_context_get_max_tile_sizes(tmm_context* ctx, int* tm, int* tn, int* tk) 
 int tmm_context_set_streams_and_tiles(tmm_context* ctx, int n_streams, int tile_m, int tile_n, int tile_k) {
     if (!ctx) return fail(TMM_ERR_INVALID, "null context");
     if (n_streams < 1 || tile_m < 1 || tile_n < 1 || tile_k < 1) return fail(TMM_ERR_INVALID, "streams and tile sizes must be >= 1");
-    ctx->n_streams = n_streams; ctx->max_tile_m = tile_m; ctx->max_tile_n = tile_n; ctx->max_tile_k = tile_k;
+    // the reference asserts tile <= max (mm_handle.cpp:136-138); here the hint is clamped and the maxima stay what make_context fixed
+    ctx->n_streams = n_streams;
+    ctx->tile_m = std::min(tile_m, ctx->max_tile_m); ctx->tile_n = std::min(tile_n, ctx->max_tile_n); ctx->tile_k = std::min(tile_k, ctx->max_tile_k);
+    for (tmm_context* ch : ctx->children) { ch->n_streams = n_streams; ch->tile_m = ctx->tile_m; ch->tile_n = ctx->tile_n; ch->tile_k = ctx->tile_k; }
+    if (ctx->solo) { ctx->solo->n_streams = n_streams; ctx->solo->tile_m = ctx->tile_m; ctx->solo->tile_n = ctx->tile_n; ctx->solo->tile_k = ctx->tile_k; }
     return TMM_OK;
 }
 
@@ -730,7 +735,7 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                 tmm::PlanInput pin_;
                 pin_.dtype = cl.dtype; pin_.ta = cl.ta; pin_.tb = cl.tb; pin_.m = m_plan; pin_.n = n_plan; pin_.k = k;
                 pin_.beta_nonzero = cl.beta_nonzero; pin_.copy_c_back = cl.copy_c_back; pin_.budget = plan_budget;
-                pin_.n_streams = ctx->n_streams; pin_.tile_m = ctx->max_tile_m; pin_.tile_n = ctx->max_tile_n; pin_.tile_k = ctx->max_tile_k;
+                pin_.n_streams = ctx->n_streams; pin_.tile_m = ctx->tile_m; pin_.tile_n = ctx->tile_n; pin_.tile_k = ctx->tile_k;
                 pin_.sm_count = tmm::sm_count();
                 pin_.parts_a = gr.pc; pin_.parts_b = gr.pr;
                 tmm::Plan pl;

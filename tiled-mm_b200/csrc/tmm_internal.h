@@ -101,7 +101,8 @@ constexpr int STAGE_SLOTS = 3;
 struct tmm_context {
     int dtype = TMM_F64;
     int n_streams = 2;
-    int max_tile_m = 5000, max_tile_n = 5000, max_tile_k = 5000;
+    int max_tile_m = 5000, max_tile_n = 5000, max_tile_k = 5000;  // fixed at creation (reference mm_handle.cpp:10-16)
+    int tile_m = 5000, tile_n = 5000, tile_k = 5000;              // current staging hints, <= the maxima (mm_handle.cpp:57-66,135-145)
     int device = 0;
     static constexpr int MAX_COMPUTE = 4, MAX_P1 = 4;
     cudaStream_t s_p1[MAX_P1] = {nullptr, nullptr, nullptr, nullptr};  // phase-1 stripe chains ([0] aliases s_compute[0])
