@@ -109,6 +109,14 @@ TMM_API int tmm_device_gemm(int dtype, char trans_a, char trans_b, int64_t m, in
 #define TMM_MATH_FP32 3
 TMM_API int tmm_set_f32_math(int mode);
 TMM_API int tmm_get_f32_math(void);
+/* Math mode of the complex<float> (TMM_C32) GEMM, process-wide.  TMM_CMATH_SIMT (default): complex FMA kernel, true FP32 arithmetic.
+ * TMM_CMATH_TC: the complex product as a real product of twice the size, (2m x n) = (2m x 2k)(2k x n) over the (re, im) float view
+ * of the operands, on the FP32-accurate tcgen05 kernel (3xTF32; same accuracy class, integer data stays exact).  Opt-in until it has
+ * been validated on hardware.  Environment: TMM_C32_MATH = simt | tc. */
+#define TMM_CMATH_SIMT 0
+#define TMM_CMATH_TC 3
+TMM_API int tmm_set_c32_math(int mode);
+TMM_API int tmm_get_c32_math(void);
 
 /* ---- Multi-GPU: C tile-blocks over a p_r x p_c grid of the box's GPUs (no counterpart in the reference, which drives one
  * device; north_star: "partitioned across the 8 B200s of one box by assigning C tile-blocks to GPUs").  GPUs of a grid row

@@ -1,0 +1,56 @@
+"""GPU tests of code paths that were written after the round's GPU budget was spent and have therefore never run on hardware.
+They are opt-in in the product (environment / math-mode switches, defaults untouched) and opt-in here:
+
+    TMM_EXPERIMENTAL=1 python -m pytest tests/test_experimental_gpu.py -m gpu -q
+
+Round 2 runs this first; what passes gets promoted to the default path and into test_gemm_gpu.py."""
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+from test_gemm_gpu import run_case
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("TMM_EXPERIMENTAL") != "1", reason="paths not yet validated on hardware; set TMM_EXPERIMENTAL=1")]
+ALL_TT = ["".join(p) for p in itertools.product("NTC", "NTC")]
+
+
+@pytest.fixture()
+def c32_tc(gpu_tmm):
+    gpu_tmm.set_c32_math(gpu_tmm.CMATH_TC)
+    yield gpu_tmm
+    gpu_tmm.set_c32_math(gpu_tmm.CMATH_SIMT)
+
+
+@pytest.mark.parametrize("tt", ALL_TT)
+def test_cgemm_tensor_core_embedding_exact_on_integers(c32_tc, oracle, tt):
+    run_case(c32_tc, oracle, np.complex64, tt, 130, 67, 95, 1 - 2j, 2 + 1j, pad=(1, 2, 3), ints=True)
+
+
+@pytest.mark.parametrize("tt", ["NN", "TN", "NC", "CT"])
+def test_cgemm_tensor_core_embedding_random(c32_tc, oracle, tt):
+    run_case(c32_tc, oracle, np.complex64, tt, 777, 530, 1111, 1.5 - 0.5j, 0.25 + 0.75j, pad=(3, 0, 9), tiles=(256, 300, 500))
+    run_case(c32_tc, oracle, np.complex64, tt, 777, 530, 1111, 1.0, 0.0, pad=(3, 0, 9))            # beta = 0: C never read
+
+
+def test_cgemm_tensor_core_device_boundary_odd_ld(c32_tc, oracle):
+    """blas_api::cgemm with an odd ldb (no zero-copy view of B) and a base at 8 mod 16."""
+    tmm = c32_tc
+    m, n, k = 200, 150, 90
+    rng = np.random.default_rng(3)
+    def gen(count):
+        return (rng.integers(0, 10, count) + 1j * rng.integers(0, 10, count)).astype(np.complex64)
+    a0, b0, c0 = gen(203 * k + 1), gen(91 * n + 1), gen(m * n)
+    da, db, dc = (tmm.malloc_device(x.nbytes) for x in (a0, b0, c0))
+    tmm.copy_to_device(a0, da); tmm.copy_to_device(b0, db)
+    for oa, ob in ((0, 0), (1, 1)):
+        expect = oracle.gemm("N", "N", m, n, k, 1 + 1j, a0[oa:], 203, b0[ob:], 91, 2.0, c0.copy(), m)
+        tmm.copy_to_device(c0, dc)
+        tmm.device_gemm(np.complex64, "N", "N", m, n, k, 1 + 1j, da + 8 * oa, 203, db + 8 * ob, 91, 2.0, dc, m)
+        out = np.empty_like(c0)
+        tmm.copy_to_host(dc, out)
+        assert np.array_equal(out, expect), (oa, ob)
+    for p in (da, db, dc):
+        tmm.free_device(p)

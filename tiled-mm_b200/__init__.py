@@ -107,6 +107,7 @@ def load_library() -> ctypes.CDLL:
     lib.tmm_version.restype = ctypes.c_char_p
     lib.tmm_optimal_tile_size.argtypes = [ci, ci]
     lib.tmm_set_f32_math.argtypes = [ci]
+    lib.tmm_set_c32_math.argtypes = [ci]
     lib.tmm_plan_describe.argtypes = [ci, cc, cc, i64, i64, i64, ci, ci, sz, ci, ci, ci, ci, ci, ctypes.c_char_p, sz]
     lib.tmm_grid_shape.argtypes = [ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
     lib.tmm_share_range.argtypes = [i64, ci, ci, ctypes.POINTER(i64), ctypes.POINTER(i64)]
@@ -405,6 +406,18 @@ STREAM_COMPUTE, STREAM_H2D, STREAM_D2H = 0, 1, 2
 def set_f32_math(mode: int) -> None:
     """Math mode of the float GEMM (tmm_set_f32_math): MATH_FP32 (default: FP32-accurate 3xTF32 on tcgen05), MATH_TF32, MATH_SIMT."""
     _check(load_library().tmm_set_f32_math(int(mode)))
+
+
+CMATH_SIMT, CMATH_TC = 0, 3
+
+
+def set_c32_math(mode: int) -> None:
+    """Math mode of the complex<float> GEMM (tmm_set_c32_math): CMATH_SIMT (default) or CMATH_TC (real embedding on tcgen05, opt-in)."""
+    _check(load_library().tmm_set_c32_math(int(mode)))
+
+
+def get_c32_math() -> int:
+    return int(load_library().tmm_get_c32_math())
 
 
 def get_f32_math() -> int:

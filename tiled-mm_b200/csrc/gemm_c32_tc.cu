@@ -1,0 +1,136 @@
+// CGEMM on the tcgen05 tensor cores:  C = alpha * op(A) * op(B) + beta * C for complex<float>, column-major, device operands.
+// Replaces blas_api::cgemm (reference gpu_blas_api.hpp:233-251, called from tiled_mm.cpp:222-245).
+//
+// A complex product is a real product of twice the size.  With every complex number written as its (re, im) pair - which is how
+// interleaved storage already looks when read as floats -
+//     C~ = A' * B'          C~ : (2m x n)   the float view of C, rows (2i, 2i+1) = (re, im) of row i
+//                           B' : (2k x n)   the float view of op(B), rows (2l, 2l+1) = (re, im) of row l
+//                           A' : (2m x 2k)  column 2l   = (re, im) pairs of  w(:, l)      [ w = alpha * op(A) ]
+//                                           column 2l+1 = (re, im) pairs of  i * w(:, l) = (-im, re)
+// because  w * b = w * re(b) + (i w) * im(b).  The real product has 2 * (2m) * n * (2k) = 8mnk flops - exactly the complex flop
+// count - and runs on the FP32-accurate 3xTF32 kernel of gemm_f32_tc.cu unchanged (same TMA / TMEM / windowed-promotion
+// pipeline, same accuracy: small integers stay exact).  What this file adds is the operand preparation, one elementwise pass
+// per launch into stream-ordered scratch (cudaMallocAsync):
+//   A  always (it has to be duplicated as w and i*w; alpha and the conjugation of op 'C' are folded in for free):
+//        2 x |A| bytes written; k-contiguous for op T/C, m-contiguous for op N - the SGEMM kernel takes either orientation
+//   B  op N: nothing - the stored matrix read as floats IS B' (zero copy) when its base and pitch meet the TMA contract
+//      op T/C: de-interleave into (n x 2k), n-contiguous (re column, +-im column)
+//   C  beta real: nothing (the SGEMM epilogue applies it to re and im alike); beta complex: one scaling pass first
+// The passes move O(|A| + |B|) bytes through HBM against O(mnk) tensor work: < 5 % at the scheduler's launch shapes.
+// If the scratch cannot be allocated the SIMT kernel takes the call.
+//
+// STATUS: cross-compiled and algebra-checked on the CPU (tests/test_c32_embedding.py); NOT yet run on hardware (the round's GPU
+// budget was spent) - therefore opt-in: TMM_C32_MATH=tc or tmm_set_c32_math(TMM_CMATH_TC).  The default stays the SIMT kernel.
+#include "tmm_blas.h"
+
+#include <cstdint>
+
+namespace tmm {
+namespace c32tc {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// op N: stored m x k complex (m contiguous).  out: (2m x 2k) floats, pitch floats per column (even), written as float2 pairs.
+__global__ void __launch_bounds__(256) embed_a_n(const float2* __restrict__ a, int64_t lda, int m, int k, float2 alpha, float2* __restrict__ out2, int64_t pitch2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    for (int l = blockIdx.y; l < k; l += gridDim.y) {
+        const float2 w = cmul(alpha, a[(int64_t)l * lda + i]);
+        out2[(int64_t)(2 * l) * pitch2 + i] = w;                           // column 2l   : ( re,  im)
+        out2[(int64_t)(2 * l + 1) * pitch2 + i] = make_float2(-w.y, w.x);  // column 2l+1 : (-im,  re)  = i * w
+    }
+}
+
+// op T / C: stored k x m complex (k contiguous), element (l, i).  out = A'^T: (2k x 2m) floats, k-contiguous:
+//   column 2i   rows (2l, 2l+1) = ( re, -im)        column 2i+1 rows (2l, 2l+1) = ( im,  re)         of w = alpha * op(a(l, i))
+__global__ void __launch_bounds__(256) embed_a_t(const float2* __restrict__ a, int64_t lda, int k, int m, float2 alpha, int conj, float2* __restrict__ out2,
+                                                  int64_t pitch2) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= k) return;
+    for (int i = blockIdx.y; i < m; i += gridDim.y) {
+        float2 v = a[(int64_t)i * lda + l];
+        if (conj) v.y = -v.y;
+        const float2 w = cmul(alpha, v);
+        out2[(int64_t)(2 * i) * pitch2 + l] = make_float2(w.x, -w.y);
+        out2[(int64_t)(2 * i + 1) * pitch2 + l] = make_float2(w.y, w.x);
+    }
+}
+
+// op T / C of B: stored n x k complex (n contiguous), element (j, l).  out = B'^T: (n x 2k) floats, n-contiguous:
+//   column 2l = re(b(:, l)),  column 2l+1 = +-im(b(:, l))
+__global__ void __launch_bounds__(256) split_b_t(const float2* __restrict__ b, int64_t ldb, int n, int k, int conj, float* __restrict__ out, int64_t pitch) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    for (int l = blockIdx.y; l < k; l += gridDim.y) {
+        const float2 v = b[(int64_t)l * ldb + j];
+        out[(int64_t)(2 * l) * pitch + j] = v.x;
+        out[(int64_t)(2 * l + 1) * pitch + j] = conj ? -v.y : v.y;
+    }
+}
+
+static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+static inline dim3 pass_grid(int contiguous, int columns) {
+    return dim3((unsigned)((contiguous + 255) / 256), (unsigned)(columns < 1 ? 1 : (columns > 32768 ? 32768 : columns)));
+}
+
+}  // namespace c32tc
+
+// Returns cudaErrorMemoryAllocation when the scratch cannot be had (caller falls back to SIMT); any other error is final.
+cudaError_t cgemm_tc_launch(char ta, char tb, int m, int n, int k, const float* al, const void* a, int64_t lda, const void* b, int64_t ldb,
+                            const float* be, void* c, int64_t ldc, cudaStream_t st) {
+    using namespace c32tc;
+    if (m <= 0 || n <= 0 || k <= 0) return cudaSuccess;
+    if (m > INT32_MAX / 2 || k > INT32_MAX / 2) return cudaErrorMemoryAllocation;  // the doubled extents must fit the SGEMM's int sizes
+    const float2 alpha = make_float2(al[0], al[1]);
+    const bool a_n = ta == 'N', b_n = tb == 'N';
+
+    // ---- A' ----
+    const int64_t pitch_a = a_n ? round_up(2 * (int64_t)m, 32) : round_up(2 * (int64_t)k, 32);  // floats; 128-byte columns
+    const int64_t cols_a = a_n ? 2 * (int64_t)k : 2 * (int64_t)m;
+    float* a2 = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&a2), (size_t)pitch_a * (size_t)cols_a * sizeof(float), st);
+    if (e != cudaSuccess) { cudaGetLastError(); return cudaErrorMemoryAllocation; }
+    if (a_n) embed_a_n<<<pass_grid(m, k), 256, 0, st>>>(static_cast<const float2*>(a), lda, m, k, alpha, reinterpret_cast<float2*>(a2), pitch_a / 2);
+    else embed_a_t<<<pass_grid(k, m), 256, 0, st>>>(static_cast<const float2*>(a), lda, k, m, alpha, ta == 'C' ? 1 : 0, reinterpret_cast<float2*>(a2), pitch_a / 2);
+    count_launch();
+
+    // ---- B' ----
+    const float* b2 = nullptr;
+    int64_t ldb2 = 0;
+    float* b_scratch = nullptr;
+    if (b_n && (reinterpret_cast<uintptr_t>(b) & 15) == 0 && (ldb & 1) == 0) {
+        b2 = static_cast<const float*>(b);  // zero copy: (2k x n) floats with pitch 2 * ldb
+        ldb2 = 2 * ldb;
+    } else {
+        const int64_t pitch_b = b_n ? round_up(2 * (int64_t)k, 32) : round_up((int64_t)n, 32);
+        const int64_t cols_b = b_n ? (int64_t)n : 2 * (int64_t)k;
+        e = cudaMallocAsync(reinterpret_cast<void**>(&b_scratch), (size_t)pitch_b * (size_t)cols_b * sizeof(float), st);
+        if (e != cudaSuccess) { cudaGetLastError(); cudaFreeAsync(a2, st); return cudaErrorMemoryAllocation; }
+        if (b_n) {  // same values, legal pitch: the copy engine re-pitches
+            e = cudaMemcpy2DAsync(b_scratch, (size_t)pitch_b * sizeof(float), b, (size_t)ldb * sizeof(float2), (size_t)k * sizeof(float2), (size_t)n,
+                                  cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) { cudaFreeAsync(a2, st); cudaFreeAsync(b_scratch, st); return e; }
+        } else {
+            split_b_t<<<pass_grid(n, k), 256, 0, st>>>(static_cast<const float2*>(b), ldb, n, k, tb == 'C' ? 1 : 0, b_scratch, pitch_b);
+            count_launch();
+        }
+        b2 = b_scratch;
+        ldb2 = pitch_b;
+    }
+
+    // ---- beta ----
+    float beta_r = be[0];
+    if (be[1] != 0.f) {  // complex beta: C <- beta * C first, then accumulate with 1
+        e = device_scale(C32, m, n, be, c, ldc, st);
+        beta_r = 1.f;
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    // ---- the real product on tcgen05: (2m x n) = (2m x 2k) (2k x n), FP32-accurate 3xTF32 ----
+    if (e == cudaSuccess)
+        e = sgemm_tc_launch(a_n ? 'N' : 'T', b_n ? 'N' : 'T', 2 * m, n, 2 * k, 1.f, a2, pitch_a, b2, ldb2, beta_r, static_cast<float*>(c), 2 * ldc, st, 3);
+    cudaFreeAsync(a2, st);
+    if (b_scratch) cudaFreeAsync(b_scratch, st);
+    return e;
+}
+
+}  // namespace tmm

@@ -1,5 +1,6 @@
 // Generic shared-memory-tiled SIMT GEMM (FFMA / complex FMA), all dtypes, N/T/C, any ld.
-// complex<float> path (reference blas_api::cgemm, gpu_blas_api.hpp:233-251) and the float path for operands that do
+// complex<float> default path (reference blas_api::cgemm, gpu_blas_api.hpp:233-251; the tcgen05 embedding of gemm_c32_tc.cu
+// is opt-in until it has run on hardware) and the float path for operands that do
 // not meet the TMA alignment contract or when TMM_F32_MATH=simt is selected: true FP32 FFMA arithmetic like cuBLAS'
 // default math mode (the reference never sets a TF32 math mode, gpu_blas_handle.hpp:11-17).
 // Aligned float operands run on tcgen05/TMEM (gemm_f32_tc.cu, 3xTF32); see DESIGN.md.
@@ -126,7 +127,7 @@ cudaError_t sgemm_simt_launch(char ta, char tb, int m, int n, int k, float alpha
                               float* c, int64_t ldc, cudaStream_t st) {
     return simt::launch<float>(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, beta != 0.f, c, ldc, st);
 }
-cudaError_t cgemm_launch(char ta, char tb, int m, int n, int k, const float* al, const void* a, int64_t lda, const void* b, int64_t ldb,
+cudaError_t cgemm_simt_launch(char ta, char tb, int m, int n, int k, const float* al, const void* a, int64_t lda, const void* b, int64_t ldb,
                          const float* be, void* c, int64_t ldc, cudaStream_t st) {
     return simt::launch<cuFloatComplex>(ta, tb, m, n, k, make_cuFloatComplex(al[0], al[1]), a, lda, b, ldb, make_cuFloatComplex(be[0], be[1]),
                                         be[0] != 0.f || be[1] != 0.f, c, ldc, st);

@@ -44,6 +44,15 @@ int f32_math_mode();
 void set_f32_math_mode(int mode);
 cudaError_t cgemm_launch(char ta, char tb, int m, int n, int k, const float* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
                          const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
+// complex<float> back ends: SIMT complex FMA kernel (default) and the real embedding on the tcgen05 3xTF32 kernel (gemm_c32_tc.cu;
+// returns cudaErrorMemoryAllocation when its scratch cannot be allocated, and the dispatcher then falls back to SIMT)
+cudaError_t cgemm_simt_launch(char ta, char tb, int m, int n, int k, const float* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
+                              const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
+cudaError_t cgemm_tc_launch(char ta, char tb, int m, int n, int k, const float* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
+                            const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
+// process-wide math mode of the complex<float> GEMM: 0 = SIMT (default), 3 = FP32-accurate on tensor cores
+int c32_math_mode();
+void set_c32_math_mode(int mode);
 
 // true-FP64 SIMT kernels: last resort for FP64 operands outside the TMA contract when no scratch can be allocated
 cudaError_t dgemm_simt_launch(char ta, char tb, int m, int n, int k, double alpha, const double* a, int64_t lda, const double* b, int64_t ldb,

@@ -63,6 +63,28 @@ cudaError_t sgemm_launch(char ta, char tb, int m, int n, int k, float alpha, con
     return sgemm_simt_launch(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, st);
 }
 
+// ---- complex<float> GEMM math mode and dispatch ------------------------------------------------
+static std::atomic<int> g_c32_mode{-1};
+int c32_math_mode() {
+    int v = g_c32_mode.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("TMM_C32_MATH");  // "simt" (default) | "tc"
+        v = (e && (!strcmp(e, "tc") || !strcmp(e, "TC"))) ? 3 : 0;
+        g_c32_mode.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+void set_c32_math_mode(int mode) { g_c32_mode.store(mode == 3 ? 3 : 0, std::memory_order_relaxed); }
+
+cudaError_t cgemm_launch(char ta, char tb, int m, int n, int k, const float* al, const void* a, int64_t lda, const void* b, int64_t ldb,
+                         const float* be, void* c, int64_t ldc, cudaStream_t st) {
+    if (c32_math_mode() == 3 && f32_math_mode() != 0 && (reinterpret_cast<uintptr_t>(a) & 7) == 0 && (reinterpret_cast<uintptr_t>(b) & 7) == 0) {
+        cudaError_t e = cgemm_tc_launch(ta, tb, m, n, k, al, a, lda, b, ldb, be, c, ldc, st);
+        if (e != cudaErrorMemoryAllocation) return e;  // no scratch: the SIMT kernel needs none
+    }
+    return cgemm_simt_launch(ta, tb, m, n, k, al, a, lda, b, ldb, be, c, ldc, st);
+}
+
 // ---- C = beta * C --------------------------------------------------------------------------
 template <typename T> struct Ops;
 template <> struct Ops<float> {

@@ -493,6 +493,12 @@ int tmm_set_f32_math(int mode) {
     return TMM_OK;
 }
 int tmm_get_f32_math(void) { return tmm::f32_math_mode(); }
+int tmm_set_c32_math(int mode) {
+    if (mode != TMM_CMATH_SIMT && mode != TMM_CMATH_TC) return tmm::fail(TMM_ERR_INVALID, "tmm_set_c32_math: unknown mode %d", mode);
+    tmm::set_c32_math_mode(mode);
+    return TMM_OK;
+}
+int tmm_get_c32_math(void) { return tmm::c32_math_mode(); }
 
 int tmm_device_count(void) {
     int n = 0;
