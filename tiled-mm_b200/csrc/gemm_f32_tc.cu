@@ -70,6 +70,7 @@ struct Params {
     uint32_t idesc;
     int terms;   // 3: FP32-accurate 3xTF32;  1: plain TF32 on the raw bits
     int window;  // k-blocks per TMEM accumulation window
+    int split_trunc;  // experimental (TMM_TC_SPLIT=trunc): hi = the raw FP32 bits (the tensor core ignores the low 13 mantissa bits), only lo is written
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
@@ -91,6 +92,15 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     else if ((h & 0x7F800000u) == 0x7F800000u) r = 0.f;  // rounded up to Inf
     hi = __uint_as_float(h);
     lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+}
+
+// Variant for hi = raw bits: the hardware reads trunc(x) (top 19 bits), so lo = x - trunc(x) (exact), rounded to TF32.
+// |lo| < 2^-10 |x| instead of 2^-11 |x| (one bit less accurate than the round-to-nearest split) but the tile is not rewritten.
+__device__ __forceinline__ float lo_of_truncated(float x) {
+    const uint32_t u = __float_as_uint(x);
+    if ((u & 0x7F800000u) == 0x7F800000u) return 0.f;  // Inf / NaN travel in hi alone
+    const float r = x - __uint_as_float(u & 0xFFFFE000u);
+    return __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -292,6 +302,15 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     const int off = idx * 16 + (idx >= OPERAND_BYTES / 16 ? OPERAND_BYTES : 0);  // skip over A lo
                     x[i] = *reinterpret_cast<const float4*>(st + off);
                 }
+                if (p.split_trunc) {
+#pragma unroll
+                    for (int i = 0; i < PER_THREAD; ++i) {
+                        const int idx = t + i * (SPLIT_WARPS * 32);
+                        const int off = idx * 16 + (idx >= OPERAND_BYTES / 16 ? OPERAND_BYTES : 0);
+                        *reinterpret_cast<float4*>(st + off + OPERAND_BYTES) =
+                            make_float4(lo_of_truncated(x[i].x), lo_of_truncated(x[i].y), lo_of_truncated(x[i].z), lo_of_truncated(x[i].w));
+                    }
+                } else
 #pragma unroll
                 for (int i = 0; i < PER_THREAD; ++i) {
                     const int idx = t + i * (SPLIT_WARPS * 32);
@@ -381,6 +400,10 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
     p.terms = terms == 1 ? 1 : 3;
     p.window = (int)env_u32("TMM_TC_WINDOW", WINDOW_KBLOCKS);
     if (p.window < 1) p.window = 1;
+    {
+        const char* sv = getenv("TMM_TC_SPLIT");  // experimental, not validated on hardware: "trunc"
+        p.split_trunc = (sv && sv[0] == 't') ? 1 : 0;
+    }
 
     static bool configured[64] = {false};
     int dev = 0;

@@ -1,0 +1,23 @@
+#!/bin/bash
+# First GPU call of round 2 (one B200, ~6 min): validate everything that was written after round 1's GPU budget ran out.
+#   make -C tools && gpurun --timeout 500 -- 'bash tools/gpu_round2.sh'
+# 1. gated experimental tests (tcgen05 CGEMM embedding)            -> promote TMM_C32_MATH=tc to the default if green
+# 2. tc_test cgemm: all nine op pairs vs cuBLAS CGEMM + timing      -> CGEMM number for DESIGN 3.4
+# 3. SGEMM split variants: precision + timing, default vs TMM_TC_SPLIT=trunc
+# 4. the regular suite + bench line (regression check)
+cd "${GRAFT_REPO_ROOT:-.}" || exit 1
+mkdir -p gpurun_out
+export LD_LIBRARY_PATH=/usr/local/cuda/lib64:$LD_LIBRARY_PATH
+T=./build/tc_test
+{
+nvidia-smi -L | head -1
+echo "== experimental pytest =="; TMM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -m gpu -q --timeout 120 2>&1 | tail -25
+echo "== tc_test cgemm =="; timeout 240 $T cgemm 2>&1 | grep -v " OK$" | tail -40
+echo "== sgemm split: round-to-nearest (default) =="; timeout 120 $T precision 2>&1 | grep -E "precision|tmm fp32|cuBLAS fp32 pedantic" | head -20
+timeout 60 $T benchone N N 8192 8192 8192 0
+echo "== sgemm split: hi = raw bits (TMM_TC_SPLIT=trunc) =="; TMM_TC_SPLIT=trunc timeout 120 $T precision 2>&1 | grep -E "precision|tmm fp32" | head -20
+TMM_TC_SPLIT=trunc timeout 60 $T benchone N N 8192 8192 8192 0
+for tt in "N N" "T T"; do TMM_TC_SPLIT=trunc timeout 120 $T check $tt 2>&1 | grep -v " OK$" | tail -5; done
+echo "== regular suite =="; timeout 600 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -8
+echo "== bench =="; timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1
+} 2>&1 | tee gpurun_out/r2_first.txt

@@ -4,6 +4,7 @@
 #include "../include/tiled_mm_b200.h"
 #include <cublas_v2.h>
 #include <cuda_runtime.h>
+#include <cuComplex.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -247,6 +248,69 @@ static void host_gemm(cublasHandle_t h, char ta, char tb, int m, int n, int k, f
     tmm_context_destroy(ctx);
 }
 
+// ---- complex<float>: the tcgen05 embedding (TMM_CMATH_TC) against cuBLAS CGEMM and the SIMT kernel -------------------------
+static void cfill(std::vector<float>& v, unsigned seed, bool ints) { fill(v, seed, ints); }
+
+static int ccheck_bench(cublasHandle_t h, char ta, char tb, int m, int n, int k, float ar_, float ai_, float br_, float bi_, int pad, bool ints, bool timing) {
+    int ar = ta == 'N' ? m : k, ac = ta == 'N' ? k : m, br = tb == 'N' ? k : n, bc = tb == 'N' ? n : k;
+    int lda = ar + pad, ldb = br + pad, ldc = m + pad;
+    std::vector<float> A((size_t)2 * lda * ac), B((size_t)2 * ldb * bc), C((size_t)2 * ldc * n);
+    cfill(A, 5, ints); cfill(B, 6, ints); cfill(C, 7, ints);
+    float *dA, *dB, *dC, *dR;
+    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dC, C.size() * 4)); CK(cudaMalloc(&dR, C.size() * 4));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    const float alpha[2] = {ar_, ai_}, beta[2] = {br_, bi_};
+    const cuComplex ca = make_cuComplex(ar_, ai_), cb = make_cuComplex(br_, bi_);
+    CK(cudaMemcpy(dR, C.data(), C.size() * 4, cudaMemcpyHostToDevice));
+    cublasCgemm(h, op(ta), op(tb), m, n, k, &ca, (const cuComplex*)dA, lda, (const cuComplex*)dB, ldb, &cb, (cuComplex*)dR, ldc);
+    std::vector<float> R(C.size()), O(C.size());
+    CK(cudaMemcpy(R.data(), dR, C.size() * 4, cudaMemcpyDeviceToHost));
+    int bad = 0;
+    for (int mode = 0; mode < 2; ++mode) {
+        tmm_set_c32_math(mode ? TMM_CMATH_TC : TMM_CMATH_SIMT);
+        CK(cudaMemcpy(dC, C.data(), C.size() * 4, cudaMemcpyHostToDevice));
+        int rc = tmm_device_gemm(TMM_C32, ta, tb, m, n, k, alpha, dA, lda, dB, ldb, beta, dC, ldc, nullptr);
+        cudaError_t se = cudaDeviceSynchronize();
+        if (rc || se != cudaSuccess) { printf("cgemm %s %c%c: rc=%d (%s) sync=%s FAIL\n", mode ? "tc" : "simt", ta, tb, rc, tmm_last_error(), cudaGetErrorString(se)); fflush(stdout); exit(2); }
+        CK(cudaMemcpy(O.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost));
+        double err = 0; size_t clobber = 0;
+        for (int j = 0; j < n; ++j) for (int i = 0; i < 2 * ldc; ++i) {
+            size_t idx = (size_t)j * 2 * ldc + i;
+            if (i < 2 * m) { double d = std::fabs((double)O[idx] - (double)R[idx]); if (!(d == d)) d = 1e30; err = std::max(err, d); }
+            else if (O[idx] != C[idx]) ++clobber;
+        }
+        double rel = err / (std::max(1, k) * (ints ? 81.0 : 1.0) * 2);
+        bool ok = rel < 4e-6 && !clobber && (!ints || err == 0);
+        if (!ok) ++bad;
+        double ms = 0;
+        if (timing) {
+            cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+            float best = 1e30f;
+            for (int r = 0; r < 4; ++r) {
+                CK(cudaEventRecord(e0)); tmm_device_gemm(TMM_C32, ta, tb, m, n, k, alpha, dA, lda, dB, ldb, beta, dC, ldc, nullptr); CK(cudaEventRecord(e1));
+                CK(cudaEventSynchronize(e1)); float t; CK(cudaEventElapsedTime(&t, e0, e1)); if (r) best = std::min(best, t);
+            }
+            ms = best;
+        }
+        printf("cgemm %-4s %c%c m=%d n=%d k=%d alpha=(%g,%g) beta=(%g,%g) pad=%d %s vs cuBLAS: max|diff|=%.3e rel=%.2e pad-clobber=%zu %s", mode ? "tc" : "simt", ta, tb, m, n, k,
+               ar_, ai_, br_, bi_, pad, ints ? "ints" : "rand", err, rel, clobber, ok ? "OK" : "FAIL");
+        if (timing) printf("  %.3f ms = %.1f TF (8mnk)", ms, 8.0 * m * (double)n * k / ms * 1e-9);
+        printf("\n"); fflush(stdout);
+    }
+    if (timing) {
+        cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        float best = 1e30f;
+        for (int r = 0; r < 4; ++r) {
+            CK(cudaEventRecord(e0)); cublasCgemm(h, op(ta), op(tb), m, n, k, &ca, (const cuComplex*)dA, lda, (const cuComplex*)dB, ldb, &cb, (cuComplex*)dR, ldc); CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1)); float t; CK(cudaEventElapsedTime(&t, e0, e1)); if (r) best = std::min(best, t);
+        }
+        printf("cgemm cuBLAS %c%c %d %d %d: %.3f ms = %.1f TF (8mnk)\n", ta, tb, m, n, k, best, 8.0 * m * (double)n * k / best * 1e-9);
+    }
+    tmm_set_c32_math(TMM_CMATH_SIMT);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dR);
+    return bad;
+}
+
 int main(int argc, char** argv) {
     std::string mode = argc > 1 ? argv[1] : "check";
     cublasHandle_t h; cublasCreate(&h);
@@ -300,6 +364,22 @@ int main(int argc, char** argv) {
         bench(h, 'N', 'N', 10000, 4800, 512, 1.f);
         bench(h, 'N', 'N', 10000, 2048, 10000, 0.f);
         return 0;
+    }
+    if (mode == "cgemm") {  // all nine op pairs, integer (exact) and random data, padded lds, complex alpha / beta; then timing
+        int bad = 0;
+        const char ops[3] = {'N', 'T', 'C'};
+        cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
+        for (char ta : ops) for (char tb : ops) {
+            bad += ccheck_bench(h, ta, tb, 130, 67, 95, 1.f, -2.f, 2.f, 1.f, 3, true, false);
+            bad += ccheck_bench(h, ta, tb, 777, 530, 1111, 1.5f, -0.5f, 0.25f, 0.f, 1, false, false);
+        }
+        bad += ccheck_bench(h, 'N', 'N', 1000, 1000, 1000, 1.f, 0.f, 0.f, 0.f, 0, false, false);
+        printf("cgemm check: %d failing\n", bad);
+        ccheck_bench(h, 'N', 'N', 8192, 8192, 8192, 1.f, 0.f, 0.f, 0.f, 0, false, true);
+        ccheck_bench(h, 'C', 'N', 8192, 8192, 8192, 1.f, 0.f, 0.f, 0.f, 0, false, true);
+        ccheck_bench(h, 'N', 'T', 8192, 8192, 8192, 1.f, 0.f, 1.f, 0.f, 0, false, true);
+        ccheck_bench(h, 'N', 'N', 10000, 2048, 10000, 1.f, 0.f, 0.f, 0.f, 0, false, true);
+        return bad ? 3 : 0;
     }
     if (mode == "benchone") { bench(h, argv[2][0], argv[3][0], atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), (float)atof(argv[7])); return 0; }
     if (mode == "host") {
