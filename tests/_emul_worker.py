@@ -1,0 +1,139 @@
+"""Worker of tests/test_scheduler_emulated.py: drives the product's REAL scheduler and multi-GPU layer (compiled as plain C++ over the
+CPU emulation in tests/emul/) through the product's own Python binding, and checks every result against the oracle.
+
+  python tests/_emul_worker.py single|grid <n_devices> <direct|nccl>
+
+Test infrastructure: the binding is pointed at tests/emul/_build/libtiledmm_emul.so here, in this process only."""
+import ctypes
+import itertools
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import _util  # noqa: E402
+import tiled_mm_b200 as tmm  # noqa: E402
+
+EMUL = ROOT / "tests" / "emul" / "_build" / "libtiledmm_emul.so"
+tmm.LIB_PATH = EMUL          # test-only redirection of the ctypes binding; the product never does this
+lib = tmm.load_library()
+lib.emul_violations.restype = ctypes.c_uint64
+lib.emul_tma_contract_violations.restype = ctypes.c_uint64
+lib.emul_unpinned_async_copies.restype = ctypes.c_uint64
+lib.emul_first_violation.restype = ctypes.c_char_p
+lib.emul_live_device_bytes.restype = ctypes.c_uint64
+lib.emul_live_device_bytes.argtypes = [ctypes.c_int]
+oracle = _util.Oracle()
+ALL_TT = ["".join(p) for p in itertools.product("NTC", "NTC")]
+
+
+def gen(rng, dtype, count):
+    v = rng.integers(0, 10, count).astype(np.float64)
+    return (v + 1j * rng.integers(0, 10, count)).astype(dtype) if np.dtype(dtype).kind == "c" else v.astype(dtype)
+
+
+def case(ctx, dtype, tt, m, n, k, alpha, beta, pad, copy_modes=(True, False), seed=0, pageable=False):
+    ta, tb = tt
+    ar, ac = _util.stored_shape(ta, m, k); br, bc = _util.stored_shape(tb, k, n)
+    lda, ldb, ldc = ar + pad[0], br + pad[1], m + pad[2]
+    rng = np.random.default_rng(seed)
+    a0, b0, c0 = gen(rng, dtype, lda * ac), gen(rng, dtype, ldb * bc), gen(rng, dtype, ldc * n)
+    expect = oracle.gemm(ta, tb, m, n, k, alpha, a0, lda, b0, ldb, beta, c0.copy(), ldc)
+    if pageable:
+        a, b = a0, b0
+    else:
+        a = tmm.malloc_pinned(dtype, a0.size); a[:] = a0
+        b = tmm.malloc_pinned(dtype, b0.size); b[:] = b0
+    for copy_c_back in copy_modes:
+        c = c0.copy() if pageable else tmm.malloc_pinned(dtype, c0.size)
+        c[:] = c0
+        tmm.gemm(ctx, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, pin_host_buffers=pageable, copy_c_back=copy_c_back)
+        if copy_c_back:
+            assert np.array_equal(np.asarray(c), expect), f"{np.dtype(dtype)} {tt} {m}x{n}x{k} copy-back result differs from the oracle"
+        else:
+            assert np.array_equal(np.asarray(c), c0), "host C written although copy_c_back = false"
+            dev = np.empty(m * n, dtype=dtype)
+            tmm.copy_to_host(ctx.get_full_device_buffer_c().data(), dev, m * n)
+            assert np.array_equal(dev.reshape(n, m), expect.reshape(n, ldc)[:, :m]), f"{tt} device-resident C differs from the oracle"
+    return ctx.last_stats()
+
+
+def check_clean(where):
+    assert lib.emul_violations() == 0, f"{where}: {lib.emul_first_violation().decode()}"
+    assert lib.emul_tma_contract_violations() == 0, f"{where}: the scheduler built a panel outside the TMA contract"
+    assert lib.emul_unpinned_async_copies() == 0, f"{where}: an async copy touched pageable host memory"
+
+
+def run_single():
+    assert tmm.device_count() >= 1
+    es = 8
+    with tmm.make_context(np.float64, 2, 64, 64, 64) as ctx:
+        for tt in ALL_TT:                                                  # resident regime, every op pair, padded lds
+            st = case(ctx, np.float64, tt, 301, 203, 409, 2.0, -1.0, (7, 13, 5), seed=1)
+            assert st.regime == 0 and st.h2d_bytes == es * (301 * 409 + 409 * 203 + 301 * 203), (tt, st.h2d_bytes)
+        check_clean("resident f64")
+        ctx.set_device_budget(4 << 20)                                     # 4 MiB: streaming ring, C super-blocks, two C buffers
+        for tt in ("NN", "TN", "NT", "CC"):
+            st = case(ctx, np.float64, tt, 700, 900, 500, 1.0, 1.0, (3, 5, 7), seed=2)
+            assert st.regime == 1, (tt, st.regime, st.c_blocks)
+        check_clean("streaming f64")
+        ctx.set_device_budget(0)
+        for shape in [(1, 1, 1), (5, 2, 2), (50, 200, 21), (129, 1, 65), (1, 300, 7), (64, 64, 2049)]:
+            case(ctx, np.float64, "TN", *shape, 1.0, 0.0, (0, 0, 0), seed=3)
+        case(ctx, np.float64, "NN", 600, 500, 400, 1.0, 1.0, (1, 2, 3), pageable=True, seed=4)   # cudaHostRegister path, unregistered again after the call
+        case(ctx, np.float64, "NN", 600, 500, 400, 1.0, 1.0, (1, 2, 3), pageable=True, seed=4)
+        check_clean("shapes + pageable")
+    for dtype, alpha, beta in [(np.complex128, 1 - 2j, 2 + 1j), (np.float32, 1.0, 1.0), (np.complex64, 1 + 1j, 1j)]:
+        with tmm.make_context(dtype, 3, 100, 70, 50) as ctx:
+            for tt in ("NN", "CT", "TC"):
+                case(ctx, dtype, tt, 257, 129, 300, alpha, beta, (1, 2, 3), seed=5)
+            ctx.set_device_budget(4 << 20)
+            case(ctx, dtype, "CN", 513, 300, 777, alpha, beta, (2, 0, 1), seed=6)
+    check_clean("other dtypes")
+    assert lib.emul_live_device_bytes(0) == 0, "device memory leaked after the contexts were destroyed"
+    print("EMUL_OK single")
+
+
+def run_grid(n_dev, plane):
+    assert tmm.device_count() == n_dev, tmm.device_count()
+    pr, pc = tmm.grid_shape(n_dev)
+    for dtype, alpha, beta in [(np.float64, 2.0, -1.0), (np.complex128, 1 - 2j, 2 + 1j)]:
+        es = np.dtype(dtype).itemsize
+        with tmm.make_context(dtype, 2, 64, 64, 64) as ctx:
+            ctx.set_devices(n_dev)
+            assert ctx.num_devices() == n_dev
+            for tt in ("NN", "TN", "NT", "CC"):
+                m, n, k = 301, 403, 209
+                st = case(ctx, dtype, tt, m, n, k, alpha, beta, (1, 2, 3), copy_modes=(True,), seed=7)
+                # every shared panel element crosses "PCIe" exactly once over the whole grid, the rest travels GPU to GPU
+                assert st.regime == 0 and st.h2d_bytes == es * (m * k + k * n + m * n), (tt, st.h2d_bytes)
+                want_peer = es * (m * k * (pc - 1) + k * n * (pr - 1))
+                assert st.peer_bytes == want_peer, (tt, st.peer_bytes, want_peer)
+            check_clean(f"grid {pr}x{pc} resident {np.dtype(dtype)}")
+            ctx.set_devices(n_dev)                                         # fresh children
+            ctx.set_device_budget(3 << 20)
+            ctx.set_devices(n_dev)                                         # children inherit the budget: streaming ring + acks
+            for tt in ("NN", "TT"):
+                st = case(ctx, dtype, tt, 900, 700, 1100, alpha, beta, (1, 2, 3), copy_modes=(True,), seed=8)
+                assert st.regime == 1, st.regime
+            check_clean(f"grid {pr}x{pc} streaming {np.dtype(dtype)}")
+            ctx.set_device_budget(0)
+            ctx.set_devices(n_dev)
+            # ragged blocks: fewer rows / columns than a balanced split would like, and a shape too small for the grid
+            for shape in [(pr, pc, 5), (pr + 1, 2 * pc + 1, 33), (7, 200, 64), (1, 1, 1)]:
+                case(ctx, dtype, "NT", *shape, alpha, beta, (0, 1, 0), copy_modes=(True,), seed=9)
+            check_clean(f"grid {pr}x{pc} ragged {np.dtype(dtype)}")
+    for d in range(n_dev):
+        assert lib.emul_live_device_bytes(d) == 0, f"device {d} memory leaked"
+    print(f"EMUL_OK grid {pr}x{pc} {plane}")
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1]
+    if mode == "single":
+        run_single()
+    else:
+        run_grid(int(sys.argv[2]), sys.argv[3])

@@ -1,0 +1,62 @@
+// TEST INFRASTRUCTURE ONLY - never part of the product.
+// Stand-in for the device GEMM layer (csrc/tmm_blas.h: the hand-written sm_100a kernels) when the scheduler runs over the CPU
+// emulation of the CUDA runtime: every launch the scheduler issues is executed by the oracle's GEMM on the "device" operands,
+// after checking what the real kernels rely on - operands inside their allocations, and A/B meeting the TMA contract
+// (16-byte aligned base, pitch a multiple of 16 bytes), which the scheduler promises for every panel it builds.
+#include "../../tiled-mm_b200/csrc/tmm_blas.h"
+
+#include <atomic>
+#include <cctype>
+#include <cstdio>
+
+extern "C" int oracle_gemm_ex(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t lda, const void* b,
+                              int64_t ldb, const void* beta, void* c, int64_t ldc, int wide);
+extern "C" void emul_check_device_range(const void* p, size_t bytes);
+
+namespace {
+std::atomic<uint64_t> g_launches{0}, g_contract_violations{0};
+std::atomic<int> g_f32_mode{3}, g_c32_mode{0};
+}
+
+extern "C" __attribute__((visibility("default"))) uint64_t emul_tma_contract_violations() { return g_contract_violations; }
+
+namespace tmm {
+
+void count_launch() { g_launches.fetch_add(1); }
+uint64_t launch_count() { return g_launches.load(); }
+int sm_count() { return 148; }
+int f32_math_mode() { return g_f32_mode; }
+void set_f32_math_mode(int m) { g_f32_mode = m; }
+int c32_math_mode() { return g_c32_mode; }
+void set_c32_math_mode(int m) { g_c32_mode = m; }
+
+cudaError_t device_scale(int dtype, int64_t m, int64_t n, const void* beta, void* c, int64_t ldc, cudaStream_t) {
+    if (m <= 0 || n <= 0) return cudaSuccess;
+    const size_t es = dtype_size(dtype);
+    emul_check_device_range(c, ((size_t)(n - 1) * ldc + m) * es);
+    // C = beta * C is the GEMM with k = 0
+    count_launch();
+    const double one[2] = {0, 0};
+    return oracle_gemm_ex(dtype, 'N', 'N', m, n, 0, one, c, m > 1 ? m : 1, c, 1, beta, c, ldc, 0) == 0 ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t lda, const void* b,
+                        int64_t ldb, const void* beta, void* c, int64_t ldc, cudaStream_t st) {
+    const char ta = (char)std::toupper((unsigned char)trans_a), tb = (char)std::toupper((unsigned char)trans_b);
+    if ((ta != 'N' && ta != 'T' && ta != 'C') || (tb != 'N' && tb != 'T' && tb != 'C') || m < 0 || n < 0 || k < 0) return cudaErrorInvalidValue;
+    if (m == 0 || n == 0) return cudaSuccess;
+    if (k == 0) return device_scale(dtype, m, n, beta, c, ldc, st);
+    const size_t es = dtype_size(dtype);
+    const int64_t ar = ta == 'N' ? m : k, ac = ta == 'N' ? k : m, br = tb == 'N' ? k : n, bc = tb == 'N' ? n : k;
+    emul_check_device_range(a, ((size_t)(ac - 1) * lda + ar) * es);
+    emul_check_device_range(b, ((size_t)(bc - 1) * ldb + br) * es);
+    emul_check_device_range(c, ((size_t)(n - 1) * ldc + m) * es);
+    if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (((size_t)lda * es) & 15) || (((size_t)ldb * es) & 15)) {
+        g_contract_violations.fetch_add(1);
+        fprintf(stderr, "[emul] operand outside the TMA contract: a %p lda %lld b %p ldb %lld es %zu\n", a, (long long)lda, b, (long long)ldb, es);
+    }
+    count_launch();
+    return oracle_gemm_ex(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, 0) == 0 ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+}  // namespace tmm

@@ -41,7 +41,9 @@ const Api& api() {
     static std::once_flag once;
     std::call_once(once, [] {
         void* h = nullptr;
-        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+        const char* override_path = getenv("TMM_NCCL_LIB");  // explicit path to an NCCL build (default: whatever libnccl.so.2 resolves to)
+        for (const char* name : {override_path, "libnccl.so.2", "libnccl.so"}) {
+            if (!name || !*name) continue;
             h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
             if (h) break;
         }
