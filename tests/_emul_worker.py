@@ -26,6 +26,12 @@ lib.emul_unpinned_async_copies.restype = ctypes.c_uint64
 lib.emul_first_violation.restype = ctypes.c_char_p
 lib.emul_live_device_bytes.restype = ctypes.c_uint64
 lib.emul_live_device_bytes.argtypes = [ctypes.c_int]
+lib.emul_races.restype = ctypes.c_uint64
+lib.emul_first_race.restype = ctypes.c_char_p
+if os.environ.get("TMM_NCCL_LIB"):  # let the race detector see that a blocking collective orders the host threads of its ranks
+    _stub = ctypes.CDLL(os.environ["TMM_NCCL_LIB"], mode=ctypes.RTLD_GLOBAL)
+    _stub.nccl_stub_set_sync_hook(ctypes.cast(lib.emul_collective, ctypes.c_void_p))
+    _stub.nccl_stub_set_stream_hook(ctypes.cast(lib.emul_collective_stream, ctypes.c_void_p))
 oracle = _util.Oracle()
 ALL_TT = ["".join(p) for p in itertools.product("NTC", "NTC")]
 
@@ -65,6 +71,7 @@ def check_clean(where):
     assert lib.emul_violations() == 0, f"{where}: {lib.emul_first_violation().decode()}"
     assert lib.emul_tma_contract_violations() == 0, f"{where}: the scheduler built a panel outside the TMA contract"
     assert lib.emul_unpinned_async_copies() == 0, f"{where}: an async copy touched pageable host memory"
+    assert lib.emul_races() == 0, f"{where}: unordered conflicting accesses (missing dependency in the schedule): {lib.emul_first_race().decode()}"
 
 
 def run_single():

@@ -12,6 +12,8 @@
 extern "C" int oracle_gemm_ex(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t lda, const void* b,
                               int64_t ldb, const void* beta, void* c, int64_t ldc, int wide);
 extern "C" void emul_check_device_range(const void* p, size_t bytes);
+extern "C" int emul_op_begin(void* stream);  // race detector: a launch enters the stream ...
+extern "C" void emul_op_access(int sid, const void* p, size_t pitch, size_t width, size_t height, int write, const char* what);  // ... and touches these regions
 
 namespace {
 std::atomic<uint64_t> g_launches{0}, g_contract_violations{0};
@@ -30,10 +32,14 @@ void set_f32_math_mode(int m) { g_f32_mode = m; }
 int c32_math_mode() { return g_c32_mode; }
 void set_c32_math_mode(int m) { g_c32_mode = m; }
 
-cudaError_t device_scale(int dtype, int64_t m, int64_t n, const void* beta, void* c, int64_t ldc, cudaStream_t) {
+cudaError_t device_scale(int dtype, int64_t m, int64_t n, const void* beta, void* c, int64_t ldc, cudaStream_t st) {
     if (m <= 0 || n <= 0) return cudaSuccess;
     const size_t es = dtype_size(dtype);
     emul_check_device_range(c, ((size_t)(n - 1) * ldc + m) * es);
+    {
+        const int sid = emul_op_begin(st);
+        emul_op_access(sid, c, (size_t)ldc * es, (size_t)m * es, (size_t)n, 1, "scale C");
+    }
     // C = beta * C is the GEMM with k = 0
     count_launch();
     const double one[2] = {0, 0};
@@ -54,6 +60,12 @@ cudaError_t device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_
     if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (((size_t)lda * es) & 15) || (((size_t)ldb * es) & 15)) {
         g_contract_violations.fetch_add(1);
         fprintf(stderr, "[emul] operand outside the TMA contract: a %p lda %lld b %p ldb %lld es %zu\n", a, (long long)lda, b, (long long)ldb, es);
+    }
+    {
+        const int sid = emul_op_begin(st);
+        emul_op_access(sid, a, (size_t)lda * es, (size_t)ar * es, (size_t)ac, 0, "gemm A");
+        emul_op_access(sid, b, (size_t)ldb * es, (size_t)br * es, (size_t)bc, 0, "gemm B");
+        emul_op_access(sid, c, (size_t)ldc * es, (size_t)m * es, (size_t)n, 1, "gemm C");
     }
     count_launch();
     return oracle_gemm_ex(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, 0) == 0 ? cudaSuccess : cudaErrorInvalidValue;

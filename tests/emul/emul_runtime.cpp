@@ -8,6 +8,10 @@
 //     so the host threads that drive different devices synchronise exactly where the GPUs would
 //   * every copy and every GEMM operand is bounds-checked against the allocation it points into ("device" memory is
 //     malloc()ed and NaN-poisoned): an index error in the scheduler is a test failure, not silent corruption
+//   * a happens-before race detector runs underneath: every stream carries a vector clock, events / host synchronisation /
+//     stream memory operations / blocking collectives add the edges CUDA guarantees, and every access to device memory (2-D copy
+//     regions, GEMM operands) is checked against earlier conflicting accesses - a missing cudaStreamWaitEvent in the scheduler,
+//     which on hardware would be an intermittent wrong result, is a deterministic test failure here
 // What it cannot show: timing, real overlap, CUDA IPC between processes (validated on hardware at 2 and 4 GPUs).
 #include <cuda_runtime_api.h>
 
@@ -17,7 +21,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
+#include <string>
+#include <vector>
 #include <mutex>
 #include <thread>
 
@@ -70,6 +77,84 @@ void check_range(const void* p, size_t span, bool device_side, bool async_host) 
 
 size_t span_2d(size_t pitch, size_t width, size_t height) { return height ? (height - 1) * pitch + width : 0; }
 
+// ---- happens-before race detector ----------------------------------------------------------------------------------------
+using Clock = std::vector<uint32_t>;
+void join(Clock& into, const Clock& from) {
+    if (into.size() < from.size()) into.resize(from.size(), 0);
+    for (size_t i = 0; i < from.size(); ++i) if (from[i] > into[i]) into[i] = from[i];
+}
+struct Access { uintptr_t base; size_t pitch, width, height; int stream; uint32_t epoch; bool write; const char* what; };
+std::mutex g_det;
+std::map<cudaStream_t, int> g_stream_id;      // nullptr (legacy stream) is id 0
+std::vector<Clock> g_vc(1);                    // per stream
+std::map<cudaEvent_t, Clock> g_event_vc;
+std::map<int, Clock> g_host_vc;                // per device: the host thread that drives it
+std::map<uintptr_t, std::deque<Access>> g_shadow;  // per device allocation
+std::map<uintptr_t, Clock> g_flag_vc;          // per 32-bit word written by a stream memory operation (or a 4-byte D2D copy of one)
+std::map<const void*, Clock> g_collective;     // per communicator: joined host clocks of its ranks
+std::atomic<uint64_t> g_races{0};
+char g_first_race[512] = "";
+
+int sid_locked(cudaStream_t s) {
+    if (!s) return 0;
+    auto it = g_stream_id.find(s);
+    if (it != g_stream_id.end()) return it->second;
+    const int id = (int)g_vc.size();
+    g_vc.emplace_back();
+    g_stream_id[s] = id;
+    return id;
+}
+// an operation enters stream s: it is ordered after everything the enqueuing host thread has synchronised with
+int begin_op_locked(cudaStream_t s) {
+    const int id = sid_locked(s);
+    join(g_vc[id], g_host_vc[t_device]);
+    if ((int)g_vc[id].size() <= id) g_vc[id].resize(id + 1, 0);
+    ++g_vc[id][id];
+    return id;
+}
+bool rows_overlap(const Access& a, const Access& b) {  // exact test on the 2-D byte sets; iterates the rows of a
+    for (size_t r = 0; r < a.height; ++r) {
+        const uintptr_t lo = a.base + r * a.pitch, hi = lo + a.width;
+        if (hi <= b.base) continue;
+        for (size_t rr = lo > b.base ? (lo - b.base) / b.pitch : 0; rr < b.height; ++rr) {
+            const uintptr_t blo = b.base + rr * b.pitch;
+            if (blo >= hi) break;
+            if (blo + b.width > lo) return true;
+        }
+    }
+    return false;
+}
+bool overlap(const Access& a, const Access& b) {
+    const uintptr_t a_end = a.base + span_2d(a.pitch, a.width, a.height), b_end = b.base + span_2d(b.pitch, b.width, b.height);
+    if (a_end <= b.base || b_end <= a.base) return false;
+    return a.height <= b.height ? rows_overlap(a, b) : rows_overlap(b, a);
+}
+void note_locked(int sid, const void* p, size_t pitch, size_t width, size_t height, bool write, const char* what) {
+    if (!p || !width || !height) return;
+    uintptr_t base = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        const Block* b = find_block(p, 1, &base);
+        if (!b || b->kind != 0 || b->bytes <= 4096) return;  // host memory, or flag / scalar scratch that is synchronisation state itself
+    }
+    Access now{reinterpret_cast<uintptr_t>(p), pitch ? pitch : width, width, height, sid, g_vc[sid][sid], write, what};
+    std::deque<Access>& log = g_shadow[base];
+    const Clock& vc = g_vc[sid];
+    for (const Access& prev : log) {
+        if (prev.stream == sid || (!prev.write && !write)) continue;
+        const uint32_t seen = prev.stream < (int)vc.size() ? vc[prev.stream] : 0;
+        if (seen >= prev.epoch || !overlap(prev, now)) continue;
+        if (g_races.fetch_add(1) == 0)
+            snprintf(g_first_race, sizeof g_first_race, "%s %s on stream %d (op %u) is not ordered after %s %s on stream %d (op %u): %p [%zu x %zu, pitch %zu]",
+                     what, write ? "write" : "read", sid, now.epoch, prev.what, prev.write ? "write" : "read", prev.stream, prev.epoch, p, width, height, now.pitch);
+        fprintf(stderr, "[emul] RACE: %s %s (stream %d) vs earlier %s %s (stream %d) at %p\n", what, write ? "write" : "read", sid, prev.what,
+                prev.write ? "write" : "read", prev.stream, p);
+        break;
+    }
+    log.push_back(now);
+    if (log.size() > 4096) log.pop_front();
+}
+
 }  // namespace
 
 extern "C" {
@@ -89,6 +174,30 @@ EMUL_API uint64_t emul_live_device_bytes(int device) {
     uint64_t s = 0;
     for (auto& kv : g_blocks) if (kv.second.kind == 0 && kv.second.device == device) s += kv.second.bytes;
     return s;
+}
+EMUL_API uint64_t emul_races() { return g_races; }
+EMUL_API const char* emul_first_race() { return g_first_race; }
+// used by the GEMM double: a launch enters `stream`, then declares its operand regions
+EMUL_API int emul_op_begin(void* stream) { std::lock_guard<std::mutex> lk(g_det); return begin_op_locked(static_cast<cudaStream_t>(stream)); }
+EMUL_API void emul_op_access(int sid, const void* p, size_t pitch, size_t width, size_t height, int write, const char* what) {
+    std::lock_guard<std::mutex> lk(g_det);
+    note_locked(sid, p, pitch, width, height, write != 0, what);
+}
+// used by the NCCL stand-in (wired up by the test worker): a blocking collective orders the host threads of its ranks.
+// phase 0 before the rendezvous (contribute), phase 1 after it (everybody has contributed: take the join)
+EMUL_API void emul_collective(const void* comm_group, int phase) {
+    std::lock_guard<std::mutex> lk(g_det);
+    if (phase == 0) join(g_collective[comm_group], g_host_vc[t_device]);
+    else join(g_host_vc[t_device], g_collective[comm_group]);
+}
+// a stream-ordered collective (the NCCL staging data plane): the ranks' streams are joined at the rendezvous, and the collective reads
+// its send buffer before / writes its receive buffer after it
+EMUL_API void emul_collective_stream(const void* comm_group, void* stream, int phase, const void* buf, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_det);
+    static std::map<const void*, Clock> acc;
+    const int sid = begin_op_locked(static_cast<cudaStream_t>(stream));
+    if (phase == 0) { note_locked(sid, buf, bytes, bytes, 1, false, "collective send"); join(acc[comm_group], g_vc[sid]); }
+    else { join(g_vc[sid], acc[comm_group]); note_locked(sid, buf, bytes, bytes, 1, true, "collective recv"); }
 }
 // used by the GEMM double (emul_blas.cpp) to bounds-check operands
 EMUL_API void emul_check_device_range(const void* p, size_t bytes) { check_range(p, bytes, true, false); }
@@ -146,6 +255,7 @@ cudaError_t cudaFree(void* p) {
         if (it == g_blocks.end() || it->second.kind != 0) { violation("cudaFree of a pointer that is not a device allocation", p, 0); return cudaErrorInvalidValue; }
         g_blocks.erase(it);
     }
+    { std::lock_guard<std::mutex> lk(g_det); g_shadow.erase(reinterpret_cast<uintptr_t>(p)); }
     free(p);
     return cudaSuccess;
 }
@@ -198,9 +308,18 @@ static void account(size_t bytes, cudaMemcpyKind kind) {
     else if (kind == cudaMemcpyDeviceToHost) g_d2h += bytes;
     else if (kind == cudaMemcpyDeviceToDevice) g_d2d += bytes;
 }
-static cudaError_t copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind, bool async) {
+static cudaError_t copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind, bool async,
+                           cudaStream_t stream = nullptr, bool host_blocks = false) {
     if (width == 0 || height == 0) return cudaSuccess;
     if (width > dpitch || width > spitch) return cudaErrorInvalidPitchValue;
+    {
+        std::lock_guard<std::mutex> lk(g_det);
+        const int sid = begin_op_locked(stream);
+        note_locked(sid, src, spitch, width, height, false, "copy");
+        note_locked(sid, dst, dpitch, width, height, true, "copy");
+        if (width == 4 && height == 1 && kind == cudaMemcpyDeviceToDevice) g_flag_vc[reinterpret_cast<uintptr_t>(dst)] = g_vc[sid];  // a counter forwarded to a peer
+        if (host_blocks) join(g_host_vc[t_device], g_vc[sid]);
+    }
     const bool dst_dev = kind == cudaMemcpyHostToDevice || kind == cudaMemcpyDeviceToDevice;
     const bool src_dev = kind == cudaMemcpyDeviceToHost || kind == cudaMemcpyDeviceToDevice;
     check_range(dst, span_2d(dpitch, width, height), dst_dev, async);
@@ -210,27 +329,64 @@ static cudaError_t copy_2d(void* dst, size_t dpitch, const void* src, size_t spi
     account(width * height, kind);
     return cudaSuccess;
 }
-cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) { return copy_2d(dst, bytes, src, bytes, bytes, 1, kind, false); }
-cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t) { return copy_2d(dst, bytes, src, bytes, bytes, 1, kind, false); }
-cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind, cudaStream_t) {
-    return copy_2d(dst, dpitch, src, spitch, width, height, kind, true);
+cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) { return copy_2d(dst, bytes, src, bytes, bytes, 1, kind, false, nullptr, true); }
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) { return copy_2d(dst, bytes, src, bytes, bytes, 1, kind, false, s); }
+cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind, cudaStream_t s) {
+    return copy_2d(dst, dpitch, src, spitch, width, height, kind, true, s);
 }
-cudaError_t cudaMemset(void* p, int v, size_t bytes) { check_range(p, bytes, true, false); memset(p, v, bytes); return cudaSuccess; }
+cudaError_t cudaMemset(void* p, int v, size_t bytes) {
+    check_range(p, bytes, true, false);
+    {
+        std::lock_guard<std::mutex> lk(g_det);
+        const int sid = begin_op_locked(nullptr);
+        note_locked(sid, p, bytes, bytes, 1, true, "memset");
+        join(g_host_vc[t_device], g_vc[sid]);
+    }
+    memset(p, v, bytes);
+    return cudaSuccess;
+}
 
 // ---- streams and events: everything already happened when it was enqueued -----------------------------------------------
 cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = reinterpret_cast<cudaStream_t>(malloc(8)); return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) {
+    { std::lock_guard<std::mutex> lk(g_det); g_stream_id.erase(s); }  // the id (and its clock slot) is retired, never reused
+    free(s);
+    return cudaSuccess;
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t s) {  // the host now knows everything enqueued on s has happened
+    std::lock_guard<std::mutex> lk(g_det);
+    join(g_host_vc[t_device], g_vc[sid_locked(s)]);
+    return cudaSuccess;
+}
+cudaError_t cudaStreamQuery(cudaStream_t s) { return cudaStreamSynchronize(s); }  // always "done" here, which is the same knowledge
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) {
+    // self-test of the detector (tests/test_scheduler_emulated.py): with TMM_EMUL_DROP_WAITS=1 every event wait is ignored, i.e.
+    // the schedule loses its cross-stream dependencies, and the detector must report races
+    static const bool drop = [] { const char* v = getenv("TMM_EMUL_DROP_WAITS"); return v && v[0] == '1'; }();
+    if (drop) return cudaSuccess;
+    std::lock_guard<std::mutex> lk(g_det);
+    auto it = g_event_vc.find(e);
+    if (it != g_event_vc.end()) join(g_vc[sid_locked(s)], it->second);  // an event that was never recorded orders nothing (CUDA semantics)
+    return cudaSuccess;
+}
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = reinterpret_cast<cudaEvent_t>(malloc(8)); return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
-cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) {
+    { std::lock_guard<std::mutex> lk(g_det); g_event_vc.erase(e); }
+    free(e);
+    return cudaSuccess;
+}
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_det);
+    const int id = sid_locked(s);
+    join(g_vc[id], g_host_vc[t_device]);
+    g_event_vc[e] = g_vc[id];
+    return cudaSuccess;
+}
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 
 // ---- stream memory operations (driver API, handed out through cudaGetDriverEntryPoint) -----------------------------------
-static int emul_wait_value32(cudaStream_t, unsigned long long addr, unsigned value, unsigned /*flags: GEQ*/) {
+static int emul_wait_value32(cudaStream_t stream, unsigned long long addr, unsigned value, unsigned /*flags: GEQ*/) {
     volatile uint32_t* p = reinterpret_cast<volatile uint32_t*>(static_cast<uintptr_t>(addr));
     const auto t0 = std::chrono::steady_clock::now();
     while ((int32_t)(*p - value) < 0) {
@@ -241,9 +397,20 @@ static int emul_wait_value32(cudaStream_t, unsigned long long addr, unsigned val
         }
     }
     std::atomic_thread_fence(std::memory_order_seq_cst);
+    {   // acquire: later work on this stream is ordered after whatever raised the counter
+        std::lock_guard<std::mutex> lk(g_det);
+        const int sid = begin_op_locked(stream);
+        auto it = g_flag_vc.find(static_cast<uintptr_t>(addr));
+        if (it != g_flag_vc.end()) join(g_vc[sid], it->second);
+    }
     return 0;
 }
-static int emul_write_value32(cudaStream_t, unsigned long long addr, unsigned value, unsigned) {
+static int emul_write_value32(cudaStream_t stream, unsigned long long addr, unsigned value, unsigned) {
+    {   // release: the counter carries everything enqueued on this stream so far
+        std::lock_guard<std::mutex> lk(g_det);
+        const int sid = begin_op_locked(stream);
+        g_flag_vc[static_cast<uintptr_t>(addr)] = g_vc[sid];
+    }
     std::atomic_thread_fence(std::memory_order_seq_cst);
     *reinterpret_cast<volatile uint32_t*>(static_cast<uintptr_t>(addr)) = value;
     return 0;

@@ -2,7 +2,9 @@
 run over a CPU emulation of the CUDA runtime (tests/emul/): every copy and every GEMM operand is bounds-checked, the GEMM launches
 are executed by the oracle, and results must be bit-exact.  This is the only place the 2x4 (8-GPU) grid, both data planes
 (peer DMA push with arrival / ack counters, NCCL staging) and the streaming ring with acknowledgements can be exercised without
-an 8-GPU box; on hardware the same code was run at 1, 2 and 4 GPUs (profiles/r1_final_*).  Test infrastructure only."""
+an 8-GPU box; on hardware the same code was run at 1, 2 and 4 GPUs (profiles/r1_final_*).  Underneath runs a vector-clock
+happens-before race detector over all device-memory accesses (it found a write-after-read hazard on the ring slot's own share in
+the streaming grid path, fixed in csrc/tmm_dist.cu `slot_pushed`).  Test infrastructure only."""
 import os
 import subprocess
 import sys
@@ -22,12 +24,15 @@ def emul_build():
     return EMUL / "_build"
 
 
-def _worker(build, args, devices, extra_env=None):
+def _worker(build, args, devices, extra_env=None, expect_failure=None):
     env = dict(os.environ)
     env.update({"TMM_EMUL_DEVICES": str(devices), "TMM_EMUL_MEM_MB": "2048", "TMM_NCCL_LIB": str(build / "libnccl.so.2"), "TMM_DIST_TIMEOUT_S": "60"})
     env.pop("TMM_DIST_NCCL", None)
     env.update(extra_env or {})
     r = subprocess.run([sys.executable, str(ROOT / "tests" / "_emul_worker.py"), *map(str, args)], capture_output=True, text=True, env=env, timeout=900)
+    if expect_failure:
+        assert r.returncode != 0 and expect_failure in r.stderr, (r.stdout[-2000:], r.stderr[-4000:])
+        return
     assert r.returncode == 0 and "EMUL_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
 
 
@@ -35,6 +40,12 @@ def test_single_gpu_scheduler_on_emulated_runtime(emul_build):
     """resident and streaming regimes, all op pairs, four types, degenerate shapes, pageable buffers; no out-of-bounds access, no
     panel outside the TMA contract, no async copy from pageable memory, no device memory left behind"""
     _worker(emul_build, ["single"], 1)
+
+
+def test_race_detector_catches_a_schedule_without_event_waits(emul_build):
+    """Mutation check of the happens-before detector underneath all of these tests: with every cudaStreamWaitEvent ignored, the very
+    same schedule must be reported as racy (H2D -> GEMM -> D2H dependencies are gone)."""
+    _worker(emul_build, ["single"], 1, {"TMM_EMUL_DROP_WAITS": "1"}, expect_failure="unordered conflicting accesses")
 
 
 @pytest.mark.parametrize("devices", [2, 3, 4, 6, 8])

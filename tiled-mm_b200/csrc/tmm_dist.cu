@@ -229,6 +229,7 @@ void link_teardown(Link& link) {
 
 int link_bind(tmm_context* ctx, Link& link, DevBuf& buf) {
     if (!link.active() || !link.direct) return TMM_OK;
+    for (auto& ev : link.slot_pushed) ev = nullptr;  // events come from the per-call pool
     std::vector<BufMsg> all;
     int rc = gather_msgs(ctx, link, describe(ctx, buf.p, buf.cap), all);
     if (rc) return rc;
@@ -310,6 +311,9 @@ static int dist_push(tmm_context* ctx, Link& link, size_t es, const char* src, i
             for (int g = 0; g < parts; ++g)
                 if (g != me) { int rc = wait_geq(ctx->s_comm, link.flags + parts + g, last); if (rc) return rc; }
         link.slot_last[ring_slot & 7] = ++link.ring_sent;
+        // ... and my own previous push out of this slot must have read my share before the next upload overwrites it (found by the
+        // race detector of tests/emul: the GEMM that frees the slot waits for the peers' shares, not for my outgoing copies)
+        if (link.slot_pushed[ring_slot & 7]) TMM_CU(cudaStreamWaitEvent(ctx->s_h2d, link.slot_pushed[ring_slot & 7], 0));
     }
     const uint32_t x = ++link.sent;
     TMM_DBG("dev %d push #%u: %lld x %lld, my columns [%lld,%lld), %d peers, slot %d", ctx->device, x, (long long)rows, (long long)cols, (long long)lo, (long long)hi, parts - 1, ring_slot);
@@ -342,6 +346,10 @@ static int dist_push(tmm_context* ctx, Link& link, size_t es, const char* src, i
         if (rc) return rc;
         for (int g = 0; g < parts; ++g)
             if (g != me) TMM_CU(cudaMemcpyAsync(link.peer_flags[g] + me, word, 4, cudaMemcpyDeviceToDevice, ctx->s_comm));
+    }
+    if (ring_slot >= 0) {
+        TMM_CU(ctx->get_event(&link.slot_pushed[ring_slot & 7]));
+        TMM_CU(cudaEventRecord(link.slot_pushed[ring_slot & 7], ctx->s_comm));
     }
     return TMM_OK;
 }

@@ -83,6 +83,7 @@ struct Link {
     uint32_t sent = 0;                     // exchanges issued on this link since attach (the same number on all its ranks)
     uint32_t ring_sent = 0, acked = 0;     // streaming ring: exchanges into ring slots / exchanges consumed here
     uint32_t slot_last[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ring exchange number that last filled each ring slot
+    cudaEvent_t slot_pushed[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // per call: my push out of each ring slot has finished
     bool active() const { return parts > 1; }
 };
 
