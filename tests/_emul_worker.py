@@ -138,9 +138,51 @@ def run_grid(n_dev, plane):
     print(f"EMUL_OK grid {pr}x{pc} {plane}")
 
 
+def run_dry(n_dev):
+    """Full-size walk through the real scheduler with address-only memory (TMM_EMUL_DRY=1): BASELINE configs[3] and [4] and a C that
+    needs super-blocks.  No arithmetic, no data movement - bounds, 64-bit offsets, ordering, protocol progress and byte counts."""
+    assert lib.emul_dry_run() == 1 and tmm.device_count() == n_dev
+    pr, pc = tmm.grid_shape(n_dev)
+    A, B, C = 0x200000000000, 0x300000000000, 0x400000000000      # host "buffers": never dereferenced in a dry run
+    cases = [
+        ("C5 dgemm 100000^3", np.float64, "NN", 100000, 100000, 100000, 0.0),
+        ("C4 zgemm 20000x20000x500000", np.complex128, "NN", 20000, 20000, 500000, 0.0),
+        ("C4 zgemm CN beta=1", np.complex128, "CN", 20000, 20000, 500000, 1.0),
+        ("dgemm TN 150000x130000x30000 (C alone exceeds one HBM)", np.float64, "TN", 150000, 130000, 30000, 1.0),
+    ]
+    for name, dtype, tt, m, n, k, beta in cases:
+        es = np.dtype(dtype).itemsize
+        ta, tb = tt
+        lda = (m if ta == "N" else k) + 8
+        ldb = (k if tb == "N" else n) + 8
+        ldc = m + 8
+        with tmm.make_context(dtype, 2, 5000, 5000, 5000) as ctx:
+            if n_dev > 1:
+                ctx.set_devices(n_dev)
+            tmm.gemm(ctx, ta, tb, m, n, k, 1.0, A, lda, B, ldb, beta, C, ldc, pin_host_buffers=False, copy_c_back=True)
+            st = ctx.last_stats()
+            abc = es * (m * k + k * n + (m * n if beta != 0 else 0))
+            assert st.d2h_bytes == es * m * n, (name, st.d2h_bytes)
+            if st.regime == 0:    # resident on every GPU: each element crosses PCIe once over the whole grid
+                assert st.h2d_bytes == abc, (name, st.h2d_bytes, abc)
+                assert st.peer_bytes == es * (m * k * (pc - 1) + k * n * (pr - 1)), (name, st.peer_bytes)
+            else:                 # streaming: panels are re-sent once per row / column of C super-blocks
+                assert st.h2d_bytes >= abc and st.h2d_bytes % es == 0, (name, st.h2d_bytes, abc)
+            print(f"  dry {name} on {pr}x{pc}: regime {st.regime}, {st.kernel_launches} launches, {st.c_blocks} C blocks, {st.k_chunks} k-chunks, "
+                  f"H2D {st.h2d_bytes / 1e9:.1f} GB, D2H {st.d2h_bytes / 1e9:.1f} GB, NVLink {st.peer_bytes / 1e9:.1f} GB", flush=True)
+        assert lib.emul_violations() == 0, f"{name}: {lib.emul_first_violation().decode()}"
+        assert lib.emul_tma_contract_violations() == 0, name
+        assert lib.emul_races() == 0, f"{name}: {lib.emul_first_race().decode()}"
+    for d in range(n_dev):
+        assert lib.emul_live_device_bytes(d) == 0
+    print(f"EMUL_OK dry {pr}x{pc}")
+
+
 if __name__ == "__main__":
     mode = sys.argv[1]
-    if mode == "single":
+    if mode == "dry":
+        run_dry(int(sys.argv[2]))
+    elif mode == "single":
         run_single()
     else:
         run_grid(int(sys.argv[2]), sys.argv[3])

@@ -12,6 +12,7 @@
 extern "C" int oracle_gemm_ex(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t lda, const void* b,
                               int64_t ldb, const void* beta, void* c, int64_t ldc, int wide);
 extern "C" void emul_check_device_range(const void* p, size_t bytes);
+extern "C" int emul_dry_run();  // address-only run: check and count, do not compute
 extern "C" int emul_op_begin(void* stream);  // race detector: a launch enters the stream ...
 extern "C" void emul_op_access(int sid, const void* p, size_t pitch, size_t width, size_t height, int write, const char* what);  // ... and touches these regions
 
@@ -43,6 +44,7 @@ cudaError_t device_scale(int dtype, int64_t m, int64_t n, const void* beta, void
     // C = beta * C is the GEMM with k = 0
     count_launch();
     const double one[2] = {0, 0};
+    if (emul_dry_run()) return cudaSuccess;
     return oracle_gemm_ex(dtype, 'N', 'N', m, n, 0, one, c, m > 1 ? m : 1, c, 1, beta, c, ldc, 0) == 0 ? cudaSuccess : cudaErrorInvalidValue;
 }
 
@@ -68,6 +70,7 @@ cudaError_t device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_
         emul_op_access(sid, c, (size_t)ldc * es, (size_t)m * es, (size_t)n, 1, "gemm C");
     }
     count_launch();
+    if (emul_dry_run()) return cudaSuccess;
     return oracle_gemm_ex(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, 0) == 0 ? cudaSuccess : cudaErrorInvalidValue;
 }
 

@@ -46,6 +46,17 @@ size_t device_total() {
     return b;
 }
 
+// Dry run (TMM_EMUL_DRY=1): allocations above 64 KiB are address ranges without backing store, copies and launches are checked
+// (bounds, ordering, byte counts) but move no data - the full-size out-of-core configurations (100000^3 on 8 x 180 GB) can then be
+// walked through the real scheduler in seconds.  Small allocations (flags, scalars) stay real: the protocol dereferences them.
+bool dry_run() {
+    static const bool on = [] { const char* v = getenv("TMM_EMUL_DRY"); return v && v[0] == '1'; }();
+    return on;
+}
+constexpr size_t DRY_REAL_LIMIT = 64 << 10;
+std::atomic<uintptr_t> g_virtual_next{0x100000000000ull};
+bool is_virtual(const void* p) { return reinterpret_cast<uintptr_t>(p) >= 0x100000000000ull && reinterpret_cast<uintptr_t>(p) < 0x700000000000ull && dry_run(); }
+
 void violation(const char* what, const void* p, size_t bytes) {
     if (g_violations.fetch_add(1) == 0) snprintf(g_first_violation, sizeof g_first_violation, "%s: %p + %zu", what, p, bytes);
     fprintf(stderr, "[emul] VIOLATION %s: %p + %zu bytes\n", what, p, bytes);
@@ -127,6 +138,13 @@ bool rows_overlap(const Access& a, const Access& b) {  // exact test on the 2-D 
 bool overlap(const Access& a, const Access& b) {
     const uintptr_t a_end = a.base + span_2d(a.pitch, a.width, a.height), b_end = b.base + span_2d(b.pitch, b.width, b.height);
     if (a_end <= b.base || b_end <= a.base) return false;
+    if (a.pitch == b.pitch && a.width <= a.pitch && b.width <= b.pitch) {
+        // same pitch (the common case: two sub-blocks of one panel): compare as rectangles on the pitch grid anchored at the lower base
+        const uintptr_t org = a.base < b.base ? a.base : b.base;
+        const size_t ra = (a.base - org) / a.pitch, ca = (a.base - org) % a.pitch, rb = (b.base - org) / b.pitch, cb = (b.base - org) % b.pitch;
+        if (ca + a.width <= a.pitch && cb + b.width <= b.pitch)
+            return ra < rb + b.height && rb < ra + a.height && ca < cb + b.width && cb < ca + a.width;
+    }
     return a.height <= b.height ? rows_overlap(a, b) : rows_overlap(b, a);
 }
 void note_locked(int sid, const void* p, size_t pitch, size_t width, size_t height, bool write, const char* what) {
@@ -175,6 +193,7 @@ EMUL_API uint64_t emul_live_device_bytes(int device) {
     for (auto& kv : g_blocks) if (kv.second.kind == 0 && kv.second.device == device) s += kv.second.bytes;
     return s;
 }
+EMUL_API int emul_dry_run() { return dry_run() ? 1 : 0; }
 EMUL_API uint64_t emul_races() { return g_races; }
 EMUL_API const char* emul_first_race() { return g_first_race; }
 // used by the GEMM double: a launch enters `stream`, then declares its operand regions
@@ -239,9 +258,13 @@ cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) {
 cudaError_t cudaMalloc(void** p, size_t bytes) {
     if (emul_live_device_bytes(t_device) + bytes > device_total()) { *p = nullptr; return cudaErrorMemoryAllocation; }
     void* q = nullptr;
-    if (posix_memalign(&q, 256, bytes ? bytes : 1)) { *p = nullptr; return cudaErrorMemoryAllocation; }
-    const uint64_t nan64 = 0x7ff8dead7fc0beefULL;  // NaN as double, and as two floats: reads of never-written device memory show up
-    for (size_t i = 0; i + 8 <= bytes; i += 8) memcpy(static_cast<char*>(q) + i, &nan64, 8);
+    if (dry_run() && bytes > DRY_REAL_LIMIT) {
+        q = reinterpret_cast<void*>(g_virtual_next.fetch_add((bytes + 0xFFFFF) & ~uintptr_t(0xFFFFF)));  // address range only
+    } else {
+        if (posix_memalign(&q, 256, bytes ? bytes : 1)) { *p = nullptr; return cudaErrorMemoryAllocation; }
+        const uint64_t nan64 = 0x7ff8dead7fc0beefULL;  // NaN as double, and as two floats: reads of never-written device memory show up
+        for (size_t i = 0; i + 8 <= bytes; i += 8) memcpy(static_cast<char*>(q) + i, &nan64, 8);
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     g_blocks[reinterpret_cast<uintptr_t>(q)] = Block{bytes ? bytes : 1, t_device, 0};
     *p = q;
@@ -256,7 +279,7 @@ cudaError_t cudaFree(void* p) {
         g_blocks.erase(it);
     }
     { std::lock_guard<std::mutex> lk(g_det); g_shadow.erase(reinterpret_cast<uintptr_t>(p)); }
-    free(p);
+    if (!is_virtual(p)) free(p);
     return cudaSuccess;
 }
 cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) {
@@ -324,7 +347,8 @@ static cudaError_t copy_2d(void* dst, size_t dpitch, const void* src, size_t spi
     const bool src_dev = kind == cudaMemcpyDeviceToHost || kind == cudaMemcpyDeviceToDevice;
     check_range(dst, span_2d(dpitch, width, height), dst_dev, async);
     check_range(src, span_2d(spitch, width, height), src_dev, async);
-    for (size_t r = 0; r < height; ++r) memcpy(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, width);
+    if (!dry_run() || (width * height <= 4096 && !is_virtual(dst) && !is_virtual(src)))  // dry run: only the protocol's own words move
+        for (size_t r = 0; r < height; ++r) memcpy(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, width);
     std::atomic_thread_fence(std::memory_order_seq_cst);
     account(width * height, kind);
     return cudaSuccess;
@@ -342,7 +366,7 @@ cudaError_t cudaMemset(void* p, int v, size_t bytes) {
         note_locked(sid, p, bytes, bytes, 1, true, "memset");
         join(g_host_vc[t_device], g_vc[sid]);
     }
-    memset(p, v, bytes);
+    if (!is_virtual(p)) memset(p, v, bytes);
     return cudaSuccess;
 }
 

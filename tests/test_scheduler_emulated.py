@@ -58,3 +58,12 @@ def test_gpu_grid_dma_push_on_emulated_runtime(emul_build, devices):
 def test_gpu_grid_nccl_staging_on_emulated_runtime(emul_build, devices):
     """same, with the NCCL all-gather staging ring as data plane (TMM_DIST_NCCL=1)"""
     _worker(emul_build, ["grid", devices, "nccl"], devices, {"TMM_DIST_NCCL": "1"})
+
+
+@pytest.mark.parametrize("devices", [1, 2, 4, 8])
+def test_full_size_configs_dry_run(emul_build, devices):
+    """BASELINE configs[3] (zgemm 20000 x 20000 x 500000) and configs[4] (dgemm 100000^3, 240 GB) plus a C that exceeds one HBM, walked
+    through the real scheduler on `devices` emulated 180 GB GPUs with address-only memory: every copy / launch is bounds- and
+    order-checked with its real 64-bit offsets, the exchange protocol must make progress, and each A / B / C element must cross the
+    host link exactly once whenever the per-GPU share fits (resident regime)."""
+    _worker(emul_build, ["dry", devices], devices, {"TMM_EMUL_DRY": "1", "TMM_EMUL_MEM_MB": "182000"})
