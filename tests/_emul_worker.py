@@ -41,13 +41,15 @@ def gen(rng, dtype, count):
     return (v + 1j * rng.integers(0, 10, count)).astype(dtype) if np.dtype(dtype).kind == "c" else v.astype(dtype)
 
 
-def case(ctx, dtype, tt, m, n, k, alpha, beta, pad, copy_modes=(True, False), seed=0, pageable=False):
+def case(ctx, dtype, tt, m, n, k, alpha, beta, pad, copy_modes=(True, False), seed=0, pageable=False, nan_c=False):
     ta, tb = tt
     ar, ac = _util.stored_shape(ta, m, k); br, bc = _util.stored_shape(tb, k, n)
     lda, ldb, ldc = ar + pad[0], br + pad[1], m + pad[2]
     rng = np.random.default_rng(seed)
     a0, b0, c0 = gen(rng, dtype, lda * ac), gen(rng, dtype, ldb * bc), gen(rng, dtype, ldc * n)
-    expect = oracle.gemm(ta, tb, m, n, k, alpha, a0, lda, b0, ldb, beta, c0.copy(), ldc)
+    if nan_c:  # beta == 0: C must never be read (reference tiled_mm.cpp:325)
+        c0[:] = np.nan
+    expect = oracle.gemm(ta.upper(), tb.upper(), m, n, k, alpha, a0, lda, b0, ldb, beta, c0.copy(), ldc)
     if pageable:
         a, b = a0, b0
     else:
@@ -58,9 +60,9 @@ def case(ctx, dtype, tt, m, n, k, alpha, beta, pad, copy_modes=(True, False), se
         c[:] = c0
         tmm.gemm(ctx, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, pin_host_buffers=pageable, copy_c_back=copy_c_back)
         if copy_c_back:
-            assert np.array_equal(np.asarray(c), expect), f"{np.dtype(dtype)} {tt} {m}x{n}x{k} copy-back result differs from the oracle"
+            assert np.array_equal(np.asarray(c), expect, equal_nan=True), f"{np.dtype(dtype)} {tt} {m}x{n}x{k} copy-back result differs from the oracle"
         else:
-            assert np.array_equal(np.asarray(c), c0), "host C written although copy_c_back = false"
+            assert np.array_equal(np.asarray(c), c0, equal_nan=True), "host C written although copy_c_back = false"
             dev = np.empty(m * n, dtype=dtype)
             tmm.copy_to_host(ctx.get_full_device_buffer_c().data(), dev, m * n)
             assert np.array_equal(dev.reshape(n, m), expect.reshape(n, ldc)[:, :m]), f"{tt} device-resident C differs from the oracle"
@@ -138,6 +140,47 @@ def run_grid(n_dev, plane):
     print(f"EMUL_OK grid {pr}x{pc} {plane}")
 
 
+def run_sweep(n_dev, n_cases, seed):
+    """Randomised sweep in the manner of the one that pinned the reference's valid domain: random element type, op
+    pair (upper / lower case), dims 1-260, ld padding 0-5, alpha / beta (incl. beta = 0 over a NaN-filled C), tile hints 1-300, 1-4
+    streams, both copy modes, tight device budgets (streaming regime with C super-blocks), contexts REUSED across calls."""
+    rng = np.random.default_rng(seed)
+    dtypes = [np.float64, np.complex128, np.float32, np.complex64]
+    done = 0
+    while done < n_cases:
+        dtype = dtypes[int(rng.integers(0, 4))]
+        cplx = np.dtype(dtype).kind == "c"
+        ctx = tmm.make_context(dtype, int(rng.integers(1, 5)), *(int(x) for x in rng.integers(1, 300, 3)))
+        if n_dev > 1:
+            ctx.set_devices(n_dev)
+        for _ in range(int(rng.integers(3, 9))):                      # several calls on one context: grow and shrink
+            if n_dev == 1 or rng.random() < 0.5:
+                budget = int(rng.choice([0, 0, 96 << 10, 256 << 10, 1 << 20]))
+                ctx.set_device_budget(budget)
+                if n_dev > 1:
+                    ctx.set_devices(n_dev)                           # children pick the budget up when they are created
+            tt = "".join(rng.choice(list("NTCntc"), 2))
+            m, n, k = (int(x) for x in rng.integers(1, 261, 3))
+            if rng.random() < 0.15:
+                k = int(rng.integers(1, 2500))                        # long k: many chunks
+            pad = tuple(int(x) for x in rng.integers(0, 6, 3))
+            alpha = complex(*rng.integers(-2, 3, 2)) if cplx else float(rng.integers(-2, 3))
+            beta = [0.0, 1.0, complex(1, -1) if cplx else -1.5][int(rng.integers(0, 3))]
+            modes = (True,) if n_dev > 1 else ((True, False) if rng.random() < 0.5 else (bool(rng.integers(0, 2)),))
+            try:
+                nan_c = beta == 0.0
+                case(ctx, dtype, tt, m, n, k, alpha, beta, pad, copy_modes=modes, seed=int(rng.integers(0, 1 << 30)), pageable=rng.random() < 0.2, nan_c=nan_c)
+            except RuntimeError as e:
+                if "budget too small" not in str(e):
+                    raise
+            done += 1
+        ctx.close()
+        check_clean(f"sweep seed {seed} after {done} cases ({np.dtype(dtype)}, {n_dev} devices)")
+    for d in range(n_dev):
+        assert lib.emul_live_device_bytes(d) == 0
+    print(f"EMUL_OK sweep {n_dev} devices, {done} cases")
+
+
 def run_dry(n_dev):
     """Full-size walk through the real scheduler with address-only memory (TMM_EMUL_DRY=1): BASELINE configs[3] and [4] and a C that
     needs super-blocks.  No arithmetic, no data movement - bounds, 64-bit offsets, ordering, protocol progress and byte counts."""
@@ -182,6 +225,8 @@ if __name__ == "__main__":
     mode = sys.argv[1]
     if mode == "dry":
         run_dry(int(sys.argv[2]))
+    elif mode == "sweep":
+        run_sweep(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
     elif mode == "single":
         run_single()
     else:

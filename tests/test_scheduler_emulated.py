@@ -67,3 +67,10 @@ def test_full_size_configs_dry_run(emul_build, devices):
     order-checked with its real 64-bit offsets, the exchange protocol must make progress, and each A / B / C element must cross the
     host link exactly once whenever the per-GPU share fits (resident regime)."""
     _worker(emul_build, ["dry", devices], devices, {"TMM_EMUL_DRY": "1", "TMM_EMUL_MEM_MB": "182000"})
+
+
+@pytest.mark.parametrize("devices,cases,seed,plane", [(1, 600, 11, "direct"), (2, 80, 12, "direct"), (4, 80, 13, "direct"), (8, 80, 14, "direct"), (6, 60, 15, "nccl")])
+def test_randomised_sweep_on_emulated_runtime(emul_build, devices, cases, seed, plane):
+    """random types / ops / shapes / lds / scalars / tile hints / budgets / copy modes on reused contexts, bit-exact against the oracle,
+    with bounds, TMA-contract and race checks on (the way SURVEY pinned the reference's own valid domain, turned on this library)"""
+    _worker(emul_build, ["sweep", devices, cases, seed], devices, {"TMM_DIST_NCCL": "1"} if plane == "nccl" else None)
