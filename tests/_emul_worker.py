@@ -181,6 +181,23 @@ def run_sweep(n_dev, n_cases, seed):
     print(f"EMUL_OK sweep {n_dev} devices, {done} cases")
 
 
+def run_replan():
+    """Free HBM shrinks between two calls (another allocation appears): the cached budget is stale, a panel allocation fails before
+    anything is enqueued, and the call must recover by re-planning into the streaming regime instead of failing."""
+    with tmm.make_context(np.float64, 2, 5000, 5000, 5000) as ctx:
+        st = case(ctx, np.float64, "NN", 500, 500, 500, 1.0, 1.0, (0, 0, 0), copy_modes=(True,), seed=1)
+        assert st.regime == 0
+        foreign = tmm.malloc_device(14 << 20)                         # somebody else takes 14 of the 32 MiB
+        st = case(ctx, np.float64, "TN", 900, 900, 900, 2.0, -1.0, (1, 2, 3), copy_modes=(True,), seed=2)
+        assert st.regime == 1, "expected the retry to land in the streaming regime"
+        st = case(ctx, np.float64, "NT", 900, 900, 900, 1.0, 0.0, (0, 0, 0), copy_modes=(True, False), seed=3)   # budget now re-read: no failure
+        tmm.free_device(foreign)
+        st = case(ctx, np.float64, "NN", 300, 300, 300, 1.0, 1.0, (0, 0, 0), copy_modes=(True,), seed=4)
+        check_clean("re-plan after allocation failure")
+    assert lib.emul_live_device_bytes(0) == 0
+    print("EMUL_OK replan")
+
+
 def run_dry(n_dev):
     """Full-size walk through the real scheduler with address-only memory (TMM_EMUL_DRY=1): BASELINE configs[3] and [4] and a C that
     needs super-blocks.  No arithmetic, no data movement - bounds, 64-bit offsets, ordering, protocol progress and byte counts."""
@@ -223,7 +240,9 @@ def run_dry(n_dev):
 
 if __name__ == "__main__":
     mode = sys.argv[1]
-    if mode == "dry":
+    if mode == "replan":
+        run_replan()
+    elif mode == "dry":
         run_dry(int(sys.argv[2]))
     elif mode == "sweep":
         run_sweep(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))

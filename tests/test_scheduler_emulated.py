@@ -74,3 +74,8 @@ def test_randomised_sweep_on_emulated_runtime(emul_build, devices, cases, seed, 
     """random types / ops / shapes / lds / scalars / tile hints / budgets / copy modes on reused contexts, bit-exact against the oracle,
     with bounds, TMA-contract and race checks on (the way SURVEY pinned the reference's own valid domain, turned on this library)"""
     _worker(emul_build, ["sweep", devices, cases, seed], devices, {"TMM_DIST_NCCL": "1"} if plane == "nccl" else None)
+
+
+def test_replan_when_free_memory_shrinks_between_calls(emul_build):
+    """a device allocation that fails before anything is enqueued is recovered by releasing staging storage and re-planning"""
+    _worker(emul_build, ["replan"], 1, {"TMM_EMUL_MEM_MB": "32"})

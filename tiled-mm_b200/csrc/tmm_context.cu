@@ -678,7 +678,10 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
         if (!rc && c_touched) rc = pin(ctx, c, (size_t)ld_c * n * cl.es, pinned_now);
     }
 
-    if (!rc) {
+    // Planning and enqueue.  A device allocation can fail although the plan fitted the budget (the budget is a cached reading of free
+    // HBM, and somebody else may have allocated since): before anything has been enqueued that is recoverable - give back this
+    // context's panel / ring / C storage, re-read the free memory and plan again (typically into the streaming regime).  Once.
+    for (int attempt = 0; !rc && attempt < 2; ++attempt) {
         const int64_t align = 128 / (int64_t)cl.es;
         void* dC = nullptr;
         int64_t ldc_dev = 0;
@@ -776,6 +779,15 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                 }
             }
         }
+        const bool nothing_enqueued = ctx->stats.h2d_copies == 0 && ctx->stats.d2h_copies == 0 && tmm::launch_count() == launches_before;
+        if (rc == TMM_ERR_NOMEM && attempt == 0 && nothing_enqueued && !ctx->grid.active() && !ctx->budget_override) {
+            fprintf(stderr, "tiled_mm_b200: device allocation failed (%s); releasing staging storage and re-planning with the current free memory\n", tmm_last_error());
+            ctx->buf_a.release(); ctx->buf_b.release(); ctx->buf_c.release();
+            ctx->budget_cached = 0;
+            rc = TMM_OK;
+            continue;
+        }
+        break;
     }
     const double t_enqueued = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     TMM_DBG("dev %d enqueued rc %d regime %d, syncing", ctx->device, rc, ctx->stats.regime);
