@@ -18,6 +18,8 @@ timeout 60 $T benchone N N 8192 8192 8192 0
 echo "== sgemm split: hi = raw bits (TMM_TC_SPLIT=trunc) =="; TMM_TC_SPLIT=trunc timeout 120 $T precision 2>&1 | grep -E "precision|tmm fp32" | head -20
 TMM_TC_SPLIT=trunc timeout 60 $T benchone N N 8192 8192 8192 0
 for tt in "N N" "T T"; do TMM_TC_SPLIT=trunc timeout 120 $T check $tt 2>&1 | grep -v " OK$" | tail -5; done
+echo "== published experiment (README figure: dgemm square, alpha=beta=1), both arms =="; timeout 400 python tools/sweep_published.py --reps 2 2>&1 | tail -12
+echo "== compute-sanitizer memcheck on the CI shapes (SURVEY 5.2) =="; timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gemm_gpu.py -m gpu -q -k "ci_and_ctest or degenerate" 2>&1 | tail -6
 echo "== regular suite =="; timeout 600 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -8
 echo "== bench =="; timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1
 } 2>&1 | tee gpurun_out/r2_first.txt
