@@ -99,6 +99,12 @@ TMM_API int tmm_copy_to_host(const void* device_from, void* host_to, size_t byte
 TMM_API int tmm_device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a_dev, int64_t ld_a,
                     const void* b_dev, int64_t ld_b, const void* beta, void* c_dev, int64_t ld_c, void* stream);
 
+/* Mixed precision (additive: the reference API has no such type; north_star names BF16 as a tcgen05 kernel family).
+ * C (float) = alpha * op(A) * op(B) + beta * C with A and B stored as bfloat16 (the upper 16 bits of an IEEE float), device pointers,
+ * column-major, any lda / ldb >= stored rows; FP32 accumulation on the tensor cores.  Runs on `stream`, does not synchronize. */
+TMM_API int tmm_device_gemm_bf16(char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, float alpha, const void* a_bf16_dev, int64_t ld_a,
+                         const void* b_bf16_dev, int64_t ld_b, float beta, float* c_dev, int64_t ld_c, void* stream);
+
 /* Math mode of the float (TMM_F32) GEMM, process-wide; the counterpart of cublasSetMathMode, which the reference never calls
  * (gpu_blas_handle.hpp:11-17 -> cuBLAS default math = FP32-accurate results).  TMM_MATH_FP32 (default) keeps that accuracy on
  * the tcgen05 tensor cores by splitting every operand into two TF32 numbers (3 MMAs per product, FP32 accumulation in TMEM);

@@ -102,6 +102,26 @@ def run_single():
             ctx.set_device_budget(4 << 20)
             case(ctx, dtype, "CN", 513, 300, 777, alpha, beta, (2, 0, 1), seed=6)
     check_clean("other dtypes")
+    # bf16 entry point: argument checking and plumbing of tmm_device_gemm_bf16 (the arithmetic here is the GEMM double's)
+    rng = np.random.default_rng(9)
+    m, n, k = 70, 50, 90
+    af, bf = (rng.integers(-8, 9, 95 * m).astype(np.float32), rng.integers(-8, 9, 55 * k).astype(np.float32))   # stored k x m (ld 95), n x k (ld 55)
+    c0 = rng.integers(0, 10, m * n).astype(np.float32)
+    to_bf16 = lambda x: (x.view(np.uint32) >> 16).astype(np.uint16)
+    da, db, dc = tmm.malloc_device(af.size * 2), tmm.malloc_device(bf.size * 2), tmm.malloc_device(c0.nbytes)
+    tmm.copy_to_device(to_bf16(af), da); tmm.copy_to_device(to_bf16(bf), db); tmm.copy_to_device(c0, dc)
+    tmm.device_gemm_bf16("T", "T", m, n, k, 2.0, da, 95, db, 55, -1.0, dc, m)
+    got = np.empty_like(c0); tmm.copy_to_host(dc, got)
+    want = oracle.gemm("T", "T", m, n, k, np.float32(2.0), af, 95, bf, 55, np.float32(-1.0), c0.copy(), m)
+    assert np.array_equal(got, want), "bf16 entry point"
+    try:
+        tmm.device_gemm_bf16("N", "N", m, n, k, 1.0, da, m - 1, db, k, 0.0, dc, m)
+        raise AssertionError("ld_a < m must be rejected")
+    except ValueError:
+        pass
+    for p in (da, db, dc):
+        tmm.free_device(p)
+    check_clean("bf16 entry")
     assert lib.emul_live_device_bytes(0) == 0, "device memory leaked after the contexts were destroyed"
     print("EMUL_OK single")
 

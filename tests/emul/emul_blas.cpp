@@ -8,6 +8,8 @@
 #include <atomic>
 #include <cctype>
 #include <cstdio>
+#include <cstring>
+#include <vector>
 
 extern "C" int oracle_gemm_ex(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t lda, const void* b,
                               int64_t ldb, const void* beta, void* c, int64_t ldc, int wide);
@@ -72,6 +74,32 @@ cudaError_t device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_
     count_launch();
     if (emul_dry_run()) return cudaSuccess;
     return oracle_gemm_ex(dtype, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, 0) == 0 ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+// bf16-input GEMM: widen on the host, then the oracle's float GEMM (exact products, like the tensor-core path)
+cudaError_t bgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, const void* a, int64_t lda, const void* b, int64_t ldb, float beta, float* c,
+                            int64_t ldc, cudaStream_t st) {
+    const int ar = ta == 'N' ? m : k, ac = ta == 'N' ? k : m, br = tb == 'N' ? k : n, bc = tb == 'N' ? n : k;
+    emul_check_device_range(a, ((size_t)(ac - 1) * lda + ar) * 2);
+    emul_check_device_range(b, ((size_t)(bc - 1) * ldb + br) * 2);
+    emul_check_device_range(c, ((size_t)(n - 1) * ldc + m) * 4);
+    {
+        const int sid = emul_op_begin(st);
+        emul_op_access(sid, a, (size_t)lda * 2, (size_t)ar * 2, (size_t)ac, 0, "bgemm A");
+        emul_op_access(sid, b, (size_t)ldb * 2, (size_t)br * 2, (size_t)bc, 0, "bgemm B");
+        emul_op_access(sid, c, (size_t)ldc * 4, (size_t)m * 4, (size_t)n, 1, "bgemm C");
+    }
+    count_launch();
+    if (emul_dry_run()) return cudaSuccess;
+    auto widen = [](const void* p, int64_t ld, int rows, int cols) {
+        std::vector<float> out((size_t)rows * cols);
+        const uint16_t* q = static_cast<const uint16_t*>(p);
+        for (int j = 0; j < cols; ++j)
+            for (int i = 0; i < rows; ++i) { const uint32_t u = (uint32_t)q[(size_t)j * ld + i] << 16; memcpy(&out[(size_t)j * rows + i], &u, 4); }
+        return out;
+    };
+    const std::vector<float> a32 = widen(a, lda, ar, ac), b32 = widen(b, ldb, br, bc);
+    return oracle_gemm_ex(F32, ta, tb, m, n, k, &alpha, a32.data(), ar > 1 ? ar : 1, b32.data(), br > 1 ? br : 1, &beta, c, ldc, 1) == 0 ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 }  // namespace tmm

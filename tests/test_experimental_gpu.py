@@ -54,3 +54,32 @@ def test_cgemm_tensor_core_device_boundary_odd_ld(c32_tc, oracle):
         assert np.array_equal(out, expect), (oa, ob)
     for p in (da, db, dc):
         tmm.free_device(p)
+
+
+@pytest.mark.parametrize("tt", ["NN", "TN", "NT", "TT"])
+def test_bf16_input_gemm(gpu_tmm, oracle, tt):
+    """tmm_device_gemm_bf16: bf16 operands widened on the device and multiplied on the tcgen05 TF32 path (exact products, FP32 accumulation)."""
+    tmm = gpu_tmm
+    ta, tb = tt
+    m, n, k = 515, 260, 777
+    rng = np.random.default_rng(21)
+    ar, ac = (m, k) if ta == "N" else (k, m)
+    br, bc = (k, n) if tb == "N" else (n, k)
+    lda, ldb = ar + 3, br + 5
+    to_bf16 = lambda x: (x.view(np.uint32) >> 16).astype(np.uint16)
+    for ints in (True, False):
+        gen = (lambda c: rng.integers(-8, 9, c).astype(np.float32)) if ints else (lambda c: (rng.random(c).astype(np.float32) - 0.5))
+        a16, b16 = to_bf16(gen(lda * ac)), to_bf16(gen(ldb * bc))
+        af, bf = (a16.astype(np.uint32) << 16).view(np.float32), (b16.astype(np.uint32) << 16).view(np.float32)   # the values the device sees
+        c0 = gen(m * n)
+        want = oracle.gemm(ta, tb, m, n, k, np.float32(1.5), af, lda, bf, ldb, np.float32(0.5), c0.copy(), m, wide=True)
+        da, db, dc = tmm.malloc_device(a16.nbytes), tmm.malloc_device(b16.nbytes), tmm.malloc_device(c0.nbytes)
+        tmm.copy_to_device(a16, da); tmm.copy_to_device(b16, db); tmm.copy_to_device(c0, dc)
+        tmm.device_gemm_bf16(ta, tb, m, n, k, 1.5, da, lda, db, ldb, 0.5, dc, m)
+        got = np.empty_like(c0); tmm.copy_to_host(dc, got)
+        for p in (da, db, dc):
+            tmm.free_device(p)
+        if ints:
+            assert np.array_equal(got, want), tt
+        else:
+            assert float(np.max(np.abs(got - want))) / (k * 0.25) <= 2e-6, tt

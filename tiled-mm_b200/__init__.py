@@ -99,6 +99,7 @@ def load_library() -> ctypes.CDLL:
     lib.tmm_copy_to_device.argtypes = [vp, vp, sz]
     lib.tmm_copy_to_host.argtypes = [vp, vp, sz]
     lib.tmm_device_gemm.argtypes = [ci, cc, cc, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, i64, vp]
+    lib.tmm_device_gemm_bf16.argtypes = [cc, cc, i64, i64, i64, ctypes.c_float, vp, i64, vp, i64, ctypes.c_float, vp, i64, vp]
     lib.tmm_context_last_stats.argtypes = [vp, ctypes.POINTER(CallStats)]
     lib.tmm_context_set_profiling.argtypes = [vp, ci]
     lib.tmm_context_set_device_budget.argtypes = [vp, sz]
@@ -352,6 +353,14 @@ def device_gemm(dtype, trans_a: str, trans_b: str, m: int, n: int, k: int, alpha
     _check(load_library().tmm_device_gemm(dtype_code(dt), ctypes.c_char(trans_a.encode()[:1]), ctypes.c_char(trans_b.encode()[:1]), m, n, k,
                                           _ptr(al), ctypes.c_void_p(a_dev), ld_a, ctypes.c_void_p(b_dev), ld_b, _ptr(be), ctypes.c_void_p(c_dev), ld_c,
                                           ctypes.c_void_p(stream)))
+
+
+def device_gemm_bf16(trans_a: str, trans_b: str, m: int, n: int, k: int, alpha: float, a_dev: int, ld_a: int, b_dev: int, ld_b: int, beta: float,
+                     c_dev: int, ld_c: int, stream: int = 0) -> None:
+    """C (float32) = alpha op(A) op(B) + beta C with A, B stored as bfloat16 on the device (additive entry point, tmm_device_gemm_bf16)."""
+    _check(load_library().tmm_device_gemm_bf16(ctypes.c_char(trans_a.encode()[:1]), ctypes.c_char(trans_b.encode()[:1]), m, n, k, alpha,
+                                               ctypes.c_void_p(a_dev), ld_a, ctypes.c_void_p(b_dev), ld_b, beta, ctypes.c_void_p(c_dev), ld_c,
+                                               ctypes.c_void_p(stream)))
 
 
 def optimal_tile_size(dim: int, max_tile: int) -> int:

@@ -50,6 +50,9 @@ cudaError_t cgemm_simt_launch(char ta, char tb, int m, int n, int k, const float
                               const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
 cudaError_t cgemm_tc_launch(char ta, char tb, int m, int n, int k, const float* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
                             const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
+// BF16 inputs, FP32 output / accumulation, on the tcgen05 TF32 path (bf16 is a subset of tf32: identical products) - gemm_bf16_tc.cu
+cudaError_t bgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb,
+                            float beta, float* c, int64_t ldc, cudaStream_t stream);
 // process-wide math mode of the complex<float> GEMM: 0 = SIMT (default), 3 = FP32-accurate on tensor cores
 int c32_math_mode();
 void set_c32_math_mode(int mode);

@@ -869,4 +869,19 @@ int tmm_device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_t n,
     return TMM_OK;
 }
 
+int tmm_device_gemm_bf16(char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, float alpha, const void* a, int64_t ld_a, const void* b, int64_t ld_b,
+                         float beta, float* c, int64_t ld_c, void* stream) {
+    const char ta = (char)std::toupper((unsigned char)trans_a), tb = (char)std::toupper((unsigned char)trans_b);
+    if ((ta != 'N' && ta != 'T' && ta != 'C') || (tb != 'N' && tb != 'T' && tb != 'C')) return fail(TMM_ERR_INVALID, "trans must be one of N, T, C");
+    if (m < 0 || n < 0 || k < 0 || m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return fail(TMM_ERR_INVALID, "bad dimension");
+    if (ld_a < std::max<int64_t>(1, ta == 'N' ? m : k) || ld_b < std::max<int64_t>(1, tb == 'N' ? k : n) || ld_c < std::max<int64_t>(1, m))
+        return fail(TMM_ERR_INVALID, "leading dimension too small");
+    if (m == 0 || n == 0) return TMM_OK;
+    if ((k > 0 && alpha != 0.f && (!a || !b)) || !c) return fail(TMM_ERR_INVALID, "null matrix pointer");
+    cudaError_t e = (k == 0 || alpha == 0.f) ? tmm::device_scale(TMM_F32, m, n, &beta, c, ld_c, (cudaStream_t)stream)
+                                             : tmm::bgemm_tc_launch(ta, tb, (int)m, (int)n, (int)k, alpha, a, ld_a, b, ld_b, beta, c, ld_c, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "device_gemm_bf16");
+    return TMM_OK;
+}
+
 }  // extern "C"
