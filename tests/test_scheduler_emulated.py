@@ -79,3 +79,11 @@ def test_randomised_sweep_on_emulated_runtime(emul_build, devices, cases, seed, 
 def test_replan_when_free_memory_shrinks_between_calls(emul_build):
     """a device allocation that fails before anything is enqueued is recovered by releasing staging storage and re-planning"""
     _worker(emul_build, ["replan"], 1, {"TMM_EMUL_MEM_MB": "32"})
+
+
+@pytest.mark.parametrize("stripes,devices", [(2, 1), (3, 1), (4, 1), (4, 4)])
+def test_phase1_column_stripes_with_staggered_c_upload(emul_build, stripes, devices):
+    """Phase 1 cut into several column stripes (forced with TMM_PLAN_P1SPLIT; the shapes of this suite are too small to get them
+    by themselves): with beta != 0 stripe s's share of C is uploaded right before k-chunk s and the stripe catches up on the chunks
+    that arrived earlier - including the case of fewer chunks than stripes."""
+    _worker(emul_build, ["sweep", devices, 400 if devices == 1 else 100, 40 + stripes], devices, {"TMM_PLAN_P1SPLIT": str(stripes)})

@@ -220,13 +220,7 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
     ctx->stats.k_chunks = (int)pl.chunks.size();
     ctx->stats.c_blocks = 1 + (int)pl.blocks.size();
 
-    // C[:, 0:n1] preload when beta != 0 (host C is read only then, reference tiled_mm.cpp:325)
     cudaEvent_t ev;
-    if (cl.beta_nonzero) {
-        TraceScope ts(ctx, ctx->s_h2d, "h2dC", 0, n1);
-        int rc = h2d_2d(cl, dC, ldc_dev, cl.c, cl.ldc, cl.m, n1, ctx->s_h2d);
-        if (rc) return rc;
-    }
     // ---- phase 1: A streams in as k-chunks with the first column block of B.  The block is cut into P1 column stripes, each a
     // chain of accumulating launches on its own high-priority stream: a chain is serial (chunk c+1 reads what chunk c wrote),
     // so a single chain drains the SMs at every launch boundary; with two or more staggered chains the block scheduler always
@@ -238,18 +232,36 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
     }
     int64_t s_off[tmm_context::MAX_P1 + 1];
     for (int s = 0; s <= P1; ++s) s_off[s] = s == P1 ? n1 : std::min<int64_t>(n1, round_up(n1 * s / P1, 64));
-    int64_t p0 = 0;
-    for (size_t ci = 0; ci < pl.chunks.size(); ++ci) {
-        const int64_t kc = pl.chunks[ci];
-        Sub sa = a_sub(cl, 0, cl.m, p0, kc);
-        Sub sb = b_sub(cl, p0, kc, 0, n1);
-        char* da = dA + ((size_t)sa.col * pa + sa.row) * es;
-        char* db = dB + ((size_t)sb.col * pb + sb.row) * es;
+    const int n_chunks = (int)pl.chunks.size();
+    std::vector<int64_t> chunk_p0(n_chunks + 1, 0);
+    for (int ci = 0; ci < n_chunks; ++ci) chunk_p0[ci + 1] = chunk_p0[ci] + pl.chunks[ci];
+    // beta != 0: host C is read (only then, reference tiled_mm.cpp:325).  Uploading the whole C[:, 0:n1] before the first chunk would
+    // keep the SMs idle for |C block| / BW_pcie (8 ms at 10000^3); instead stripe s's C travels right before k-chunk s, so the first
+    // chain starts after ONE stripe of C and the later stripes join one chunk apart, catching up on the chunks that arrived first.
+    auto upload_c_stripe = [&](int sidx) -> int {
+        const int64_t js = s_off[sidx], ws = s_off[sidx + 1] - js;
+        if (ws <= 0) return TMM_OK;
+        TraceScope ts(ctx, ctx->s_h2d, "h2dC", js, ws);
+        return h2d_2d(cl, (char*)dC + (size_t)js * ldc_dev * es, ldc_dev, cl.c + (size_t)js * cl.ldc * es, cl.ldc, cl.m, ws, ctx->s_h2d);
+    };
+    auto launch_stripe_chunk = [&](int sidx, int ci) -> int {
+        const int64_t js = s_off[sidx], ws = s_off[sidx + 1] - js;
+        if (ws <= 0) return TMM_OK;
+        const int64_t p0 = chunk_p0[ci], kc = pl.chunks[ci];
+        const Sub sa = a_sub(cl, 0, cl.m, p0, kc), sbs = b_sub(cl, p0, kc, js, ws);
+        TraceScope ts(ctx, ctx->s_p1[sidx], "gemm1", js, ws, kc);
+        return launch_gemm(cl, cl.m, ws, kc, dA + ((size_t)sa.col * pa + sa.row) * es, pa, dB + ((size_t)sbs.col * pb + sbs.row) * es, pb,
+                           ci == 0 ? cl.beta : (const void*)cl.one, (char*)dC + (size_t)js * ldc_dev * es, ldc_dev, ctx->s_p1[sidx]);
+    };
+    for (int ci = 0; ci < n_chunks; ++ci) {
+        const int64_t p0 = chunk_p0[ci], kc = pl.chunks[ci];
+        if (cl.beta_nonzero && ci < P1) { int rc = upload_c_stripe(ci); if (rc) return rc; }
+        const Sub sa = a_sub(cl, 0, cl.m, p0, kc), sb = b_sub(cl, p0, kc, 0, n1);
         {
             TraceScope ts(ctx, ctx->s_h2d, "h2dAB", p0, kc);
-            int rc = fetch_a(cl, da, pa, sa);
+            int rc = fetch_a(cl, dA + ((size_t)sa.col * pa + sa.row) * es, pa, sa);
             if (rc) return rc;
-            rc = fetch_b(cl, db, pb, sb);
+            rc = fetch_b(cl, dB + ((size_t)sb.col * pb + sb.row) * es, pb, sb);
             if (rc) return rc;
         }
         {
@@ -257,16 +269,20 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
             if (rc) return rc;
         }
         for (int s = 0; s < P1; ++s) {
-            const int64_t js = s_off[s], ws = s_off[s + 1] - js;
-            if (ws <= 0) continue;
-            Sub sbs = b_sub(cl, p0, kc, js, ws);
-            TraceScope ts(ctx, ctx->s_p1[s], "gemm1", js, ws, kc);
-            int rc = launch_gemm(cl, cl.m, ws, kc, da, pa, dB + ((size_t)sbs.col * pb + sbs.row) * es, pb, ci == 0 ? cl.beta : (const void*)cl.one,
-                                 (char*)dC + (size_t)js * ldc_dev * es, ldc_dev, ctx->s_p1[s]);
+            if (cl.beta_nonzero && s > ci) continue;                      // this stripe's C has not been sent yet
+            if (cl.beta_nonzero && s == ci)                               // it has now: catch up on the chunks that are already here
+                for (int cj = 0; cj < ci; ++cj) { int rc = launch_stripe_chunk(s, cj); if (rc) return rc; }
+            int rc = launch_stripe_chunk(s, ci);
             if (rc) return rc;
         }
-        p0 += kc;
     }
+    if (cl.beta_nonzero)
+        for (int s = n_chunks; s < P1; ++s) {                             // fewer k-chunks than stripes: the remaining chains start here
+            int rc = upload_c_stripe(s);
+            if (!rc) rc = panels_ready(cl, &ctx->s_p1[s], 1);
+            for (int cj = 0; cj < n_chunks && !rc; ++cj) rc = launch_stripe_chunk(s, cj);
+            if (rc) return rc;
+        }
     if (cl.copy_c_back) {
         // stripes finish in order; each leaves for the host as soon as its chain is done
         for (int s = 0; s < P1; ++s) {

@@ -15,6 +15,7 @@ size_t elem_size(int dt) { return dt == 0 ? 4 : (dt == 1 ? 8 : (dt == 2 ? 8 : 16
 // FP64 DMMA GEMM 35.6 TFLOP/s, pinned H2D 55.6 GB/s (48 GB/s while D2H runs).
 constexpr double kFlops = 35e12;
 constexpr double kH2D = 52e9;
+constexpr double kD2H = 52e9;
 constexpr int64_t BM = 128, BN = 64;  // CTA tile of the FP64 kernels
 
 // developer knobs for schedule experiments (never needed for correctness)
@@ -80,14 +81,26 @@ Plan make_plan(const PlanInput& in) {
         //  phase 2 overlap the D2H of finished C blocks with the H2D of later B blocks)
         const double margin = env_or("TMM_PLAN_MARGIN", 1.3);
         int64_t n1 = std::min<int64_t>(n, 1024);
+        bool d2h_bound = false;
         const double sa = 1.0 / std::max(1, in.parts_a), sb = 1.0 / std::max(1, in.parts_b);  // upload shares on a GPU grid
         const double denom = F * (double)m / kFlops - margin * (double)es * sb / kH2D;
         if (denom > 0) {
             const double need = margin * (double)es * sa * (double)m / kH2D / denom;
             n1 = (int64_t)std::min<double>((double)n, std::max(512.0, need));
         }
+        {
+            // The first block's C can only leave once every k-chunk of A has arrived, i.e. at the end of phase 1; its D2H is hidden
+            // only if the remaining columns still have at least that much GEMM work: d2h(n1) <= gemm(n - n1), which bounds n1 by
+            // n * rho / (1 + rho), rho = (F k / P) / (es / BW_d2h).  Without the bound, mid-size products (~4000 - 8000 square in FP64)
+            // ran as ONE phase and ended with the D2H of the whole C exposed.  (Timeline model tools/model_resident.py, calibrated on
+            // the measured 10000^3, whose n1 = 5504 is below its bound of 6600 and unchanged: 9 - 20 % shorter calls predicted for
+            // n = 4000 ... 7000; to be measured.  TMM_PLAN_D2H_BOUND=0 switches the bound off.)
+            const double rho = F * (double)k / kFlops * (kD2H / (double)es);
+            const int64_t cap = (int64_t)(0.85 * (double)n * rho / (1.0 + rho));  // 15 % slack: the D2H competes with H2D for host memory
+            if (in.copy_c_back && env_or("TMM_PLAN_D2H_BOUND", 1.0) != 0.0 && n1 > cap) { n1 = std::max<int64_t>(std::min<int64_t>(n, 1024), cap); d2h_bound = true; }
+        }
         n1 = std::min<int64_t>(n, round_up(n1, BN));
-        if (n1 < n) {
+        if (n1 < n && !d2h_bound) {
             // nudge n1 upwards (at most 12 %) to the width whose CTA count fills whole waves best
             const int64_t tiles_m = (m + BM - 1) / BM;
             int64_t best = n1;
