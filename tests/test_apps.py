@@ -82,6 +82,16 @@ def test_cxxopts_shim_parses_like_the_reference_expects(tmp_path):
 
 
 # ---------------------------------------------------------------------------------------------------------------- GPU
+@pytest.fixture(scope="module")
+def gpu_apps(gpu_tmm):
+    """The binaries normally travel with the repository (built by __graft_entry__.build()); if they did not, build them on the box
+    (same image: g++ is there; the reference's own sources are not, so bin/ref-* may legitimately be absent)."""
+    if not (BIN / "test-multiply").exists() or not (BIN / "multiply").exists():
+        r = subprocess.run(["make", "-C", str(ROOT / "apps"), "-j4", "all"], capture_output=True, text=True, env=_env())
+        assert r.returncode == 0, r.stderr[-3000:]
+    return BIN
+
+
 CTEST_CASES = [  # reference tests/CMakeLists.txt:12-15 (the 10000^3 and 12345x23456x67891 cases are covered by test_gemm_gpu / bench)
     ("-m", 1000, "-n", 1000, "-k", 1000),
     ("-m", 1234, "-n", 4567, "-k", 1357),
@@ -90,7 +100,7 @@ CTEST_CASES = [  # reference tests/CMakeLists.txt:12-15 (the 10000^3 and 12345x2
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", CTEST_CASES)
-def test_own_test_multiply_ctest_cases(gpu_tmm, case):
+def test_own_test_multiply_ctest_cases(gpu_apps, case):
     r = _run(BIN / "test-multiply", *case)
     assert r.returncode == 0 and "The result is CORRECT" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
 
@@ -102,14 +112,14 @@ def test_own_test_multiply_ctest_cases(gpu_tmm, case):
     ("--type", "c", "-t", "NC", "-m", 129, "-n", 65, "-k", 300, "--beta", -1),
     ("--type", "d", "-t", "tt", "-m", 5, "-n", 2, "-k", 2, "--tile_m", 4, "--tile_n", 4, "--tile_k", 4),
 ])
-def test_own_test_multiply_types_and_transposes(gpu_tmm, args):
+def test_own_test_multiply_types_and_transposes(gpu_apps, args):
     r = _run(BIN / "test-multiply", *args)
     assert r.returncode == 0 and "The result is CORRECT" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", CTEST_CASES)
-def test_reference_test_app_passes_on_this_library(gpu_tmm, case):
+def test_reference_test_app_passes_on_this_library(gpu_apps, case):
     """The reference's tests/test-multiply.cpp, compiled unchanged, run against this library (binary built where the reference
     sources exist; it travels with the repository)."""
     exe = BIN / "ref-test-multiply"
@@ -120,7 +130,7 @@ def test_reference_test_app_passes_on_this_library(gpu_tmm, case):
 
 
 @pytest.mark.gpu
-def test_multiply_report_format(gpu_tmm):
+def test_multiply_report_format(gpu_apps):
     for exe in (BIN / "multiply", BIN / "ref-multiply"):
         if not exe.exists():
             continue
