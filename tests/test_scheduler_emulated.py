@@ -87,3 +87,8 @@ def test_phase1_column_stripes_with_staggered_c_upload(emul_build, stripes, devi
     by themselves): with beta != 0 stripe s's share of C is uploaded right before k-chunk s and the stripe catches up on the chunks
     that arrived earlier - including the case of fewer chunks than stripes."""
     _worker(emul_build, ["sweep", devices, 400 if devices == 1 else 100, 40 + stripes], devices, {"TMM_PLAN_P1SPLIT": str(stripes)})
+
+
+def test_one_c_stripe_per_k_chunk_experiment(emul_build):
+    """TMM_PLAN_CSTRIPES=chunks (opt-in schedule experiment for beta != 0: as many column stripes as k-chunks, more stripes than streams)"""
+    _worker(emul_build, ["sweep", 1, 500, 61], 1, {"TMM_PLAN_CSTRIPES": "chunks"})

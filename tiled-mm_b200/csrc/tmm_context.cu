@@ -230,11 +230,30 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
         const char* v = getenv("TMM_PLAN_P1SPLIT");
         if (v && *v) P1 = std::max(1, std::min<int>(std::min<int64_t>(tmm_context::MAX_P1, (n1 + 63) / 64), atoi(v)));
     }
-    int64_t s_off[tmm_context::MAX_P1 + 1];
-    for (int s = 0; s <= P1; ++s) s_off[s] = s == P1 ? n1 : std::min<int64_t>(n1, round_up(n1 * s / P1, 64));
     const int n_chunks = (int)pl.chunks.size();
     std::vector<int64_t> chunk_p0(n_chunks + 1, 0);
     for (int ci = 0; ci < n_chunks; ++ci) chunk_p0[ci + 1] = chunk_p0[ci] + pl.chunks[ci];
+    // NS column stripes over P1 streams (stripe j runs on stream j % P1).  Default: NS = P1 equal stripes.
+    constexpr int MAX_STRIPES = 16;
+    int NS = P1;
+    int64_t s_off[MAX_STRIPES + 1];
+    for (int s = 0; s <= NS; ++s) s_off[s] = s == NS ? n1 : std::min<int64_t>(n1, round_up(n1 * s / NS, 64));
+    if (cl.beta_nonzero) {
+        // Experiment (TMM_PLAN_CSTRIPES=<count> | chunks; not the default until measured): with beta != 0 the work that is unlocked per
+        // uploaded byte is largest when the columns of C arrive at the same pace as the k-columns of A, i.e. one stripe per k-chunk
+        // with widths in proportion to the chunk widths, instead of a few fat stripes whose C delays the first chunks.
+        const char* v = getenv("TMM_PLAN_CSTRIPES");
+        if (v && *v) {
+            const int want = (v[0] == 'c') ? n_chunks : atoi(v);
+            const int ns = std::max(1, std::min(std::min(want, n_chunks), std::min<int>(MAX_STRIPES, (int)((n1 + 63) / 64))));
+            if (ns > 1 && cl.k > 0) {
+                NS = ns;
+                P1 = std::min<int>(tmm_context::MAX_P1, NS);
+                // stripe boundaries follow the k-chunk boundaries, scaled from [0, k) to [0, n1); the chunks beyond NS share the last stripe
+                for (int s = 0; s <= NS; ++s) s_off[s] = s == NS ? n1 : std::min<int64_t>(n1, round_up((int64_t)((double)chunk_p0[s] / (double)chunk_p0[NS] * (double)n1), 64));
+            }
+        }
+    }
     // beta != 0: host C is read (only then, reference tiled_mm.cpp:325).  Uploading the whole C[:, 0:n1] before the first chunk would
     // keep the SMs idle for |C block| / BW_pcie (8 ms at 10000^3); instead stripe s's C travels right before k-chunk s, so the first
     // chain starts after ONE stripe of C and the later stripes join one chunk apart, catching up on the chunks that arrived first.
@@ -249,13 +268,13 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
         if (ws <= 0) return TMM_OK;
         const int64_t p0 = chunk_p0[ci], kc = pl.chunks[ci];
         const Sub sa = a_sub(cl, 0, cl.m, p0, kc), sbs = b_sub(cl, p0, kc, js, ws);
-        TraceScope ts(ctx, ctx->s_p1[sidx], "gemm1", js, ws, kc);
+        TraceScope ts(ctx, ctx->s_p1[sidx % P1], "gemm1", js, ws, kc);
         return launch_gemm(cl, cl.m, ws, kc, dA + ((size_t)sa.col * pa + sa.row) * es, pa, dB + ((size_t)sbs.col * pb + sbs.row) * es, pb,
-                           ci == 0 ? cl.beta : (const void*)cl.one, (char*)dC + (size_t)js * ldc_dev * es, ldc_dev, ctx->s_p1[sidx]);
+                           ci == 0 ? cl.beta : (const void*)cl.one, (char*)dC + (size_t)js * ldc_dev * es, ldc_dev, ctx->s_p1[sidx % P1]);
     };
     for (int ci = 0; ci < n_chunks; ++ci) {
         const int64_t p0 = chunk_p0[ci], kc = pl.chunks[ci];
-        if (cl.beta_nonzero && ci < P1) { int rc = upload_c_stripe(ci); if (rc) return rc; }
+        if (cl.beta_nonzero && ci < NS) { int rc = upload_c_stripe(ci); if (rc) return rc; }
         const Sub sa = a_sub(cl, 0, cl.m, p0, kc), sb = b_sub(cl, p0, kc, 0, n1);
         {
             TraceScope ts(ctx, ctx->s_h2d, "h2dAB", p0, kc);
@@ -268,7 +287,7 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
             int rc = panels_ready(cl, ctx->s_p1, P1);
             if (rc) return rc;
         }
-        for (int s = 0; s < P1; ++s) {
+        for (int s = 0; s < NS; ++s) {
             if (cl.beta_nonzero && s > ci) continue;                      // this stripe's C has not been sent yet
             if (cl.beta_nonzero && s == ci)                               // it has now: catch up on the chunks that are already here
                 for (int cj = 0; cj < ci; ++cj) { int rc = launch_stripe_chunk(s, cj); if (rc) return rc; }
@@ -277,19 +296,19 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
         }
     }
     if (cl.beta_nonzero)
-        for (int s = n_chunks; s < P1; ++s) {                             // fewer k-chunks than stripes: the remaining chains start here
+        for (int s = n_chunks; s < NS; ++s) {                             // fewer k-chunks than stripes: the remaining chains start here
             int rc = upload_c_stripe(s);
-            if (!rc) rc = panels_ready(cl, &ctx->s_p1[s], 1);
+            if (!rc) rc = panels_ready(cl, &ctx->s_p1[s % P1], 1);
             for (int cj = 0; cj < n_chunks && !rc; ++cj) rc = launch_stripe_chunk(s, cj);
             if (rc) return rc;
         }
     if (cl.copy_c_back) {
         // stripes finish in order; each leaves for the host as soon as its chain is done
-        for (int s = 0; s < P1; ++s) {
+        for (int s = 0; s < NS; ++s) {
             const int64_t js = s_off[s], ws = s_off[s + 1] - js;
             if (ws <= 0) continue;
             CU(ctx->get_event(&ev));
-            CU(cudaEventRecord(ev, ctx->s_p1[s]));
+            CU(cudaEventRecord(ev, ctx->s_p1[s % P1]));
             CU(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
             const int64_t piece = std::max<int64_t>(64, round_up(ws / 2, 64));
             for (int64_t j = js; j < js + ws; j += piece) {

@@ -19,6 +19,11 @@ echo "== sgemm split: hi = raw bits (TMM_TC_SPLIT=trunc) =="; TMM_TC_SPLIT=trunc
 TMM_TC_SPLIT=trunc timeout 60 $T benchone N N 8192 8192 8192 0
 for tt in "N N" "T T"; do TMM_TC_SPLIT=trunc timeout 120 $T check $tt 2>&1 | grep -v " OK$" | tail -5; done
 echo "== published experiment (README figure: dgemm square, alpha=beta=1), both arms =="; timeout 400 python tools/sweep_published.py --reps 2 2>&1 | tail -12
+echo "== beta = 1 at 10000^3: default stripes vs one C stripe per k-chunk =="
+timeout 60 python tools/e2e.py --beta 1 --reps 4 2>&1 | tail -1
+TMM_PLAN_CSTRIPES=chunks timeout 60 python tools/e2e.py --beta 1 --reps 4 2>&1 | tail -1
+echo "== mid-size products: n1 bound on / off =="
+for n in 4000 6000 8000; do timeout 60 python tools/e2e.py --m $n --n $n --k $n --reps 5 2>&1 | tail -1; TMM_PLAN_D2H_BOUND=0 timeout 60 python tools/e2e.py --m $n --n $n --k $n --reps 5 2>&1 | tail -1; done
 echo "== compute-sanitizer memcheck on the CI shapes (SURVEY 5.2) =="; timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gemm_gpu.py -m gpu -q -k "ci_and_ctest or degenerate" 2>&1 | tail -6
 echo "== regular suite =="; timeout 600 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -8
 echo "== bench =="; timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1
