@@ -235,6 +235,7 @@ cudaError_t cudaGetDeviceProperties_v2(cudaDeviceProp* p, int) {
 cudaError_t cudaDeviceGetStreamPriorityRange(int* least, int* greatest) { *least = 0; *greatest = -5; return cudaSuccess; }
 cudaError_t cudaDeviceEnablePeerAccess(int peer, unsigned) { return (peer >= 0 && peer < device_count()) ? cudaSuccess : cudaErrorInvalidDevice; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+cudaError_t cudaDeviceGetPCIBusId(char* id, int len, int dev) { snprintf(id, (size_t)len, "0000:%02x:00.0", 0x10 + dev); return cudaSuccess; }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) {
     switch (e) {

@@ -26,6 +26,9 @@
 #include <cstring>
 #include <thread>
 
+#include <sys/syscall.h>
+#include <unistd.h>
+
 namespace tmm {
 
 static thread_local std::string g_last_error;
@@ -878,9 +881,60 @@ int tmm_plan_describe(int dtype, char trans_a, char trans_b, int64_t m, int64_t 
     return TMM_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// NUMA node of a CUDA device from sysfs (-1: unknown / single node)
+int device_numa_node(int dev) {
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, (int)sizeof bdf, dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char* q = bdf; *q; ++q) *q = (char)std::tolower((unsigned char)*q);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/numa_node";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+// While alive, this thread's page allocations prefer `node` (MPOL_PREFERRED: soft, falls back when the node is full); the previous
+// policy is restored afterwards.  Raw syscalls: no libnuma dependency; any failure (seccomp, no NUMA) simply leaves the policy alone.
+struct NumaPreference {
+    static constexpr unsigned long MAXNODE = 1024;
+    int old_mode = 0;
+    unsigned long old_mask[MAXNODE / 64] = {0};
+    bool active = false;
+    explicit NumaPreference(int node) {
+#if defined(__linux__) && defined(SYS_set_mempolicy) && defined(SYS_get_mempolicy)
+        if (node < 0 || node >= (int)MAXNODE) return;
+        if (syscall(SYS_get_mempolicy, &old_mode, old_mask, MAXNODE + 1, nullptr, 0ul) != 0) return;
+        unsigned long mask[MAXNODE / 64] = {0};
+        mask[node / 64] |= 1ul << (node % 64);
+        active = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, MAXNODE + 1) == 0;
+#else
+        (void)node;
+#endif
+    }
+    ~NumaPreference() {
+#if defined(__linux__) && defined(SYS_set_mempolicy)
+        if (active) syscall(SYS_set_mempolicy, old_mode, old_mode == 0 ? nullptr : old_mask, old_mode == 0 ? 0ul : MAXNODE + 1);
+#endif
+    }
+};
+}  // namespace
+
+extern "C" {
+
 int tmm_malloc_pinned(size_t bytes, void** out) {
     if (!out) return fail(TMM_ERR_INVALID, "out is null");
     *out = nullptr;
+    // Pinned pages on the NUMA node of the calling thread's current device: a panel that has to cross the socket interconnect on
+    // its way to the PCIe root port shares that link with every other GPU of the far socket ("NUMA-local pinned pages").
+    // TMM_PINNED_NUMA=0 leaves placement to the caller (numactl, first touch).
+    static const bool numa_on = [] { const char* v = getenv("TMM_PINNED_NUMA"); return !(v && v[0] == '0'); }();
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; }
+    NumaPreference pref(numa_on && dev >= 0 ? device_numa_node(dev) : -1);
     CU(cudaHostAlloc(out, bytes ? bytes : 1, 0));  // flags 0, reference util.hpp:67
     return TMM_OK;
 }
