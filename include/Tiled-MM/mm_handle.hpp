@@ -24,25 +24,24 @@ template <> struct tmm_dtype<std::complex<double>> { static constexpr int value 
 template <typename Scalar>
 class mm_handle {
 public:
-    mm_handle(int streams, int max_tile_m, int max_tile_n, int max_tile_k);
+    // construction fixes the maxima that get_max_tile_sizes() reports; nothing is allocated yet
+    mm_handle(int n_streams, int tile_m_max, int tile_n_max, int tile_k_max);
     ~mm_handle();
-
     mm_handle(mm_handle&&) = delete;
     mm_handle(const mm_handle&) = delete;
     mm_handle& operator=(const mm_handle&& other) = delete;
 
-    void set_num_streams(int streams);
+    // stream count and tile geometry: staging hints for the scheduler (never results) and the geometry of the slabs below
     int get_num_streams();
-
-    gpu_context& get_gpu_context();
-
-    void set_tile_sizes(int tile_size_m, int tile_size_n, int tile_size_k);
-    void set_tile_sizes(int tile_size);
-    void set_full_sizes(int m, int n, int k);
-    std::tuple<int, int, int> optimal_tile_sizes(int m, int n, int k);
+    void set_num_streams(int n_streams);
+    void set_tile_sizes(int tile_m, int tile_n, int tile_k);
+    void set_tile_sizes(int tile);
+    void set_streams_and_tiles(int n_streams, int tile_m, int tile_n, int tile_k);
     std::tuple<int, int, int> get_max_tile_sizes();
+    std::tuple<int, int, int> optimal_tile_sizes(int m, int n, int k);  // per dimension: what the reference would tile (m, n, k) with
 
-    void set_streams_and_tiles(int streams, int tile_size_m, int tile_size_n, int tile_size_k);
+    void set_full_sizes(int m, int n, int k);  // size the device-resident C to m x n now
+    gpu_context& get_gpu_context();            // the context's streams, as the reference's accessor type
 
     // per-stream tile slabs (n_streams x tile): caller-visible device scratch, allocated on first use; the scheduler itself
     // stages through context-owned panels / rings instead (csrc/tmm_context.cu)

@@ -9,16 +9,10 @@ namespace gpu {
 
 blas_api::OperationType get_blas_operation(char trans);
 
+// C = alpha * op(A) * op(B) + beta * C; a, b, c are host pointers (same parameter order, types and defaults as the reference)
 template <typename Scalar>
-void gemm(mm_handle<Scalar>& handle,
-          char trans_a, char trans_b,
-          int m, int n, int k,
-          Scalar alpha,
-          Scalar* a, int ld_a,
-          Scalar* b, int ld_b,
-          Scalar beta,
-          Scalar* c, int ld_c,
-          bool pin_host_buffers = true, bool copy_c_back = true);
+void gemm(mm_handle<Scalar>& handle, char trans_a, char trans_b, int m, int n, int k, Scalar alpha, Scalar* a, int ld_a, Scalar* b, int ld_b, Scalar beta,
+          Scalar* c, int ld_c, bool pin_host_buffers = true, bool copy_c_back = true);
 
 // 64-bit sizes (the reference's int offsets overflow at 2^31 elements, tiled_matrix.cpp:62-67)
 template <typename Scalar>
