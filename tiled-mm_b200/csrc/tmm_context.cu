@@ -848,12 +848,26 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
         fprintf(stderr, "[tmm trace] host: enqueue done at %.3f ms, all streams idle at %.3f ms after entry\n", t_enqueued,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
         fprintf(stderr, "[tmm trace] %-28s %10s %10s %9s\n", "op", "start_ms", "end_ms", "dur_ms");
+        // TMM_TRACE_FILE=<path>: the same timeline as a Chrome / Perfetto trace (one row per stream, one process per device), appended
+        const char* trace_path = getenv("TMM_TRACE_FILE");
+        FILE* tf = (trace_path && *trace_path) ? fopen(trace_path, "a") : nullptr;
+        auto stream_name = [&](cudaStream_t st) -> std::string {
+            if (st == ctx->s_h2d) return "H2D";
+            if (st == ctx->s_d2h) return "D2H";
+            if (st == ctx->s_comm) return "NVLink";
+            for (int i = 0; i < tmm_context::MAX_P1; ++i) if (st == ctx->s_p1[i]) return "phase-1 stripe chain " + std::to_string(i);
+            for (int i = 0; i < tmm_context::MAX_COMPUTE; ++i) if (st == ctx->s_compute[i]) return "column blocks " + std::to_string(i);
+            return "stream";
+        };
         for (auto& op : ctx->trace_ops) {
             float a = 0, b = 0;
             cudaEventElapsedTime(&a, trace_t0, op.e0);
             cudaEventElapsedTime(&b, trace_t0, op.e1);
             fprintf(stderr, "[tmm trace] %-28s %10.3f %10.3f %9.3f\n", op.name.c_str(), a, b, b - a);
+            if (tf) fprintf(tf, "{\"name\":\"%s\",\"ph\":\"X\",\"ts\":%.1f,\"dur\":%.1f,\"pid\":%d,\"tid\":\"%s\"},\n", op.name.c_str(), a * 1e3, (b - a) * 1e3,
+                            ctx->device, stream_name(op.stream).c_str());
         }
+        if (tf) fclose(tf);
     }
     if (rc == TMM_ERR_NOMEM) ctx->budget_cached = 0;  // free memory changed under us: re-query next time
     ctx->stats.kernel_ms = kernel_ms_total;

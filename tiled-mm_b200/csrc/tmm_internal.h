@@ -120,7 +120,7 @@ struct tmm_context {
     bool profiling = false;
     bool pin_cache = false;
     bool trace = false;
-    struct TraceOp { std::string name; cudaEvent_t e0, e1; };
+    struct TraceOp { std::string name; cudaEvent_t e0, e1; cudaStream_t stream; };
     std::vector<TraceOp> trace_ops;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
     std::map<const void*, size_t> pinned;
@@ -173,7 +173,7 @@ struct TraceScope {
         cudaEventRecord(e0, st);
         char buf[96];
         snprintf(buf, sizeof buf, "%s(%lld,%lld,%lld)", name, (long long)a, (long long)b, (long long)d);
-        ctx->trace_ops.push_back({buf, e0, e1});
+        ctx->trace_ops.push_back({buf, e0, e1, st});
         idx = ctx->trace_ops.size() - 1;
     }
     ~TraceScope() { if (idx != (size_t)-1) cudaEventRecord(ctx->trace_ops[idx].e1, st); }
