@@ -83,3 +83,27 @@ def test_bf16_input_gemm(gpu_tmm, oracle, tt):
             assert np.array_equal(got, want), tt
         else:
             assert float(np.max(np.abs(got - want))) / (k * 0.25) <= 2e-6, tt
+
+
+@pytest.mark.skipif(os.environ.get("TMM_BF16_NATIVE") != "1", reason="run with TMM_BF16_NATIVE=1: native kind::f16 path for k-contiguous bf16 operands")
+def test_bf16_native_kind_f16_tn(gpu_tmm, oracle):
+    tmm = gpu_tmm
+    to_bf16 = lambda x: (x.view(np.uint32) >> 16).astype(np.uint16)
+    rng = np.random.default_rng(22)
+    for (m, n, k, ints) in [(128, 128, 64, True), (515, 260, 777, True), (1000, 900, 4100, False)]:
+        lda = ldb = -(-k // 8) * 8 + 8                    # 16-byte pitch: the TMA contract of the native path
+        gen = (lambda c: rng.integers(-8, 9, c).astype(np.float32)) if ints else (lambda c: (rng.random(c).astype(np.float32) - 0.5))
+        a16, b16 = to_bf16(gen(lda * m)), to_bf16(gen(ldb * n))
+        af, bf = (a16.astype(np.uint32) << 16).view(np.float32), (b16.astype(np.uint32) << 16).view(np.float32)
+        c0 = gen(m * n)
+        want = oracle.gemm("T", "N", m, n, k, np.float32(1.0), af, lda, bf, ldb, np.float32(1.0), c0.copy(), m, wide=True)
+        da, db, dc = tmm.malloc_device(a16.nbytes), tmm.malloc_device(b16.nbytes), tmm.malloc_device(c0.nbytes)
+        tmm.copy_to_device(a16, da); tmm.copy_to_device(b16, db); tmm.copy_to_device(c0, dc)
+        tmm.device_gemm_bf16("T", "N", m, n, k, 1.0, da, lda, db, ldb, 1.0, dc, m)
+        got = np.empty_like(c0); tmm.copy_to_host(dc, got)
+        for p in (da, db, dc):
+            tmm.free_device(p)
+        if ints:
+            assert np.array_equal(got, want), (m, n, k)
+        else:
+            assert float(np.max(np.abs(got - want))) / (k * 0.25) <= 2e-6, (m, n, k)

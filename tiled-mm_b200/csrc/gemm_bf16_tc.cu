@@ -13,6 +13,7 @@
 #include "tmm_blas.h"
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace tmm {
 namespace bf16tc {
@@ -33,6 +34,11 @@ cudaError_t bgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
     using namespace bf16tc;
     if (m <= 0 || n <= 0) return cudaSuccess;
     if (k <= 0) return device_scale(F32, m, n, &beta, c, ldc, st);
+    {
+        static const bool native = [] { const char* v = getenv("TMM_BF16_NATIVE"); return v && v[0] == '1'; }();
+        if (native && ta != 'N' && tb == 'N' && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0 && (lda & 7) == 0 && (ldb & 7) == 0)
+            return bgemm_tc_native_tn_launch(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, st);
+    }
     const int ar = ta == 'N' ? m : k, ac = ta == 'N' ? k : m, br = tb == 'N' ? k : n, bc = tb == 'N' ? n : k;
     const int64_t pa = round_up(ar, 32), pb = round_up(br, 32);  // 128-byte columns: TMA-legal for any input ld
     float *a32 = nullptr, *b32 = nullptr;

@@ -70,6 +70,8 @@ struct Params {
     uint32_t idesc;
     int terms;   // 3: FP32-accurate 3xTF32;  1: plain TF32 on the raw bits
     int window;  // k-blocks per TMEM accumulation window
+    int bk;          // operand elements per k-block: 32 FP32 (= 128 B); 64 for the 16-bit variant below - the byte geometry is the same
+    int f16_kind;    // experimental: operands are bf16, K-major, multiplied by kind::f16 MMAs (one term); see bgemm_tc_native_launch
     int split_trunc;  // experimental (TMM_TC_SPLIT=trunc): hi = the raw FP32 bits (the tensor core ignores the low 13 mantissa bits), only lo is written
 };
 
@@ -139,7 +141,7 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     const int total_tiles = p.tiles_m * p.tiles_n;
-    const int kblocks = (p.k + BK - 1) / BK;
+    const int kblocks = (p.k + p.bk - 1) / p.bk;
 
     // Every role starts with its share of the warpgroup-wide register reallocation (setmaxnreg): the control and split
     // warpgroups hand registers to the accumulate/epilogue warpgroup.
@@ -161,15 +163,15 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     unsigned char* sb = sa + 2 * OPERAND_BYTES;
                     if (p.a_mn_major) {
 #pragma unroll
-                        for (int j = 0; j < BM / ATOM_MN; ++j) ptx::tma_load_2d(sa + j * MN_BOX_BYTES, &tmap_a, &full_bar[stage], tm * BM + j * ATOM_MN, kb * BK);
+                        for (int j = 0; j < BM / ATOM_MN; ++j) ptx::tma_load_2d(sa + j * MN_BOX_BYTES, &tmap_a, &full_bar[stage], tm * BM + j * ATOM_MN, kb * p.bk);
                     } else {
-                        ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, tm * BM);
+                        ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * p.bk, tm * BM);
                     }
                     if (p.b_mn_major) {
 #pragma unroll
-                        for (int j = 0; j < BN / ATOM_MN; ++j) ptx::tma_load_2d(sb + j * MN_BOX_BYTES, &tmap_b, &full_bar[stage], tn * BN + j * ATOM_MN, kb * BK);
+                        for (int j = 0; j < BN / ATOM_MN; ++j) ptx::tma_load_2d(sb + j * MN_BOX_BYTES, &tmap_b, &full_bar[stage], tn * BN + j * ATOM_MN, kb * p.bk);
                     } else {
-                        ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, tn * BN);
+                        ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * p.bk, tn * BN);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -208,7 +210,8 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                             tc::mma_tf32(d_tmem, da_hi, db_lo, p.idesc, 1u);
                             tc::mma_tf32(d_tmem, da_hi, db_hi, p.idesc, 1u);
                         } else {
-                            tc::mma_tf32(d_tmem, da_hi, db_hi, p.idesc, first);
+                            if (p.f16_kind) tc::mma_f16(d_tmem, da_hi, db_hi, p.idesc, first);
+                            else tc::mma_tf32(d_tmem, da_hi, db_hi, p.idesc, first);
                         }
                     }
                     tc::mma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
@@ -398,6 +401,7 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
     p.desc_b = b_mn ? desc_mn : desc_k; p.kstep_b = b_mn ? kstep_mn : UMMA_K * 4;
     p.idesc = tc::instr_desc(tc::FMT_TF32, BM, BN, a_mn, b_mn);
     p.terms = terms == 1 ? 1 : 3;
+    p.bk = BK; p.f16_kind = 0;
     p.window = (int)env_u32("TMM_TC_WINDOW", WINDOW_KBLOCKS);
     if (p.window < 1) p.window = 1;
     {
@@ -405,6 +409,57 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
         p.split_trunc = (sv && sv[0] == 't') ? 1 : 0;
     }
 
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(sgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+    if (tiles > INT32_MAX) return cudaErrorInvalidValue;
+    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    sgemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(map_a, map_b, p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// Experimental (TMM_BF16_NATIVE=1, not yet run on hardware): bf16 operands straight through kind::f16 MMAs for the "TN" case, where both
+// operands are k-contiguous.  A 128 x 64 bf16 tile has exactly the byte geometry of the 128 x 32 FP32 K-major tile above (128-byte rows,
+// SWIZZLE_128B, 32 bytes per UMMA_K slice - 16 bf16 instead of 8 tf32), so the same kernel runs it with a BF16 tensor map, bk = 64 and
+// the f16 instruction kind; no widening pass, twice the MMA rate.  Other op pairs keep the widening path of gemm_bf16_tc.cu.
+cudaError_t bgemm_tc_native_tn_launch(int m, int n, int k, float alpha, const void* a, int64_t lda, const void* b, int64_t ldb, float beta, float* c,
+                                      int64_t ldc, cudaStream_t stream) {
+    using namespace f32tc;
+    if (m <= 0 || n <= 0) return cudaSuccess;
+    if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (lda & 7) || (ldb & 7)) return cudaErrorInvalidValue;
+    auto encode = reinterpret_cast<CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill)>(
+        tensormap_encode_fn());
+    if (!encode) return cudaErrorInvalidValue;
+    constexpr int BK16 = 64;
+    auto make = [&](CUtensorMap* map, const void* base, uint64_t rows_k, uint64_t cols, uint64_t ld) {
+        cuuint64_t dims[2] = {rows_k, cols};
+        cuuint64_t strides[1] = {ld * 2};
+        cuuint32_t box[2] = {BK16, BM};
+        cuuint32_t estr[2] = {1, 1};
+        return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUtensorMap map_a, map_b;
+    if (make(&map_a, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda) != CUDA_SUCCESS || make(&map_b, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+    Params p;
+    p.c = c; p.ldc = ldc; p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta;
+    p.read_c = (beta != 0.f);
+    p.tiles_m = (m + BM - 1) / BM; p.tiles_n = (n + BN - 1) / BN;
+    p.a_mn_major = 0; p.b_mn_major = 0;
+    p.desc_a = p.desc_b = tc::smem_desc_template(16, 8 * 128, tc::LAYOUT_SW128);
+    p.kstep_a = p.kstep_b = 32;  // 16 bf16
+    p.idesc = tc::instr_desc(tc::FMT_BF16, BM, BN, false, false);
+    p.terms = 1; p.window = WINDOW_KBLOCKS; p.split_trunc = 0;
+    p.bk = BK16; p.f16_kind = 1;
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);

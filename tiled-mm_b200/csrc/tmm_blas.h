@@ -53,6 +53,9 @@ cudaError_t cgemm_tc_launch(char ta, char tb, int m, int n, int k, const float* 
 // BF16 inputs, FP32 output / accumulation, on the tcgen05 TF32 path (bf16 is a subset of tf32: identical products) - gemm_bf16_tc.cu
 cudaError_t bgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb,
                             float beta, float* c, int64_t ldc, cudaStream_t stream);
+// experimental native kind::f16 variant for k-contiguous operands (op(A) = T, op(B) = N); TMM_BF16_NATIVE=1
+cudaError_t bgemm_tc_native_tn_launch(int m, int n, int k, float alpha, const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, float beta, float* c,
+                                      int64_t ldc, cudaStream_t stream);
 // process-wide math mode of the complex<float> GEMM: 0 = SIMT (default), 3 = FP32-accurate on tensor cores
 int c32_math_mode();
 void set_c32_math_mode(int mode);
