@@ -102,6 +102,28 @@ def run_single():
             ctx.set_device_budget(4 << 20)
             case(ctx, dtype, "CN", 513, 300, 777, alpha, beta, (2, 0, 1), seed=6)
     check_clean("other dtypes")
+    # BLAS quick returns and argument errors - the same front end the GPU build runs
+    with tmm.make_context(np.float64) as ctx:
+        for shape in [(0, 5, 5), (5, 0, 5), (5, 5, 0), (7, 3, 0)]:
+            if shape[0] * shape[1]:
+                case(ctx, np.float64, "NN", *shape, 1.0, 2.0, (1, 1, 1), seed=10)        # k = 0: C = beta C
+            else:                                                                        # empty C: nothing to do, nothing dereferenced
+                tmm.gemm(ctx, "N", "N", *shape, 1.0, None, max(1, shape[0]), None, max(1, shape[2]), 0.0, None, max(1, shape[0]), False, True)
+        case(ctx, np.float64, "TN", 40, 30, 20, 0.0, -1.5, (1, 2, 3), seed=11)          # alpha = 0: C = beta C, A and B never touched
+        buf = tmm.malloc_pinned(np.float64, 64)
+        for bad in [lambda: tmm.gemm(ctx, "X", "N", 2, 2, 2, 1.0, buf, 2, buf, 2, 0.0, buf, 2, False, True),
+                    lambda: tmm.gemm(ctx, "N", "N", 4, 2, 2, 1.0, buf, 2, buf, 2, 0.0, buf, 4, False, True),
+                    lambda: tmm.gemm(ctx, "N", "N", 2, 2, 4, 1.0, buf, 2, buf, 2, 0.0, buf, 2, False, True),
+                    lambda: tmm.gemm(ctx, "N", "N", 2, 2, 2, 1.0, buf, 2, buf, 2, 0.0, buf, 1, False, True),
+                    lambda: tmm.gemm(ctx, "N", "N", -1, 2, 2, 1.0, buf, 2, buf, 2, 0.0, buf, 2, False, True),
+                    lambda: tmm.gemm(ctx, "N", "N", 2, 2, 2, 1.0, None, 2, buf, 2, 0.0, buf, 2, False, True)]:
+            try:
+                bad()
+                raise AssertionError("invalid call was accepted")
+            except ValueError:
+                pass
+        tmm.gemm(ctx, "n", "t", 2, 2, 2, 1.0, buf, 2, buf, 2, 0.0, buf, 2, False, True)   # lower case accepted (tiled_mm.cpp:503-504)
+    check_clean("quick returns and argument errors")
     # bf16 entry point: argument checking and plumbing of tmm_device_gemm_bf16 (the arithmetic here is the GEMM double's)
     rng = np.random.default_rng(9)
     m, n, k = 70, 50, 90
