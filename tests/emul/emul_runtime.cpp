@@ -55,7 +55,13 @@ bool dry_run() {
 }
 constexpr size_t DRY_REAL_LIMIT = 64 << 10;
 std::atomic<uintptr_t> g_virtual_next{0x100000000000ull};
-bool is_virtual(const void* p) { return reinterpret_cast<uintptr_t>(p) >= 0x100000000000ull && reinterpret_cast<uintptr_t>(p) < 0x700000000000ull && dry_run(); }
+// address-only memory: device ranges handed out by the dry-run cudaMalloc, and the window the dry-run test uses for its host "buffers"
+// (exact ranges, not a heuristic: sanitizer allocators place real heap memory at similar-looking addresses)
+bool is_virtual(const void* p) {
+    if (!dry_run()) return false;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    return (a >= 0x100000000000ull && a < g_virtual_next.load()) || (a >= 0x200000000000ull && a < 0x500000000000ull);
+}
 
 void violation(const char* what, const void* p, size_t bytes) {
     if (g_violations.fetch_add(1) == 0) snprintf(g_first_violation, sizeof g_first_violation, "%s: %p + %zu", what, p, bytes);

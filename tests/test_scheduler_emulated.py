@@ -92,3 +92,21 @@ def test_phase1_column_stripes_with_staggered_c_upload(emul_build, stripes, devi
 def test_one_c_stripe_per_k_chunk_experiment(emul_build):
     """TMM_PLAN_CSTRIPES=chunks (opt-in schedule experiment for beta != 0: as many column stripes as k-chunks, more stripes than streams)"""
     _worker(emul_build, ["sweep", 1, 500, 61], 1, {"TMM_PLAN_CSTRIPES": "chunks"})
+
+
+def test_scheduler_under_address_and_ub_sanitizers():
+    """The same scheduler sources built with -fsanitize=address,undefined (the reference has no sanitizer coverage): a random
+    sweep on one device and on a 2x2 grid must finish without a report (heap / stack overflows in the host-side bookkeeping, signed
+    overflow in the 64-bit offset arithmetic, ...)."""
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not asan or not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
+    r = subprocess.run(["make", "-C", str(EMUL), "-j4", "SAN=1", "all"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    build = EMUL / "_build_asan"
+    san_env = {"TMM_EMUL_LIB": str(build / "libtiledmm_emul.so"), "LD_PRELOAD": asan, "ASAN_OPTIONS": "detect_leaks=0:halt_on_error=1",
+               "UBSAN_OPTIONS": "halt_on_error=1:print_stacktrace=1"}
+    _worker(build, ["sweep", 1, 250, 81], 1, san_env)
+    _worker(build, ["sweep", 4, 60, 82], 4, dict(san_env, TMM_PLAN_P1SPLIT="3"))
+    _worker(build, ["dry", 8], 8, dict(san_env, TMM_EMUL_DRY="1", TMM_EMUL_MEM_MB="182000"))
