@@ -25,6 +25,8 @@ timeout 60 python tools/e2e.py --beta 1 --reps 4 2>&1 | tail -1
 TMM_PLAN_CSTRIPES=chunks timeout 60 python tools/e2e.py --beta 1 --reps 4 2>&1 | tail -1
 echo "== mid-size products: n1 bound on / off =="
 for n in 4000 6000 8000; do timeout 60 python tools/e2e.py --m $n --n $n --k $n --reps 5 2>&1 | tail -1; TMM_PLAN_D2H_BOUND=0 timeout 60 python tools/e2e.py --m $n --n $n --k $n --reps 5 2>&1 | tail -1; done
+echo "== cublasXt comparator (the reference's headline comparison), tuned block 4000 and default =="
+for n in 4000 10000 16000; do timeout 120 ./build/cublasxt-multiply -m $n -n $n -k $n -r 2 --beta 1 --block 4000 2>&1 | grep -E "Avg Time|Throughput"; timeout 60 bin/multiply -m $n -n $n -k $n -r 2 --beta 1 2>&1 | grep -E "Avg Time|Throughput" | head -2; done
 echo "== compute-sanitizer memcheck on the CI shapes (SURVEY 5.2) =="; timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gemm_gpu.py -m gpu -q -k "ci_and_ctest or degenerate" 2>&1 | tail -6
 echo "== regular suite =="; timeout 600 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -8
 echo "== bench =="; timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1
