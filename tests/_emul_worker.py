@@ -247,6 +247,7 @@ def run_dry(n_dev):
     pr, pc = tmm.grid_shape(n_dev)
     A, B, C = 0x200000000000, 0x300000000000, 0x400000000000      # host "buffers": never dereferenced in a dry run
     cases = [
+        ("headline dgemm 10000^3 beta=1 (four column stripes, staggered C upload)", np.float64, "NN", 10000, 10000, 10000, 1.0),
         ("C5 dgemm 100000^3", np.float64, "NN", 100000, 100000, 100000, 0.0),
         ("C4 zgemm 20000x20000x500000", np.complex128, "NN", 20000, 20000, 500000, 0.0),
         ("C4 zgemm CN beta=1", np.complex128, "CN", 20000, 20000, 500000, 1.0),
