@@ -240,6 +240,42 @@ def run_replan():
     print("EMUL_OK replan")
 
 
+def run_threads(n_threads, per_thread):
+    """One context per host thread, all on the same device, calls in flight concurrently (the reference's intended use: 'one handle
+    per host thread').  ctypes releases the GIL during tmm_gemm, so the library's process-wide state is really shared."""
+    import threading
+    errors = []
+
+    def body(tid):
+        try:
+            rng = np.random.default_rng(1000 + tid)
+            dtype = [np.float64, np.complex128, np.float32, np.complex64][tid % 4]
+            with tmm.make_context(dtype, 2, 64, 64, 64) as ctx:
+                for i in range(per_thread):
+                    m, n, k = (int(x) for x in rng.integers(1, 200, 3))
+                    if i % 7 == 3:
+                        ctx.set_device_budget(256 << 10)
+                    elif i % 7 == 5:
+                        ctx.set_device_budget(0)
+                    try:
+                        case(ctx, dtype, "".join(rng.choice(list("NTC"), 2)), m, n, k, 1.0, [0.0, 1.0][i % 2], (1, 0, 2), copy_modes=(bool(i % 3),), seed=tid * 10000 + i)
+                    except RuntimeError as e:
+                        if "budget too small" not in str(e):
+                            raise
+        except BaseException as e:  # noqa: BLE001 - reported by the main thread
+            errors.append(f"thread {tid}: {type(e).__name__}: {e}")
+
+    threads = [threading.Thread(target=body, args=(t,)) for t in range(n_threads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    check_clean("concurrent contexts")
+    assert lib.emul_live_device_bytes(0) == 0
+    print(f"EMUL_OK threads {n_threads} x {per_thread}")
+
+
 def run_dry(n_dev):
     """Full-size walk through the real scheduler with address-only memory (TMM_EMUL_DRY=1): BASELINE configs[3] and [4] and a C that
     needs super-blocks.  No arithmetic, no data movement - bounds, 64-bit offsets, ordering, protocol progress and byte counts."""
@@ -283,7 +319,9 @@ def run_dry(n_dev):
 
 if __name__ == "__main__":
     mode = sys.argv[1]
-    if mode == "replan":
+    if mode == "threads":
+        run_threads(int(sys.argv[2]), int(sys.argv[3]))
+    elif mode == "replan":
         run_replan()
     elif mode == "dry":
         run_dry(int(sys.argv[2]))

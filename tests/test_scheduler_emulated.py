@@ -110,3 +110,8 @@ def test_scheduler_under_address_and_ub_sanitizers():
     _worker(build, ["sweep", 1, 250, 81], 1, san_env)
     _worker(build, ["sweep", 4, 60, 82], 4, dict(san_env, TMM_PLAN_P1SPLIT="3"))
     _worker(build, ["dry", 8], 8, dict(san_env, TMM_EMUL_DRY="1", TMM_EMUL_MEM_MB="182000"))
+
+
+def test_one_context_per_host_thread_concurrently(emul_build):
+    """eight host threads, one context each, calls in flight at the same time on one device"""
+    _worker(emul_build, ["threads", 8, 60], 1)
