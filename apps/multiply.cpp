@@ -10,6 +10,9 @@
 #include <chrono>
 #include <complex>
 #include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
 
 namespace {
 
@@ -17,12 +20,38 @@ template <typename T> T make_scalar(double v) { return T(v); }
 template <typename T> struct flops_per_fma { static constexpr double value = 2.0; };
 template <typename R> struct flops_per_fma<std::complex<R>> { static constexpr double value = 8.0; };
 
+// The reference fills A and B with ones (examples/multiply.cpp:156-160).  For the out-of-core sizes (hundreds of GB) a single-threaded
+// std::fill takes minutes, and all-ones operands draw less power than real data; --random 1 fills with uniform(-1, 1) values from
+// one xorshift generator per thread instead.  Either way the fill runs on all host cores.
 template <typename T>
-int run(const cli::Problem& p, long long repetitions) {
+void parallel_fill(T* ptr, size_t count, bool random, unsigned seed) {
+    const unsigned n_threads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < n_threads; ++t)
+        pool.emplace_back([=] {
+            const size_t lo = count * t / n_threads, hi = count * (t + 1) / n_threads;
+            if (!random) { std::fill(ptr + lo, ptr + hi, T(1)); return; }
+            unsigned long long x = 0x9E3779B97F4A7C15ull * (seed * 64ull + t + 1);
+            for (size_t i = lo; i < hi; ++i) {
+                x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+                ptr[i] = T((double)(x >> 11) * (2.0 / 9007199254740992.0) - 1.0);
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+
+template <typename T>
+int run(const cli::Problem& p, long long repetitions, bool random, const std::string& variants) {
     const double flops_per_mul = flops_per_fma<T>::value * (double)p.m * (double)p.n * (double)p.k;
-    T* a_host = gpu::malloc_pinned<T>((size_t)p.ld_a * p.a_cols, T(1));
-    T* b_host = gpu::malloc_pinned<T>((size_t)p.ld_b * p.b_cols, T(1));
-    T* c_host = gpu::malloc_pinned<T>((size_t)p.ld_c * p.n, T(0));
+    const size_t na = (size_t)p.ld_a * p.a_cols, nb = (size_t)p.ld_b * p.b_cols, nc = (size_t)p.ld_c * p.n;
+    void *pa = nullptr, *pb = nullptr, *pc = nullptr;
+    gpu::check_tmm_status(tmm_malloc_pinned(na * sizeof(T), &pa));
+    gpu::check_tmm_status(tmm_malloc_pinned(nb * sizeof(T), &pb));
+    gpu::check_tmm_status(tmm_malloc_pinned(nc * sizeof(T), &pc));
+    T *a_host = static_cast<T*>(pa), *b_host = static_cast<T*>(pb), *c_host = static_cast<T*>(pc);
+    parallel_fill(a_host, na, random, 1);
+    parallel_fill(b_host, nb, random, 2);
+    std::memset(pc, 0, nc * sizeof(T));
     auto ctx = gpu::make_context<T>((int)p.n_streams, (int)p.tile_m, (int)p.tile_n, (int)p.tile_k);
     const T alpha = make_scalar<T>(p.alpha), beta = make_scalar<T>(p.beta);
 
@@ -31,6 +60,7 @@ int run(const cli::Problem& p, long long repetitions) {
               << "==================================================" << std::endl;
     for (int variant = 0; variant < 2; ++variant) {
         const bool copy_c_back = variant == 0;
+        if ((copy_c_back && variants == "device") || (!copy_c_back && variants == "back")) continue;
         std::cout << (copy_c_back ? " 1) The version with copying C to back to host: " : " 2) The version without copying C to back to host: ") << std::endl;
         if (copy_c_back && p.gpus > 1) gpu::check_tmm_status(tmm_context_set_devices(ctx->native(), (int)p.gpus, nullptr));
         if (!copy_c_back && p.gpus > 1) gpu::check_tmm_status(tmm_context_set_devices(ctx->native(), 1, nullptr));  // device C lives on one GPU
@@ -57,19 +87,24 @@ int run(const cli::Problem& p, long long repetitions) {
 }  // namespace
 
 int main(int argc, char** argv) {
-    cli::Args args(cli::gemm_options(true));
+    auto table = cli::gemm_options(true);
+    table.push_back({"", "variants", "both", "both | back | device: run the copy-C-back variant, the device-resident-C variant, or both (the reference runs both)."});
+    table.push_back({"", "random", "0", "1: fill A and B with uniform(-1,1) values instead of ones (realistic power draw)."});
+    cli::Args args(table);
     if (!args.read(argc, argv)) return 2;
     if (args.help_requested) { args.usage("multiply", "Benchmarking Tiled-MM: measures the runtime of the tiled out-of-core GEMM."); return 0; }
     cli::Problem p;
     if (!cli::problem_from(args, &p)) return 0;  // the reference also exits 0 after its [ERROR] message (examples/multiply.cpp:83-91)
     const long long repetitions = std::max<long long>(1, args.integer("n_rep"));
+    const bool random = args.integer("random") != 0;
+    const std::string variants = args.text("variants");
     cli::print_banner(p, repetitions);
     try {
         switch (p.type) {
-        case 's': return run<float>(p, repetitions);
-        case 'c': return run<std::complex<float>>(p, repetitions);
-        case 'z': return run<std::complex<double>>(p, repetitions);
-        default: return run<double>(p, repetitions);
+        case 's': return run<float>(p, repetitions, random, variants);
+        case 'c': return run<std::complex<float>>(p, repetitions, random, variants);
+        case 'z': return run<std::complex<double>>(p, repetitions, random, variants);
+        default: return run<double>(p, repetitions, random, variants);
         }
     } catch (const std::exception& e) {
         std::cerr << "multiply: " << e.what() << std::endl;
