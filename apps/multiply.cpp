@@ -41,7 +41,7 @@ void parallel_fill(T* ptr, size_t count, bool random, unsigned seed) {
 }
 
 template <typename T>
-int run(const cli::Problem& p, long long repetitions, bool random, const std::string& variants) {
+int run(const cli::Problem& p, long long repetitions, bool random, const std::string& variants, long long warmup) {
     const double flops_per_mul = flops_per_fma<T>::value * (double)p.m * (double)p.n * (double)p.k;
     const size_t na = (size_t)p.ld_a * p.a_cols, nb = (size_t)p.ld_b * p.b_cols, nc = (size_t)p.ld_c * p.n;
     void *pa = nullptr, *pb = nullptr, *pc = nullptr;
@@ -65,8 +65,8 @@ int run(const cli::Problem& p, long long repetitions, bool random, const std::st
         if (copy_c_back && p.gpus > 1) gpu::check_tmm_status(tmm_context_set_devices(ctx->native(), (int)p.gpus, nullptr));
         if (!copy_c_back && p.gpus > 1) gpu::check_tmm_status(tmm_context_set_devices(ctx->native(), 1, nullptr));  // device C lives on one GPU
         auto start = std::chrono::steady_clock::now();
-        for (long long i = 0; i < repetitions + 1; ++i) {
-            if (i == 1) start = std::chrono::steady_clock::now();  // run 0 warms the context up (examples/multiply.cpp:170-176)
+        for (long long i = 0; i < repetitions + warmup; ++i) {
+            if (i == warmup) start = std::chrono::steady_clock::now();  // the first run warms the context up (examples/multiply.cpp:170-176)
             gpu::gemm64<T>(*ctx, p.trans_a, p.trans_b, p.m, p.n, p.k, alpha, a_host, p.ld_a, b_host, p.ld_b, beta, c_host, p.ld_c,
                            /*pin_host_buffers=*/false, copy_c_back);
         }
@@ -89,6 +89,7 @@ int run(const cli::Problem& p, long long repetitions, bool random, const std::st
 int main(int argc, char** argv) {
     auto table = cli::gemm_options(true);
     table.push_back({"", "variants", "both", "both | back | device: run the copy-C-back variant, the device-resident-C variant, or both (the reference runs both)."});
+    table.push_back({"", "warmup", "1", "Untimed runs before the timed ones (the reference does one); 0 for runs that take minutes."});
     table.push_back({"", "random", "0", "1: fill A and B with uniform(-1,1) values instead of ones (realistic power draw)."});
     cli::Args args(table);
     if (!args.read(argc, argv)) return 2;
@@ -98,13 +99,14 @@ int main(int argc, char** argv) {
     const long long repetitions = std::max<long long>(1, args.integer("n_rep"));
     const bool random = args.integer("random") != 0;
     const std::string variants = args.text("variants");
+    const long long warmup = std::max<long long>(0, args.integer("warmup"));
     cli::print_banner(p, repetitions);
     try {
         switch (p.type) {
-        case 's': return run<float>(p, repetitions, random, variants);
-        case 'c': return run<std::complex<float>>(p, repetitions, random, variants);
-        case 'z': return run<std::complex<double>>(p, repetitions, random, variants);
-        default: return run<double>(p, repetitions, random, variants);
+        case 's': return run<float>(p, repetitions, random, variants, warmup);
+        case 'c': return run<std::complex<float>>(p, repetitions, random, variants, warmup);
+        case 'z': return run<std::complex<double>>(p, repetitions, random, variants, warmup);
+        default: return run<double>(p, repetitions, random, variants, warmup);
         }
     } catch (const std::exception& e) {
         std::cerr << "multiply: " << e.what() << std::endl;

@@ -10,5 +10,5 @@ AVAIL_GB=$(awk '/MemAvailable/ {print int($2/1048576)}' /proc/meminfo)
 N=100000; [ "$AVAIL_GB" -lt 300 ] && N=60000
 {
 echo "gpus $G, MemAvailable ${AVAIL_GB} GB, n = $N"; nvidia-smi -L | wc -l
-timeout 360 bin/multiply -m $N -n $N -k $N -r 1 --gpus $G --random 1 --variants back 2>&1 | grep -E "Avg Time|Throughput|last call|error|ERROR"
+timeout 360 bin/multiply -m $N -n $N -k $N -r 1 --gpus $G --random 1 --variants back --warmup 0 2>&1 | grep -E "Avg Time|Throughput|last call|error|ERROR"
 } 2>&1 | tee gpurun_out/r2_c5_${G}gpu.txt
