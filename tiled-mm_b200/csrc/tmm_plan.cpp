@@ -13,7 +13,9 @@ size_t elem_size(int dt) { return dt == 0 ? 4 : (dt == 1 ? 8 : (dt == 2 ? 8 : 16
 
 // Throughput model used only to size chunks (never a correctness input).  Measured on B200 (profiles/r1_probe_b200.txt):
 // FP64 DMMA GEMM 35.6 TFLOP/s, pinned H2D 55.6 GB/s (48 GB/s while D2H runs).
-constexpr double kFlops = 35e12;
+constexpr double kFlopsF64 = 35e12;   // DGEMM / ZGEMM (8mnk counted for complex): DMMA pipe
+constexpr double kFlopsF32 = 140e12;  // SGEMM, FP32-accurate 3xTF32 on tcgen05 (profiles/r1_tc_sgemm_v2.txt); with the FP64 figure the planner
+                                      // chose a first block 2 - 5x too narrow for float and left the SMs idle while A streamed in
 constexpr double kH2D = 52e9;
 constexpr double kD2H = 52e9;
 constexpr int64_t BM = 128, BN = 64;  // CTA tile of the FP64 kernels
@@ -70,6 +72,7 @@ Plan make_plan(const PlanInput& in) {
     const size_t full_a = (size_t)p.pitch_a * p.a_cols * es, full_b = (size_t)p.pitch_b * p.b_cols * es;
     const size_t full_c = in.copy_c_back ? (size_t)p.pitch_c * n * es : 0;
     const double F = (in.dtype >= 2) ? 8.0 : 2.0;
+    const double kFlops = in.dtype == 0 ? env_or("TMM_PLAN_F32_FLOPS", kFlopsF32) : kFlopsF64;  // complex<float> still runs the SIMT kernel by default
     const int64_t kc_cap = std::max<int64_t>(256, std::min<int64_t>(2048, round_up(std::max(64, in.tile_k), 64)));
 
     if (full_a + full_b + full_c <= in.budget) {
@@ -95,9 +98,16 @@ Plan make_plan(const PlanInput& in) {
             // ran as ONE phase and ended with the D2H of the whole C exposed.  (Timeline model tools/model_resident.py, calibrated on
             // the measured 10000^3, whose n1 = 5504 is below its bound of 6600 and unchanged: 9 - 20 % shorter calls predicted for
             // n = 4000 ... 7000; to be measured.  TMM_PLAN_D2H_BOUND=0 switches the bound off.)
-            const double rho = F * (double)k / kFlops * (kD2H / (double)es);
+            // (per column of C: the D2H costs es m / BW; the window that hides it is the longer of the column's GEMM and its own upload)
+            const double hide = std::max(F * (double)m * (double)k / kFlops, (double)es * ((double)k * sb + (in.beta_nonzero ? (double)m : 0.0)) / kH2D);
+            const double rho = hide / ((double)es * (double)m / kD2H);
             const int64_t cap = (int64_t)(0.85 * (double)n * rho / (1.0 + rho));  // 15 % slack: the D2H competes with H2D for host memory
-            if (in.copy_c_back && env_or("TMM_PLAN_D2H_BOUND", 1.0) != 0.0 && n1 > cap) { n1 = std::max<int64_t>(std::min<int64_t>(n, 1024), cap); d2h_bound = true; }
+            if (in.copy_c_back && env_or("TMM_PLAN_D2H_BOUND", 1.0) != 0.0) {
+                if (n1 > cap) { n1 = std::max<int64_t>(std::min<int64_t>(n, 1024), cap); d2h_bound = true; }
+                // PCIe-bound whatever we do (denom <= 0): the widest first block whose D2H still hides is also the one that leaves the
+                // least GEMM work for after the last byte of B has arrived
+                else if (denom <= 0 && cap > n1) { n1 = std::min<int64_t>(n, cap); d2h_bound = true; }
+            }
         }
         n1 = std::min<int64_t>(n, round_up(n1, BN));
         if (n1 < n && !d2h_bound) {

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Host-to-host timing of one configuration (GPU box; development tool).  Under torchrun it runs the grid path.
-   python tools/e2e.py [--m M --n N --k K --tt NN --dtype d|z --beta 0 --reps 6 --trace]"""
+   python tools/e2e.py [--m M --n N --k K --tt NN --dtype s|d|c|z --beta 0 --reps 6 --trace]"""
 import argparse, os, sys, time
 from pathlib import Path
 import numpy as np
@@ -21,7 +21,7 @@ if world > 1:
     import torch, torch.distributed as dist
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
-dt = np.float64 if args.dtype == "d" else np.complex128
+dt = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}[args.dtype]
 m, n, k = args.m, args.n, args.k
 ta, tb = args.tt
 ar, ac = (m, k) if ta == "N" else (k, m)
@@ -29,7 +29,7 @@ br, bc = (k, n) if tb == "N" else (n, k)
 a = tmm.malloc_pinned(dt, ar * ac); b = tmm.malloc_pinned(dt, br * bc); c = tmm.malloc_pinned(dt, m * n)
 rng = np.random.default_rng(rank)
 for arr in (a, b):
-    v = arr.view(np.float64)
+    v = arr.view(np.float32 if args.dtype in "sc" else np.float64)
     for off in range(0, v.size, 1 << 24):
         v[off:off + (1 << 24)] = rng.random(min(1 << 24, v.size - off)) - 0.5
 ctx = tmm.make_context(dt, 2, 5000, 5000, 5000)
@@ -41,7 +41,7 @@ grid = None
 if world > 1:
     from tiled_mm_b200 import multi_gpu
     grid = multi_gpu.GridGemm(ctx, dist)
-flops = (2.0 if args.dtype == "d" else 8.0) * m * n * k * world
+flops = (2.0 if args.dtype in "sd" else 8.0) * m * n * k * world
 best = 1e30
 for r in range(args.reps):
     if dist is not None:

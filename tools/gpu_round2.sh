@@ -27,6 +27,8 @@ echo "== mid-size products: n1 bound on / off =="
 for n in 4000 6000 8000; do timeout 60 python tools/e2e.py --m $n --n $n --k $n --reps 5 2>&1 | tail -1; TMM_PLAN_D2H_BOUND=0 timeout 60 python tools/e2e.py --m $n --n $n --k $n --reps 5 2>&1 | tail -1; done
 echo "== cublasXt comparator (the reference's headline comparison), tuned block 4000 and default =="
 for n in 4000 10000 16000; do timeout 120 ./build/cublasxt-multiply -m $n -n $n -k $n -r 2 --beta 1 --block 4000 2>&1 | grep -E "Avg Time|Throughput"; timeout 60 bin/multiply -m $n -n $n -k $n -r 2 --beta 1 2>&1 | grep -E "Avg Time|Throughput" | head -2; done
+echo "== SGEMM host-to-host: planner with the float rate (default) vs the round-1 FP64 rate =="
+for n in 10000 16000; do timeout 60 python tools/e2e.py --dtype s --m $n --n $n --k $n --reps 4 2>&1 | tail -1; TMM_PLAN_F32_FLOPS=35e12 TMM_PLAN_D2H_BOUND=0 timeout 60 python tools/e2e.py --dtype s --m $n --n $n --k $n --reps 4 2>&1 | tail -1; done
 echo "== compute-sanitizer memcheck on the CI shapes (SURVEY 5.2) =="; timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gemm_gpu.py -m gpu -q -k "ci_and_ctest or degenerate" 2>&1 | tail -6
 echo "== regular suite =="; timeout 600 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -8
 echo "== bench =="; timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1
