@@ -68,3 +68,31 @@ def test_out_of_core_configs_stream(tmm):
     # tiny budget forces C super-blocks with two buffers
     p = tmm.plan_describe(np.float64, "N", "N", 6000, 6000, 3000, False, True, 128 << 20)
     assert p["regime"] == 1 and p["n_cbuf"] == 2 and (p["MB"] < 6000 or p["NB"] < 6000)
+
+
+def test_headline_plan_is_the_measured_one(tmm):
+    """The plan of BASELINE configs[1] is pinned to the one that was measured on hardware (profiles/r1_e2e_trace_10000.txt, 58.6 ms):
+    planner changes made without a GPU must not move it."""
+    p = tmm.plan_describe(np.float64, "N", "N", 10000, 10000, 10000, False, True, int(0.92 * 178e9))
+    assert p["regime"] == 0 and p["n1"] == 5504
+    assert p["chunks"] == [256, 320, 384, 448, 512, 640, 768, 960, 1152, 1408, 1728, 1424]
+    assert p["blocks"] == [1664, 1664, 896, 272]
+
+
+def test_timeline_model_reproduces_the_measured_calls(tmm):
+    """tools/model_resident.py is only a design aid, but the schedule changes made after the last hardware run lean on it: it has to
+    reproduce the two calls it was calibrated against (dgemm 10000^3: 58.60 ms, sgemm 10000^3 with the round-1 plan: 21.73 ms)."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import model_resident as mr
+    t, _, _, _ = mr.predict(10000, 10000, 10000, 0.0)
+    assert abs(t * 1e3 - 58.6) < 1.0, t
+    round1_f32_plan = {"regime": 0, "n1": 2368, "chunks": [256, 320, 384, 512, 640, 832, 1088, 1408, 1856, 2704], "blocks": [1664, 1664, 1664, 1664, 704, 272]}
+    saved = mr.P
+    try:
+        mr.P = 140e12
+        t, _, _, _ = mr.predict(10000, 10000, 10000, 0.0, plan=round1_f32_plan, es=4)
+    finally:
+        mr.P = saved
+    assert abs(t * 1e3 - 21.73) < 1.0, t
