@@ -54,7 +54,7 @@ def test_cpp_dropin_headers_compile(tmp_path):
     src = tmp_path / "caller.cpp"
     src.write_text(
         "#include <Tiled-MM/tiled_mm.hpp>\n#include <Tiled-MM/device_vector.hpp>\n#include <Tiled-MM/util.hpp>\n#include <Tiled-MM/gpu_blas_handle.hpp>\n"
-        "#include <Tiled-MM/gpu_blas_api.hpp>\n#include <Tiled-MM/gpu_runtime_api.hpp>\n#include <Tiled-MM/device_buffer.hpp>\n#include <Tiled-MM/gpu_context.hpp>\n"
+        "#include <Tiled-MM/gpu_blas_api.hpp>\n#include <Tiled-MM/gpu_runtime_api.hpp>\n#include <Tiled-MM/device_buffer.hpp>\n#include <Tiled-MM/gpu_context.hpp>\n#include <Tiled-MM/tiled_matrix.hpp>\n#include <Tiled-MM/tile_coord.hpp>\n"
         "int run(int m, int n, int k) {\n"
         "  auto a = gpu::malloc_pinned<double>(size_t(m) * k, 1); auto b = gpu::malloc_pinned<double>(size_t(k) * n, 1);\n"
         "  auto c = gpu::malloc_pinned<double>(size_t(m) * n, 0);\n"
@@ -69,11 +69,36 @@ def test_cpp_dropin_headers_compile(tmp_path):
         "  gpu::device_buffer<double>& ab = ctx->get_device_buffer_a(); gpu::tile_dim td = ab.get_tile_sizes();\n"
         "  double* slab1 = ctx->get_device_buffer_c().stream_buffer(1); double* base = ctx->get_device_buffer_b().data(); (void)slab1; (void)base;\n"
         "  gpu::gpu_context& gc = ctx->get_gpu_context(); cudaStream_t s0 = gc.get_stream(0); cudaStream_t rs = gc.get_result_stream().stream(); gpu::device_stream& ds = gc.get_device_stream(1); (void)s0; (void)rs; (void)ds;\n"
-        "  int t0 = td.rows() + td.cols() + td.size() + std::get<2>(ctx->get_max_tile_sizes()) + gc.get_num_streams();\n"
+        "  gpu::tiled_matrix<double> tmx(a, m, k, m, gpu::tile_dim(7, 5)); gpu::tile_coord tc(1, 2);\n"
+        "  int tq = tmx.num_tiles_row() + tmx.num_tiles_col() + tmx.tile_dimensions(tc).rows() + tmx.tile_offset(tc) + (tmx.tile_data(tc) != nullptr);\n"
+        "  int t0 = tq + td.rows() + td.cols() + td.size() + std::get<2>(ctx->get_max_tile_sizes()) + gc.get_num_streams();\n"
         "  return (int)ctx->get_num_streams() + (int)std::get<0>(ctx->optimal_tile_sizes(m, n, k)) + (gpu::get_blas_operation('T') == gpu::blas_api::operation::Transpose) + t0;\n"
         "}\n")
     subprocess.run(["g++", "-std=c++14", "-Wall", "-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include", "-c", str(src), "-o", str(tmp_path / "c.o")],
                    check=True)
+
+
+def test_tiling_view_header_matches_the_reference_rules(tmp_path, oracle):
+    """include/Tiled-MM/tiled_matrix.hpp (kept for callers that include it): clamp, ceiling tile count, remainder tile, offsets - the
+    rules of reference tiled_matrix.cpp:8-23,62-80, here with 64-bit offsets; tile counts cross-checked against the oracle's restatement."""
+    src = tmp_path / "tm.cpp"
+    src.write_text(
+        "#include <Tiled-MM/tiled_matrix.hpp>\n#include <cstdio>\n#include <cstdlib>\n"
+        "int main(int argc, char** argv) {\n"
+        "  double buf[1]; int rows = atoi(argv[1]), cols = atoi(argv[2]), tr = atoi(argv[3]), tc = atoi(argv[4]);\n"
+        "  gpu::tiled_matrix<double> t(buf, rows, cols, rows + 3, gpu::tile_dim(tr, tc));\n"
+        "  gpu::tile_coord last(t.num_tiles_row() - 1, t.num_tiles_col() - 1);\n"
+        "  printf(\"%d %d %d %d %zu\\n\", t.num_tiles_row(), t.num_tiles_col(), t.tile_dimensions(last).rows(), t.tile_dimensions(last).cols(), t.tile_offset64(last));\n"
+        "}\n")
+    exe = tmp_path / "tm"
+    subprocess.run(["g++", "-std=c++14", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    for rows, cols, tr, tc in [(12345, 23456, 4115, 2932), (5, 2, 4, 4), (50, 200, 4, 4), (1000, 1000, 5000, 5000), (60000, 60000, 5000, 5000)]:
+        out = subprocess.run([str(exe), str(rows), str(cols), str(tr), str(tc)], check=True, capture_output=True, text=True).stdout.split()
+        ntr, ntc, lr, lc, off = (int(x) for x in out)
+        ctr, ctc = min(tr, rows), min(tc, cols)
+        assert ntr == oracle.lib.oracle_num_tiles(rows, ctr) and ntc == oracle.lib.oracle_num_tiles(cols, ctc)
+        assert lr == rows - ctr * (ntr - 1) and lc == cols - ctc * (ntc - 1)
+        assert off == (ntc - 1) * ctc * (rows + 3) + (ntr - 1) * ctr   # beyond 2^31 for the last case
 
 
 def test_no_cpu_fallback_without_gpu(tmm):
