@@ -26,6 +26,13 @@ constexpr StatusType Success = TMM_OK;
 inline const char* get_string(StatusType) { return tmm_last_error(); }
 }  // namespace status
 
+// handle life cycle (reference gpu_blas_api.hpp:167-192 forwards these to cublasCreate / cublasDestroy / cublasSetStream): a handle is
+// the stream its GEMMs run on, so creating one yields the default stream and binding a stream overwrites it
+inline StatusType create(HandleType* handle) { *handle = nullptr; return status::Success; }
+inline StatusType destroy(HandleType) { return status::Success; }
+template <typename Stream>
+inline StatusType set_stream(HandleType& handle, Stream stream) { handle = reinterpret_cast<HandleType>(stream); return status::Success; }
+
 inline char op_char(OperationType op) { return op == OpNone ? 'N' : (op == OpTranspose ? 'T' : 'C'); }
 
 // device pointers, column-major, host-pointer scalars: the cuBLAS v2 calling convention the reference uses

@@ -69,6 +69,7 @@ def test_cpp_dropin_headers_compile(tmp_path):
         "  gpu::device_buffer<double>& ab = ctx->get_device_buffer_a(); gpu::tile_dim td = ab.get_tile_sizes();\n"
         "  double* slab1 = ctx->get_device_buffer_c().stream_buffer(1); double* base = ctx->get_device_buffer_b().data(); (void)slab1; (void)base;\n"
         "  gpu::gpu_context& gc = ctx->get_gpu_context(); cudaStream_t s0 = gc.get_stream(0); cudaStream_t rs = gc.get_result_stream().stream(); gpu::device_stream& ds = gc.get_device_stream(1); (void)s0; (void)rs; (void)ds;\n"
+        "  gpu::blas_api::HandleType bh; gpu::blas_api::create(&bh); gpu::blas_api::set_stream(bh, s0); gpu::blas_api::destroy(bh);\n"
         "  gpu::tiled_matrix<double> tmx(a, m, k, m, gpu::tile_dim(7, 5)); gpu::tile_coord tc(1, 2);\n"
         "  int tq = tmx.num_tiles_row() + tmx.num_tiles_col() + tmx.tile_dimensions(tc).rows() + tmx.tile_offset(tc) + (tmx.tile_data(tc) != nullptr);\n"
         "  int t0 = tq + td.rows() + td.cols() + td.size() + std::get<2>(ctx->get_max_tile_sizes()) + gc.get_num_streams();\n"
