@@ -116,6 +116,8 @@ def run_single():
                     lambda: tmm.gemm(ctx, "N", "N", 2, 2, 4, 1.0, buf, 2, buf, 2, 0.0, buf, 2, False, True),
                     lambda: tmm.gemm(ctx, "N", "N", 2, 2, 2, 1.0, buf, 2, buf, 2, 0.0, buf, 1, False, True),
                     lambda: tmm.gemm(ctx, "N", "N", -1, 2, 2, 1.0, buf, 2, buf, 2, 0.0, buf, 2, False, True),
+                    lambda: tmm.gemm(ctx, "N", "N", 2**31 - 1, 2**31 - 1, 2**31 - 1, 1.0, buf, 2**31 - 1, buf, 2**31 - 1, 0.0, buf, 2**31 - 1, False, True),
+                    lambda: tmm.gemm(ctx, "N", "N", 2**31, 2, 2, 1.0, buf, 2**31, buf, 2, 0.0, buf, 2**31, False, True),
                     lambda: tmm.gemm(ctx, "N", "N", 2, 2, 2, 1.0, None, 2, buf, 2, 0.0, buf, 2, False, True)]:
             try:
                 bad()

@@ -680,6 +680,12 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
     if (m < 0 || n < 0 || k < 0) return fail(TMM_ERR_INVALID, "negative dimension");
     if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return fail(TMM_ERR_INVALID, "dimension exceeds 2^31-1");
     if (!alpha || !beta) return fail(TMM_ERR_INVALID, "alpha/beta null");
+    {   // byte counts are formed in size_t: refuse shapes whose matrices could not be addressed rather than let a product wrap
+        const double limit = 4.0e18, es_d = (double)tmm::dtype_size(ctx->dtype);
+        const double rows_a = (double)std::max<int64_t>(ld_a, 1), rows_b = (double)std::max<int64_t>(ld_b, 1), rows_c = (double)std::max<int64_t>(ld_c, 1);
+        if (rows_a * (double)std::max(m, k) * es_d > limit || rows_b * (double)std::max(n, k) * es_d > limit || rows_c * (double)n * es_d > limit)
+            return fail(TMM_ERR_INVALID, "matrix too large to address (more than 4e18 bytes)");
+    }
     cl.m = m; cl.n = n; cl.k = k; cl.alpha = alpha; cl.beta = beta;
     cl.a = (const char*)a; cl.b = (const char*)b; cl.c = (char*)c;
     cl.lda = ld_a; cl.ldb = ld_b; cl.ldc = ld_c;
