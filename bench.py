@@ -167,6 +167,12 @@ class NumaLocal:
                 pass
 
 
+def workload_name(size: int, streams: int = 2) -> str:
+    """One name for the workload, used by both arms (the driver compares the arms on `config`)."""
+    return (f"README miniapp (BASELINE configs[1]): dgemm m=n=k={size} NN alpha=1 beta=0, pinned host buffers, tile 5000^3, {streams} streams, "
+            "pin_host_buffers=false, copy_c_back=true")
+
+
 def grid_shape(n: int):
     return {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}.get(n, (1, n))
 
@@ -180,7 +186,7 @@ def run_reference(args, rank: int, world: int) -> None:
     size = args.size
     base = {"impl": "reference", "metric": "host-to-host dgemm TFLOP/s", "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"README miniapp: dgemm m=n=k={size} NN alpha=1 beta=0, pinned host buffers, tile 5000^3, 2 streams, pin_host_buffers=false, copy_c_back=true",
+            "config": {"workload": workload_name(size),
                        "l2": "inputs (2 x 800 MB) larger than L2", "note": "reference is single-GPU: at N>1 rank 0 runs it on one GPU"}}
     try:
         import tiled_mm_b200 as tmm
@@ -357,8 +363,7 @@ def main():
             "metric": "host-to-host dgemm TFLOP/s", "value": round(value_tf, 3), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"README miniapp (BASELINE configs[1]): dgemm m=n=k={size} NN alpha=1 beta=0, pinned host buffers, tile hints 5000^3, "
-                                   f"{args.streams} streams" + (f"; weak-scaled over a {pr}x{pc} C-block grid, global {pr*m}x{pc*n}x{k}, A/B panel slices all-gathered over NVLink" if world > 1 else ""),
+            "config": {"workload": workload_name(size, args.streams) + (f"; weak-scaled over a {pr}x{pc} C-block grid, global {pr*m}x{pc*n}x{k}, A/B panel shares pushed peer-to-peer over NVLink" if world > 1 else ""),
                        "l2": "inputs (A, B = 800 MB each) larger than the 126 MB L2; no flush needed",
                        "host_buffers": f"cudaHostAlloc, first touched on the GPU-local NUMA node ({numa.bound} CPUs)" if numa.bound else "cudaHostAlloc (no NUMA binding applied)",
                        "value_is": "device-resident DGEMM (tmm_device_gemm, operands in HBM)", "e2e_is": "tmm_gemm with host pointers (H2D + GEMM + D2H)"},
