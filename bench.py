@@ -367,7 +367,9 @@ def main():
                        "l2": "inputs (A, B = 800 MB each) larger than the 126 MB L2; no flush needed",
                        "host_buffers": f"cudaHostAlloc, first touched on the GPU-local NUMA node ({numa.bound} CPUs)" if numa.bound else "cudaHostAlloc (no NUMA binding applied)",
                        "value_is": "device-resident DGEMM (tmm_device_gemm, operands in HBM)", "e2e_is": "tmm_gemm with host pointers (H2D + GEMM + D2H)"},
-            "e2e": {"value": round(e2e_tf, 3), "unit": "TFLOP/s", "ms_per_step": round(e2e_ms, 3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "nvlink_bytes_per_step": peer,
+            "e2e": {"value": round(e2e_tf, 3), "unit": "TFLOP/s", "ms_per_step": round(e2e_ms, 3),
+                    "timing": "host clock around K synchronous calls (each returns only when every stream of the call is idle and host C is complete), "
+                              "bracketed by barrier + cudaDeviceSynchronize, max over ranks", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "nvlink_bytes_per_step": peer,
                     "frac_of_host_roofline": round(e2e_tf / world / roof_simple, 4),
                     "host_roofline": {"formula": "min(FP64 peak, AI x PCIe H2D BW)", "tflops": round(roof_simple, 2), "ai_flop_per_byte": round(ai, 1),
                                       "duplex_tflops": round(flops / t_duplex * 1e-12, 2), "active_bound": "fp64" if roof_simple >= FP64_PEAK_TFLOPS - 1e-9 else "pcie",
