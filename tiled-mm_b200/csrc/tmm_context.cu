@@ -215,6 +215,8 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
         int rc = tmm::link_bind(ctx, ctx->grid.rowl, ctx->buf_a);
         if (!rc) rc = tmm::link_bind(ctx, ctx->grid.coll, ctx->buf_b);
         if (rc) return rc;
+        for (void* old : ctx->retired) cudaFree(old);  // every peer has re-mapped: nobody holds the outgrown buffers any more
+        ctx->retired.clear();
     }
     char* dA = (char*)ctx->buf_a.p;
     char* dB = (char*)ctx->buf_b.p;
@@ -381,6 +383,8 @@ int run_streaming(Call& cl, const tmm::Plan& pl, void* dC_full, int64_t ldc_full
         int rc = tmm::link_bind(ctx, ctx->grid.rowl, ctx->buf_a);
         if (!rc) rc = tmm::link_bind(ctx, ctx->grid.coll, ctx->buf_b);
         if (rc) return rc;
+        for (void* old : ctx->retired) cudaFree(old);  // every peer has re-mapped: nobody holds the outgrown buffers any more
+        ctx->retired.clear();
     }
     cudaStream_t cs = ctx->s_compute[0];
     std::vector<cudaEvent_t> slot_free(SLOTS, nullptr);
@@ -598,6 +602,7 @@ void tmm_context_destroy(tmm_context* ctx) {
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
     ctx->buf_a.release(); ctx->buf_b.release(); ctx->buf_c.release(); ctx->full_c.release();
+    for (void* old : ctx->retired) cudaFree(old);
     delete ctx;
 }
 

@@ -402,6 +402,7 @@ int dist_exchange(tmm_context* ctx, Link& link, size_t es, const char* src, int6
 }
 
 void dist_release(tmm_context* ctx) {
+    ctx->buf_a.retire = ctx->buf_b.retire = nullptr;
     link_teardown(ctx->grid.rowl);
     link_teardown(ctx->grid.coll);
     ctx->grid = Grid{};
@@ -422,6 +423,9 @@ static int attach(tmm_context* ctx, int pr, int pc, int row, int col, const nccl
     if (pr > 1) NC(nc.CommInitRank(&g.coll.comm, pr, *col_id, row));
     int rc = link_setup(ctx, g.rowl);
     if (!rc) rc = link_setup(ctx, g.coll);
+    // panel buffers that a peer may have mapped are retired, not freed, when they are outgrown (freed after the next link_bind)
+    ctx->buf_a.retire = (g.rowl.active() && g.rowl.direct) ? &ctx->retired : nullptr;
+    ctx->buf_b.retire = (g.coll.active() && g.coll.direct) ? &ctx->retired : nullptr;
     ctx->budget_cached = 0;
     TMM_DBG("dev %d attached rc %d", ctx->device, rc);
     return rc;

@@ -40,9 +40,13 @@ inline int64_t round_up64(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;  // bytes
+    // When peers of a GPU grid have this buffer mapped (CUDA IPC), it must not be freed before they have closed their mapping
+    // ("cudaFree on an exported region before cudaIpcCloseMemHandle in the importing context is undefined behaviour"): a buffer that is
+    // outgrown is parked here instead and freed after the next link_bind, whose closing collective comes after every peer has re-mapped.
+    std::vector<void*>* retire = nullptr;
     cudaError_t reserve(size_t bytes, double slack = 1.0) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        if (p) { if (retire) retire->push_back(p); else cudaFree(p); p = nullptr; cap = 0; }
         size_t want = (size_t)std::ceil((double)bytes * slack);
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess && slack > 1.0) { want = bytes; e = cudaMalloc(&p, want); }
@@ -132,6 +136,7 @@ struct tmm_context {
     size_t stage_slot_bytes = 0;            // bytes of one share (send slot); a recv slot holds `parts` of them
     int stage_next = 0;
     cudaEvent_t stage_send_free[tmm::STAGE_SLOTS] = {nullptr, nullptr, nullptr};
+    std::vector<void*> retired;             // outgrown panel buffers that peers may still have mapped (DevBuf::retire)
     std::vector<tmm_context*> children;     // single-process multi-GPU: one child context per device, driven by host threads
     tmm_context* solo = nullptr;            // plain context on the first device for shapes too small to split
 
