@@ -757,7 +757,7 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                 }
                 if (!rc && cl.beta_nonzero) rc = h2d_2d(cl, dC, ldc_dev, cl.c, cl.ldc, m, n, ctx->s_h2d);
                 if (!rc) {
-                    cudaEvent_t ev;
+                    cudaEvent_t ev = nullptr;
                     if ((e = ctx->get_event(&ev)) != cudaSuccess || (e = cudaEventRecord(ev, ctx->s_h2d)) != cudaSuccess ||
                         (e = cudaStreamWaitEvent(ctx->s_compute[0], ev, 0)) != cudaSuccess ||
                         (e = tmm::device_scale(cl.dtype, m, n, beta, dC, ldc_dev, ctx->s_compute[0])) != cudaSuccess)
@@ -871,11 +871,11 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
             return "stream";
         };
         for (auto& op : ctx->trace_ops) {
-            float a = 0, b = 0;
-            cudaEventElapsedTime(&a, trace_t0, op.e0);
-            cudaEventElapsedTime(&b, trace_t0, op.e1);
-            fprintf(stderr, "[tmm trace] %-28s %10.3f %10.3f %9.3f\n", op.name.c_str(), a, b, b - a);
-            if (tf) fprintf(tf, "{\"name\":\"%s\",\"ph\":\"X\",\"ts\":%.1f,\"dur\":%.1f,\"pid\":%d,\"tid\":\"%s\"},\n", op.name.c_str(), a * 1e3, (b - a) * 1e3,
+            float t_start = 0, t_end = 0;
+            cudaEventElapsedTime(&t_start, trace_t0, op.e0);
+            cudaEventElapsedTime(&t_end, trace_t0, op.e1);
+            fprintf(stderr, "[tmm trace] %-28s %10.3f %10.3f %9.3f\n", op.name.c_str(), t_start, t_end, t_end - t_start);
+            if (tf) fprintf(tf, "{\"name\":\"%s\",\"ph\":\"X\",\"ts\":%.1f,\"dur\":%.1f,\"pid\":%d,\"tid\":\"%s\"},\n", op.name.c_str(), t_start * 1e3, (t_end - t_start) * 1e3,
                             ctx->device, stream_name(op.stream).c_str());
         }
         if (tf) fclose(tf);
