@@ -278,6 +278,56 @@ def run_threads(n_threads, per_thread):
     print(f"EMUL_OK threads {n_threads} x {per_thread}")
 
 
+def run_drysweep(n_dev, n_cases, seed):
+    """Address-only sweep over REALISTIC sizes (dims up to 60000, budgets from 1 GiB to all of HBM): every plan shape the scheduler can
+    produce at scale - several column stripes, many k-chunks, phase-2 blocks, C super-blocks with two buffers, ring reuse - is walked with
+    bounds, ordering and byte-count checks, without arithmetic."""
+    assert lib.emul_dry_run() == 1
+    rng = np.random.default_rng(seed)
+    pr, pc = tmm.grid_shape(n_dev)
+    A, B, C = 0x200000000000, 0x300000000000, 0x400000000000
+    dtypes = [np.float64, np.complex128, np.float32, np.complex64]
+    done = 0
+    while done < n_cases:
+        dtype = dtypes[int(rng.integers(0, 4))]
+        es = np.dtype(dtype).itemsize
+        with tmm.make_context(dtype, int(rng.integers(1, 5)), *(int(x) for x in rng.integers(64, 8000, 3))) as ctx:
+            if n_dev > 1:
+                ctx.set_devices(n_dev)
+            for _ in range(4):
+                budget = int(rng.choice([0, 0, 1 << 30, 6 << 30, 40 << 30]))
+                ctx.set_device_budget(budget)
+                if n_dev > 1:
+                    ctx.set_devices(n_dev)
+                m, n, k = (int(x) for x in np.exp(rng.uniform(np.log(64), np.log(60000), 3)))
+                ta, tb = rng.choice(list("NTC"), 2)
+                lda = (m if ta == "N" else k) + int(rng.integers(0, 9))
+                ldb = (k if tb == "N" else n) + int(rng.integers(0, 9))
+                ldc = m + int(rng.integers(0, 9))
+                beta = float(rng.integers(0, 2))
+                back = True if n_dev > 1 else bool(rng.integers(0, 2))
+                try:
+                    tmm.gemm(ctx, ta, tb, m, n, k, 1.0, A, lda, B, ldb, beta, C, ldc, pin_host_buffers=False, copy_c_back=back)
+                except RuntimeError as e:
+                    if "budget too small" not in str(e) and "out of memory" not in str(e):
+                        raise
+                    continue
+                st = ctx.last_stats()
+                once = es * (m * k + k * n + (m * n if beta else 0))
+                assert st.d2h_bytes == (es * m * n if back else 0), (m, n, k, st.d2h_bytes)
+                if st.regime == 0 and (n_dev == 1 or (m >= pr and n >= pc)):
+                    assert st.h2d_bytes == once, (np.dtype(dtype), ta + tb, m, n, k, st.h2d_bytes, once)
+                else:
+                    assert st.h2d_bytes >= once or n_dev > 1, (m, n, k, st.h2d_bytes, once)
+                done += 1
+        assert lib.emul_violations() == 0, lib.emul_first_violation().decode()
+        assert lib.emul_tma_contract_violations() == 0
+        assert lib.emul_races() == 0, lib.emul_first_race().decode()
+    for d in range(n_dev):
+        assert lib.emul_live_device_bytes(d) == 0
+    print(f"EMUL_OK drysweep {n_dev} devices, {done} cases")
+
+
 def run_dry(n_dev):
     """Full-size walk through the real scheduler with address-only memory (TMM_EMUL_DRY=1): BASELINE configs[3] and [4] and a C that
     needs super-blocks.  No arithmetic, no data movement - bounds, 64-bit offsets, ordering, protocol progress and byte counts."""
@@ -321,7 +371,9 @@ def run_dry(n_dev):
 
 if __name__ == "__main__":
     mode = sys.argv[1]
-    if mode == "threads":
+    if mode == "drysweep":
+        run_drysweep(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
+    elif mode == "threads":
         run_threads(int(sys.argv[2]), int(sys.argv[3]))
     elif mode == "replan":
         run_replan()

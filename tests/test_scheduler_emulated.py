@@ -115,3 +115,10 @@ def test_scheduler_under_address_and_ub_sanitizers():
 def test_one_context_per_host_thread_concurrently(emul_build):
     """eight host threads, one context each, calls in flight at the same time on one device"""
     _worker(emul_build, ["threads", 8, 60], 1)
+
+
+@pytest.mark.parametrize("devices,cases", [(1, 2000), (4, 200), (8, 200)])
+def test_address_only_sweep_over_realistic_sizes(emul_build, devices, cases):
+    """random shapes up to 60000 per dimension, all types / ops, budgets from 1 GiB to all of HBM, walked without arithmetic: every plan
+    structure the scheduler produces at scale is bounds-, order- and byte-count-checked"""
+    _worker(emul_build, ["drysweep", devices, cases, 500 + devices], devices, {"TMM_EMUL_DRY": "1", "TMM_EMUL_MEM_MB": "182000"})
