@@ -159,7 +159,9 @@ void note_locked(int sid, const void* p, size_t pitch, size_t width, size_t heig
     {
         std::lock_guard<std::mutex> lk(g_mu);
         const Block* b = find_block(p, 1, &base);
-        if (!b || b->kind != 0 || b->bytes <= 4096) return;  // host memory, or flag / scalar scratch that is synchronisation state itself
+        if (!b || b->bytes <= 4096) return;  // untracked (pageable) host memory, or flag / scalar scratch that is synchronisation state itself
+        // tracked host blocks (cudaHostAlloc / cudaHostRegister) are checked too: the H2D read of a block of host C (beta != 0) against
+        // the D2H write of the result into the same block
     }
     Access now{reinterpret_cast<uintptr_t>(p), pitch ? pitch : width, width, height, sid, g_vc[sid][sid], write, what};
     std::deque<Access>& log = g_shadow[base];
@@ -305,6 +307,7 @@ cudaError_t cudaFreeHost(void* p) {
         if (it == g_blocks.end() || it->second.kind != 1) return cudaErrorInvalidValue;
         g_blocks.erase(it);
     }
+    { std::lock_guard<std::mutex> lk(g_det); g_shadow.erase(reinterpret_cast<uintptr_t>(p)); }
     free(p);
     return cudaSuccess;
 }
@@ -315,10 +318,14 @@ cudaError_t cudaHostRegister(void* p, size_t bytes, unsigned) {
     return cudaSuccess;
 }
 cudaError_t cudaHostUnregister(void* p) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_blocks.find(reinterpret_cast<uintptr_t>(p));
-    if (it == g_blocks.end() || it->second.kind != 2) return cudaErrorHostMemoryNotRegistered;
-    g_blocks.erase(it);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_blocks.find(reinterpret_cast<uintptr_t>(p));
+        if (it == g_blocks.end() || it->second.kind != 2) return cudaErrorHostMemoryNotRegistered;
+        g_blocks.erase(it);
+    }
+    std::lock_guard<std::mutex> lk2(g_det);  // never nested inside g_mu: the detector takes them in the other order
+    g_shadow.erase(reinterpret_cast<uintptr_t>(p));
     return cudaSuccess;
 }
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* attr, const void* p) {
