@@ -796,6 +796,7 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                 pin_.n_streams = ctx->n_streams; pin_.tile_m = ctx->tile_m; pin_.tile_n = ctx->tile_n; pin_.tile_k = ctx->tile_k;
                 pin_.sm_count = tmm::sm_count();
                 pin_.parts_a = gr.pc; pin_.parts_b = gr.pr;
+                if (cl.dtype == TMM_C32 && tmm::c32_math_mode() == TMM_CMATH_TC) pin_.flops = 140e12;  // complex<float> on the tcgen05 kernel (8mnk real flops)
                 tmm::Plan pl;
                 if (!rc) pl = tmm::make_plan(pin_);
                 ctx->stats.regime = pl.regime;

@@ -20,6 +20,7 @@ struct PlanInput {
     size_t budget = 0;  // device bytes available for A/B/C storage of this call (full device C excluded when copy_c_back = false)
     int n_streams = 2, tile_m = 5000, tile_n = 5000, tile_k = 5000;  // user hints
     int sm_count = 148;
+    double flops = 0;  // GEMM rate the schedule is sized for (flop/s; 0 = the default of the element type) - timing model only
     int parts_a = 1, parts_b = 1;  // GPU grid: this rank uploads 1/parts_a of every A panel and 1/parts_b of every B panel (timing model only)
 };
 
