@@ -94,6 +94,11 @@ def run_single():
             case(ctx, np.float64, "TN", *shape, 1.0, 0.0, (0, 0, 0), seed=3)
         case(ctx, np.float64, "NN", 600, 500, 400, 1.0, 1.0, (1, 2, 3), pageable=True, seed=4)   # cudaHostRegister path, unregistered again after the call
         case(ctx, np.float64, "NN", 600, 500, 400, 1.0, 1.0, (1, 2, 3), pageable=True, seed=4)
+        # a pageable operand of 288 MB: registered in 2 MiB-aligned pieces from several host threads, all of them released after the call
+        lib.emul_registered_host_blocks.restype = ctypes.c_uint64
+        for tt in ("NN", "TN"):
+            case(ctx, np.float64, tt, 36000, 8, 1000, 1.0, 1.0, (0, 0, 0), copy_modes=(True,), pageable=True, seed=12)
+            assert lib.emul_registered_host_blocks() == 0, "host registrations left behind"
         check_clean("shapes + pageable")
     for dtype, alpha, beta in [(np.complex128, 1 - 2j, 2 + 1j), (np.float32, 1.0, 1.0), (np.complex64, 1 + 1j, 1j)]:
         with tmm.make_context(dtype, 3, 100, 70, 50) as ctx:

@@ -87,7 +87,19 @@ void check_range(const void* p, size_t span, bool device_side, bool async_host) 
         if (!b || b->kind != 0) violation("device range outside any device allocation", p, span);
     } else {
         const Block* head = find_block(p, 1);
-        if (head && !b) violation("host range runs past its pinned / registered block", p, span);
+        if (head && !b) {
+            // a range may span several registrations that touch (the product registers a large buffer in 2 MiB-aligned pieces)
+            uintptr_t at = reinterpret_cast<uintptr_t>(p);
+            const uintptr_t end = at + span;
+            bool covered = true;
+            while (at < end) {
+                uintptr_t base = 0;
+                const Block* piece = find_block(reinterpret_cast<const void*>(at), 1, &base);
+                if (!piece || piece->kind == 0) { covered = false; break; }
+                at = base + piece->bytes;
+            }
+            if (!covered) violation("host range runs past its pinned / registered block", p, span);
+        }
         if (async_host && !head) g_unpinned_async.fetch_add(1);
     }
 }
@@ -200,6 +212,12 @@ EMUL_API uint64_t emul_live_device_bytes(int device) {
     uint64_t s = 0;
     for (auto& kv : g_blocks) if (kv.second.kind == 0 && kv.second.device == device) s += kv.second.bytes;
     return s;
+}
+EMUL_API uint64_t emul_registered_host_blocks() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    uint64_t n = 0;
+    for (auto& kv : g_blocks) if (kv.second.kind == 2) ++n;
+    return n;
 }
 EMUL_API int emul_dry_run() { return dry_run() ? 1 : 0; }
 EMUL_API uint64_t emul_races() { return g_races; }

@@ -515,6 +515,38 @@ int pin(tmm_context* ctx, const void* p, size_t bytes, std::vector<const void*>&
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) { if (attr.type == cudaMemoryTypeHost) return TMM_OK; }
     else cudaGetLastError();
+    // Large one-shot registrations dominate a call on pageable memory (page-locking runs at a few GB/s): the range is cut at
+    // 2 MiB boundaries and the pieces are registered from several host threads at once.  TMM_PIN_THREADS=1 keeps one cudaHostRegister.
+    static const int pin_threads = [] { const char* v = getenv("TMM_PIN_THREADS"); int t = (v && *v) ? atoi(v) : 4; return t < 1 ? 1 : (t > 16 ? 16 : t); }();
+    if (!ctx->pin_cache && pin_threads > 1 && bytes >= ((size_t)256 << 20)) {
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(p), hi = lo + bytes, huge = (uintptr_t)2 << 20;
+        std::vector<uintptr_t> cut = {lo};
+        for (int t = 1; t < pin_threads; ++t) {
+            const uintptr_t c = (lo + bytes / pin_threads * t + huge - 1) / huge * huge;
+            if (c > cut.back() && c < hi) cut.push_back(c);
+        }
+        cut.push_back(hi);
+        const size_t pieces = cut.size() - 1;
+        std::vector<cudaError_t> res(pieces, cudaSuccess);
+        std::vector<std::thread> pool;
+        for (size_t i = 0; i < pieces; ++i)
+            pool.emplace_back([&, i] {
+                cudaSetDevice(ctx->device);
+                res[i] = cudaHostRegister(reinterpret_cast<void*>(cut[i]), cut[i + 1] - cut[i], cudaHostRegisterDefault);
+            });
+        for (auto& th : pool) th.join();
+        cudaError_t bad = cudaSuccess;
+        for (size_t i = 0; i < pieces; ++i)
+            if (res[i] != cudaSuccess && res[i] != cudaErrorHostMemoryAlreadyRegistered) bad = res[i];
+        for (size_t i = 0; i < pieces; ++i) {
+            if (res[i] != cudaSuccess) continue;
+            if (bad != cudaSuccess) cudaHostUnregister(reinterpret_cast<void*>(cut[i]));
+            else pinned_now.push_back(reinterpret_cast<const void*>(cut[i]));
+        }
+        cudaGetLastError();
+        if (bad != cudaSuccess) return cuda_fail(bad, "cudaHostRegister");
+        return TMM_OK;
+    }
     cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
     if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return TMM_OK; }  // already DMA-able: nothing to do, nothing to undo
     if (e != cudaSuccess) return cuda_fail(e, "cudaHostRegister");

@@ -29,6 +29,8 @@ echo "== cublasXt comparator (the reference's headline comparison), tuned block 
 for n in 4000 10000 16000; do timeout 120 ./build/cublasxt-multiply -m $n -n $n -k $n -r 2 --beta 1 --block 4000 2>&1 | grep -E "Avg Time|Throughput"; timeout 60 bin/multiply -m $n -n $n -k $n -r 2 --beta 1 2>&1 | grep -E "Avg Time|Throughput" | head -2; done
 echo "== SGEMM host-to-host: planner with the float rate (default) vs the round-1 FP64 rate =="
 for n in 10000 16000; do timeout 60 python tools/e2e.py --dtype s --m $n --n $n --k $n --reps 4 2>&1 | tail -1; TMM_PLAN_F32_FLOPS=35e12 TMM_PLAN_D2H_BOUND=0 timeout 60 python tools/e2e.py --dtype s --m $n --n $n --k $n --reps 4 2>&1 | tail -1; done
+echo "== the reference's DEFAULT call mode (pin_host_buffers=true on pageable memory): 1 vs 4 vs 8 registration threads, and the reference =="
+for t in 1 4 8; do TMM_PIN_THREADS=$t timeout 120 python tools/pin_study.py 10000 2>&1 | tail -2 | head -1; done; timeout 120 python tools/pin_study.py 10000 2>&1 | tail -1
 echo "== compute-sanitizer memcheck on the CI shapes (SURVEY 5.2) =="; timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gemm_gpu.py -m gpu -q -k "ci_and_ctest or degenerate" 2>&1 | tail -6
 echo "== regular suite =="; timeout 600 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -8
 echo "== bench =="; timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1
