@@ -8,6 +8,7 @@
 #include "cli.hpp"
 
 #include <chrono>
+#include <cstdlib>
 #include <complex>
 #include <cstdio>
 #include <cstring>
@@ -95,7 +96,8 @@ int main(int argc, char** argv) {
     if (!args.read(argc, argv)) return 2;
     if (args.help_requested) { args.usage("multiply", "Benchmarking Tiled-MM: measures the runtime of the tiled out-of-core GEMM."); return 0; }
     cli::Problem p;
-    if (!cli::problem_from(args, &p)) return 0;  // the reference also exits 0 after its [ERROR] message (examples/multiply.cpp:83-91)
+    if (!cli::problem_from(args, &p)) return 0;
+    if (p.gpus > 1) setenv("TMM_PINNED_NUMA", "interleave", 0);  // one copy of A, B, C read by the GPUs of both sockets: spread its pages  // the reference also exits 0 after its [ERROR] message (examples/multiply.cpp:83-91)
     const long long repetitions = std::max<long long>(1, args.integer("n_rep"));
     const bool random = args.integer("random") != 0;
     const std::string variants = args.text("variants");

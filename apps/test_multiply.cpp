@@ -14,6 +14,7 @@
 #include "cli.hpp"
 
 #include <chrono>
+#include <cstdlib>
 #include <complex>
 #include <random>
 
@@ -182,6 +183,7 @@ int main(int argc, char** argv) {
     if (args.help_requested) { args.usage("test-multiply", "Testing Tiled-MM: checks the result of the tiled out-of-core GEMM."); return 0; }
     cli::Problem p;
     if (!cli::problem_from(args, &p)) return 0;
+    if (p.gpus > 1) setenv("TMM_PINNED_NUMA", "interleave", 0);  // one copy of A, B, C read by the GPUs of both sockets: spread its pages
     cli::print_banner(p, 1);
     try {
         switch (p.type) {

@@ -957,15 +957,45 @@ int device_numa_node(int dev) {
 }
 // While alive, this thread's page allocations prefer `node` (MPOL_PREFERRED: soft, falls back when the node is full); the previous
 // policy is restored afterwards.  Raw syscalls: no libnuma dependency; any failure (seccomp, no NUMA) simply leaves the policy alone.
+// nodes listed in /sys/devices/system/node/online ("0-1", "0,2-3"), as a bit mask; empty when there is one node or none
+std::vector<unsigned long> online_numa_nodes(unsigned long maxnode, int* count) {
+    std::vector<unsigned long> mask(maxnode / 64, 0ul);
+    *count = 0;
+    FILE* f = fopen("/sys/devices/system/node/online", "r");
+    if (!f) return mask;
+    char buf[256] = {0};
+    if (!fgets(buf, sizeof buf, f)) buf[0] = 0;
+    fclose(f);
+    char* save = nullptr;
+    for (char* tok = strtok_r(buf, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {
+        int lo = 0, hi = 0;
+        const int got = sscanf(tok, "%d-%d", &lo, &hi);
+        if (got < 1) continue;
+        if (got == 1) hi = lo;
+        for (int nd = lo; nd <= hi && nd < (int)maxnode; ++nd) { mask[nd / 64] |= 1ul << (nd % 64); ++*count; }
+    }
+    return mask;
+}
+// While alive, this thread's page allocations prefer `node` (MPOL_PREFERRED: soft, falls back when the node is full) or, with
+// node == INTERLEAVE, are spread page by page over all nodes (for buffers that every GPU of a two-socket box reads); the previous
+// policy is restored afterwards.  Raw syscalls: no libnuma dependency; any failure (seccomp, no NUMA) simply leaves the policy alone.
 struct NumaPreference {
     static constexpr unsigned long MAXNODE = 1024;
+    static constexpr int INTERLEAVE = -2;
     int old_mode = 0;
     unsigned long old_mask[MAXNODE / 64] = {0};
     bool active = false;
     explicit NumaPreference(int node) {
 #if defined(__linux__) && defined(SYS_set_mempolicy) && defined(SYS_get_mempolicy)
-        if (node < 0 || node >= (int)MAXNODE) return;
+        if (node == -1 || node >= (int)MAXNODE) return;
         if (syscall(SYS_get_mempolicy, &old_mode, old_mask, MAXNODE + 1, nullptr, 0ul) != 0) return;
+        if (node == INTERLEAVE) {
+            int count = 0;
+            std::vector<unsigned long> all = online_numa_nodes(MAXNODE, &count);
+            if (count < 2) return;
+            active = syscall(SYS_set_mempolicy, 3 /* MPOL_INTERLEAVE */, all.data(), MAXNODE + 1) == 0;
+            return;
+        }
         unsigned long mask[MAXNODE / 64] = {0};
         mask[node / 64] |= 1ul << (node % 64);
         active = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, MAXNODE + 1) == 0;
@@ -989,10 +1019,15 @@ int tmm_malloc_pinned(size_t bytes, void** out) {
     // Pinned pages on the NUMA node of the calling thread's current device: a panel that has to cross the socket interconnect on
     // its way to the PCIe root port shares that link with every other GPU of the far socket ("NUMA-local pinned pages").
     // TMM_PINNED_NUMA=0 leaves placement to the caller (numactl, first touch).
-    static const bool numa_on = [] { const char* v = getenv("TMM_PINNED_NUMA"); return !(v && v[0] == '0'); }();
+    // TMM_PINNED_NUMA=interleave spreads the pages over all nodes instead: for buffers that GPUs on both sockets read (one process driving
+    // the whole box through tmm_context_set_devices).
+    const char* mode = getenv("TMM_PINNED_NUMA");
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; }
-    NumaPreference pref(numa_on && dev >= 0 ? device_numa_node(dev) : -1);
+    int node = -1;
+    if (mode && (mode[0] == 'i' || mode[0] == 'I')) node = NumaPreference::INTERLEAVE;
+    else if (!(mode && mode[0] == '0') && dev >= 0) node = device_numa_node(dev);
+    NumaPreference pref(node);
     CU(cudaHostAlloc(out, bytes ? bytes : 1, 0));  // flags 0, reference util.hpp:67
     return TMM_OK;
 }
