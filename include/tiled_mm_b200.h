@@ -130,7 +130,9 @@ TMM_API int tmm_get_c32_math(void);
  * over its own PCIe link and the shares are all-gathered over NVLink (NCCL, loaded at run time).  k is never split.
  *
  * (1) One process, many GPUs - the drop-in path: after tmm_context_set_devices(ctx, n, ids) every tmm_gemm(ctx, ...) with
- *     copy_c_back != 0 splits C over n child contexts (one host thread each).  ids == NULL means devices 0..n-1.
+ *     copy_c_back != 0 splits C over n child contexts (one host thread each); a call with copy_c_back == 0 runs on the first device
+ *     and tmm_context_device_c() follows it there.  ids == NULL means devices 0..n-1.  The environment variable TMM_DEVICES=n does
+ *     the same for every context an application creates, without a code change.
  * (2) One process per GPU (torchrun / MPI): each rank creates a context on its device and joins the grid with
  *     tmm_context_attach_grid(); tmm_gemm(ctx, ...) then computes THIS RANK's C block: m, n are the block's extents, a points
  *     at the rank's rows of op(A) (its A row-panel, full k), b at its columns of op(B), c at its block (ld_c = host ld).

@@ -333,6 +333,26 @@ def run_drysweep(n_dev, n_cases, seed):
     print(f"EMUL_OK drysweep {n_dev} devices, {done} cases")
 
 
+def run_auto(n_dev):
+    """TMM_DEVICES=n: contexts created by the application drive n GPUs without any code change; copy_c_back=false calls land on the
+    first device and get_full_device_buffer_c() follows them there."""
+    assert int(os.environ["TMM_DEVICES"]) == n_dev
+    for dtype, alpha, beta in [(np.float64, 2.0, -1.0), (np.complex64, 1 - 1j, 1j)]:
+        with tmm.make_context(dtype, 2, 64, 64, 64) as ctx:
+            assert ctx.num_devices() == n_dev
+            for tt in ("NN", "CT"):
+                st = case(ctx, dtype, tt, 301, 403, 209, alpha, beta, (1, 2, 3), copy_modes=(True,), seed=20)
+                assert st.peer_bytes > 0, "the grid was not used"
+                st = case(ctx, dtype, tt, 301, 403, 209, alpha, beta, (1, 2, 3), copy_modes=(False,), seed=21)   # device-resident C
+                assert st.peer_bytes == 0
+            ctx.set_full_sizes(50, 60, 1)
+            assert ctx.get_full_device_buffer_c().size() == 3000 and ctx.get_full_device_buffer_c().data() != 0
+    check_clean("TMM_DEVICES")
+    for d in range(n_dev):
+        assert lib.emul_live_device_bytes(d) == 0
+    print(f"EMUL_OK auto {n_dev}")
+
+
 def run_dry(n_dev):
     """Full-size walk through the real scheduler with address-only memory (TMM_EMUL_DRY=1): BASELINE configs[3] and [4] and a C that
     needs super-blocks.  No arithmetic, no data movement - bounds, 64-bit offsets, ordering, protocol progress and byte counts."""
@@ -376,7 +396,9 @@ def run_dry(n_dev):
 
 if __name__ == "__main__":
     mode = sys.argv[1]
-    if mode == "drysweep":
+    if mode == "auto":
+        run_auto(int(sys.argv[2]))
+    elif mode == "drysweep":
         run_drysweep(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
     elif mode == "threads":
         run_threads(int(sys.argv[2]), int(sys.argv[3]))

@@ -122,3 +122,8 @@ def test_address_only_sweep_over_realistic_sizes(emul_build, devices, cases):
     """random shapes up to 60000 per dimension, all types / ops, budgets from 1 GiB to all of HBM, walked without arithmetic: every plan
     structure the scheduler produces at scale is bounds-, order- and byte-count-checked"""
     _worker(emul_build, ["drysweep", devices, cases, 500 + devices], devices, {"TMM_EMUL_DRY": "1", "TMM_EMUL_MEM_MB": "182000"})
+
+
+def test_tmm_devices_environment_switch(emul_build):
+    """TMM_DEVICES=4: an unchanged caller gets a 2x2 grid; device-resident C calls still work (first device)"""
+    _worker(emul_build, ["auto", 4], 4, {"TMM_DEVICES": "4"})

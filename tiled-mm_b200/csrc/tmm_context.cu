@@ -616,6 +616,14 @@ int tmm_context_create(int dtype, int n_streams, int max_tile_m, int max_tile_n,
     for (int i = 1; i < tmm_context::MAX_P1; ++i)
         if ((e = cudaStreamCreateWithPriority(&ctx->s_p1[i], cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) { tmm_context_destroy(ctx); return cuda_fail(e, "cudaStreamCreateWithPriority"); }
     *out = ctx;
+    // TMM_DEVICES=n: every context created by the application drives the first n GPUs of the box (tmm_context_set_devices) - a caller
+    // written for the reference gets the whole box without touching its code.  Not applied to the contexts the library creates itself.
+    static const int auto_devices = [] { const char* v = getenv("TMM_DEVICES"); return (v && *v) ? atoi(v) : 0; }();
+    if (auto_devices > 1 && !tmm::creating_internal_context()) {
+        const int use = std::min(auto_devices, ndev);
+        if (use > 1 && tmm_context_set_devices(ctx, use, nullptr) != TMM_OK)
+            fprintf(stderr, "tiled_mm_b200: TMM_DEVICES=%d could not be honoured (%s); this context stays on device %d\n", auto_devices, tmm_last_error(), ctx->device);
+    }
     return TMM_OK;
 }
 
@@ -669,10 +677,18 @@ int tmm_context_optimal_tile_sizes(tmm_context* ctx, int m, int n, int k, int* t
     return TMM_OK;
 }
 
-void* tmm_context_device_c(tmm_context* ctx) { return ctx ? ctx->full_c.p : nullptr; }
-size_t tmm_context_device_c_size(tmm_context* ctx) { return ctx ? ctx->full_c_elems : 0; }
+namespace {
+// the context that holds the device-resident C: the context itself, or - when it drives several devices - the plain context on the first one
+tmm_context* device_c_owner(tmm_context* ctx) {
+    if (!ctx || ctx->children.empty()) return ctx;
+    return ctx->children[0]->grid.active() ? ctx->solo : ctx->children[0];
+}
+}  // namespace
+void* tmm_context_device_c(tmm_context* ctx) { ctx = device_c_owner(ctx); return ctx ? ctx->full_c.p : nullptr; }
+size_t tmm_context_device_c_size(tmm_context* ctx) { ctx = device_c_owner(ctx); return ctx ? ctx->full_c_elems : 0; }
 
 int tmm_context_reserve_device_c(tmm_context* ctx, int64_t m, int64_t n) {
+    ctx = device_c_owner(ctx);
     if (!ctx) return fail(TMM_ERR_INVALID, "null context");
     if (m < 1 || n < 1) return fail(TMM_ERR_INVALID, "set_full_sizes: dimensions must be >= 1");  // asserts in the reference, mm_handle.cpp:75-77
     DeviceGuard guard(ctx->device);

@@ -24,6 +24,10 @@
 
 namespace tmm {
 const char* last_error_cstr();
+static thread_local int t_internal_context = 0;
+bool creating_internal_context() { return t_internal_context > 0; }
+InternalContextScope::InternalContextScope() { ++t_internal_context; }
+InternalContextScope::~InternalContextScope() { --t_internal_context; }
 bool debug_on() {
     static const bool on = [] { const char* v = getenv("TMM_DEBUG"); return v && v[0] == '1'; }();
     return on;
@@ -441,7 +445,14 @@ int multi_gemm(tmm_context* parent, char ta, char tb, int64_t m, int64_t n, int6
     const size_t es = dtype_size(parent->dtype);
     const char TA = (char)std::toupper((unsigned char)ta), TB = (char)std::toupper((unsigned char)tb);
     parent->stats = tmm_call_stats{};
-    if (!copy_c_back) return fail(TMM_ERR_INVALID, "copy_c_back=false on a multi-GPU context: C blocks live on different devices; call tmm_gemm on tmm_context_child(ctx, i)");
+    if (!copy_c_back) {
+        // The result has to be ONE column-major device matrix (get_full_device_buffer_c, ld = m): such a call runs on the plain context
+        // of the first device, and the parent's device-C accessors follow it there.  The grid is for results that go back to the host.
+        tmm_context* one = parent->children[0]->grid.active() ? parent->solo : parent->children[0];
+        const int rc1 = tmm_gemm(one, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, pin, copy_c_back);
+        parent->stats = one->stats;
+        return rc1;
+    }
     if (m < 0 || n < 0 || k < 0) return fail(TMM_ERR_INVALID, "negative dimension");
     if (m == 0 || n == 0) return TMM_OK;
     if ((TA != 'N' && TA != 'T' && TA != 'C') || (TB != 'N' && TB != 'T' && TB != 'C')) return fail(TMM_ERR_INVALID, "trans must be one of N, T, C (got '%c','%c')", ta, tb);
@@ -578,6 +589,7 @@ int tmm_context_set_devices(tmm_context* ctx, int n_devices, const int* device_i
     int prev = 0;
     cudaGetDevice(&prev);
     int rc = TMM_OK;
+    tmm::InternalContextScope internal;  // the contexts created below are the library's own
     for (int i = 0; i < n_devices && !rc; ++i) {
         cudaSetDevice(ids[i]);
         tmm_context* ch = nullptr;

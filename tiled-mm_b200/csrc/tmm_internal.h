@@ -185,6 +185,10 @@ struct TraceScope {
 };
 
 
+// true while the library itself is creating a context (children of a multi-device context): TMM_DEVICES must not recurse into them
+bool creating_internal_context();
+struct InternalContextScope { InternalContextScope(); ~InternalContextScope(); };
+
 // ---- multi-GPU layer (tmm_dist.cu) ----
 // Agree on the planning inputs across the grid (max block dims, min budget) and check that k / flags match everywhere.
 int dist_agree(tmm_context* ctx, int64_t m, int64_t n, int64_t k, int flags, size_t budget, int64_t* m_plan, int64_t* n_plan, size_t* budget_min);
