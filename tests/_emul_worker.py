@@ -353,6 +353,35 @@ def run_auto(n_dev):
     print(f"EMUL_OK auto {n_dev}")
 
 
+def run_faults():
+    """Fault injection (the reference has none): the n-th device allocation / the n-th 2-D copy of a call fails.  The call
+    must come back with an error or recover (allocation failures before anything is enqueued are re-planned), never crash or hang; the
+    context must stay usable - the next call is correct - and nothing may leak."""
+    lib.emul_inject_fault.argtypes = [ctypes.c_int, ctypes.c_long]
+    outcomes = {"error": 0, "recovered": 0, "not reached": 0}
+    for kind, name in ((0, "cudaMalloc"), (1, "cudaMemcpy2DAsync")):
+        for budget in (0, 2 << 20):
+            for nth in range(1, 12):
+                ctx = tmm.make_context(np.float64, 2, 64, 64, 64)
+                ctx.set_device_budget(budget)
+                case(ctx, np.float64, "NN", 150, 140, 130, 1.0, 1.0, (1, 2, 3), copy_modes=(True,), seed=30)      # warm: buffers exist
+                ctx.set_device_budget(budget)
+                lib.emul_inject_fault(kind, nth)
+                try:
+                    case(ctx, np.float64, "TN", 400, 380, 500, 2.0, -1.0, (1, 2, 3), copy_modes=(True, False), seed=31)   # larger: buffers must grow
+                    outcomes["recovered" if kind == 0 and nth <= 4 else "not reached"] += 1
+                except RuntimeError as e:
+                    assert "GPU ERROR" in str(e), str(e)
+                    outcomes["error"] += 1
+                lib.emul_inject_fault(kind, 0)
+                case(ctx, np.float64, "NT", 300, 200, 250, 1.0, 0.0, (0, 1, 0), copy_modes=(True, False), seed=32)       # the context still works
+                ctx.close()
+                assert lib.emul_live_device_bytes(0) == 0, f"{name} #{nth}: device memory leaked"
+                assert lib.emul_violations() == 0, lib.emul_first_violation().decode()
+    assert outcomes["error"] > 0, outcomes
+    print(f"EMUL_OK faults {outcomes}")
+
+
 def run_dry(n_dev):
     """Full-size walk through the real scheduler with address-only memory (TMM_EMUL_DRY=1): BASELINE configs[3] and [4] and a C that
     needs super-blocks.  No arithmetic, no data movement - bounds, 64-bit offsets, ordering, protocol progress and byte counts."""
@@ -396,7 +425,9 @@ def run_dry(n_dev):
 
 if __name__ == "__main__":
     mode = sys.argv[1]
-    if mode == "auto":
+    if mode == "faults":
+        run_faults()
+    elif mode == "auto":
         run_auto(int(sys.argv[2]))
     elif mode == "drysweep":
         run_drysweep(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))

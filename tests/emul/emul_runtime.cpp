@@ -63,6 +63,16 @@ bool is_virtual(const void* p) {
     return (a >= 0x100000000000ull && a < g_virtual_next.load()) || (a >= 0x200000000000ull && a < 0x500000000000ull);
 }
 
+// fault injection: the n-th cudaMalloc / n-th 2-D copy / n-th stream-memory wait from now on fails once (0 = off)
+std::atomic<long> g_fail_malloc{0}, g_fail_copy{0};
+bool take_fault(std::atomic<long>& counter) {
+    long v = counter.load();
+    while (v > 0) {
+        if (counter.compare_exchange_weak(v, v - 1)) return v == 1;
+    }
+    return false;
+}
+
 void violation(const char* what, const void* p, size_t bytes) {
     if (g_violations.fetch_add(1) == 0) snprintf(g_first_violation, sizeof g_first_violation, "%s: %p + %zu", what, p, bytes);
     fprintf(stderr, "[emul] VIOLATION %s: %p + %zu bytes\n", what, p, bytes);
@@ -219,6 +229,7 @@ EMUL_API uint64_t emul_registered_host_blocks() {
     for (auto& kv : g_blocks) if (kv.second.kind == 2) ++n;
     return n;
 }
+EMUL_API void emul_inject_fault(int kind, long nth) { (kind == 0 ? g_fail_malloc : g_fail_copy).store(nth); }
 EMUL_API int emul_dry_run() { return dry_run() ? 1 : 0; }
 EMUL_API uint64_t emul_races() { return g_races; }
 EMUL_API const char* emul_first_race() { return g_first_race; }
@@ -283,6 +294,7 @@ cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) {
 
 // ---- memory ------------------------------------------------------------------------------------------------------------
 cudaError_t cudaMalloc(void** p, size_t bytes) {
+    if (take_fault(g_fail_malloc)) { *p = nullptr; return cudaErrorMemoryAllocation; }
     if (emul_live_device_bytes(t_device) + bytes > device_total()) { *p = nullptr; return cudaErrorMemoryAllocation; }
     void* q = nullptr;
     if (dry_run() && bytes > DRY_REAL_LIMIT) {
@@ -388,6 +400,7 @@ static cudaError_t copy_2d(void* dst, size_t dpitch, const void* src, size_t spi
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) { return copy_2d(dst, bytes, src, bytes, bytes, 1, kind, false, nullptr, true); }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) { return copy_2d(dst, bytes, src, bytes, bytes, 1, kind, false, s); }
 cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind, cudaStream_t s) {
+    if (take_fault(g_fail_copy)) return cudaErrorLaunchFailure;
     return copy_2d(dst, dpitch, src, spitch, width, height, kind, true, s);
 }
 cudaError_t cudaMemset(void* p, int v, size_t bytes) {

@@ -127,3 +127,8 @@ def test_address_only_sweep_over_realistic_sizes(emul_build, devices, cases):
 def test_tmm_devices_environment_switch(emul_build):
     """TMM_DEVICES=4: an unchanged caller gets a 2x2 grid; device-resident C calls still work (first device)"""
     _worker(emul_build, ["auto", 4], 4, {"TMM_DEVICES": "4"})
+
+
+def test_fault_injection_allocation_and_copy_failures(emul_build):
+    """the n-th cudaMalloc / cudaMemcpy2DAsync of a call fails: error or recovery, never a crash, a hang or a leak; the context stays usable"""
+    _worker(emul_build, ["faults"], 1)
