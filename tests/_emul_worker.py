@@ -382,6 +382,36 @@ def run_faults():
     print(f"EMUL_OK faults {outcomes}")
 
 
+def run_grid_faults(n_dev):
+    """A device allocation fails on ONE GPU of the grid in the middle of a sequence of calls: every rank must give the call up together
+    (nobody may enqueue work that waits for shares which never come - that would be a hang), and the grid must serve the next call."""
+    lib.emul_inject_fault.argtypes = [ctypes.c_int, ctypes.c_long]
+    import time
+    errors = 0
+    for plane_budget in (0, 3 << 20):
+        for nth in (1, 2, 3, 5, 8):
+            ctx = tmm.make_context(np.float64, 2, 64, 64, 64)
+            ctx.set_device_budget(plane_budget)
+            ctx.set_devices(n_dev)
+            case(ctx, np.float64, "NN", 200, 180, 160, 1.0, 0.0, (0, 0, 0), copy_modes=(True,), seed=40)
+            lib.emul_inject_fault(0, nth)
+            t0 = time.time()
+            try:
+                case(ctx, np.float64, "TN", 900, 700, 1100, 2.0, -1.0, (1, 2, 3), copy_modes=(True,), seed=41)   # larger: panels must grow
+            except RuntimeError as e:
+                assert "GPU ERROR" in str(e), str(e)
+                errors += 1
+            assert time.time() - t0 < 20, "the grid did not give the call up together (a rank waited for its peers)"
+            lib.emul_inject_fault(0, 0)
+            case(ctx, np.float64, "NT", 500, 400, 300, 1.0, 1.0, (0, 1, 0), copy_modes=(True,), seed=42)
+            ctx.close()
+            for d in range(n_dev):
+                assert lib.emul_live_device_bytes(d) == 0, f"device {d}: memory leaked"
+            assert lib.emul_violations() == 0, lib.emul_first_violation().decode()
+    assert errors > 0
+    print(f"EMUL_OK gridfaults {n_dev} devices, {errors} failed calls handled")
+
+
 def run_dry(n_dev):
     """Full-size walk through the real scheduler with address-only memory (TMM_EMUL_DRY=1): BASELINE configs[3] and [4] and a C that
     needs super-blocks.  No arithmetic, no data movement - bounds, 64-bit offsets, ordering, protocol progress and byte counts."""
@@ -425,7 +455,9 @@ def run_dry(n_dev):
 
 if __name__ == "__main__":
     mode = sys.argv[1]
-    if mode == "faults":
+    if mode == "gridfaults":
+        run_grid_faults(int(sys.argv[2]))
+    elif mode == "faults":
         run_faults()
     elif mode == "auto":
         run_auto(int(sys.argv[2]))

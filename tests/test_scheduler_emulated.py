@@ -132,3 +132,10 @@ def test_tmm_devices_environment_switch(emul_build):
 def test_fault_injection_allocation_and_copy_failures(emul_build):
     """the n-th cudaMalloc / cudaMemcpy2DAsync of a call fails: error or recovery, never a crash, a hang or a leak; the context stays usable"""
     _worker(emul_build, ["faults"], 1)
+
+
+@pytest.mark.parametrize("devices,plane", [(2, "direct"), (8, "direct"), (4, "nccl")])
+def test_grid_gives_a_call_up_together_when_one_gpu_cannot_allocate(emul_build, devices, plane):
+    """fault injection on a GPU grid: an allocation fails on one rank - all ranks return an error for that call (no rank is left waiting
+    for shares), nothing leaks, and the same contexts compute the next call correctly"""
+    _worker(emul_build, ["gridfaults", devices], devices, {"TMM_DIST_NCCL": "1"} if plane == "nccl" else None)

@@ -209,15 +209,15 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
     const size_t es = cl.es;
     const int64_t pa = pl.pitch_a, pb = pl.pitch_b;
     cudaError_t e;
-    if ((e = ctx->buf_a.reserve(pl.bytes_a)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(A panels)");
-    if ((e = ctx->buf_b.reserve(pl.bytes_b)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(B panels)");
+    int alloc_rc = TMM_OK;
+    if ((e = ctx->buf_a.reserve(pl.bytes_a)) != cudaSuccess) alloc_rc = cuda_fail(e, "cudaMalloc(A panels)");
+    else if ((e = ctx->buf_b.reserve(pl.bytes_b)) != cudaSuccess) alloc_rc = cuda_fail(e, "cudaMalloc(B panels)");
     if (ctx->grid.active()) {
-        int rc = tmm::link_bind(ctx, ctx->grid.rowl, ctx->buf_a);
-        if (!rc) rc = tmm::link_bind(ctx, ctx->grid.coll, ctx->buf_b);
+        int rc = tmm::grid_bind(ctx, alloc_rc);  // collective even when the allocation failed here: the peers must not start without us
         if (rc) return rc;
         for (void* old : ctx->retired) cudaFree(old);  // every peer has re-mapped: nobody holds the outgrown buffers any more
         ctx->retired.clear();
-    }
+    } else if (alloc_rc) return alloc_rc;
     char* dA = (char*)ctx->buf_a.p;
     char* dB = (char*)ctx->buf_b.p;
     const int ncs = ctx->n_compute();
@@ -375,17 +375,17 @@ int run_streaming(Call& cl, const tmm::Plan& pl, void* dC_full, int64_t ldc_full
     const int64_t MB = pl.MB, NB = pl.NB, kc = pl.kc;
     const bool c_is_full = pl.c_is_full;
     cudaError_t e;
-    if ((e = ctx->buf_a.reserve(pl.bytes_a)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(A ring)");
-    if ((e = ctx->buf_b.reserve(pl.bytes_b)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(B ring)");
-    if (!c_is_full && (e = ctx->buf_c.reserve(pl.bytes_c)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(C blocks)");
+    int alloc_rc = TMM_OK;
+    if ((e = ctx->buf_a.reserve(pl.bytes_a)) != cudaSuccess) alloc_rc = cuda_fail(e, "cudaMalloc(A ring)");
+    else if ((e = ctx->buf_b.reserve(pl.bytes_b)) != cudaSuccess) alloc_rc = cuda_fail(e, "cudaMalloc(B ring)");
+    else if (!c_is_full && (e = ctx->buf_c.reserve(pl.bytes_c)) != cudaSuccess) alloc_rc = cuda_fail(e, "cudaMalloc(C blocks)");
 
     if (ctx->grid.active()) {
-        int rc = tmm::link_bind(ctx, ctx->grid.rowl, ctx->buf_a);
-        if (!rc) rc = tmm::link_bind(ctx, ctx->grid.coll, ctx->buf_b);
+        int rc = tmm::grid_bind(ctx, alloc_rc);  // collective even when the allocation failed here: the peers must not start without us
         if (rc) return rc;
         for (void* old : ctx->retired) cudaFree(old);  // every peer has re-mapped: nobody holds the outgrown buffers any more
         ctx->retired.clear();
-    }
+    } else if (alloc_rc) return alloc_rc;
     cudaStream_t cs = ctx->s_compute[0];
     std::vector<cudaEvent_t> slot_free(SLOTS, nullptr);
     cudaEvent_t cbuf_free[2] = {nullptr, nullptr};
@@ -821,9 +821,11 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                 size_t plan_budget = budget;
                 const tmm::Grid& gr = ctx->grid;
                 bool need_stage = false;  // only links that could not map peer memory stage their shares through NCCL
+                int rc_before_agree = TMM_OK;
                 if (gr.active()) {
                     const int flags = (cl.ta << 16) | (cl.tb << 8) | (cl.beta_nonzero ? 2 : 0) | (cl.copy_c_back ? 1 : 0);
                     rc = tmm::dist_agree(ctx, m, n, k, flags, budget, &m_plan, &n_plan, &plan_budget);
+                    rc_before_agree = rc;
                     need_stage = (gr.rowl.active() && !gr.rowl.direct) || (gr.coll.active() && !gr.coll.direct);
                     if (!rc && need_stage) {
                         // staging rings for the all-gathers: shares of at most one k-chunk of A / one column block of B
@@ -864,7 +866,8 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                     }
                     rc = tmm::dist_reserve_stage(ctx, share, std::max(gr.pr, gr.pc));
                 }
-                if (rc) {}
+                const bool agreed = gr.active() && !rc_before_agree && pl.error.empty();  // every rank of the grid got this far with the same plan
+                if (rc) { if (agreed) tmm::grid_bind(ctx, rc); }  // (staging ring) tell the peers we are out: they are about to bind
                 else if (!pl.error.empty()) rc = fail(TMM_ERR_NOMEM, "%s (budget %zu B)", pl.error.c_str(), plan_budget);
                 else if (pl.regime == tmm::REGIME_RESIDENT) {
                     if (cl.copy_c_back) {
@@ -872,6 +875,7 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                         dC = ctx->buf_c.p;
                     }
                     if (!rc) rc = run_resident(cl, pl, dC, cl.copy_c_back ? pl.pitch_c : ldc_dev);
+                    else if (agreed) tmm::grid_bind(ctx, rc);
                 } else {
                     rc = run_streaming(cl, pl, cl.copy_c_back ? nullptr : dC, ldc_dev);
                 }

@@ -231,28 +231,48 @@ void link_teardown(Link& link) {
 }
 }  // namespace
 
-int link_bind(tmm_context* ctx, Link& link, DevBuf& buf) {
-    if (!link.active() || !link.direct) return TMM_OK;
+// Collective over the link, once per call and on EVERY rank of it, whatever happened locally: `local_ok == false` (an allocation failed
+// here, or another link already reported a failure) is spread to the peers, so that all ranks give the call up together instead of
+// some of them enqueueing work that waits for shares which will never come.
+int link_bind(tmm_context* ctx, Link& link, DevBuf& buf, bool local_ok) {
+    if (!link.active()) return local_ok ? TMM_OK : TMM_ERR_CUDA;
     for (auto& ev : link.slot_pushed) ev = nullptr;  // events come from the per-call pool
-    std::vector<BufMsg> all;
-    int rc = gather_msgs(ctx, link, describe(ctx, buf.p, buf.cap), all);
-    if (rc) return rc;
-    bool ok = true;
-    for (int g = 0; g < link.parts; ++g) {
-        if (g == link.me) { link.peer_base[g] = static_cast<char*>(buf.p); continue; }
-        const std::string key = key_of(all[g]);
-        if (key == link.peer_key[g] && link.peer_base[g]) continue;  // same allocation as last call: mapping still valid
-        if (link.peer_ipc[g] && link.peer_base[g]) cudaIpcCloseMemHandle(link.peer_base[g]);
-        bool via = false;
-        link.peer_base[g] = static_cast<char*>(map_peer(ctx, all[g], &via));
-        link.peer_ipc[g] = via; link.peer_key[g] = key;
-        if (!link.peer_base[g]) ok = false;
+    bool ok = local_ok;
+    int rc;
+    if (link.direct) {
+        std::vector<BufMsg> all;
+        rc = gather_msgs(ctx, link, describe(ctx, local_ok ? buf.p : nullptr, local_ok ? buf.cap : 0), all);
+        if (rc) return rc;
+        for (int g = 0; g < link.parts; ++g) {
+            if (g == link.me) { link.peer_base[g] = static_cast<char*>(buf.p); continue; }
+            if (!all[g].ptr) { ok = false; continue; }  // that peer could not allocate its panel
+            if (!local_ok) continue;
+            const std::string key = key_of(all[g]);
+            if (key == link.peer_key[g] && link.peer_base[g]) continue;  // same allocation as last call: mapping still valid
+            if (link.peer_ipc[g] && link.peer_base[g]) cudaIpcCloseMemHandle(link.peer_base[g]);
+            bool via = false;
+            link.peer_base[g] = static_cast<char*>(map_peer(ctx, all[g], &via));
+            link.peer_ipc[g] = via; link.peer_key[g] = key;
+            if (!link.peer_base[g]) ok = false;
+        }
+        link.local_base = static_cast<char*>(buf.p);
     }
-    link.local_base = static_cast<char*>(buf.p);
     bool everyone = false;
     if ((rc = all_ok(ctx, link, ok, &everyone))) return rc;
-    if (!everyone) return fail(TMM_ERR_CUDA, "GPU ERROR: could not map a peer GPU's panel buffer (CUDA IPC / peer access); set TMM_DIST_NCCL=1 to use NCCL staging");
+    if (!everyone)
+        return local_ok ? fail(TMM_ERR_CUDA, "GPU ERROR: a peer GPU of the grid could not allocate or map its panel buffer for this call (CUDA IPC / peer access / "
+                                             "out of memory); set TMM_DIST_NCCL=1 to use NCCL staging if mapping is the problem")
+                        : TMM_ERR_CUDA;
     return TMM_OK;
+}
+
+// Both links, always both, rows first: a failure anywhere in the grid reaches every rank (the failing rank's row learns it in the first
+// round and passes it on to all columns in the second).  Returns 0 only if every rank of the grid is ready to enqueue.
+int grid_bind(tmm_context* ctx, int local_rc) {
+    const int r1 = link_bind(ctx, ctx->grid.rowl, ctx->buf_a, local_rc == TMM_OK);
+    const int r2 = link_bind(ctx, ctx->grid.coll, ctx->buf_b, local_rc == TMM_OK && r1 == TMM_OK);
+    if (local_rc) return local_rc;
+    return r1 ? r1 : r2;
 }
 
 int link_wait(tmm_context* ctx, Link& link, cudaStream_t stream) {

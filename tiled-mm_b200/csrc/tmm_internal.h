@@ -201,7 +201,10 @@ int dist_reserve_stage(tmm_context* ctx, size_t share_bytes, int parts);
 int dist_exchange(tmm_context* ctx, Link& link, size_t es, const char* src, int64_t spitch, int64_t rows, int64_t cols, char* dst, int64_t dpitch,
                   int ring_slot = -1);
 // Per call, after the panel buffer of this link is allocated: (re)map the peers' buffers (collective over the link).
-int link_bind(tmm_context* ctx, Link& link, DevBuf& buf);
+int link_bind(tmm_context* ctx, Link& link, DevBuf& buf, bool local_ok = true);
+// Once per call on every rank of the grid, before anything is enqueued: binds both links and spreads a local failure (local_rc != 0) to
+// all ranks, so that the grid gives a call up together.  Returns 0 only if every rank is ready.
+int grid_bind(tmm_context* ctx, int local_rc);
 // Make `stream` wait until every peer's share of all exchanges issued so far on the link has arrived (direct links only).
 int link_wait(tmm_context* ctx, Link& link, cudaStream_t stream);
 // Streaming ring: tell the peers (after the work queued on `stream`) that one more ring exchange has been consumed here;
