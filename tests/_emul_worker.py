@@ -412,6 +412,88 @@ def run_grid_faults(n_dev):
     print(f"EMUL_OK gridfaults {n_dev} devices, {errors} failed calls handled")
 
 
+def run_ranks(world):
+    """The one-process-per-GPU entry point (tmm_context_attach_grid, what torchrun / MPI jobs use), played by `world` host threads with one
+    emulated device each.  With TMM_DIST_FORCE_IPC=1 the peers' panels are imported through the (emulated) CUDA IPC calls, so the
+    bookkeeping of imports - close before re-import when a peer's buffer changed, and never free an allocation that a peer still has
+    imported (outgrown buffers are retired) - is checked: the emulation reports a cudaFree of an imported allocation."""
+    import threading
+    from tiled_mm_b200 import multi_gpu
+    lib.emul_set_device.argtypes = [ctypes.c_int]
+    lib.emul_open_ipc_imports.restype = ctypes.c_uint64
+    pr, pc = tmm.grid_shape(world)
+    barrier = threading.Barrier(world)
+    ids, errors = {}, []
+    cases = [(np.float64, "NN", 300, 260, 200, (0, 0, 0), 1.0, 0.0, 0), (np.float64, "TN", 513, 300, 777, (3, 5, 7), 2.0, -1.0, 0),       # panels grow
+             (np.float64, "NT", 900, 700, 1100, (1, 2, 3), 1.0, 1.0, 3 << 20),                                                         # streaming ring
+             (np.float64, "CN", 200, 150, 100, (1, 0, 2), 1.0, 1.0, 0), (np.float64, "NN", 1200, 1000, 640, (0, 0, 0), 1.0, 0.0, 0),    # shrink, grow again
+             (np.complex128, "CT", 301, 403, 209, (1, 2, 3), 1 - 2j, 2 + 1j, 0)]
+
+    def body(rank):
+        try:
+            assert lib.emul_set_device(rank) == 0
+            row, col = rank // pc, rank % pc
+            if pc > 1 and col == 0:
+                ids[("row", row)] = tmm.dist_unique_id()
+            if pr > 1 and row == 0:
+                ids[("col", col)] = tmm.dist_unique_id()
+            barrier.wait()
+            ctxs = {}
+            for ci, (dtype, tt, m, n, k, pad, alpha, beta, budget) in enumerate(cases):
+                key = np.dtype(dtype)
+                if key not in ctxs:
+                    ctxs[key] = tmm.make_context(dtype, 2, 64, 64, 64)
+                    ctxs[key].attach_grid(pr, pc, row, col, ids.get(("row", row)), ids.get(("col", col)))
+                ctx = ctxs[key]
+                ctx.set_device_budget(budget)
+                ta, tb = tt
+                ar, ac = _util.stored_shape(ta, m, k); br, bc = _util.stored_shape(tb, k, n)
+                lda, ldb, ldc = ar + pad[0], br + pad[1], m + pad[2]
+                rng = np.random.default_rng(100 + ci)                   # the same full problem on every rank
+                a0, b0, c0 = gen(rng, dtype, lda * ac), gen(rng, dtype, ldb * bc), gen(rng, dtype, ldc * n)
+                expect = oracle.gemm(ta, tb, m, n, k, alpha, a0, lda, b0, ldb, beta, c0.copy(), ldc).reshape(n, ldc)
+                i0, i1, j0, j1 = multi_gpu.block_of(rank, world, m, n)
+                es = np.dtype(dtype).itemsize
+                oa = i0 if ta == "N" else i0 * lda
+                ob = j0 * ldb if tb == "N" else j0
+                ap = tmm.malloc_pinned(dtype, a0.size); ap[:] = a0
+                bp = tmm.malloc_pinned(dtype, b0.size); bp[:] = b0
+                cp = tmm.malloc_pinned(dtype, c0.size); cp[:] = c0
+                tmm.gemm(ctx, ta, tb, i1 - i0, j1 - j0, k, alpha, ap.ctypes.data + oa * es, lda, bp.ctypes.data + ob * es, ldb, beta,
+                         cp.ctypes.data + (j0 * ldc + i0) * es, ldc, pin_host_buffers=False, copy_c_back=True)
+                got = np.asarray(cp).reshape(n, ldc)
+                assert np.array_equal(got[j0:j1, i0:i1], expect[j0:j1, i0:i1]), f"rank {rank} case {ci}: block differs from the oracle"
+                mask = np.ones((n, ldc), dtype=bool); mask[j0:j1, i0:i1] = False
+                assert np.array_equal(got[mask], c0.reshape(n, ldc)[mask]), f"rank {rank} case {ci}: wrote outside its block"
+                assert ctx.last_stats().regime == (1 if budget else 0)
+            barrier.wait()
+            if rank == 0:
+                check_clean("ranks")
+                if os.environ.get("TMM_DIST_FORCE_IPC") == "1":
+                    assert lib.emul_open_ipc_imports() > 0, "the IPC branch was not taken"
+                # teardown is not collective (a rank may free its panels while a peer still has them imported - as on hardware, where the
+                # processes are about to exit); only the steady state above is held to the no-free-while-imported rule
+                os.environ["TMM_EMUL_ALLOW_FREE_WHILE_IMPORTED"] = "1"
+            barrier.wait()
+            for c in ctxs.values():
+                c.close()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(f"rank {rank}: {type(e).__name__}: {e}")
+            barrier.abort()
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    assert lib.emul_violations() == 0, lib.emul_first_violation().decode()
+    assert lib.emul_open_ipc_imports() == 0, "imports left open"
+    for d in range(world):
+        assert lib.emul_live_device_bytes(d) == 0
+    print(f"EMUL_OK ranks {pr}x{pc}")
+
+
 def run_dry(n_dev):
     """Full-size walk through the real scheduler with address-only memory (TMM_EMUL_DRY=1): BASELINE configs[3] and [4] and a C that
     needs super-blocks.  No arithmetic, no data movement - bounds, 64-bit offsets, ordering, protocol progress and byte counts."""
@@ -455,7 +537,9 @@ def run_dry(n_dev):
 
 if __name__ == "__main__":
     mode = sys.argv[1]
-    if mode == "gridfaults":
+    if mode == "ranks":
+        run_ranks(int(sys.argv[2]))
+    elif mode == "gridfaults":
         run_grid_faults(int(sys.argv[2]))
     elif mode == "faults":
         run_faults()

@@ -33,6 +33,7 @@ namespace {
 struct Block { size_t bytes; int device; int kind; };  // kind: 0 device, 1 pinned host (cudaHostAlloc), 2 registered host
 std::mutex g_mu;
 std::map<uintptr_t, Block> g_blocks;
+std::map<uintptr_t, int> g_ipc_imports;  // exporting allocation -> open CUDA IPC imports (under g_mu)
 thread_local int t_device = 0;
 std::atomic<uint64_t> g_h2d{0}, g_d2h{0}, g_d2d{0}, g_violations{0}, g_unpinned_async{0};
 char g_first_violation[256] = "";
@@ -230,6 +231,13 @@ EMUL_API uint64_t emul_registered_host_blocks() {
     return n;
 }
 EMUL_API void emul_inject_fault(int kind, long nth) { (kind == 0 ? g_fail_malloc : g_fail_copy).store(nth); }
+EMUL_API int emul_set_device(int d) { return (int)cudaSetDevice(d); }  // for test threads that play one rank each
+EMUL_API uint64_t emul_open_ipc_imports() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    uint64_t n = 0;
+    for (auto& kv : g_ipc_imports) n += (uint64_t)kv.second;
+    return n;
+}
 EMUL_API int emul_dry_run() { return dry_run() ? 1 : 0; }
 EMUL_API uint64_t emul_races() { return g_races; }
 EMUL_API const char* emul_first_race() { return g_first_race; }
@@ -315,6 +323,8 @@ cudaError_t cudaFree(void* p) {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_blocks.find(reinterpret_cast<uintptr_t>(p));
         if (it == g_blocks.end() || it->second.kind != 0) { violation("cudaFree of a pointer that is not a device allocation", p, 0); return cudaErrorInvalidValue; }
+        if (g_ipc_imports.count(reinterpret_cast<uintptr_t>(p)) && !getenv("TMM_EMUL_ALLOW_FREE_WHILE_IMPORTED"))
+            violation("cudaFree of an allocation that a peer still has imported through CUDA IPC (undefined behaviour on hardware)", p, it->second.bytes);
         g_blocks.erase(it);
     }
     { std::lock_guard<std::mutex> lk(g_det); g_shadow.erase(reinterpret_cast<uintptr_t>(p)); }
@@ -366,9 +376,36 @@ cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* attr, const void* p)
     attr->device = b && b->kind == 0 ? b->device : 0;
     return cudaSuccess;
 }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }  // one process: peer access is enough
-cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+// CUDA IPC, emulated inside one address space (the product takes this branch for same-process peers only with TMM_DIST_FORCE_IPC=1):
+// a handle names the exporting allocation; every import is counted, and freeing an allocation that is still imported somewhere is
+// reported - on hardware that is undefined behaviour ("cudaFree on an exported region before cudaIpcCloseMemHandle in the importer").
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_blocks.find(reinterpret_cast<uintptr_t>(p));
+    if (it == g_blocks.end() || it->second.kind != 0) return cudaErrorInvalidValue;  // only whole device allocations are exported here
+    memset(h, 0, sizeof *h);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    memcpy(h->reserved, &a, sizeof a);
+    memcpy(h->reserved + 8, "emul-ipc", 8);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+    uintptr_t a = 0;
+    memcpy(&a, h.reserved, sizeof a);
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_blocks.find(a);
+    if (memcmp(h.reserved + 8, "emul-ipc", 8) != 0 || it == g_blocks.end() || it->second.kind != 0) { *p = nullptr; return cudaErrorInvalidResourceHandle; }
+    ++g_ipc_imports[a];
+    *p = reinterpret_cast<void*>(a);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ipc_imports.find(reinterpret_cast<uintptr_t>(p));
+    if (it == g_ipc_imports.end() || it->second <= 0) { violation("cudaIpcCloseMemHandle of something that is not imported", p, 0); return cudaErrorInvalidValue; }
+    if (--it->second == 0) g_ipc_imports.erase(it);
+    return cudaSuccess;
+}
 
 static void account(size_t bytes, cudaMemcpyKind kind) {
     if (kind == cudaMemcpyHostToDevice) g_h2d += bytes;

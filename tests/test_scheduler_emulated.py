@@ -139,3 +139,11 @@ def test_grid_gives_a_call_up_together_when_one_gpu_cannot_allocate(emul_build, 
     """fault injection on a GPU grid: an allocation fails on one rank - all ranks return an error for that call (no rank is left waiting
     for shares), nothing leaks, and the same contexts compute the next call correctly"""
     _worker(emul_build, ["gridfaults", devices], devices, {"TMM_DIST_NCCL": "1"} if plane == "nccl" else None)
+
+
+@pytest.mark.parametrize("world,extra", [(2, {"TMM_DIST_FORCE_IPC": "1"}), (4, {"TMM_DIST_FORCE_IPC": "1"}), (8, {"TMM_DIST_FORCE_IPC": "1"}), (4, {"TMM_DIST_NCCL": "1"}), (8, {})])
+def test_one_rank_per_gpu_entry_point_with_emulated_ipc(emul_build, world, extra):
+    """tmm_context_attach_grid (the torchrun / MPI entry point) played by one host thread per emulated GPU: growing, shrinking and
+    streaming calls on reused contexts, bit-exact per block; through the emulated CUDA IPC calls the import bookkeeping is checked
+    (re-import when a peer's buffer changed, outgrown buffers retired instead of freed while imported, everything closed at teardown)."""
+    _worker(emul_build, ["ranks", world], world, extra)

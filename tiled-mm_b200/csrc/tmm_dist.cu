@@ -154,7 +154,10 @@ BufMsg describe(tmm_context* ctx, void* p, size_t bytes) {
 void* map_peer(tmm_context* ctx, const BufMsg& msg, bool* via_ipc) {
     *via_ipc = false;
     if (!msg.ptr) return nullptr;
-    if (msg.pid == (int64_t)getpid()) {  // same process: peer access is enough
+    // (TMM_DIST_FORCE_IPC=1 sends same-process peers through the IPC branch as well: only meaningful on the emulated runtime of tests/emul,
+    //  where it lets the bookkeeping of imported handles be exercised without a second process; real CUDA cannot import its own export)
+    static const bool force_ipc = [] { const char* v = getenv("TMM_DIST_FORCE_IPC"); return v && v[0] == '1'; }();
+    if (msg.pid == (int64_t)getpid() && !force_ipc) {  // same process: peer access is enough
         if (msg.dev != ctx->device) {
             cudaError_t e = cudaDeviceEnablePeerAccess(msg.dev, 0);
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return nullptr; }
@@ -205,12 +208,12 @@ int link_setup(tmm_context* ctx, Link& link) {
     int rc = gather_msgs(ctx, link, describe(ctx, fl, 1024), all);
     if (rc) return rc;
     link.peer_flags.assign(link.parts, nullptr);
-    std::vector<bool> ipc(link.parts, false);
+    link.peer_flags_ipc.assign(link.parts, false);
     for (int g = 0; g < link.parts && ok; ++g) {
         if (g == link.me) { link.peer_flags[g] = link.flags; continue; }
         bool via = false;
         link.peer_flags[g] = static_cast<uint32_t*>(map_peer(ctx, all[g], &via));
-        ipc[g] = via;
+        link.peer_flags_ipc[g] = via;
         if (!link.peer_flags[g]) ok = false;
     }
     bool everyone = false;
@@ -224,7 +227,8 @@ int link_setup(tmm_context* ctx, Link& link) {
 void link_teardown(Link& link) {
     const nccl::Api& nc = nccl::api();
     link_unmap(link);
-    // mapped peer flag blocks opened through IPC are released with the process; the local block is freed here
+    for (size_t g = 0; g < link.peer_flags.size(); ++g)  // imported flag blocks of the peers
+        if (g < link.peer_flags_ipc.size() && link.peer_flags_ipc[g] && link.peer_flags[g]) cudaIpcCloseMemHandle(link.peer_flags[g]);
     if (link.flags) cudaFree(link.flags);
     if (link.comm && nc.ok) nc.CommDestroy(link.comm);
     link = Link{};

@@ -80,6 +80,7 @@ struct Link {
     bool direct = false;
     uint32_t* flags = nullptr;             // my flag block (device): arrive[parts] | ack[parts] | word[2]
     std::vector<uint32_t*> peer_flags;     // the peers' flag blocks, mapped
+    std::vector<bool> peer_flags_ipc;      // peer_flags[g] came from cudaIpcOpenMemHandle (closed at teardown)
     std::vector<char*> peer_base;          // the peers' panel buffers for the current call, mapped ([me] = mine)
     std::vector<std::string> peer_key;     // what peer_base[g] was mapped from (pid, pointer, IPC handle)
     std::vector<bool> peer_ipc;            // peer_base[g] came from cudaIpcOpenMemHandle (close when replaced)
