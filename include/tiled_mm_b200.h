@@ -51,7 +51,8 @@ TMM_API void tmm_context_destroy(tmm_context* ctx);
 
 /* gpu::gemm<Scalar>(handle, trans_a, trans_b, m, n, k, alpha, a, ld_a, b, ld_b, beta, c, ld_c,
  *                   pin_host_buffers, copy_c_back)  — tiled_mm.hpp:69-79, tiled_mm.cpp:492-624.
- * a, b, c are HOST pointers.  Synchronous: returns after all device work; with copy_c_back != 0 host C
+ * a, b, c are HOST pointers (device pointers are accepted as an extension: all operands on the context's device -> one launch on them,
+ * result in c or in the context's device C; a mix of host and device operands is staged with direction-inferring copies).  Synchronous: returns after all device work; with copy_c_back != 0 host C
  * holds the result, otherwise it stays in the context's device C (tmm_context_device_c), column-major
  * with ld = m.  beta == 0 => C is never read (NaN-safe).  64-bit sizes: the reference's int offsets
  * overflow at 2^31 elements (tiled_matrix.cpp:62-67); these do not. */

@@ -131,6 +131,34 @@ def run_single():
                 pass
         tmm.gemm(ctx, "n", "t", 2, 2, 2, 1.0, buf, 2, buf, 2, 0.0, buf, 2, False, True)   # lower case accepted (tiled_mm.cpp:503-504)
     check_clean("quick returns and argument errors")
+    check_clean("before device-pointer operands")
+    # device-pointer operands (additive): all on the device -> one launch, no staging; mixed -> scheduler with inferred copies
+    for dtype, alpha, beta in [(np.float64, 2.0, -1.0), (np.complex128, 1 - 2j, 1j)]:
+        rng = np.random.default_rng(77)
+        m, n, k, lda, ldb, ldc = 130, 95, 170, 133, 171, 131                 # odd leading dimensions on purpose
+        a0, b0, c0 = gen(rng, dtype, lda * k), gen(rng, dtype, ldb * n), gen(rng, dtype, ldc * n)
+        expect = oracle.gemm("N", "N", m, n, k, alpha, a0, lda, b0, ldb, beta, c0.copy(), ldc)
+        da, db, dc = tmm.malloc_device(a0.nbytes), tmm.malloc_device(b0.nbytes), tmm.malloc_device(c0.nbytes)
+        tmm.copy_to_device(a0, da); tmm.copy_to_device(b0, db)
+        with tmm.make_context(dtype, 2, 64, 64, 64) as ctx:
+            tmm.copy_to_device(c0, dc)
+            tmm.gemm(ctx, "N", "N", m, n, k, alpha, da, lda, db, ldb, beta, dc, ldc, pin_host_buffers=True, copy_c_back=True)   # all three on the device
+            assert ctx.last_stats().h2d_bytes == 0 and ctx.last_stats().kernel_launches == 1
+            out = np.empty_like(c0); tmm.copy_to_host(dc, out)
+            assert np.array_equal(out, expect), "device operands, result in place"
+            tmm.copy_to_device(c0, dc)
+            tmm.gemm(ctx, "N", "N", m, n, k, alpha, da, lda, db, ldb, beta, dc, ldc, pin_host_buffers=False, copy_c_back=False)  # result in the context's C
+            out2 = np.empty(m * n, dtype=dtype); tmm.copy_to_host(ctx.get_full_device_buffer_c().data(), out2, m * n)
+            assert np.array_equal(out2.reshape(n, m), expect.reshape(n, ldc)[:, :m]), "device operands, device-resident C"
+            tmm.copy_to_host(dc, out); assert np.array_equal(out, c0), "c must not be written when copy_c_back = false"
+            ch = tmm.malloc_pinned(dtype, c0.size); ch[:] = c0                                                                  # mixed: A on the device, B and C on the host
+            bh = tmm.malloc_pinned(dtype, b0.size); bh[:] = b0
+            tmm.gemm(ctx, "N", "N", m, n, k, alpha, da, lda, bh, ldb, beta, ch, ldc, pin_host_buffers=False, copy_c_back=True)
+            assert np.array_equal(np.asarray(ch), expect), "mixed host / device operands"
+        for p in (da, db, dc):
+            tmm.free_device(p)
+    lib.emul_reset_tma_contract_violations()   # odd-ld USER operands went straight to the GEMM layer here (the real one re-pitches them)
+    check_clean("device-pointer operands")
     # bf16 entry point: argument checking and plumbing of tmm_device_gemm_bf16 (the arithmetic here is the GEMM double's)
     rng = np.random.default_rng(9)
     m, n, k = 70, 50, 90

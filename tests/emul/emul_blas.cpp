@@ -24,6 +24,8 @@ std::atomic<int> g_f32_mode{3}, g_c32_mode{0};
 }
 
 extern "C" __attribute__((visibility("default"))) uint64_t emul_tma_contract_violations() { return g_contract_violations; }
+// the counter is about panels the SCHEDULER builds; user-supplied device operands may have any ld (the real dispatcher re-pitches them)
+extern "C" __attribute__((visibility("default"))) void emul_reset_tma_contract_violations() { g_contract_violations = 0; }
 
 namespace tmm {
 

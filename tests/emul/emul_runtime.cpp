@@ -424,8 +424,16 @@ static cudaError_t copy_2d(void* dst, size_t dpitch, const void* src, size_t spi
         if (width == 4 && height == 1 && kind == cudaMemcpyDeviceToDevice) g_flag_vc[reinterpret_cast<uintptr_t>(dst)] = g_vc[sid];  // a counter forwarded to a peer
         if (host_blocks) join(g_host_vc[t_device], g_vc[sid]);
     }
-    const bool dst_dev = kind == cudaMemcpyHostToDevice || kind == cudaMemcpyDeviceToDevice;
-    const bool src_dev = kind == cudaMemcpyDeviceToHost || kind == cudaMemcpyDeviceToDevice;
+    bool dst_dev = kind == cudaMemcpyHostToDevice || kind == cudaMemcpyDeviceToDevice;
+    bool src_dev = kind == cudaMemcpyDeviceToHost || kind == cudaMemcpyDeviceToDevice;
+    if (kind == cudaMemcpyDefault) {  // unified addressing: the direction follows from where the pointers live
+        std::lock_guard<std::mutex> lk(g_mu);
+        const Block* bd = find_block(dst, 1);
+        const Block* bs = find_block(src, 1);
+        dst_dev = bd && bd->kind == 0;
+        src_dev = bs && bs->kind == 0;
+        kind = dst_dev ? (src_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice) : (src_dev ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+    }
     check_range(dst, span_2d(dpitch, width, height), dst_dev, async);
     check_range(src, span_2d(spitch, width, height), src_dev, async);
     if (!dry_run() || (width * height <= 4096 && !is_virtual(dst) && !is_virtual(src)))  // dry run: only the protocol's own words move

@@ -107,3 +107,36 @@ def test_bf16_native_kind_f16_tn(gpu_tmm, oracle):
             assert np.array_equal(got, want), (m, n, k)
         else:
             assert float(np.max(np.abs(got - want))) / (k * 0.25) <= 2e-6, (m, n, k)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32])
+def test_device_pointer_operands(gpu_tmm, oracle, dtype):
+    """tmm_gemm with DEVICE pointers (additive): all operands on the device -> one launch on them (any ld), result in place or in the
+    context's device C; a mix of host and device operands -> the scheduler with direction-inferring copies."""
+    tmm = gpu_tmm
+    cplx = np.dtype(dtype).kind == "c"
+    alpha, beta = (1 - 2j, 1j) if cplx else (2.0, -1.0)
+    rng = np.random.default_rng(5)
+    m, n, k, lda, ldb, ldc = 1030, 995, 1170, 1033, 1171, 1031
+    def gen(count):
+        v = rng.integers(0, 10, count).astype(np.float64)
+        return (v + 1j * rng.integers(0, 10, count)).astype(dtype) if cplx else v.astype(dtype)
+    a0, b0, c0 = gen(lda * k), gen(ldb * n), gen(ldc * n)
+    expect = oracle.gemm("N", "N", m, n, k, alpha, a0, lda, b0, ldb, beta, c0.copy(), ldc)
+    da, db, dc = tmm.malloc_device(a0.nbytes), tmm.malloc_device(b0.nbytes), tmm.malloc_device(c0.nbytes)
+    tmm.copy_to_device(a0, da); tmm.copy_to_device(b0, db); tmm.copy_to_device(c0, dc)
+    with tmm.make_context(dtype) as ctx:
+        tmm.gemm(ctx, "N", "N", m, n, k, alpha, da, lda, db, ldb, beta, dc, ldc, pin_host_buffers=True, copy_c_back=True)
+        assert ctx.last_stats().h2d_bytes == 0
+        out = np.empty_like(c0); tmm.copy_to_host(dc, out)
+        assert np.array_equal(out, expect)
+        tmm.copy_to_device(c0, dc)
+        tmm.gemm(ctx, "N", "N", m, n, k, alpha, da, lda, db, ldb, beta, dc, ldc, pin_host_buffers=False, copy_c_back=False)
+        out2 = np.empty(m * n, dtype=dtype); tmm.copy_to_host(ctx.get_full_device_buffer_c().data(), out2, m * n)
+        assert np.array_equal(out2.reshape(n, m), expect.reshape(n, ldc)[:, :m])
+        ch = tmm.malloc_pinned(dtype, c0.size); ch[:] = c0
+        bh = tmm.malloc_pinned(dtype, b0.size); bh[:] = b0
+        tmm.gemm(ctx, "N", "N", m, n, k, alpha, da, lda, bh, ldb, beta, ch, ldc, pin_host_buffers=False, copy_c_back=True)
+        assert np.array_equal(np.asarray(ch), expect)
+    for p in (da, db, dc):
+        tmm.free_device(p)

@@ -85,6 +85,7 @@ struct Call {
     char* c;
     int64_t lda, ldb, ldc;
     bool copy_c_back, beta_nonzero;
+    bool device_operands = false;  // a, b or c is a DEVICE pointer (additive: the reference takes host pointers only): copies infer their direction
     // stored shapes (reference tiled_mm.cpp:507-514)
     int64_t a_rows, a_cols, b_rows, b_cols;
     unsigned char one[16];  // scalar 1 of the dtype (beta' for k-chunks > 0, tiled_mm.cpp:309)
@@ -110,14 +111,16 @@ bool scalar_is_zero(int dtype, const void* p) {
 // ---- copy helpers (64-bit offsets throughout; reference copy_tile_* tiled_mm.cpp:45-123) -----------
 int h2d_2d(Call& cl, void* dst, int64_t dpitch_elems, const char* src, int64_t spitch_elems, int64_t rows, int64_t cols, cudaStream_t st) {
     if (rows <= 0 || cols <= 0) return TMM_OK;
-    CU(cudaMemcpy2DAsync(dst, (size_t)dpitch_elems * cl.es, src, (size_t)spitch_elems * cl.es, (size_t)rows * cl.es, (size_t)cols, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpy2DAsync(dst, (size_t)dpitch_elems * cl.es, src, (size_t)spitch_elems * cl.es, (size_t)rows * cl.es, (size_t)cols,
+                         cl.device_operands ? cudaMemcpyDefault : cudaMemcpyHostToDevice, st));
     cl.ctx->stats.h2d_bytes += (uint64_t)rows * cols * cl.es;
     cl.ctx->stats.h2d_copies++;
     return TMM_OK;
 }
 int d2h_2d(Call& cl, char* dst, int64_t dpitch_elems, const void* src, int64_t spitch_elems, int64_t rows, int64_t cols, cudaStream_t st) {
     if (rows <= 0 || cols <= 0) return TMM_OK;
-    CU(cudaMemcpy2DAsync(dst, (size_t)dpitch_elems * cl.es, src, (size_t)spitch_elems * cl.es, (size_t)rows * cl.es, (size_t)cols, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpy2DAsync(dst, (size_t)dpitch_elems * cl.es, src, (size_t)spitch_elems * cl.es, (size_t)rows * cl.es, (size_t)cols,
+                         cl.device_operands ? cudaMemcpyDefault : cudaMemcpyDeviceToHost, st));
     cl.ctx->stats.d2h_bytes += (uint64_t)rows * cols * cl.es;
     cl.ctx->stats.d2h_copies++;
     return TMM_OK;
@@ -513,7 +516,9 @@ int pin(tmm_context* ctx, const void* p, size_t bytes, std::vector<const void*>&
     // memory that is already page-locked (cudaHostAlloc / gpu::malloc_pinned, or registered by the caller) needs nothing:
     // the reference would fail in cudaHostRegister here (tiled_mm.cpp:532-549); accepting it is a superset
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) { if (attr.type == cudaMemoryTypeHost) return TMM_OK; }
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) {
+        if (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) return TMM_OK;  // nothing to page-lock
+    }
     else cudaGetLastError();
     // Large one-shot registrations dominate a call on pageable memory (page-locking runs at a few GB/s): the range is cut at
     // 2 MiB boundaries and the pieces are registered from several host threads at once.  TMM_PIN_THREADS=1 keeps one cudaHostRegister.
@@ -764,6 +769,48 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
     if ((need_ab && (!a || !b)) || (c_touched && !c)) return fail(TMM_ERR_INVALID, "null matrix pointer");
 
     DeviceGuard guard(ctx->device);
+    // Device-pointer operands (additive; the reference takes host pointers only).  All operands already on this context's
+    // device: there is nothing to stream - one launch of the device GEMM on them (any ld / alignment, csrc/tmm_common.cu), the result in
+    // c itself or, with copy_c_back = false, in the context's device C.  A mix of host and device operands goes through the scheduler
+    // with copies that infer their direction.
+    {
+        auto where = [&](const void* p, int* dev) {
+            cudaPointerAttributes attr;
+            *dev = -1;
+            if (!p) return 0;
+            if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+            if (attr.type == cudaMemoryTypeDevice) { *dev = attr.device; return 1; }
+            return 0;
+        };
+        int da = -1, db = -1, dc = -1;
+        const int na = where(a, &da), nb = where(b, &db), nc = where(c, &dc);
+        cl.device_operands = (na + nb + nc) > 0;
+        if (cl.device_operands && ctx->grid.active())
+            return fail(TMM_ERR_INVALID, "device-pointer operands are not supported on a GPU grid (the panel exchange uploads from host memory)");
+        const bool all_here = need_ab && na && nb && (nc || !c_touched) && da == ctx->device && db == ctx->device && (!nc || dc == ctx->device);
+        if (all_here) {
+            cudaStream_t st = ctx->s_compute[0];
+            void* dC = c;
+            int64_t ldd = ld_c;
+            cudaError_t e = cudaSuccess;
+            int rc0 = TMM_OK;
+            if (!cl.copy_c_back) {
+                if ((size_t)m * n * cl.es > ctx->full_c.cap) ctx->budget_cached = 0;
+                if ((e = ctx->full_c.reserve((size_t)m * n * cl.es, 1.2)) != cudaSuccess) rc0 = cuda_fail(e, "cudaMalloc(full C)");
+                ctx->full_c_elems = (size_t)m * n;
+                dC = ctx->full_c.p; ldd = m;
+                if (!rc0 && cl.beta_nonzero &&
+                    (e = cudaMemcpy2DAsync(dC, (size_t)ldd * cl.es, c, (size_t)ld_c * cl.es, (size_t)m * cl.es, (size_t)n, cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
+                    rc0 = cuda_fail(e, "cudaMemcpy2DAsync(C)");
+            }
+            if (!rc0 && (e = tmm::device_gemm(cl.dtype, cl.ta, cl.tb, m, n, k, alpha, a, ld_a, b, ld_b, beta, dC, ldd, st)) != cudaSuccess) rc0 = cuda_fail(e, "device_gemm");
+            if ((e = cudaStreamSynchronize(st)) != cudaSuccess && !rc0) rc0 = cuda_fail(e, "cudaStreamSynchronize");
+            ctx->stats.kernel_launches = tmm::launch_count() - launches_before;
+            ctx->stats.c_blocks = 1; ctx->stats.k_chunks = 1;
+            ctx->stats.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+            return rc0;
+        }
+    }
     if (ctx->trace && ctx->get_timing_event(&trace_t0) == cudaSuccess) cudaEventRecord(trace_t0, ctx->s_h2d);
     std::vector<const void*> pinned_now;
     int rc = TMM_OK;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of round 2 (one B200, ~6 min): validate everything that was written after round 1's GPU budget ran out.
 #   make -C tools && gpurun --timeout 500 -- 'bash tools/gpu_round2.sh'
-# 1. gated experimental tests (tcgen05 CGEMM embedding)            -> promote TMM_C32_MATH=tc to the default if green
+# 1. gated experimental tests (tcgen05 CGEMM embedding, BF16 entry points, device-pointer operands)            -> promote TMM_C32_MATH=tc to the default if green
 # 2. tc_test cgemm: all nine op pairs vs cuBLAS CGEMM + timing      -> CGEMM number for DESIGN 3.4
 # 3. SGEMM split variants: precision + timing, default vs TMM_TC_SPLIT=trunc
 # 4. the regular suite + bench line (regression check)
