@@ -11,6 +11,7 @@
 // STATUS: cross-compiled; the widening pass has not run on hardware yet (round-1 GPU budget spent) - the entry point is new and
 // touches no existing path; tests/test_experimental_gpu.py covers it when TMM_EXPERIMENTAL=1.
 #include "tmm_blas.h"
+#include "tmm_prepass.cuh"
 
 #include <cstdint>
 #include <cstdlib>
@@ -18,12 +19,7 @@
 namespace tmm {
 namespace bf16tc {
 
-// stored rows x cols bf16 (ld_in elements per column) -> fp32 with pitch floats per column
-__global__ void __launch_bounds__(256) widen(const uint16_t* __restrict__ in, int64_t ld_in, int rows, int cols, float* __restrict__ out, int64_t pitch) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows) return;
-    for (int c = blockIdx.y; c < cols; c += gridDim.y) out[(int64_t)c * pitch + r] = __uint_as_float((uint32_t)in[(int64_t)c * ld_in + r] << 16);
-}
+using c32tc::widen;  // tmm_prepass.cuh
 
 static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 

@@ -22,51 +22,12 @@
 // STATUS: cross-compiled and algebra-checked on the CPU (tests/test_c32_embedding.py); NOT yet run on hardware (the round's GPU
 // budget was spent) - therefore opt-in: TMM_C32_MATH=tc or tmm_set_c32_math(TMM_CMATH_TC).  The default stays the SIMT kernel.
 #include "tmm_blas.h"
+#include "tmm_prepass.cuh"  // embed_a_n, embed_a_t, split_b_t: device code only, also compiled for the CPU by tests/test_prepass_kernels.py
 
 #include <cstdint>
 
 namespace tmm {
 namespace c32tc {
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-
-// op N: stored m x k complex (m contiguous).  out: (2m x 2k) floats, pitch floats per column (even), written as float2 pairs.
-__global__ void __launch_bounds__(256) embed_a_n(const float2* __restrict__ a, int64_t lda, int m, int k, float2 alpha, float2* __restrict__ out2, int64_t pitch2) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    for (int l = blockIdx.y; l < k; l += gridDim.y) {
-        const float2 w = cmul(alpha, a[(int64_t)l * lda + i]);
-        out2[(int64_t)(2 * l) * pitch2 + i] = w;                           // column 2l   : ( re,  im)
-        out2[(int64_t)(2 * l + 1) * pitch2 + i] = make_float2(-w.y, w.x);  // column 2l+1 : (-im,  re)  = i * w
-    }
-}
-
-// op T / C: stored k x m complex (k contiguous), element (l, i).  out = A'^T: (2k x 2m) floats, k-contiguous:
-//   column 2i   rows (2l, 2l+1) = ( re, -im)        column 2i+1 rows (2l, 2l+1) = ( im,  re)         of w = alpha * op(a(l, i))
-__global__ void __launch_bounds__(256) embed_a_t(const float2* __restrict__ a, int64_t lda, int k, int m, float2 alpha, int conj, float2* __restrict__ out2,
-                                                  int64_t pitch2) {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= k) return;
-    for (int i = blockIdx.y; i < m; i += gridDim.y) {
-        float2 v = a[(int64_t)i * lda + l];
-        if (conj) v.y = -v.y;
-        const float2 w = cmul(alpha, v);
-        out2[(int64_t)(2 * i) * pitch2 + l] = make_float2(w.x, -w.y);
-        out2[(int64_t)(2 * i + 1) * pitch2 + l] = make_float2(w.y, w.x);
-    }
-}
-
-// op T / C of B: stored n x k complex (n contiguous), element (j, l).  out = B'^T: (n x 2k) floats, n-contiguous:
-//   column 2l = re(b(:, l)),  column 2l+1 = +-im(b(:, l))
-__global__ void __launch_bounds__(256) split_b_t(const float2* __restrict__ b, int64_t ldb, int n, int k, int conj, float* __restrict__ out, int64_t pitch) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    for (int l = blockIdx.y; l < k; l += gridDim.y) {
-        const float2 v = b[(int64_t)l * ldb + j];
-        out[(int64_t)(2 * l) * pitch + j] = v.x;
-        out[(int64_t)(2 * l + 1) * pitch + j] = conj ? -v.y : v.y;
-    }
-}
 
 static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 static inline dim3 pass_grid(int contiguous, int columns) {

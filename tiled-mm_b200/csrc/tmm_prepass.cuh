@@ -1,0 +1,59 @@
+// Elementwise operand-preparation kernels of the tcgen05 CGEMM embedding (gemm_c32_tc.cu) and of the BF16 entry point (gemm_bf16_tc.cu).
+// Device code only - no runtime calls, no launch syntax - so that the very same source is also compiled for the CPU (with a ten-line
+// shim for blockIdx / threadIdx / float2) by tests/test_prepass_kernels.py, which runs every "thread" in a loop and compares the
+// result with the numpy restatement of the embedding: these kernels were written after the round's GPU budget was spent.
+#pragma once
+#include <cstdint>
+
+namespace tmm {
+namespace c32tc {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// op N: stored m x k complex (m contiguous).  out: (2m x 2k) floats, pitch floats per column (even), written as float2 pairs.
+static __global__ void __launch_bounds__(256) embed_a_n(const float2* __restrict__ a, int64_t lda, int m, int k, float2 alpha, float2* __restrict__ out2, int64_t pitch2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    for (int l = blockIdx.y; l < k; l += gridDim.y) {
+        const float2 w = cmul(alpha, a[(int64_t)l * lda + i]);
+        out2[(int64_t)(2 * l) * pitch2 + i] = w;                           // column 2l   : ( re,  im)
+        out2[(int64_t)(2 * l + 1) * pitch2 + i] = make_float2(-w.y, w.x);  // column 2l+1 : (-im,  re)  = i * w
+    }
+}
+
+// op T / C: stored k x m complex (k contiguous), element (l, i).  out = A'^T: (2k x 2m) floats, k-contiguous:
+//   column 2i   rows (2l, 2l+1) = ( re, -im)        column 2i+1 rows (2l, 2l+1) = ( im,  re)         of w = alpha * op(a(l, i))
+static __global__ void __launch_bounds__(256) embed_a_t(const float2* __restrict__ a, int64_t lda, int k, int m, float2 alpha, int conj, float2* __restrict__ out2,
+                                                  int64_t pitch2) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= k) return;
+    for (int i = blockIdx.y; i < m; i += gridDim.y) {
+        float2 v = a[(int64_t)i * lda + l];
+        if (conj) v.y = -v.y;
+        const float2 w = cmul(alpha, v);
+        out2[(int64_t)(2 * i) * pitch2 + l] = make_float2(w.x, -w.y);
+        out2[(int64_t)(2 * i + 1) * pitch2 + l] = make_float2(w.y, w.x);
+    }
+}
+
+// op T / C of B: stored n x k complex (n contiguous), element (j, l).  out = B'^T: (n x 2k) floats, n-contiguous:
+//   column 2l = re(b(:, l)),  column 2l+1 = +-im(b(:, l))
+static __global__ void __launch_bounds__(256) split_b_t(const float2* __restrict__ b, int64_t ldb, int n, int k, int conj, float* __restrict__ out, int64_t pitch) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    for (int l = blockIdx.y; l < k; l += gridDim.y) {
+        const float2 v = b[(int64_t)l * ldb + j];
+        out[(int64_t)(2 * l) * pitch + j] = v.x;
+        out[(int64_t)(2 * l + 1) * pitch + j] = conj ? -v.y : v.y;
+    }
+}
+
+// stored rows x cols bf16 (ld_in elements per column) -> fp32 with pitch floats per column
+static __global__ void __launch_bounds__(256) widen(const uint16_t* __restrict__ in, int64_t ld_in, int rows, int cols, float* __restrict__ out, int64_t pitch) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    for (int c = blockIdx.y; c < cols; c += gridDim.y) out[(int64_t)c * pitch + r] = __uint_as_float((uint32_t)in[(int64_t)c * ld_in + r] << 16);
+}
+
+}  // namespace c32tc
+}  // namespace tmm
