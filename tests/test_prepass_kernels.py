@@ -21,6 +21,7 @@ static dim3 blockIdx, threadIdx, blockDim, gridDim;
 struct float2 { float x, y; };
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 #define __global__
 #define __device__
 #define __forceinline__ inline
@@ -46,6 +47,9 @@ void run_embed_a_t(const float* a, long lda, int k, int m, float ar, float ai, i
 }
 void run_split_b_t(const float* b, long ldb, int n, int k, int conj, float* out, long pitch, int cap) {
     launch(split_b_t, pass_grid(n, k, cap), dim3(256), (const float2*)b, (int64_t)ldb, n, k, conj, out, (int64_t)pitch);
+}
+void run_split(const float* x, long count, float* hi, float* lo, float* lo_trunc) {
+    for (long i = 0; i < count; ++i) { tmm::f32tc::split_tf32(x[i], hi[i], lo[i]); lo_trunc[i] = tmm::f32tc::lo_of_truncated(x[i]); }
 }
 void run_widen(const uint16_t* in, long ld, int rows, int cols, float* out, long pitch, int cap) {
     launch(widen, pass_grid(rows, cols, cap), dim3(256), in, (int64_t)ld, rows, cols, out, (int64_t)pitch);
@@ -110,3 +114,27 @@ def test_widen_kernel(kernels):
     want = (bf.astype(np.uint32) << 16).view(np.float32).reshape(cols, ld)[:, :rows]
     assert np.array_equal(out[:, :rows].view(np.uint32), want.view(np.uint32))
     assert np.all(out[:, rows:] == 7), "padding of the widened panel must stay untouched"
+
+
+def test_tf32_operand_splits(kernels):
+    """split_tf32 (the hardware-validated round-to-nearest split of the FP32-accurate SGEMM) and lo_of_truncated (the experimental
+    raw-bits variant): hi and lo are TF32 numbers, hi + lo reproduces x to 2^-21 |x| or better, special values travel in hi alone."""
+    rng = np.random.default_rng(6)
+    x = np.concatenate([(rng.standard_normal(20000) * 10.0 ** rng.integers(-30, 30, 20000)).astype(np.float32),
+                        np.array([0.0, -0.0, 1.0, -1.0, 3.0, 1e-45, -1e-40, 3.4028235e38, np.inf, -np.inf, np.nan, 9.0, 1 + 2 ** -11, 1 + 2 ** -12], np.float32)])
+    hi, lo, lot = (np.zeros_like(x) for _ in range(3))
+    kernels.run_split(_fp(x), ctypes.c_long(x.size), _fp(hi), _fp(lo), _fp(lot))
+    low13 = np.uint32(0x1FFF)
+    assert np.all((hi.view(np.uint32) & low13) == 0) and np.all((lo.view(np.uint32) & low13) == 0) and np.all((lot.view(np.uint32) & low13) == 0)
+    fin = np.isfinite(x) & (np.abs(x) < 1e38) & (np.abs(x) > 1e-30)
+    xd = x[fin].astype(np.float64)
+    assert np.max(np.abs(hi[fin].astype(np.float64) + lo[fin] - xd) / np.abs(xd)) <= 2.0 ** -21      # round-to-nearest split: ~2^-23
+    trunc = (x.view(np.uint32) & ~low13).view(np.float32)
+    assert np.max(np.abs(trunc[fin].astype(np.float64) + lot[fin] - xd) / np.abs(xd)) <= 2.0 ** -20  # raw-bits split: one bit less
+    ints = np.arange(-2048, 2049, dtype=np.float32)                                                   # small integers are exact in TF32: lo = 0
+    h2, l2, lt2 = (np.zeros_like(ints) for _ in range(3))
+    kernels.run_split(_fp(ints), ctypes.c_long(ints.size), _fp(h2), _fp(l2), _fp(lt2))
+    assert np.array_equal(h2, ints) and not l2.any() and not lt2.any()
+    special = ~np.isfinite(x)
+    assert np.all(lo[special] == 0) and np.all(lot[special] == 0) and np.array_equal(np.isnan(hi[special]), np.isnan(x[special]))
+    assert np.array_equal(hi[np.isinf(x)], x[np.isinf(x)])

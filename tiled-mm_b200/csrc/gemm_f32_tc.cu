@@ -33,6 +33,7 @@
 // All m / n / k edges are handled by TMA zero fill plus masked stores.
 #include "tmm_blas.h"
 #include "tmm_tc.cuh"
+#include "tmm_prepass.cuh"  // split_tf32, lo_of_truncated (device code only; also compiled for the CPU by tests/test_prepass_kernels.py)
 
 #include <cstdio>
 #include <cstdlib>
@@ -83,26 +84,6 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
     const int width = min(GROUP_COLS, tiles_n - first);
     tm = r / width;
     tn = first + (r - tm * width);
-}
-
-// x -> (hi, lo): hi = x rounded to TF32 (nearest, ties away), lo = (x - hi) rounded to TF32; Inf/NaN keep lo = 0
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    const uint32_t u = __float_as_uint(x);
-    uint32_t h = (u + 0x1000u) & 0xFFFFE000u;
-    float r = x - __uint_as_float(h);
-    if ((u & 0x7F800000u) == 0x7F800000u) { h = (u & 0x007FFFFFu) ? 0x7FC00000u : u; r = 0.f; }
-    else if ((h & 0x7F800000u) == 0x7F800000u) r = 0.f;  // rounded up to Inf
-    hi = __uint_as_float(h);
-    lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
-}
-
-// Variant for hi = raw bits: the hardware reads trunc(x) (top 19 bits), so lo = x - trunc(x) (exact), rounded to TF32.
-// |lo| < 2^-10 |x| instead of 2^-11 |x| (one bit less accurate than the round-to-nearest split) but the tile is not rewritten.
-__device__ __forceinline__ float lo_of_truncated(float x) {
-    const uint32_t u = __float_as_uint(x);
-    if ((u & 0x7F800000u) == 0x7F800000u) return 0.f;  // Inf / NaN travel in hi alone
-    const float r = x - __uint_as_float(u & 0xFFFFE000u);
-    return __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)

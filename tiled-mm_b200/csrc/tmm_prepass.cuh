@@ -56,4 +56,28 @@ static __global__ void __launch_bounds__(256) widen(const uint16_t* __restrict__
 }
 
 }  // namespace c32tc
+
+namespace f32tc {
+
+// x -> (hi, lo): hi = x rounded to TF32 (nearest, ties away), lo = (x - hi) rounded to TF32; Inf/NaN keep lo = 0
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    const uint32_t u = __float_as_uint(x);
+    uint32_t h = (u + 0x1000u) & 0xFFFFE000u;
+    float r = x - __uint_as_float(h);
+    if ((u & 0x7F800000u) == 0x7F800000u) { h = (u & 0x007FFFFFu) ? 0x7FC00000u : u; r = 0.f; }
+    else if ((h & 0x7F800000u) == 0x7F800000u) r = 0.f;  // rounded up to Inf
+    hi = __uint_as_float(h);
+    lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+}
+
+// Variant for hi = raw bits: the hardware reads trunc(x) (top 19 bits), so lo = x - trunc(x) (exact), rounded to TF32.
+// |lo| < 2^-10 |x| instead of 2^-11 |x| (one bit less accurate than the round-to-nearest split) but the tile is not rewritten.
+__device__ __forceinline__ float lo_of_truncated(float x) {
+    const uint32_t u = __float_as_uint(x);
+    if ((u & 0x7F800000u) == 0x7F800000u) return 0.f;  // Inf / NaN travel in hi alone
+    const float r = x - __uint_as_float(u & 0xFFFFE000u);
+    return __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+}
+
+}  // namespace f32tc
 }  // namespace tmm
