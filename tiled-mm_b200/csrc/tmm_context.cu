@@ -521,8 +521,9 @@ int pin(tmm_context* ctx, const void* p, size_t bytes, std::vector<const void*>&
     }
     else cudaGetLastError();
     // Large one-shot registrations dominate a call on pageable memory (page-locking runs at a few GB/s): the range is cut at
-    // 2 MiB boundaries and the pieces are registered from several host threads at once.  TMM_PIN_THREADS=1 keeps one cudaHostRegister.
-    static const int pin_threads = [] { const char* v = getenv("TMM_PIN_THREADS"); int t = (v && *v) ? atoi(v) : 4; return t < 1 ? 1 : (t > 16 ? 16 : t); }();
+    // 2 MiB boundaries and the pieces are registered from several host threads at once.  Opt-in (TMM_PIN_THREADS=n > 1) until a tile
+    // copy that spans two adjacent registrations has been timed on hardware; the default is one cudaHostRegister, like the reference.
+    static const int pin_threads = [] { const char* v = getenv("TMM_PIN_THREADS"); int t = (v && *v) ? atoi(v) : 1; return t < 1 ? 1 : (t > 16 ? 16 : t); }();
     if (!ctx->pin_cache && pin_threads > 1 && bytes >= ((size_t)256 << 20)) {
         const uintptr_t lo = reinterpret_cast<uintptr_t>(p), hi = lo + bytes, huge = (uintptr_t)2 << 20;
         std::vector<uintptr_t> cut = {lo};

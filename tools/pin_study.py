@@ -24,7 +24,7 @@ with tmm.make_context(np.float64) as ctx:
         tmm.gemm(ctx, "N", "N", n, n, n, 1.0, a, n, b, n, 0.0, c, n, pin_host_buffers=True, copy_c_back=True)
         dt = time.perf_counter() - t0
         best = min(best, dt) if r else best
-        print(f"  ours  TMM_PIN_THREADS={os.environ.get('TMM_PIN_THREADS', '4')}: run {r}: {dt * 1e3:.1f} ms")
+        print(f"  ours  TMM_PIN_THREADS={os.environ.get('TMM_PIN_THREADS', '1')}: run {r}: {dt * 1e3:.1f} ms")
     print(f"ours, pin_host_buffers=true on pageable memory, n={n}: best {best * 1e3:.1f} ms = {2.0 * n ** 3 / best * 1e-12:.2f} TFLOP/s")
 try:
     import _util
