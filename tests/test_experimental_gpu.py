@@ -140,3 +140,23 @@ def test_device_pointer_operands(gpu_tmm, oracle, dtype):
         assert np.array_equal(np.asarray(ch), expect)
     for p in (da, db, dc):
         tmm.free_device(p)
+
+
+@pytest.fixture()
+def a_via_tmem():
+    """TMM_TC_ATMEM=1: the FP32-accurate SGEMM takes its A operand from tensor memory (sgemm_tc_ts_kernel); read per launch."""
+    os.environ["TMM_TC_ATMEM"] = "1"
+    yield
+    os.environ.pop("TMM_TC_ATMEM", None)
+
+
+@pytest.mark.parametrize("tt", ALL_TT)
+def test_sgemm_a_through_tmem_exact_on_integers(gpu_tmm, oracle, a_via_tmem, tt):
+    """All op pairs (k- and m-contiguous A tiles, both B orientations), ragged edges in m, n and k, beta != 0 and beta = 0."""
+    run_case(gpu_tmm, oracle, np.float32, tt, 130, 67, 95, 2.0, -1.0, pad=(0, 0, 3), ints=True)      # ld multiples of 4 floats: the TMA contract
+    run_case(gpu_tmm, oracle, np.float32, tt, 1000, 520, 1100, 1.0, 0.0, pad=(4, 8, 0), ints=True)   # several tiles, 35 k-blocks, 9 windows
+
+
+@pytest.mark.parametrize("tt", ["NN", "TN", "NT", "TT"])
+def test_sgemm_a_through_tmem_random(gpu_tmm, oracle, a_via_tmem, tt):
+    run_case(gpu_tmm, oracle, np.float32, tt, 777, 530, 4100, 1.5, 0.25, pad=(3, 2, 9), tiles=(256, 300, 500))
