@@ -86,8 +86,12 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
     tn = first + (r - tm * width);
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
-sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+// The kernel body, parameterised by the ring geometry: NSTAGES stages of [A | (A lo) | B | (B lo)] with B at B_OFF bytes from A.
+//   <3, 2 * OPERAND_BYTES>  the FP32-accurate layout (hi | lo twins, 64 KB per stage)                     -> sgemm_tc_kernel
+//   <6, OPERAND_BYTES>      raw tiles only (plain TF32 / native 16-bit: no split stage, 32 KB per stage)  -> sgemm_tc_deep_kernel
+template <int NSTAGES, int B_OFF>
+__device__ __forceinline__ void sgemm_tc_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const Params& p) {
+    constexpr int STAGES = NSTAGES, STAGE_BYTES = 2 * B_OFF;
     extern __shared__ unsigned char smem_raw[];
     // swizzled tiles need 1024-byte alignment: [stage: A hi | A lo | B hi | B lo] x STAGES, then the barriers
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -141,7 +145,7 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     tc::mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * OPERAND_BYTES);
                     unsigned char* sa = base + stage * STAGE_BYTES;
-                    unsigned char* sb = sa + 2 * OPERAND_BYTES;
+                    unsigned char* sb = sa + B_OFF;
                     if (p.a_mn_major) {
 #pragma unroll
                         for (int j = 0; j < BM / ATOM_MN; ++j) ptx::tma_load_2d(sa + j * MN_BOX_BYTES, &tmap_a, &full_bar[stage], tm * BM + j * ATOM_MN, kb * p.bk);
@@ -178,7 +182,7 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     tc::fence_after_thread_sync();
                     const uint32_t a_hi = ptx::smem_u32(base + stage * STAGE_BYTES);
                     const uint32_t a_lo = a_hi + OPERAND_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * OPERAND_BYTES;
+                    const uint32_t b_hi = a_hi + B_OFF;
                     const uint32_t b_lo = b_hi + OPERAND_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ++ks) {
@@ -321,6 +325,23 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         tc::fence_after_thread_sync();
         tc::tmem_dealloc(tmem_base, TMEM_COLS);
     }
+}
+
+
+__global__ void __launch_bounds__(THREADS, 1)
+sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+    sgemm_tc_body<STAGES, 2 * OPERAND_BYTES>(tmap_a, tmap_b, p);
+}
+
+// Experimental (TMM_TC_TF32_STAGES=6, not yet run on hardware): the one-term modes (plain TF32, native bf16) leave the lo twins of the
+// ring unused, so the same shared memory holds SIX 32 KB stages instead of three.  Why it should matter: in one-term mode a k-block is
+// only 256 cycles of MMA work, the measured 866 cycles per k-block (352 TF) equal one TMA round trip (~2600 cycles) divided by the
+// three stages in flight - the ring is latency-bound, not bandwidth-bound.
+constexpr int DEEP_STAGES = 6;
+constexpr int DEEP_SMEM_BYTES = DEEP_STAGES * 2 * OPERAND_BYTES + 1024 + 256;
+__global__ void __launch_bounds__(THREADS, 1)
+sgemm_tc_deep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+    sgemm_tc_body<DEEP_STAGES, OPERAND_BYTES>(tmap_a, tmap_b, p);
 }
 
 // ---- experimental variant: the A operand goes through TENSOR MEMORY (TMM_TC_ATMEM=1; written after the round's GPU time ran out) ----
@@ -703,6 +724,17 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
             configured_ts[dev] = true;
         }
         sgemm_tc_ts_kernel<<<grid, THREADS, TS_SMEM_BYTES, stream>>>(map_a, map_b, p);
+        count_launch();
+        return cudaGetLastError();
+    }
+    if (p.terms == 1 && env_u32("TMM_TC_TF32_STAGES", STAGES) == (uint32_t)DEEP_STAGES) {  // experimental: six raw stages for the one-term mode
+        static bool configured_deep[64] = {false};
+        if (dev >= 0 && dev < 64 && !configured_deep[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(sgemm_tc_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEEP_SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            configured_deep[dev] = true;
+        }
+        sgemm_tc_deep_kernel<<<grid, THREADS, DEEP_SMEM_BYTES, stream>>>(map_a, map_b, p);
         count_launch();
         return cudaGetLastError();
     }
