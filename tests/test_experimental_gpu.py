@@ -142,10 +142,11 @@ def test_device_pointer_operands(gpu_tmm, oracle, dtype):
         tmm.free_device(p)
 
 
-@pytest.fixture()
-def a_via_tmem():
-    """TMM_TC_ATMEM=1: the FP32-accurate SGEMM takes its A operand from tensor memory (sgemm_tc_ts_kernel); read per launch."""
-    os.environ["TMM_TC_ATMEM"] = "1"
+@pytest.fixture(params=["1", "2"], ids=["one-cta", "cta-pair"])
+def a_via_tmem(request):
+    """TMM_TC_ATMEM=1: the FP32-accurate SGEMM takes its A operand from tensor memory (sgemm_tc_ts_kernel<false>);
+    =2: additionally CTA pairs sharing 256 x 128 tiles through cta_group::2 MMAs (sgemm_tc_ts_kernel<true>).  Read per launch."""
+    os.environ["TMM_TC_ATMEM"] = request.param
     yield
     os.environ.pop("TMM_TC_ATMEM", None)
 

@@ -35,6 +35,7 @@
 #include "tmm_tc.cuh"
 #include "tmm_prepass.cuh"  // split_tf32, lo_of_truncated (device code only; also compiled for the CPU by tests/test_prepass_kernels.py)
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -371,8 +372,22 @@ static_assert(TS_A_COL0 + TS_STAGES * TS_A_SLOT_COLS <= TS_TMEM_COLS, "TMEM budg
 static_assert(TS_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(REGS_CONTROL + REGS_EPILOGUE + TS_REGS_SPLIT_A + TS_REGS_SPLIT_B <= 4 * 128, "setmaxnreg budget of the 512 x 128 launch allocation");
 
+// PAIR = true (TMM_TC_ATMEM=2): clusters of two CTAs share one 256 x 128 tile through cta_group::2 MMAs.  Each CTA loads and splits ITS
+// 128 rows of A (into its own tensor memory) and only ITS 64-column half of B (shared memory); the CTA of rank 0 issues the MMAs
+// for both (M = 256: rows 0-127 accumulate in its TMEM, rows 128-255 in the peer's), reading each half of B once for both SMs:
+//     per CTA and k-block: TMA write 24 + split read 24 + B hi/lo write 16 + MMA reads of B 12 x 2 = 24  ->  88 KB (0.39 x of 224):
+//     the shared-memory port (~700 cycles) drops below the MMA time (768 cycles).
+// Protocol differences: the split warps and the accumulate warps of BOTH CTAs arrive on rank 0's ready / acc_empty barriers (remote
+// arrive, release / acquire at cluster scope); tcgen05.commit multicasts the stage-free and window-full arrivals to both CTAs;
+// TMEM is allocated / freed with the cta_group::2 forms by the same warp of both CTAs; cluster barriers bracket the kernel.
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+    constexpr int B_ROWS = PAIR ? BN / 2 : BN;             // columns of the tile whose B this CTA loads and splits
+    constexpr int B_BYTES = B_ROWS * BK * 4;
+    const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;                 // 0 = the CTA that issues the MMAs
+    const int worker = PAIR ? (int)tc::cluster_id_x() : (int)blockIdx.x;     // tile loop: one worker per CTA / per CTA pair
+    const int workers = PAIR ? (int)tc::cluster_count_x() : (int)gridDim.x;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + TS_STAGES * TS_STAGE_BYTES);  // TMA landed                   -> split warps
@@ -389,19 +404,23 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
         for (int s = 0; s < TS_STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&ready_bar[s], SPLIT_WARPS);
+            ptx::mbar_init(&ready_bar[s], PAIR ? 2 * SPLIT_WARPS : SPLIT_WARPS);
             ptx::mbar_init(&empty_bar[s], 1);
         }
 #pragma unroll
         for (int b = 0; b < TS_ACC_BUFS; ++b) {
             ptx::mbar_init(&acc_full_bar[b], 1);
-            ptx::mbar_init(&acc_empty_bar[b], 4);
+            ptx::mbar_init(&acc_empty_bar[b], PAIR ? 8 : 4);
         }
         ptx::fence_mbar_init();
     }
-    if (warp == WARP_TMEM) tc::tmem_alloc(tmem_slot, TS_TMEM_COLS);
+    if (warp == WARP_TMEM) {
+        if (PAIR) tc::tmem_alloc_pair(tmem_slot, TS_TMEM_COLS);
+        else tc::tmem_alloc(tmem_slot, TS_TMEM_COLS);
+    }
     tc::fence_before_thread_sync();
     __syncthreads();
+    if (PAIR) tc::cluster_sync();  // the peer's barriers are initialised and its tensor memory is allocated before anything arrives there
     tc::fence_after_thread_sync();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -416,25 +435,25 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             ptx::prefetch_tensormap(&tmap_b);
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = worker; tile < total_tiles; tile += workers) {
                 int tm, tn;
                 tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * OPERAND_BYTES);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], OPERAND_BYTES + B_BYTES);
                     unsigned char* sa = base + stage * TS_STAGE_BYTES;
                     unsigned char* sb = sa + OPERAND_BYTES;
                     if (p.a_mn_major) {
 #pragma unroll
-                        for (int j = 0; j < BM / ATOM_MN; ++j) ptx::tma_load_2d(sa + j * MN_BOX_BYTES, &tmap_a, &full_bar[stage], tm * BM + j * ATOM_MN, kb * BK);
+                        for (int j = 0; j < BM / ATOM_MN; ++j) ptx::tma_load_2d(sa + j * MN_BOX_BYTES, &tmap_a, &full_bar[stage], (tm * (PAIR ? 2 : 1) + (int)rank) * BM + j * ATOM_MN, kb * BK);
                     } else {
-                        ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, tm * BM);
+                        ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, (tm * (PAIR ? 2 : 1) + (int)rank) * BM);
                     }
                     if (p.b_mn_major) {
 #pragma unroll
-                        for (int j = 0; j < BN / ATOM_MN; ++j) ptx::tma_load_2d(sb + j * MN_BOX_BYTES, &tmap_b, &full_bar[stage], tn * BN + j * ATOM_MN, kb * BK);
+                        for (int j = 0; j < B_ROWS / ATOM_MN; ++j) ptx::tma_load_2d(sb + j * MN_BOX_BYTES, &tmap_b, &full_bar[stage], tn * BN + (int)rank * B_ROWS + j * ATOM_MN, kb * BK);
                     } else {
-                        ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, tn * BN);
+                        ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, tn * BN + (int)rank * B_ROWS);  // box of B_ROWS rows (host side)
                     }
                     if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -444,18 +463,20 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     } else if (warp == WARP_MMA) {
         // ===== MMA issuer: A from tensor memory, B from shared memory =====
         ptx::setmaxnreg_dec<REGS_CONTROL>();
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = worker; tile < total_tiles; tile += workers) {
                 uint32_t d_tmem = 0;
                 for (int kb = 0, wk = 0; kb < kblocks; ++kb) {
                     if (wk == 0) {
-                        tc::mbar_wait_guarded(&acc_empty_bar[acc], acc_phase ^ 1);
+                        if (PAIR) tc::mbar_wait_cluster_guarded(&acc_empty_bar[acc], acc_phase ^ 1);
+                        else tc::mbar_wait_guarded(&acc_empty_bar[acc], acc_phase ^ 1);
                         tc::fence_after_thread_sync();
                         d_tmem = tmem_base + acc * BN;
                     }
-                    tc::mbar_wait_guarded(&ready_bar[stage], phase);
+                    if (PAIR) tc::mbar_wait_cluster_guarded(&ready_bar[stage], phase);
+                    else tc::mbar_wait_guarded(&ready_bar[stage], phase);
                     tc::fence_after_thread_sync();
                     const uint32_t b_hi = ptx::smem_u32(base + stage * TS_STAGE_BYTES + OPERAND_BYTES);
                     const uint32_t b_lo = b_hi + OPERAND_BYTES;
@@ -466,14 +487,22 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         const uint32_t first = (wk | ks) ? 1u : 0u;
                         const uint32_t ta_hi = a_slot + ks * UMMA_K, ta_lo = ta_hi + BK;
                         const uint64_t db_hi = tc::smem_desc(p.desc_b, b_hi + ob), db_lo = tc::smem_desc(p.desc_b, b_lo + ob);
-                        tc::mma_tf32_ts(d_tmem, ta_lo, db_hi, p.idesc, first);  // small terms first
-                        tc::mma_tf32_ts(d_tmem, ta_hi, db_lo, p.idesc, 1u);
-                        tc::mma_tf32_ts(d_tmem, ta_hi, db_hi, p.idesc, 1u);
+                        if (PAIR) {
+                            tc::mma_tf32_ts_pair(d_tmem, ta_lo, db_hi, p.idesc, first);
+                            tc::mma_tf32_ts_pair(d_tmem, ta_hi, db_lo, p.idesc, 1u);
+                            tc::mma_tf32_ts_pair(d_tmem, ta_hi, db_hi, p.idesc, 1u);
+                        } else {
+                            tc::mma_tf32_ts(d_tmem, ta_lo, db_hi, p.idesc, first);  // small terms first
+                            tc::mma_tf32_ts(d_tmem, ta_hi, db_lo, p.idesc, 1u);
+                            tc::mma_tf32_ts(d_tmem, ta_hi, db_hi, p.idesc, 1u);
+                        }
                     }
-                    tc::mma_commit(&empty_bar[stage]);  // shared-memory stage AND TMEM A slot reusable once these MMAs have read them
+                    if (PAIR) tc::mma_commit_pair(&empty_bar[stage], 3);  // ... in both CTAs
+                    else tc::mma_commit(&empty_bar[stage]);  // shared-memory stage AND TMEM A slot reusable once these MMAs have read them
                     if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
                     if (++wk == p.window || kb == kblocks - 1) {
-                        tc::mma_commit(&acc_full_bar[acc]);
+                        if (PAIR) tc::mma_commit_pair(&acc_full_bar[acc], 3);
+                        else tc::mma_commit(&acc_full_bar[acc]);
                         if (++acc == TS_ACC_BUFS) { acc = 0; acc_phase ^= 1; }
                         wk = 0;
                     }
@@ -488,7 +517,7 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         int acc = 0;
         uint32_t acc_phase = 0;
         const int windows = (kblocks + p.window - 1) / p.window;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = worker; tile < total_tiles; tile += workers) {
             int tm, tn;
             tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
             float sum[BN];
@@ -507,7 +536,7 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     if (h == BN / 64 - 1) {
                         tc::fence_before_thread_sync();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&acc_empty_bar[acc]);
+                        if (lane == 0) { if (PAIR) tc::mbar_arrive_cluster(&acc_empty_bar[acc], 0); else ptx::mbar_arrive(&acc_empty_bar[acc]); }
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -517,7 +546,7 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 }
                 if (++acc == TS_ACC_BUFS) { acc = 0; acc_phase ^= 1; }
             }
-            const int row = tm * BM + q * 32 + lane;
+            const int row = (tm * (PAIR ? 2 : 1) + (int)rank) * BM + q * 32 + lane;
             const bool row_ok = row < p.m;
             const int col0 = tn * BN;
             float* cp = p.c + (int64_t)col0 * p.ldc + row;
@@ -547,7 +576,7 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + TS_A_COL0;
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = worker; tile < total_tiles; tile += workers) {
             for (int kb = 0; kb < kblocks; ++kb) {
                 tc::mbar_wait_guarded(&full_bar[stage], phase);
                 const unsigned char* sa = base + stage * TS_STAGE_BYTES;
@@ -583,7 +612,7 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 tc::tmem_st_wait();
                 tc::fence_before_thread_sync();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&ready_bar[stage]);
+                if (lane == 0) { if (PAIR) tc::mbar_arrive_cluster(&ready_bar[stage], 0); else ptx::mbar_arrive(&ready_bar[stage]); }
                 if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -591,12 +620,12 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         // ===== B split in shared memory: raw FP32 -> (hi in place, lo in the twin buffer) =====
         ptx::setmaxnreg_dec<TS_REGS_SPLIT_B>();
         const int t = threadIdx.x - TS_WARP_SPLIT_B0 * 32;
-        constexpr int CHUNKS = OPERAND_BYTES / 16;
+        constexpr int CHUNKS = B_BYTES / 16;
         constexpr int PER_THREAD = CHUNKS / 128;
         static_assert(CHUNKS % 128 == 0, "chunk split");
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = worker; tile < total_tiles; tile += workers) {
             for (int kb = 0; kb < kblocks; ++kb) {
                 tc::mbar_wait_guarded(&full_bar[stage], phase);
                 unsigned char* sb = base + stage * TS_STAGE_BYTES + OPERAND_BYTES;
@@ -620,7 +649,7 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 }
                 tc::fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&ready_bar[stage]);
+                if (lane == 0) { if (PAIR) tc::mbar_arrive_cluster(&ready_bar[stage], 0); else ptx::mbar_arrive(&ready_bar[stage]); }
                 if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -628,9 +657,11 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
     tc::fence_before_thread_sync();
     __syncthreads();
+    if (PAIR) tc::cluster_sync();  // no CTA frees its tensor memory or exits while the peer may still read it or arrive on its barriers
     if (warp == WARP_TMEM) {
         tc::fence_after_thread_sync();
-        tc::tmem_dealloc(tmem_base, TS_TMEM_COLS);
+        if (PAIR) tc::tmem_dealloc_pair(tmem_base, TS_TMEM_COLS);
+        else tc::tmem_dealloc(tmem_base, TS_TMEM_COLS);
     }
 }
 
@@ -671,10 +702,11 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
     const CUtensorMapSwizzle swz_k = CU_TENSOR_MAP_SWIZZLE_128B;
     const CUtensorMapSwizzle swz_mn = (CUtensorMapSwizzle)env_u32("TMM_TC_MN_SWIZZLE", (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     // experimental (TMM_TC_ATMEM=1, FP32-accurate mode only): A through tensor memory, sgemm_tc_ts_kernel
-    bool a_via_tmem = false;
+    bool a_via_tmem = false, cta_pairs = false;  // TMM_TC_ATMEM=2: additionally CTA pairs (cta_group::2), sgemm_tc_ts_kernel<true>
     if (terms != 1) {
         const char* tv = getenv("TMM_TC_ATMEM");
-        a_via_tmem = tv && tv[0] == '1';
+        a_via_tmem = tv && (tv[0] == '1' || tv[0] == '2');
+        cta_pairs = tv && tv[0] == '2';
     }
     // A: op(A) is m x k.  N: stored m x k (m contiguous) -> boxes [32 m x BK];  T/C: stored k x m (k contiguous) -> one box [BK x BM]
     // (A through TMEM: the m-contiguous boxes are loaded unswizzled - threads read them, not the tensor core)
@@ -682,7 +714,9 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
              : make_map(&map_a, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, BK, BM, swz_k);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "[tiled-mm_b200] cuTensorMapEncodeTiled(A, f32) failed: %d\n", (int)r); return cudaErrorInvalidValue; }
     // B: op(B) is k x n.  N: stored k x n (k contiguous) -> one box [BK x BN];  T/C: stored n x k (n contiguous) -> boxes [32 n x BK]
-    r = b_mn ? make_map(&map_b, b, (uint64_t)n, (uint64_t)k, (uint64_t)ldb, ATOM_MN, BK, swz_mn) : make_map(&map_b, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, BK, BN, swz_k);
+    // (CTA pairs: each CTA loads its half of the tile's columns - a k-contiguous box of BN / 2 rows)
+    r = b_mn ? make_map(&map_b, b, (uint64_t)n, (uint64_t)k, (uint64_t)ldb, ATOM_MN, BK, swz_mn)
+             : make_map(&map_b, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, BK, cta_pairs ? BN / 2 : BN, swz_k);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "[tiled-mm_b200] cuTensorMapEncodeTiled(B, f32) failed: %d\n", (int)r); return cudaErrorInvalidValue; }
 
     Params p;
@@ -716,14 +750,35 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
     const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
     if (tiles > INT32_MAX) return cudaErrorInvalidValue;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    if (a_via_tmem && cta_pairs) {
+        p.tiles_m = (m + 2 * BM - 1) / (2 * BM);  // a pair works on 256 x 128 tiles
+        p.idesc = tc::instr_desc(tc::FMT_TF32, 2 * BM, BN, false, b_mn);
+        static bool configured_pair[64] = {false};
+        if (dev >= 0 && dev < 64 && !configured_pair[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(sgemm_tc_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            configured_pair[dev] = true;
+        }
+        const int64_t pair_tiles = (int64_t)p.tiles_m * p.tiles_n;
+        const int pairs = (int)std::min<int64_t>(pair_tiles, sm_count() / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = TS_SMEM_BYTES; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, sgemm_tc_ts_kernel<true>, map_a, map_b, p);
+        count_launch();
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
     if (a_via_tmem) {
         p.idesc = tc::instr_desc(tc::FMT_TF32, BM, BN, false, b_mn);  // A in TMEM is K-major whatever op(A) is
         if (dev >= 0 && dev < 64 && !configured_ts[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(sgemm_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
+            cudaError_t e = cudaFuncSetAttribute(sgemm_tc_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
             if (e != cudaSuccess) return e;
             configured_ts[dev] = true;
         }
-        sgemm_tc_ts_kernel<<<grid, THREADS, TS_SMEM_BYTES, stream>>>(map_a, map_b, p);
+        sgemm_tc_ts_kernel<false><<<grid, THREADS, TS_SMEM_BYTES, stream>>>(map_a, map_b, p);
         count_launch();
         return cudaGetLastError();
     }

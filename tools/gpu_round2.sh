@@ -24,6 +24,11 @@ for tt in "N N" "T N" "N T" "T T"; do TMM_TC_ATMEM=1 timeout 120 $T check $tt 2>
 TMM_TC_ATMEM=1 timeout 120 $T precision 2>&1 | grep -E "precision|tmm fp32" | head -20
 for tt in "N N" "T N" "N T" "T T"; do TMM_TC_ATMEM=1 timeout 60 $T benchone $tt 8192 8192 8192 0; done
 TMM_TC_ATMEM=1 TMM_TC_SPLIT=trunc timeout 60 $T benchone N N 8192 8192 8192 0
+echo "== sgemm, A through tensor memory + CTA pairs (TMM_TC_ATMEM=2: cta_group::2, 88 KB per CTA and k-block) =="
+for tt in "N N" "T N" "N T" "T T"; do TMM_TC_ATMEM=2 timeout 120 $T check $tt 2>&1 | grep -v " OK$" | tail -5; done
+TMM_TC_ATMEM=2 timeout 120 $T precision 2>&1 | grep -E "precision|tmm fp32" | head -20
+for tt in "N N" "T T"; do TMM_TC_ATMEM=2 timeout 60 $T benchone $tt 8192 8192 8192 0; done
+TMM_TC_ATMEM=2 TMM_TC_SPLIT=trunc timeout 60 $T benchone N N 8192 8192 8192 0
 echo "== plain TF32 mode (one MMA per product): 3 stages (measured 352 TF) vs six 32 KB stages (TMM_TC_TF32_STAGES=6) =="
 for tt in "N N" "T T"; do TMM_TC_TF32_STAGES=6 timeout 120 $T check $tt 2>&1 | grep -E "tf32-mode|FAIL" | tail -3; done   # check ends with a TF32-mode case (expect ~1e-4)
 TMM_TC_TF32_STAGES=6 timeout 60 $T benchone N N 8192 8192 8192 0   # the "tmm tf32" column; compare with the default run above
