@@ -760,13 +760,21 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
             configured_pair[dev] = true;
         }
         const int64_t pair_tiles = (int64_t)p.tiles_m * p.tiles_n;
-        const int pairs = (int)std::min<int64_t>(pair_tiles, sm_count() / 2);
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = TS_SMEM_BYTES; cfg.stream = stream;
+        cfg.gridDim = dim3(2 * (sm_count() / 2)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = TS_SMEM_BYTES; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
+        // the kernel is persistent: launch no more pairs than can be resident at once (a GPC with an odd number of SMs strands one)
+        static int resident_pairs[64] = {0};
+        if (dev >= 0 && dev < 64 && resident_pairs[dev] == 0) {
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, sgemm_tc_ts_kernel<true>, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); nc = sm_count() / 2; }
+            resident_pairs[dev] = nc;
+        }
+        const int pairs = (int)std::min<int64_t>(pair_tiles, (dev >= 0 && dev < 64) ? resident_pairs[dev] : sm_count() / 2);
+        cfg.gridDim = dim3(2 * pairs);
         cudaError_t e = cudaLaunchKernelEx(&cfg, sgemm_tc_ts_kernel<true>, map_a, map_b, p);
         count_launch();
         return e != cudaSuccess ? e : cudaGetLastError();
