@@ -587,13 +587,13 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     if (p.a_mn_major) {
                         // box q of the tile = rows 32q .. 32q+31, unswizzled: [k][32 m]
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) x[j] = *reinterpret_cast<const float*>(sa + q * MN_BOX_BYTES + (h * 16 + j) * (ATOM_MN * 4) + lane * 4);
+                        for (int j = 0; j < 16; ++j) x[j] = *reinterpret_cast<const float*>(sa + ts_a_elem_offset_mnmajor(row, h * 16 + j));
                     } else {
                         // row `row` = 128 bytes; 16-byte chunk c is stored at position c ^ (row & 7) (SWIZZLE_128B, tile 1024-B aligned)
 #pragma unroll
                         for (int c4 = 0; c4 < 4; ++c4) {
                             const int c = h * 4 + c4;
-                            const float4 v = *reinterpret_cast<const float4*>(sa + row * (BK * 4) + ((c ^ (row & 7)) << 4));
+                            const float4 v = *reinterpret_cast<const float4*>(sa + ts_a_chunk_offset_kmajor(row, c));
                             x[c4 * 4 + 0] = v.x; x[c4 * 4 + 1] = v.y; x[c4 * 4 + 2] = v.z; x[c4 * 4 + 3] = v.w;
                         }
                     }

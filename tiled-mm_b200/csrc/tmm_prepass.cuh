@@ -79,5 +79,13 @@ __device__ __forceinline__ float lo_of_truncated(float x) {
     return __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
 }
 
+// sgemm_tc_ts_kernel (A operand through tensor memory): where element (row, k) of the landed 128 x 32 FP32 A tile sits in shared
+// memory, as a byte offset from the (1024-byte aligned) start of the tile.
+//   k-contiguous tile: ONE TMA box [32 k x 128 rows] with SWIZZLE_128B - row r is 128 bytes, its 16-byte chunk c is stored at chunk
+//   position c ^ (r & 7) (address bits [4,7) xor-ed with bits [7,10))
+__device__ __forceinline__ int ts_a_chunk_offset_kmajor(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+//   m-contiguous tile: FOUR unswizzled TMA boxes [32 m x 32 k], box = row / 32, inside a box [k][32 m]
+__device__ __forceinline__ int ts_a_elem_offset_mnmajor(int row, int k) { return (row >> 5) * 4096 + k * 128 + (row & 31) * 4; }
+
 }  // namespace f32tc
 }  // namespace tmm
