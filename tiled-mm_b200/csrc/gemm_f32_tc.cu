@@ -647,7 +647,7 @@ sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     }
                     *reinterpret_cast<float4*>(sb + off + OPERAND_BYTES) = lo;
                 }
-                tc::fence_proxy_async_smem();
+                if (PAIR) tc::fence_proxy_async_all(); else tc::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) { if (PAIR) tc::mbar_arrive_cluster(&ready_bar[stage], 0); else ptx::mbar_arrive(&ready_bar[stage]); }
                 if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }

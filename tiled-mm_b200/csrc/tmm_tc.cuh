@@ -37,6 +37,8 @@ __device__ __forceinline__ void fence_before_thread_sync() { asm volatile("tcgen
 __device__ __forceinline__ void fence_after_thread_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads, TMA)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// the same for all state spaces: used when the reader is the tensor core of the PEER CTA of a pair (cta_group::2 reads both CTAs' tiles)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the whole CTA
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
