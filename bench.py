@@ -114,8 +114,8 @@ def host_cores() -> int:
 
 
 def cpu_baseline_dgemm(size: int) -> dict:
-    """Host BLAS dgemm (numpy -> OpenBLAS, all cores) on a bounded sample of the workload: the full m x n with k cut to
-    k/4 (about 10-20 s of CPU work on this box), scaled by flops."""
+    """Host BLAS dgemm (numpy -> OpenBLAS, all cores) on the workload itself (m = n = k = size), repeated until about 10 s of CPU
+    work have been timed (at most 8 runs; one run if the box's cores need longer than that for a single product)."""
     m = n = size
     k = size
     rng = np.random.default_rng(0)
