@@ -3,7 +3,7 @@
 #   make -C tools && gpurun --timeout 500 -- 'bash tools/gpu_round2.sh'
 # 1. gated experimental tests (tcgen05 CGEMM embedding, BF16 entry points, device-pointer operands)            -> promote TMM_C32_MATH=tc to the default if green
 # 2. tc_test cgemm: all nine op pairs vs cuBLAS CGEMM + timing      -> CGEMM number for DESIGN 3.4
-# 3. SGEMM variants: precision + timing, default vs TMM_TC_SPLIT=trunc vs TMM_TC_ATMEM=1 (A operand through tensor memory)
+# 3. SGEMM split variants: precision + timing, default vs TMM_TC_SPLIT=trunc   (the new tcgen05 kernel variants: tools/gpu_round2_tc.sh)
 # 4. the regular suite + bench line (regression check)
 cd "${GRAFT_REPO_ROOT:-.}" || exit 1
 mkdir -p gpurun_out
@@ -19,19 +19,6 @@ timeout 60 $T benchone N N 8192 8192 8192 0
 echo "== sgemm split: hi = raw bits (TMM_TC_SPLIT=trunc) =="; TMM_TC_SPLIT=trunc timeout 120 $T precision 2>&1 | grep -E "precision|tmm fp32" | head -20
 TMM_TC_SPLIT=trunc timeout 60 $T benchone N N 8192 8192 8192 0
 for tt in "N N" "T T"; do TMM_TC_SPLIT=trunc timeout 120 $T check $tt 2>&1 | grep -v " OK$" | tail -5; done
-echo "== sgemm, A operand through tensor memory (TMM_TC_ATMEM=1: 144 instead of 224 KB of shared-memory traffic per k-block) =="
-for tt in "N N" "T N" "N T" "T T"; do TMM_TC_ATMEM=1 timeout 120 $T check $tt 2>&1 | grep -v " OK$" | tail -5; done
-TMM_TC_ATMEM=1 timeout 120 $T precision 2>&1 | grep -E "precision|tmm fp32" | head -20
-for tt in "N N" "T N" "N T" "T T"; do TMM_TC_ATMEM=1 timeout 60 $T benchone $tt 8192 8192 8192 0; done
-TMM_TC_ATMEM=1 TMM_TC_SPLIT=trunc timeout 60 $T benchone N N 8192 8192 8192 0
-echo "== sgemm, A through tensor memory + CTA pairs (TMM_TC_ATMEM=2: cta_group::2, 88 KB per CTA and k-block) =="
-for tt in "N N" "T N" "N T" "T T"; do TMM_TC_ATMEM=2 timeout 120 $T check $tt 2>&1 | grep -v " OK$" | tail -5; done
-TMM_TC_ATMEM=2 timeout 120 $T precision 2>&1 | grep -E "precision|tmm fp32" | head -20
-for tt in "N N" "T T"; do TMM_TC_ATMEM=2 timeout 60 $T benchone $tt 8192 8192 8192 0; done
-TMM_TC_ATMEM=2 TMM_TC_SPLIT=trunc timeout 60 $T benchone N N 8192 8192 8192 0
-echo "== plain TF32 mode (one MMA per product): 3 stages (measured 352 TF) vs six 32 KB stages (TMM_TC_TF32_STAGES=6) =="
-for tt in "N N" "T T"; do TMM_TC_TF32_STAGES=6 timeout 120 $T check $tt 2>&1 | grep -E "tf32-mode|FAIL" | tail -3; done   # check ends with a TF32-mode case (expect ~1e-4)
-TMM_TC_TF32_STAGES=6 timeout 60 $T benchone N N 8192 8192 8192 0   # the "tmm tf32" column; compare with the default run above
 echo "== published experiment (README figure: dgemm square, alpha=beta=1), both arms =="; timeout 400 python tools/sweep_published.py --reps 2 2>&1 | tail -12
 echo "== beta = 1 at 10000^3: default stripes vs one C stripe per k-chunk =="
 timeout 60 python tools/e2e.py --beta 1 --reps 4 2>&1 | tail -1
