@@ -14,11 +14,13 @@ T=./build/tc_test
 nvidia-smi -L | head -1
 echo "== default kernel (reference point) =="; timeout 60 $T benchone N N 8192 8192 8192 0
 echo "== sgemm, A operand through tensor memory (TMM_TC_ATMEM=1: 144 instead of 224 KB of shared-memory traffic per k-block) =="
+for tt in "N N" "T N"; do TMM_TC_ATMEM=1 timeout 60 $T probe $tt 2>&1 | head -40; done   # single tile, single k-block: which A element reached which accumulator position (silent = all right)
 for tt in "N N" "T N" "N T" "T T"; do TMM_TC_ATMEM=1 timeout 120 $T check $tt 2>&1 | grep -v " OK$" | tail -5; done
 TMM_TC_ATMEM=1 timeout 120 $T precision 2>&1 | grep -E "precision|tmm fp32" | head -20
 for tt in "N N" "T N" "N T" "T T"; do TMM_TC_ATMEM=1 timeout 60 $T benchone $tt 8192 8192 8192 0; done
 TMM_TC_ATMEM=1 TMM_TC_SPLIT=trunc timeout 60 $T benchone N N 8192 8192 8192 0
 echo "== sgemm, A through tensor memory + CTA pairs (TMM_TC_ATMEM=2: cta_group::2, 88 KB per CTA and k-block) =="
+for tt in "N N" "T N"; do TMM_TC_ATMEM=2 timeout 60 $T probe $tt 2>&1 | head -40; done   # one pair tile: rows 0-127 only (rank 1 works on zero-filled rows)
 for tt in "N N" "T N" "N T" "T T"; do TMM_TC_ATMEM=2 timeout 120 $T check $tt 2>&1 | grep -v " OK$" | tail -5; done
 TMM_TC_ATMEM=2 timeout 120 $T precision 2>&1 | grep -E "precision|tmm fp32" | head -20
 for tt in "N N" "T T"; do TMM_TC_ATMEM=2 timeout 60 $T benchone $tt 8192 8192 8192 0; done
