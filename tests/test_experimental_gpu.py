@@ -161,3 +161,23 @@ def test_sgemm_a_through_tmem_exact_on_integers(gpu_tmm, oracle, a_via_tmem, tt)
 @pytest.mark.parametrize("tt", ["NN", "TN", "NT", "TT"])
 def test_sgemm_a_through_tmem_random(gpu_tmm, oracle, a_via_tmem, tt):
     run_case(gpu_tmm, oracle, np.float32, tt, 777, 530, 4100, 1.5, 0.25, pad=(3, 2, 9), tiles=(256, 300, 500))
+
+
+@pytest.fixture(params=["i8", "i8:7"], ids=["8-slices", "7-slices"])
+def f64_on_int8(request):
+    """TMM_F64_MATH=i8[:S]: DGEMM as S (S + 1) / 2 exact int8 slice GEMMs on tcgen05 (gemm_f64_i8.cu); read per launch."""
+    os.environ["TMM_F64_MATH"] = request.param
+    yield
+    os.environ.pop("TMM_F64_MATH", None)
+
+
+@pytest.mark.parametrize("tt", ALL_TT)
+def test_dgemm_on_int8_tensor_cores_exact_on_integers(gpu_tmm, oracle, f64_on_int8, tt):
+    run_case(gpu_tmm, oracle, np.float64, tt, 130, 67, 95, 2.0, -1.0, pad=(1, 2, 3), ints=True)
+    run_case(gpu_tmm, oracle, np.float64, tt, 1000, 520, 1100, 1.0, 0.0, pad=(4, 8, 0), ints=True)
+
+
+@pytest.mark.parametrize("tt", ["NN", "TN", "NT", "TT"])
+def test_dgemm_on_int8_tensor_cores_random_within_the_fp64_bound(gpu_tmm, oracle, f64_on_int8, tt):
+    """uniform(-1, 1) data against the tests' FP64 tolerance (1e-15 relative to k max|A| max|B|, tests/_util.py)."""
+    run_case(gpu_tmm, oracle, np.float64, tt, 777, 530, 4100, 1.5, 0.25, pad=(3, 2, 9), tiles=(256, 300, 500))

@@ -60,6 +60,12 @@ cudaError_t bgemm_tc_native_tn_launch(int m, int n, int k, float alpha, const vo
 int c32_math_mode();
 void set_c32_math_mode(int mode);
 
+// experimental FP64 emulation on the int8 tensor cores (gemm_f64_i8.cu; TMM_F64_MATH=i8[:slices], default off): slice count of the process
+// (0 = DMMA), and the launcher - any ld / alignment; cudaErrorMemoryAllocation = no scratch, the caller runs the DMMA kernel instead
+int f64_i8_slices();
+cudaError_t dgemm_i8_launch(char ta, char tb, int m, int n, int k, double alpha, const double* a, int64_t lda, const double* b, int64_t ldb, double beta,
+                            double* c, int64_t ldc, cudaStream_t stream, int slices);
+
 // true-FP64 SIMT kernels: last resort for FP64 operands outside the TMA contract when no scratch can be allocated
 cudaError_t dgemm_simt_launch(char ta, char tb, int m, int n, int k, double alpha, const double* a, int64_t lda, const double* b, int64_t ldb,
                               double beta, double* c, int64_t ldc, cudaStream_t stream);

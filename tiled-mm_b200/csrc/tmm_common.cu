@@ -163,6 +163,11 @@ cudaError_t repitch(Operand& op, int64_t rows, int64_t cols, size_t es, cudaStre
 static cudaError_t fp64_gemm(int dtype, char ta, char tb, int m, int n, int k, const void* alpha, const void* a, int64_t lda, const void* b, int64_t ldb,
                              const void* beta, void* c, int64_t ldc, cudaStream_t st) {
     const size_t es = dtype_size(dtype);
+    if (dtype == F64 && f64_i8_slices() > 0) {  // experimental opt-in: FP64-accurate product on the int8 tensor cores
+        cudaError_t ei = dgemm_i8_launch(ta, tb, m, n, k, *static_cast<const double*>(alpha), static_cast<const double*>(a), lda, static_cast<const double*>(b), ldb,
+                                         *static_cast<const double*>(beta), static_cast<double*>(c), ldc, st, f64_i8_slices());
+        if (ei != cudaErrorMemoryAllocation) return ei;  // no scratch: the DMMA kernel below needs none
+    }
     Operand A{a, lda}, B{b, ldb};
     cudaError_t e = repitch(A, ta == 'N' ? m : k, ta == 'N' ? k : m, es, st);
     if (e == cudaSuccess) e = repitch(B, tb == 'N' ? k : n, tb == 'N' ? n : k, es, st);

@@ -1,0 +1,70 @@
+// Operand preparation of the experimental FP64-emulating DGEMM (gemm_f64_i8.cu, TMM_F64_MATH=i8): every row of op(A) and every column
+// of op(B) is scaled by a power of two and cut into signed 7-bit slices, stored as int8 matrices with k contiguous.
+// Device code only - no runtime calls, no launch syntax - so that tests/test_slice_kernels.py compiles the very same source for the
+// CPU (blockIdx / threadIdx shim) and compares it with the numpy restatement of tools/fp64_emulation_study.py.
+//
+//   x[i, l] = 2^e[i] * sum_s 2^-(P0 + BITS s) * q_s[i, l]  +  remainder,     |q_s| <= 2^(BITS-1) = 64,   |remainder| <= 2^(e[i] - P0 - BITS S) / 2
+// e[i] = exponent of the largest magnitude of the row (|x| < 2^e), q_s = round-to-nearest of the running remainder: all steps are exact in
+// FP64 (scaling by powers of two, rint, one subtraction of a representable number).  Finite inputs only.
+#pragma once
+#include <cstdint>
+
+namespace tmm {
+namespace f64i8 {
+
+constexpr int SLICE_BITS = 7;
+constexpr int P0 = SLICE_BITS - 1;       // fractional bits of slice 0
+constexpr int NO_DATA = -2000000000;     // e[] of a row that holds only zeros (cudaMemset pattern 0x88 = -2004318072 is below it)
+constexpr int MAX_SLICES = 10;
+
+// |x| < 2^e with e minimal for normal numbers (x = f * 2^e, 0.5 <= f < 1); zeros report NO_DATA; denormals count as < 2^-1022
+__device__ __forceinline__ int exponent_above(double x) {
+    const uint64_t u = (uint64_t)__double_as_longlong(x) & 0x7FFFFFFFFFFFFFFFull;
+    if (u == 0) return NO_DATA;
+    const int biased = (int)(u >> 52);
+    return biased == 0 ? -1022 : biased - 1022;
+}
+
+// e[i] = max over l of exponent_above(x[i, l]); element (i, l) at x[i * stride_row + l * stride_k].  e[] preset below NO_DATA.
+// grid.x covers the rows (one thread each), grid.y splits the k range.
+static __global__ void __launch_bounds__(256) row_exponents(const double* __restrict__ x, int64_t stride_row, int64_t stride_k, int rows, int k, int k_per_block,
+                                                            int* __restrict__ e) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const int l0 = blockIdx.y * k_per_block, l1 = l0 + k_per_block < k ? l0 + k_per_block : k;
+    int best = NO_DATA;
+    const double* p = x + (int64_t)i * stride_row;
+    for (int l = l0; l < l1; ++l) {
+        const int ex = exponent_above(p[(int64_t)l * stride_k]);
+        best = ex > best ? ex : best;
+    }
+    if (best > NO_DATA) atomicMax(&e[i], best);
+}
+
+// q_s[i, l] for s < slices, written as int8 at out[s * slice_stride + i * pitch + l] (bytes); four consecutive l per thread (one 32-bit store
+// per slice); grid.x covers groups of four k-values, grid.y the rows (grid-stride).
+static __global__ void __launch_bounds__(256) slice_rows(const double* __restrict__ x, int64_t stride_row, int64_t stride_k, int rows, int k, const int* __restrict__ e,
+                                                         int8_t* __restrict__ out, int64_t pitch, int64_t slice_stride, int slices) {
+    const int l4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (l4 >= k) return;
+    for (int i = blockIdx.y; i < rows; i += gridDim.y) {
+        const int ei = e[i] <= NO_DATA ? 0 : e[i];
+        double r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = (l4 + j < k) ? scalbn(x[(int64_t)i * stride_row + (int64_t)(l4 + j) * stride_k], -ei) : 0.0;
+        for (int s = 0; s < slices; ++s) {
+            const int p = P0 + SLICE_BITS * s;
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double q = rint(scalbn(r[j], p));
+                r[j] -= scalbn(q, -p);
+                packed |= ((uint32_t)(uint8_t)(int8_t)(int)q) << (8 * j);
+            }
+            *reinterpret_cast<uint32_t*>(out + (int64_t)s * slice_stride + (int64_t)i * pitch + l4) = packed;
+        }
+    }
+}
+
+}  // namespace f64i8
+}  // namespace tmm

@@ -1,0 +1,25 @@
+#!/bin/bash
+# Round 2, experimental FP64 emulation on the int8 tensor cores (TMM_F64_MATH=i8[:slices], gemm_f64_i8.cu; one B200, ~4 min):
+#   make -C tools && gpurun --timeout 420 -- 'bash tools/gpu_round2_i8.sh'
+# Default stays DMMA.  The kernel's waits are guarded (a broken pipeline traps after ~10 s).  What to look at:
+#   1. devtest check: max|diff| / k against cuBLAS DGEMM for all four op pairs (bound of the parity tests: 1e-15)
+#   2. device-resident rate at 10000^3 / 8192^3 for 8 and 7 slices against the DMMA kernel (35.4 TF) -> is the kind::i8 pipeline efficient enough?
+#   3. host-to-host 10000^3: does the call become PCIe-bound (46 TF roofline instead of 36.9)?
+cd "${GRAFT_REPO_ROOT:-.}" || exit 1
+mkdir -p gpurun_out
+export LD_LIBRARY_PATH=/usr/local/cuda/lib64:$LD_LIBRARY_PATH
+D=./build/devtest
+{
+nvidia-smi -L | head -1
+echo "== check vs cuBLAS, 8 slices =="; TMM_F64_MATH=i8 timeout 120 $D check 2>&1 | tail -45
+echo "== check vs cuBLAS, 7 slices =="; TMM_F64_MATH=i8:7 timeout 120 $D check 2>&1 | grep -E "FAIL|error|rc=" | head -20
+echo "== device-resident, DMMA (reference point) =="; timeout 60 $D benchone N N 10000 10000 10000 0
+for s in 8 7 6; do echo "== device-resident, int8 emulation, $s slices =="; TMM_F64_MATH=i8:$s timeout 90 $D benchone N N 10000 10000 10000 0; done
+TMM_F64_MATH=i8 timeout 90 $D benchone T T 8192 8192 8192 0
+TMM_F64_MATH=i8 timeout 90 $D benchone N N 10000 1408 512 1     # a phase-1 launch shape of the scheduler: slicing overhead shows here
+echo "== host-to-host 10000^3: DMMA, then 8 and 7 slices =="
+timeout 60 python tools/e2e.py --reps 4 2>&1 | tail -1
+TMM_F64_MATH=i8 timeout 90 python tools/e2e.py --reps 4 2>&1 | tail -1
+TMM_F64_MATH=i8:7 timeout 90 python tools/e2e.py --reps 4 2>&1 | tail -1
+echo "== gated pytest =="; TMM_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_experimental_gpu.py -m gpu -q -k "int8" --timeout 100 2>&1 | tail -8
+} 2>&1 | tee gpurun_out/r2_f64_i8.txt
