@@ -163,9 +163,10 @@ def test_sgemm_a_through_tmem_random(gpu_tmm, oracle, a_via_tmem, tt):
     run_case(gpu_tmm, oracle, np.float32, tt, 777, 530, 4100, 1.5, 0.25, pad=(3, 2, 9), tiles=(256, 300, 500))
 
 
-@pytest.fixture(params=["i8", "i8:7"], ids=["8-slices", "7-slices"])
+@pytest.fixture(params=["i8", "i8:7", "i8p", "i8p:7"], ids=["8-slices", "7-slices", "pairs-8-slices", "pairs-7-slices"])
 def f64_on_int8(request):
-    """TMM_F64_MATH=i8[:S]: DGEMM as S (S + 1) / 2 exact int8 slice GEMMs on tcgen05 (gemm_f64_i8.cu); read per launch."""
+    """TMM_F64_MATH=i8[:S]: DGEMM as S (S + 1) / 2 exact int8 slice GEMMs on tcgen05 (gemm_f64_i8.cu); i8p[:S]: the version on CTA pairs with
+    256 x 256 tiles, one launch per group.  Read per launch."""
     os.environ["TMM_F64_MATH"] = request.param
     yield
     os.environ.pop("TMM_F64_MATH", None)

@@ -151,3 +151,21 @@ def test_emulated_product_meets_the_fp64_parity_bound(kernels, ta, tb):
             assert np.array_equal(c, a @ b)
         else:
             assert err <= 1e-16, err   # the parity tests allow 1e-15
+        # the CTA-pair version (igemm_group_kernel) sums over g in GLOBAL memory: one launch per group, C = beta C + alpha 2^(..) acc first,
+        # then S - 1 read-modify-writes, each rounded to FP64
+        alpha, beta = 1.5, 0.25
+        c0 = rng.random((m, n)) - 0.5 if not ints else rng.integers(0, 10, (m, n)).astype(np.float64)
+        cg = c0.copy()
+        exps = ea.astype(np.int64)[:, None] + eb.astype(np.int64)[None, :]
+        for g in range(S - 1, -1, -1):
+            acc = np.zeros((m, n), np.int64)
+            for s in range(g + 1):
+                acc += qa[s, :m, :k].astype(np.int64) @ qb[g - s, :n, :k].astype(np.int64).T
+            add = alpha * np.ldexp(acc.astype(np.float64), exps - (2 * p0 + bits * g))
+            cg = add + beta * cg if g == S - 1 else cg + add
+        ref2 = alpha * ref + beta * c0.astype(np.longdouble)
+        err2 = float(np.max(np.abs(cg.astype(np.longdouble) - ref2))) / (k * np.abs(a).max() * np.abs(b).max())
+        if ints:
+            assert np.array_equal(cg, alpha * (a @ b) + beta * c0)
+        else:
+            assert err2 <= 2e-16, err2

@@ -15,6 +15,11 @@ echo "== check vs cuBLAS, 8 slices =="; TMM_F64_MATH=i8 timeout 120 $D check 2>&
 echo "== check vs cuBLAS, 7 slices =="; TMM_F64_MATH=i8:7 timeout 120 $D check 2>&1 | grep -E "FAIL|error|rc=" | head -20
 echo "== device-resident, DMMA (reference point) =="; timeout 60 $D benchone N N 10000 10000 10000 0
 for s in 8 7 6; do echo "== device-resident, int8 emulation, $s slices =="; TMM_F64_MATH=i8:$s timeout 90 $D benchone N N 10000 10000 10000 0; done
+echo "== CTA-pair version (i8p: 256 x 256 tiles, cta_group::2, one launch per group) =="
+TMM_F64_MATH=i8p timeout 120 $D check 2>&1 | grep -E "FAIL|error|rc=|OK" | tail -24
+for s in 8 7; do TMM_F64_MATH=i8p:$s timeout 90 $D benchone N N 10000 10000 10000 0; done
+TMM_F64_MATH=i8p timeout 90 python tools/e2e.py --reps 4 2>&1 | tail -1
+echo "== other shapes =="
 TMM_F64_MATH=i8 timeout 90 $D benchone T T 8192 8192 8192 0
 TMM_F64_MATH=i8 timeout 90 $D benchone N N 10000 1408 512 1     # a phase-1 launch shape of the scheduler: slicing overhead shows here
 echo "== host-to-host 10000^3: DMMA, then 8 and 7 slices =="
