@@ -72,7 +72,7 @@ Plan make_plan(const PlanInput& in) {
     const size_t full_a = (size_t)p.pitch_a * p.a_cols * es, full_b = (size_t)p.pitch_b * p.b_cols * es;
     const size_t full_c = in.copy_c_back ? (size_t)p.pitch_c * n * es : 0;
     const double F = (in.dtype >= 2) ? 8.0 : 2.0;
-    const double kFlops = in.flops > 0 ? in.flops : (in.dtype == 0 ? env_or("TMM_PLAN_F32_FLOPS", kFlopsF32) : kFlopsF64);  // complex<float>: SIMT unless the caller says otherwise
+    const double kFlops = in.flops > 0 ? in.flops : (in.dtype == 0 ? env_or("TMM_PLAN_F32_FLOPS", kFlopsF32) : env_or("TMM_PLAN_F64_FLOPS", kFlopsF64));  // complex<float>: SIMT unless the caller says otherwise
     const int64_t kc_cap = std::max<int64_t>(256, std::min<int64_t>(2048, round_up(std::max(64, in.tile_k), 64)));
 
     if (full_a + full_b + full_c <= in.budget) {
