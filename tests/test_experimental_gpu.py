@@ -182,3 +182,25 @@ def test_dgemm_on_int8_tensor_cores_exact_on_integers(gpu_tmm, oracle, f64_on_in
 def test_dgemm_on_int8_tensor_cores_random_within_the_fp64_bound(gpu_tmm, oracle, f64_on_int8, tt):
     """uniform(-1, 1) data against the tests' FP64 tolerance (1e-15 relative to k max|A| max|B|, tests/_util.py)."""
     run_case(gpu_tmm, oracle, np.float64, tt, 777, 530, 4100, 1.5, 0.25, pad=(3, 2, 9), tiles=(256, 300, 500))
+
+
+def test_dgemm_on_int8_non_finite_rows_and_columns(gpu_tmm, f64_on_int8):
+    """An Inf / NaN in row i of A or column j of B makes row i / column j of C non-finite (NaN here); everything else stays exact."""
+    tmm = gpu_tmm
+    m, n, k = 200, 150, 300
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 10, (k, m)).astype(np.float64).T.copy(order="F")   # column-major m x k
+    b = rng.integers(0, 10, (n, k)).astype(np.float64).T.copy(order="F")   # column-major k x n
+    a[7, 11] = np.inf; b[5, 140] = np.nan
+    c = np.zeros((m, n), order="F")
+    da, db, dc = (tmm.malloc_device(x.nbytes) for x in (a, b, c))
+    tmm.copy_to_device(a.reshape(-1, order="F"), da); tmm.copy_to_device(b.reshape(-1, order="F"), db); tmm.copy_to_device(c.reshape(-1, order="F"), dc)
+    tmm.device_gemm(np.float64, "N", "N", m, n, k, 1.0, da, m, db, k, 0.0, dc, m)
+    out = np.empty(m * n); tmm.copy_to_host(dc, out)
+    out = out.reshape(n, m).T
+    for p in (da, db, dc):
+        tmm.free_device(p)
+    bad = np.zeros((m, n), bool); bad[7, :] = True; bad[:, 140] = True
+    assert np.all(~np.isfinite(out[bad])) and np.all(np.isfinite(out[~bad]))
+    a0, b0 = a.copy(), b.copy(); a0[7, 11] = 0; b0[5, 140] = 0
+    assert np.array_equal(out[~bad], (a0 @ b0)[~bad])

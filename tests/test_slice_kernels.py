@@ -117,6 +117,21 @@ def test_slices_match_the_restatement(kernels, study, rows_contiguous, row_cap):
     assert not np.abs(q[1:, 9, :k]).any(), "small integers live entirely in slice 0"
 
 
+@pytest.mark.parametrize("rows_contiguous", [True, False])
+def test_non_finite_rows_are_marked_and_sliced_as_zero(kernels, rows_contiguous):
+    rng = np.random.default_rng(13)
+    rows, k, S = 9, 300, 4
+    x = rng.standard_normal((rows, k))
+    x[2, 17] = np.inf; x[4, 0] = np.nan; x[6, k - 1] = -np.inf
+    ld = rows if rows_contiguous else k
+    stored = np.ascontiguousarray(x.T if rows_contiguous else x).reshape(-1)
+    e, q = prepare(kernels, stored, rows_contiguous, rows, k, ld, S)
+    bad = np.array([2, 4, 6])
+    assert np.all(e[bad] >= 5000) and np.all(e[np.setdiff1d(np.arange(rows), bad)] < 100)
+    assert not q[:, bad, :k].any()
+    assert q[0, 0, :k].any()
+
+
 @pytest.mark.parametrize("ta,tb", [("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")])
 def test_emulated_product_meets_the_fp64_parity_bound(kernels, ta, tb):
     """Slices from the kernels (all four stored orientations) -> exact integer slice products -> the epilogue's arithmetic, in its order."""

@@ -6,6 +6,7 @@
 // by a power of two and cut into S signed 7-bit slices (tmm_slice.cuh); slice products are EXACT int8 x int8 -> int32 GEMMs, and
 //     C = 2^(ea[i] + eb[j]) * sum_{g < S} 2^-(2 P0 + 7 g) * ( sum_{s + t = g} Qa_s Qb_t^T )[i, j]      (terms with s + t >= S dropped)
 // Accuracy (tools/fp64_emulation_study.py): S = 7 -> 2e-16, S = 8 -> the error of native FP64, relative to k max|A| max|B|; integer data exact.
+// Non-finite operands: a row of op(A) / column of op(B) holding an Inf or NaN is detected by the exponent pass and its row / column of C is NaN.
 //
 // One kernel does the S (S + 1) / 2 slice GEMMs of a tile back to back - for a fixed g they share their scale, so they are ONE integer GEMM
 // over the concatenated k range [Qa_0 | .. | Qa_g] [Qb_g | .. | Qb_0]^T accumulated in one int32 TMEM window - and keeps the FP64 sums in
@@ -212,14 +213,16 @@ dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const bool row_ok = row < p.m;
             const int col0 = tn * BN + h * 64;
             int e_row = row_ok ? p.ea[row] : 0;
-            if (e_row <= NO_DATA) e_row = 0;  // all-zero row: its sums are zero anyway
+            const bool bad_row = e_row >= NON_FINITE;  // an Inf / NaN in this row of op(A): the whole row of the product is non-finite
+            if (e_row <= NO_DATA || bad_row) e_row = 0;  // all-zero row: its sums are zero anyway
             double* cp = p.c + (int64_t)col0 * p.ldc + row;
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
                 if (row_ok && col0 + j < p.n) {
                     int e_col = p.eb[col0 + j];
-                    if (e_col <= NO_DATA) e_col = 0;
-                    const double prod = p.alpha * scalbn(sum[j], e_row + e_col);
+                    const bool bad = bad_row || e_col >= NON_FINITE;
+                    if (e_col <= NO_DATA || bad) e_col = 0;
+                    const double prod = bad ? __longlong_as_double(0x7FF8000000000000ll) : p.alpha * scalbn(sum[j], e_row + e_col);
                     cp[(int64_t)j * p.ldc] = p.read_c ? prod + p.beta * cp[(int64_t)j * p.ldc] : prod;
                 }
             }
@@ -432,7 +435,8 @@ igemm_group_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const int row = tm * TILE_M + (int)rank * BM + q * 32 + lane;
             const bool row_ok = row < p.m;
             int e_row = row_ok ? p.ea[row] : 0;
-            if (e_row <= NO_DATA) e_row = 0;
+            const bool bad_row = e_row >= NON_FINITE;
+            if (e_row <= NO_DATA || bad_row) e_row = 0;
             for (int w = 0; w < windows; ++w) {
                 tc::mbar_wait_guarded(&acc_full_bar[acc], acc_phase);
                 tc::fence_after_thread_sync();
@@ -453,8 +457,9 @@ igemm_group_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     for (int j = 0; j < 32; ++j) {
                         if (row_ok && col0 + j < p.n) {
                             int e_col = p.eb[col0 + j];
-                            if (e_col <= NO_DATA) e_col = 0;
-                            const double add = p.alpha * scalbn((double)(int)v[j], e_row + e_col + shift);
+                            const bool bad = bad_row || e_col >= NON_FINITE;
+                            if (e_col <= NO_DATA || bad) e_col = 0;
+                            const double add = bad ? __longlong_as_double(0x7FF8000000000000ll) : p.alpha * scalbn((double)(int)v[j], e_row + e_col + shift);
                             double* dst = cp + (int64_t)j * p.ldc;
                             if (overwrite) *dst = p.read_c ? add + p.beta * *dst : add;
                             else *dst += add;

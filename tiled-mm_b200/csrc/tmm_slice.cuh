@@ -5,7 +5,8 @@
 //
 //   x[i, l] = 2^e[i] * sum_s 2^-(P0 + BITS s) * q_s[i, l]  +  remainder,     |q_s| <= 2^(BITS-1) = 64,   |remainder| <= 2^(e[i] - P0 - BITS S) / 2
 // e[i] = exponent of the largest magnitude of the row (|x| < 2^e), q_s = round-to-nearest of the running remainder: all steps are exact in
-// FP64 (scaling by powers of two, rint, one subtraction of a representable number).  Finite inputs only.
+// FP64 (scaling by powers of two, rint, one subtraction of a representable number).  A row with an Inf or NaN is marked (e = NON_FINITE, zero
+// slices) and comes out of the GEMM as NaN - a DGEMM would fill that row of C with Inf / NaN as well.
 #pragma once
 #include <cstdint>
 
@@ -16,12 +17,14 @@ constexpr int SLICE_BITS = 7;
 constexpr int P0 = SLICE_BITS - 1;       // fractional bits of slice 0
 constexpr int NO_DATA = -2000000000;     // e[] of a row that holds only zeros (cudaMemset pattern 0x88 = -2004318072 is below it)
 constexpr int MAX_SLICES = 10;
+constexpr int NON_FINITE = 5000;         // e[] of a row that holds an Inf or a NaN: its slices are zero, the GEMM epilogue writes NaN for it
 
 // |x| < 2^e with e minimal for normal numbers (x = f * 2^e, 0.5 <= f < 1); zeros report NO_DATA; denormals count as < 2^-1022
 __device__ __forceinline__ int exponent_above(double x) {
     const uint64_t u = (uint64_t)__double_as_longlong(x) & 0x7FFFFFFFFFFFFFFFull;
     if (u == 0) return NO_DATA;
     const int biased = (int)(u >> 52);
+    if (biased == 2047) return NON_FINITE;
     return biased == 0 ? -1022 : biased - 1022;
 }
 
@@ -48,10 +51,11 @@ static __global__ void __launch_bounds__(256) slice_rows(const double* __restric
     const int l4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (l4 >= k) return;
     for (int i = blockIdx.y; i < rows; i += gridDim.y) {
-        const int ei = e[i] <= NO_DATA ? 0 : e[i];
+        const bool finite_row = e[i] < NON_FINITE;
+        const int ei = (e[i] <= NO_DATA || !finite_row) ? 0 : e[i];
         double r[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) r[j] = (l4 + j < k) ? scalbn(x[(int64_t)i * stride_row + (int64_t)(l4 + j) * stride_k], -ei) : 0.0;
+        for (int j = 0; j < 4; ++j) r[j] = (finite_row && l4 + j < k) ? scalbn(x[(int64_t)i * stride_row + (int64_t)(l4 + j) * stride_k], -ei) : 0.0;
         for (int s = 0; s < slices; ++s) {
             const int p = P0 + SLICE_BITS * s;
             uint32_t packed = 0;
