@@ -11,7 +11,7 @@ export LD_LIBRARY_PATH=/usr/local/cuda/lib64:$LD_LIBRARY_PATH
 T=./build/tc_test
 {
 nvidia-smi -L | head -1
-echo "== experimental pytest =="; TMM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -m gpu -q --timeout 120 2>&1 | tail -25
+echo "== experimental pytest =="; TMM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -m gpu -q --timeout 120 -k "not tmem and not int8" 2>&1 | tail -25   # the kernel variants have their own scripts (a trap would poison this process)
 echo "== native bf16 kind::f16 (TN) =="; TMM_BF16_NATIVE=1 TMM_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_experimental_gpu.py -m gpu -q -k bf16 --timeout 100 2>&1 | tail -6
 echo "== tc_test cgemm =="; timeout 240 $T cgemm 2>&1 | grep -v " OK$" | tail -40
 echo "== sgemm split: round-to-nearest (default) =="; timeout 120 $T precision 2>&1 | grep -E "precision|tmm fp32|cuBLAS fp32 pedantic" | head -20
