@@ -28,5 +28,6 @@ TMM_F64_MATH=i8 timeout 90 python tools/e2e.py --reps 4 2>&1 | tail -1
 TMM_F64_MATH=i8:7 timeout 90 python tools/e2e.py --reps 4 2>&1 | tail -1
 TMM_F64_MATH=i8p TMM_PLAN_F64_FLOPS=60e12 timeout 90 python tools/e2e.py --reps 4 2>&1 | tail -1   # schedule sized for a faster GEMM (wider first block)
 TMM_F64_MATH=i8 TMM_PLAN_P1SPLIT=1 timeout 90 python tools/e2e.py --reps 4 2>&1 | tail -1   # one phase-1 stripe: every A chunk is sliced once instead of four times
-echo "== gated pytest =="; TMM_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_experimental_gpu.py -m gpu -q -k "int8" --timeout 100 2>&1 | tail -8
+echo "== gated pytest (one process per variant) =="
+for v in "8-slices and not pairs" "7-slices and not pairs" "pairs-8-slices" "pairs-7-slices"; do TMM_EXPERIMENTAL=1 timeout 150 python -m pytest tests/test_experimental_gpu.py -m gpu -q -k "int8 and $v" --timeout 100 2>&1 | tail -4; done
 } 2>&1 | tee gpurun_out/r2_f64_i8.txt

@@ -28,5 +28,6 @@ TMM_TC_ATMEM=2 TMM_TC_SPLIT=trunc timeout 60 $T benchone N N 8192 8192 8192 0
 echo "== plain TF32 mode (one MMA per product): 3 stages (measured 352 TF) vs six 32 KB stages (TMM_TC_TF32_STAGES=6) =="
 for tt in "N N" "T T"; do TMM_TC_TF32_STAGES=6 timeout 120 $T check $tt 2>&1 | grep -E "tf32-mode|FAIL" | tail -3; done   # check ends with a TF32-mode case (expect ~1e-4)
 TMM_TC_TF32_STAGES=6 timeout 60 $T benchone N N 8192 8192 8192 0   # the "tmm tf32" column; compare with the default run above
-echo "== gated pytest for the variants =="; TMM_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_experimental_gpu.py -m gpu -q -k "tmem" --timeout 100 2>&1 | tail -8
+echo "== gated pytest for the variants (one process per variant: a trap poisons its CUDA context) =="
+for v in one-cta cta-pair; do TMM_EXPERIMENTAL=1 timeout 150 python -m pytest tests/test_experimental_gpu.py -m gpu -q -k "tmem and $v" --timeout 100 2>&1 | tail -4; done
 } 2>&1 | tee gpurun_out/r2_tc_variants.txt
