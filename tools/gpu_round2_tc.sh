@@ -12,6 +12,7 @@ export LD_LIBRARY_PATH=/usr/local/cuda/lib64:$LD_LIBRARY_PATH
 T=./build/tc_test
 {
 nvidia-smi -L | head -1
+echo "== unit probes: tcgen05.st/ld round trip, tf32 MMA with A from smem / from TMEM, i8 MMA (one CTA, one MMA each) =="; timeout 60 ./build/tc_probe2
 echo "== default kernel (reference point) =="; timeout 60 $T benchone N N 8192 8192 8192 0
 echo "== sgemm, A operand through tensor memory (TMM_TC_ATMEM=1: 144 instead of 224 KB of shared-memory traffic per k-block) =="
 for tt in "N N" "T N"; do TMM_TC_ATMEM=1 timeout 60 $T probe $tt 2>&1 | head -40; done   # single tile, single k-block: which A element reached which accumulator position (silent = all right)
