@@ -44,8 +44,12 @@ void run_prepare(const double* x, long stride_row, long stride_k, int rows, int 
     const int k_per_block = 512;
     launch(row_exponents, dim3((unsigned)((rows + 255) / 256), (unsigned)((k + k_per_block - 1) / k_per_block)), dim3(256), x, (int64_t)stride_row, (int64_t)stride_k, rows, k,
            k_per_block, e);
-    launch(slice_rows, dim3((unsigned)((k + 1023) / 1024), (unsigned)(rows < row_cap ? rows : row_cap)), dim3(256), x, (int64_t)stride_row, (int64_t)stride_k, rows, k,
-           (const int*)e, out, (int64_t)pitch, (int64_t)slice_stride, slices);
+    if (stride_row == 1)   // as in prepare(): the coalesced variant for row-contiguous operands (k-group cap lowered with row_cap to exercise its grid-stride loop)
+        launch(slice_rows_contiguous, dim3((unsigned)((rows + 255) / 256), (unsigned)(((k + 15) / 16) < row_cap ? ((k + 15) / 16) : row_cap)), dim3(256), x, (int64_t)stride_k,
+               rows, k, (const int*)e, out, (int64_t)pitch, (int64_t)slice_stride, slices);
+    else
+        launch(slice_rows, dim3((unsigned)((k + 1023) / 1024), (unsigned)(rows < row_cap ? rows : row_cap)), dim3(256), x, (int64_t)stride_row, (int64_t)stride_k, rows, k,
+               (const int*)e, out, (int64_t)pitch, (int64_t)slice_stride, slices);
 }
 }
 '''
@@ -107,8 +111,8 @@ def test_slices_match_the_restatement(kernels, study, rows_contiguous, row_cap):
     for s in range(S):
         assert np.array_equal(q[s, :rows, :k].astype(np.int64), q_np[s]), s
         assert np.abs(q[s, :rows, :k].astype(np.int64)).max() <= 2 ** (bits - 1)
-        tail = q[s, :rows, k:(k + 3) // 4 * 4]
-        assert not tail.any(), "the k tail of the last group of four must be written as zeros"
+        tail = q[s, :rows, k:(k + 15) // 16 * 16 if rows_contiguous else (k + 3) // 4 * 4]
+        assert not tail.any(), "the k tail of the last group must be written as zeros"
     # reconstruction: the slices reproduce x to the stated remainder
     ee = np.where(zero_rows, 0, e).astype(np.int64)
     recon = sum(np.ldexp(q[s, :rows, :k].astype(np.float64), -(p0 + bits * s)) for s in range(S))

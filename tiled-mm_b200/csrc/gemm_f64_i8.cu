@@ -262,7 +262,11 @@ static cudaError_t prepare(const double* x, int64_t stride_row, int64_t stride_k
     const int k_per_block = 512;
     row_exponents<<<dim3((unsigned)((rows + 255) / 256), (unsigned)((k + k_per_block - 1) / k_per_block)), 256, 0, st>>>(x, stride_row, stride_k, rows, k, k_per_block, e);
     count_launch();
-    slice_rows<<<dim3((unsigned)((k + 1023) / 1024), (unsigned)std::min(rows, 32768)), 256, 0, st>>>(x, stride_row, stride_k, rows, k, e, out, pitch, slice_stride, slices);
+    if (stride_row == 1)  // rows contiguous in memory (op(A) = N, op(B) = T): coalesced along the rows
+        slice_rows_contiguous<<<dim3((unsigned)((rows + 255) / 256), (unsigned)std::min((k + 15) / 16, 4096)), 256, 0, st>>>(x, stride_k, rows, k, e, out, pitch, slice_stride,
+                                                                                                                   slices);
+    else
+        slice_rows<<<dim3((unsigned)((k + 1023) / 1024), (unsigned)std::min(rows, 32768)), 256, 0, st>>>(x, stride_row, stride_k, rows, k, e, out, pitch, slice_stride, slices);
     count_launch();
     return cudaGetLastError();
 }

@@ -70,5 +70,33 @@ static __global__ void __launch_bounds__(256) slice_rows(const double* __restric
     }
 }
 
+// The same for operands whose ROWS are contiguous in memory (stride_row == 1: op(A) = N, op(B) = T): consecutive threads take consecutive
+// rows, so every read is a coalesced run along the rows; a thread handles sixteen k-values and stores them as one 16-byte vector per slice.
+// grid.x covers the rows, grid.y groups of sixteen k-values (grid-stride).  pitch and slice_stride are multiples of 16.
+static __global__ void __launch_bounds__(256) slice_rows_contiguous(const double* __restrict__ x, int64_t stride_k, int rows, int k, const int* __restrict__ e,
+                                                                    int8_t* __restrict__ out, int64_t pitch, int64_t slice_stride, int slices) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const bool finite_row = e[i] < NON_FINITE;
+    const int ei = (e[i] <= NO_DATA || !finite_row) ? 0 : e[i];
+    for (int l16 = blockIdx.y * 16; l16 < k; l16 += gridDim.y * 16) {
+        double r[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = (finite_row && l16 + j < k) ? scalbn(x[(int64_t)(l16 + j) * stride_k + i], -ei) : 0.0;
+        for (int s = 0; s < slices; ++s) {
+            const int p = P0 + SLICE_BITS * s;
+            uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const double q = rint(scalbn(r[j], p));
+                r[j] -= scalbn(q, -p);
+                w[j >> 2] |= ((uint32_t)(uint8_t)(int8_t)(int)q) << (8 * (j & 3));
+            }
+            uint32_t* dst = reinterpret_cast<uint32_t*>(out + (int64_t)s * slice_stride + (int64_t)i * pitch + l16);
+            dst[0] = w[0]; dst[1] = w[1]; dst[2] = w[2]; dst[3] = w[3];
+        }
+    }
+}
+
 }  // namespace f64i8
 }  // namespace tmm
