@@ -63,7 +63,7 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t desc_a, uint64
 }
 // D[tmem] (+)= A[tmem] * B[smem]^T : the A operand is read from tensor memory (lane = row, one 32-bit column per k), so it costs
 // no shared-memory bandwidth.  A in TMEM is always K-major: the instruction descriptor's "A is MN-major" bit must be 0.
-// (experimental - gemm_f32_tc_ts.cu, TMM_TC_ATMEM=1; not yet run on hardware)
+// (experimental - gemm_f32_tc.cu sgemm_tc_ts_kernel, TMM_TC_ATMEM=1; not yet run on hardware)
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
