@@ -11,7 +11,7 @@ export LD_LIBRARY_PATH=/usr/local/cuda/lib64:$LD_LIBRARY_PATH
 D=./build/devtest
 {
 nvidia-smi -L | head -1
-echo "== unit probe: one kind::i8 MMA on hand-written tiles =="; timeout 60 ./build/tc_probe2 4
+echo "== unit probe: one kind::i8 MMA on hand-written tiles =="; timeout 60 ./build/tc_probe2 4; timeout 60 ./build/tc_probe2 7   # 7 = the CTA-pair shape of the i8p version
 echo "== check vs cuBLAS, 8 slices =="; TMM_F64_MATH=i8 timeout 120 $D check 2>&1 | tail -45
 echo "== check vs cuBLAS, 7 slices =="; TMM_F64_MATH=i8:7 timeout 120 $D check 2>&1 | grep -E "FAIL|error|rc=" | head -20
 echo "== device-resident, DMMA (reference point) =="; timeout 60 $D benchone N N 10000 10000 10000 0

@@ -5,7 +5,7 @@
 //   2  kind::tf32 MMA, A from shared memory (the hardware-validated form: checks this probe's own hand-written SWIZZLE_128B tiles)
 //   3  kind::tf32 MMA, A from TENSOR MEMORY ([a_tmem] form; lane = row, one 32-bit column per k)
 //   4  kind::i8 MMA, both operands from shared memory, int32 accumulator
-//   5, 6  the same tf32 MMAs on a CTA pair (cta_group::2, M = 256): see pair_probe_kernel
+//   5, 6, 7  tf32 (A from shared / tensor memory) and i8 MMAs on a CTA pair (cta_group::2, M = 256): see pair_probe_kernel
 // Every wait is guarded (trap after ~10 s).
 #include "../tiled-mm_b200/csrc/tmm_tc.cuh"
 
@@ -91,15 +91,22 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(int mode, const unsigned 
 
 // ---- CTA-pair probes (cluster of two): M = 256, N = 128, one cta_group::2 MMA issued by rank 0 -------------------------------------------
 //   5  kind::tf32, A and B from shared memory   6  kind::tf32, A from tensor memory   (each CTA: its 128 rows of A, its 64-row half of B)
+//   7  kind::i8, M = 256, N = 256 (the shape of igemm_group_kernel): each CTA its 128 rows of A and its 128-row half of B, 256 int32 columns
 // Exercises exactly the pieces sgemm_tc_ts_kernel<true> / igemm_group_kernel add: cta_group::2 TMEM allocation, remote arrive on rank 0's
 // barrier + cluster-scope acquire wait, the pair MMA reading both CTAs' operands, the multicast commit, cluster barriers.
+__device__ __forceinline__ void mma_i8_pair_ss(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(desc_a), "l"(desc_b),
+                 "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+constexpr int PAIR_TMEM_COLS = 512, PAIR_A_COL = 256;  // D in columns 0..255 at most, A (TMEM) from column 256
 __device__ __forceinline__ void mma_tf32_pair_ss(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(desc_a), "l"(desc_b),
                  "r"(idesc), "r"(accumulate)
                  : "memory");
 }
 
-// a_tiles: two 16 KB images (rank 0, rank 1); b_tiles: two 16 KB images holding 64 rows each; a_rows: [256][16]; out: [256][128]
+// a_tiles: two 16 KB images (rank 0, rank 1); b_tiles: two 16 KB images holding 64 (modes 5, 6) or 128 (mode 7) rows each; a_rows: [256][16]; out: [256][N]
 __global__ void __launch_bounds__(128, 1) pair_probe_kernel(int mode, const unsigned char* a_tiles, const unsigned char* b_tiles, const uint32_t* a_rows, uint32_t* out) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(128, 1) pair_probe_kernel(int mode, const unsi
     const int t = threadIdx.x, warp = t >> 5;
     const uint32_t rank = tc::cluster_ctarank();
     if (t == 0) { ptx::mbar_init(ready_bar, 2); ptx::mbar_init(done_bar, 1); ptx::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc_pair(slot, TMEM_COLS);
+    if (warp == 0) tc::tmem_alloc_pair(slot, PAIR_TMEM_COLS);
     for (int i = t; i < TILE_BYTES / 16; i += 128) {
         reinterpret_cast<uint4*>(sa)[i] = reinterpret_cast<const uint4*>(a_tiles + rank * TILE_BYTES)[i];
         reinterpret_cast<uint4*>(sb)[i] = reinterpret_cast<const uint4*>(b_tiles + rank * TILE_BYTES)[i];
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(128, 1) pair_probe_kernel(int mode, const unsi
         uint32_t v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = a_rows[(rank * 128 + t) * 16 + j];
-        tc::tmem_st_32x32b_x16(lane_base + A_COL, v);
+        tc::tmem_st_32x32b_x16(lane_base + PAIR_A_COL, v);
         tc::tmem_st_wait();
         tc::fence_before_thread_sync();
     }
@@ -140,41 +147,46 @@ __global__ void __launch_bounds__(128, 1) pair_probe_kernel(int mode, const unsi
         const uint64_t da = tc::smem_desc(dtmpl, ptx::smem_u32(sa)), db = tc::smem_desc(dtmpl, ptx::smem_u32(sb));
         const uint32_t idesc = tc::instr_desc(tc::FMT_TF32, 256, 128, false, false);
         if (mode == 5) mma_tf32_pair_ss(tmem, da, db, idesc, 0u);
-        else tc::mma_tf32_ts_pair(tmem, tmem + A_COL, db, idesc, 0u);
+        else if (mode == 6) tc::mma_tf32_ts_pair(tmem, tmem + PAIR_A_COL, db, idesc, 0u);
+        else mma_i8_pair_ss(tmem, da, db, (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24), 0u);
         tc::mma_commit_pair(done_bar, 3);
     }
     tc::mbar_wait_guarded(done_bar, 0);
     tc::fence_after_thread_sync();
+    const int n_cols = mode == 7 ? 256 : 128;
 #pragma unroll 1
-    for (int cb = 0; cb < 4; ++cb) {
+    for (int cb = 0; cb < n_cols / 32; ++cb) {
         uint32_t v[32];
         tc::tmem_ld_32x32b_x32(lane_base + cb * 32, v);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) out[(rank * 128 + t) * 128 + cb * 32 + j] = v[j];
+        for (int j = 0; j < 32; ++j) out[(rank * 128 + t) * n_cols + cb * 32 + j] = v[j];
     }
     tc::fence_before_thread_sync();
     __syncthreads();
     tc::cluster_sync();
-    if (warp == 0) { tc::fence_after_thread_sync(); tc::tmem_dealloc_pair(tmem, TMEM_COLS); }
+    if (warp == 0) { tc::fence_after_thread_sync(); tc::tmem_dealloc_pair(tmem, PAIR_TMEM_COLS); }
 }
 
 static int run_pair(int mode) {
-    const int K = 8;
+    const bool i8 = mode == 7;
+    const int K = i8 ? 32 : 8, N = i8 ? 256 : 128;
     std::vector<unsigned char> a_tiles(2 * TILE_BYTES, 0), b_tiles(2 * TILE_BYTES, 0);
-    std::vector<uint32_t> a_rows(256 * 16, 0), out(256 * 128, 0xDEADBEEFu);
+    std::vector<uint32_t> a_rows(256 * 16, 0), out(256 * N, 0xDEADBEEFu);
     auto A = [&](int i, int k) { return (i * 3 + k * 5) % 11 - 5; };
     auto B = [&](int j, int k) { return (j * 7 + k * 2) % 9 - 4; };
     for (int i = 0; i < 256; ++i)
         for (int k = 0; k < K; ++k) {
+            if (i8) { a_tiles[(i / 128) * TILE_BYTES + sw128(i % 128, k)] = (unsigned char)(signed char)A(i, k); continue; }
             float f = (float)A(i, k);
             memcpy(&a_tiles[(i / 128) * TILE_BYTES + sw128(i % 128, 4 * k)], &f, 4);
             memcpy(&a_rows[i * 16 + k], &f, 4);
         }
-    for (int j = 0; j < 128; ++j)
-        for (int k = 0; k < K; ++k) {
+    for (int j = 0; j < N; ++j)
+        for (int k = 0; k < K; ++k) {   // rank r holds columns (N / 2) r .. (N / 2) r + N / 2 - 1 of the tile
+            if (i8) { b_tiles[(j / (N / 2)) * TILE_BYTES + sw128(j % (N / 2), k)] = (unsigned char)(signed char)B(j, k); continue; }
             float f = (float)B(j, k);
-            memcpy(&b_tiles[(j / 64) * TILE_BYTES + sw128(j % 64, 4 * k)], &f, 4);   // rank r holds columns 64 r .. 64 r + 63 of the tile
+            memcpy(&b_tiles[(j / (N / 2)) * TILE_BYTES + sw128(j % (N / 2), 4 * k)], &f, 4);
         }
     unsigned char *da, *db; uint32_t *dr, *dout;
     CK(cudaMalloc(&da, a_tiles.size())); CK(cudaMalloc(&db, b_tiles.size())); CK(cudaMalloc(&dr, a_rows.size() * 4)); CK(cudaMalloc(&dout, out.size() * 4));
@@ -193,17 +205,15 @@ static int run_pair(int mode) {
     if (e != cudaSuccess) { printf("probe %d: kernel failed: %s\n", mode, cudaGetErrorString(e)); return 1; }
     CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
     int wrong = 0, fi = -1, fj = -1;
+    auto got = [&](int i, int j) { if (i8) return (double)(int)out[i * N + j]; float f; memcpy(&f, &out[i * N + j], 4); return (double)f; };
+    auto want = [&](int i, int j) { double s = 0; for (int k = 0; k < K; ++k) s += (double)A(i, k) * B(j, k); return s; };
     for (int i = 0; i < 256; ++i)
-        for (int j = 0; j < 128; ++j) {
-            double s = 0;
-            for (int k = 0; k < K; ++k) s += (double)A(i, k) * B(j, k);
-            float f; memcpy(&f, &out[i * 128 + j], 4);
-            if ((double)f != s) { if (!wrong) { fi = i; fj = j; } ++wrong; }
-        }
-    printf("probe %d (CTA pair, M = 256, tf32, A from %s): %s", mode, mode == 5 ? "shared memory" : "tensor memory", wrong ? "WRONG" : "OK");
+        for (int j = 0; j < N; ++j)
+            if (got(i, j) != want(i, j)) { if (!wrong) { fi = i; fj = j; } ++wrong; }
+    printf("probe %d (CTA pair, M = 256, N = %d, %s, A from %s): %s", mode, N, i8 ? "i8" : "tf32", mode == 6 ? "tensor memory" : "shared memory", wrong ? "WRONG" : "OK");
     if (wrong) {
-        printf("  %d wrong of %d, first at (%d,%d); rows wrong per CTA:", wrong, 256 * 128, fi, fj);
-        for (int r = 0; r < 2; ++r) { int c = 0; for (int i = 128 * r; i < 128 * r + 128; ++i) for (int j = 0; j < 128; ++j) { double s = 0; for (int k = 0; k < K; ++k) s += (double)A(i, k) * B(j, k); float f; memcpy(&f, &out[i * 128 + j], 4); c += (double)f != s; } printf(" rank %d: %d", r, c); }
+        printf("  %d wrong of %d, first at (%d,%d): got %g expected %g; wrong per CTA:", wrong, 256 * N, fi, fj, got(fi, fj), want(fi, fj));
+        for (int r = 0; r < 2; ++r) { int c = 0; for (int i = 128 * r; i < 128 * r + 128; ++i) for (int j = 0; j < N; ++j) c += got(i, j) != want(i, j); printf(" rank %d: %d", r, c); }
     }
     printf("\n");
     cudaFree(da); cudaFree(db); cudaFree(dr); cudaFree(dout);
@@ -274,7 +284,7 @@ static int run(int mode) {
 int main(int argc, char** argv) {
     int bad = 0;
     if (argc > 1) return atoi(argv[1]) >= 5 ? run_pair(atoi(argv[1])) : run(atoi(argv[1]));
-    for (int mode = 1; mode <= 6; ++mode) {
+    for (int mode = 1; mode <= 7; ++mode) {
         bad += mode >= 5 ? run_pair(mode) : run(mode);
         if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { printf("context lost after probe %d; run the rest one by one: tc_probe2 <n>\n", mode); return 3; }
     }
