@@ -325,15 +325,25 @@ def main():
     for _ in range(args.warmup):
         e2e_step()
     barrier()
-    launches0 = tmm.total_kernel_launches()
-    with ClockSampler(local_rank) as cs_e2e:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
+    def timed_e2e():
+        launches_before = tmm.total_kernel_launches()
+        with ClockSampler(local_rank) as sampler:
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_step()
+            barrier()
+            ms = (time.perf_counter() - t0) / args.steps * 1e3
+        return max_over_ranks(ms), sampler, tmm.total_kernel_launches() - launches_before
+
+    e2e_ms, cs_e2e, launches = timed_e2e()
+    # a timed region that saw a hardware / thermal slowdown on any rank is measured again, once (all ranks decide together)
+    remeasured = False
+    slow = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if max_over_ranks(1.0 if slow & set(cs_e2e.summary()["reasons"]) else 0.0) > 0.0:
+        time.sleep(5.0)
         barrier()
-        e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
-    e2e_ms = max_over_ranks(e2e_ms)
-    launches = tmm.total_kernel_launches() - launches0
+        e2e_ms, cs_e2e, launches = timed_e2e()
+        remeasured = True
     e2e_tf = world * flops / (e2e_ms * 1e-3) * 1e-12
     stt = ctx.last_stats()
     h2d, d2h, peer = int(stt.h2d_bytes), int(stt.d2h_bytes), int(stt.peer_bytes)
@@ -359,6 +369,7 @@ def main():
         roof_simple = min(FP64_PEAK_TFLOPS, ai * PCIE_H2D_GBS * 1e-3)
         t_duplex = max(flops / (FP64_PEAK_TFLOPS * 1e12), 8.0 * (m * k / pc + k * n / pr) / (PCIE_H2D_GBS * 1e9), 8.0 * m * n / (PCIE_D2H_GBS * 1e9))
         clocks = cs_e2e.summary()
+        clocks["remeasured_after_slowdown"] = remeasured
         out = {
             "metric": "host-to-host dgemm TFLOP/s", "value": round(value_tf, 3), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
