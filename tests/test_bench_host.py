@@ -42,3 +42,75 @@ def test_bench_refuses_to_run_without_a_gpu():
         return
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "1", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+MOCK_RUNNER = r'''
+import runpy, sys, types
+import numpy as np
+
+# ---- a stand-in for torch: just enough surface for bench.py's single-GPU flow ----
+torch = types.ModuleType("torch")
+torch.float64 = "f64"; torch.int64 = "i64"
+class _Stream: cuda_stream = 0
+class _Event:
+    clock = [0.0]
+    def __init__(self, enable_timing=False): self.t = 0.0
+    def record(self, st=None): _Event.clock[0] += 1.0; self.t = _Event.clock[0]
+    def elapsed_time(self, other): return max(other.t - self.t, 0.5)
+class _Dev:
+    def __init__(self, n): self.a = np.zeros(n)
+    def copy_(self, x): return self
+    def data_ptr(self): return 0
+    def view(self, *s): return self
+    def t(self): return self
+cuda = types.SimpleNamespace(is_available=lambda: True, set_device=lambda i: None, current_stream=lambda: _Stream(), Event=_Event,
+                             synchronize=lambda: None, empty_cache=lambda: None)
+torch.cuda = cuda
+torch.empty = lambda n, dtype=None, device=None: _Dev(n)
+torch.from_numpy = lambda x: x
+torch.matmul = lambda a, b: None
+torch.device = lambda *a: None
+sys.modules["torch"] = torch
+
+# ---- a stand-in for the library: gemm really multiplies (numpy), so the benchmark's linearity check has something to check ----
+tmm = types.ModuleType("tiled_mm_b200")
+state = {"launches": 0}
+class _Stats: h2d_bytes = 2 * 64 * 64 * 8; d2h_bytes = 64 * 64 * 8; peer_bytes = 0
+class _Ctx:
+    def last_stats(self): return _Stats()
+    def close(self): pass
+def gemm(ctx, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, pin_host_buffers=False, copy_c_back=True):
+    A = np.asarray(a).reshape(k, lda)[:, :m].T
+    B = np.asarray(b).reshape(n, ldb)[:, :k].T
+    np.asarray(c).reshape(n, ldc)[:, :m] = (alpha * (A @ B)).T
+    state["launches"] += 7
+def device_gemm(*a, **k): state["launches"] += 1
+tmm.device_count = lambda: 1
+tmm.malloc_pinned = lambda dtype, count: np.zeros(count, dtype)
+tmm.make_context = lambda *a, **k: _Ctx()
+tmm.gemm = gemm
+tmm.device_gemm = device_gemm
+tmm.total_kernel_launches = lambda: state["launches"]
+sys.modules["tiled_mm_b200"] = tmm
+
+sys.argv = ["bench.py", "--size", "64", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"]
+runpy.run_path(BENCH, run_name="__main__")
+'''
+
+
+def test_bench_main_flow_on_stand_ins(tmp_path):
+    """The whole single-GPU flow of bench.py (both timed legs, the re-measure decision, the JSON line) executed on stand-ins for torch and
+    for the library - guards the benchmark's own code against slips that would only show on the GPU box."""
+    import json
+    runner = tmp_path / "run_bench.py"
+    runner.write_text("BENCH = %r\n" % str(ROOT / "bench.py") + MOCK_RUNNER)
+    r = subprocess.run([sys.executable, str(runner)], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "e2e",
+                "gpu_launches", "roofline", "clocks"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3 and line["dtype"] == "f64" and line["gpu_launches"] == 14
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+    assert line["clocks"]["remeasured_after_slowdown"] is False and "workload" in line["config"]
