@@ -75,3 +75,23 @@ def test_experimental_kernels_carry_their_instructions(sass):
         assert has(ops, "UTCIMMA.2CTA") and has(ops, "UTCBAR.2CTA") and no_local_memory(ops), name
     for name, ops in kernels(sass, "sgemm_tc_deep_kernel").items():
         assert has(ops, "UTCHMMA") and no_local_memory(ops), name
+
+
+def test_hot_kernels_fit_their_occupancy_budget():
+    """cuobjdump -res-usage: the TMA / tensor-core kernels are compiled for 128 registers (2 x 256-thread CTAs per SM for the FP64 kernels,
+    one 512-thread CTA for the tcgen05 kernels - the warpgroups then re-balance with setmaxnreg) and use no stack and no local memory."""
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(exe).exists() or not LIB.exists():
+        pytest.skip("cuobjdump or the built library is not available")
+    text = subprocess.run([exe, "-res-usage", str(LIB)], capture_output=True, text=True, timeout=600, check=True).stdout
+    lines = text.splitlines()
+    seen = 0
+    for i, line in enumerate(lines):
+        m = re.search(r"Function (\S+):", line)
+        if not m or not any(k in m.group(1) for k in ("dgemm_kernel", "zgemm_kernel", "sgemm_tc", "dgemm_i8_kernel", "igemm_group_kernel")):
+            continue
+        usage = lines[i + 1]
+        reg, stack, local = (int(re.search(rf"{k}:(\d+)", usage).group(1)) for k in ("REG", "STACK", "LOCAL"))
+        assert reg <= 128 and stack == 0 and local == 0, (m.group(1), usage)
+        seen += 1
+    assert seen >= 12
