@@ -103,8 +103,8 @@ def mma_async(sim, pipes, stage, bars_empty, on_done=None, lo=5, hi=60):
 # ------------------------------------------------------------------------------------------------------------------------------------------
 # sgemm_tc_ts_kernel<PAIR>: STAGES = 4, ACC_BUFS = 2, split warps = 4 (A -> TMEM) + 4 (B in smem); pair: both CTAs' split warps and accumulate
 # warps arrive on rank 0's ready / acc_empty barriers, commits are multicast
-def build_ts(sim, pair, tiles, kblocks, window):
-    STAGES, ACCS, SPLIT_WARPS = 4, 2, 8
+def build_ts(sim, pair, tiles, kblocks, window, stages=4, accs=2):
+    STAGES, ACCS, SPLIT_WARPS = stages, accs, 8
     ncta = 2 if pair else 1
     full = [[Barrier(1) for _ in range(STAGES)] for _ in range(ncta)]
     ready = [Barrier(2 * SPLIT_WARPS if pair else SPLIT_WARPS) for _ in range(STAGES)]        # rank 0's
@@ -309,6 +309,16 @@ def test_sgemm_a_through_tmem_protocol(pair, tiles, kblocks, window):
     for seed in range(12):
         sim = Sim(seed)
         build_ts(sim, pair, tiles, kblocks, window)
+        sim.run()
+
+
+@pytest.mark.parametrize("tiles,kblocks,window", [(1, 1, 4), (3, 5, 4), (2, 9, 4), (4, 3, 1)])
+def test_default_sgemm_kernel_protocol(tiles, kblocks, window):
+    """sgemm_tc_kernel (the hardware-validated default): the same roles with a 3-stage ring and four window accumulators; the split stage of
+    all eight warps works in shared memory.  Kept here so that a change to that kernel's pipeline is checked before it costs GPU time."""
+    for seed in range(8):
+        sim = Sim(seed)
+        build_ts(sim, False, tiles, kblocks, window, stages=3, accs=4)
         sim.run()
 
 
