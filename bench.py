@@ -243,6 +243,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        os.environ.setdefault("TMM_DIST_TIMEOUT_S", "60")  # a grid call here takes ~60 ms: if a peer dies, give up after a minute instead of the library's 10
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
