@@ -11,10 +11,17 @@ ap.add_argument("--m", type=int, default=10000); ap.add_argument("--n", type=int
 ap.add_argument("--tt", default="NN"); ap.add_argument("--dtype", default="d"); ap.add_argument("--beta", type=float, default=0.0)
 ap.add_argument("--reps", type=int, default=6); ap.add_argument("--trace", action="store_true"); ap.add_argument("--budget", type=float, default=0.0)
 ap.add_argument("--copy-c-back", type=int, default=1); ap.add_argument("--devices", type=int, default=0)
+ap.add_argument("--fill", default="rand", help="rand | const (timing only: skips the slow host RNG)")
+ap.add_argument("--trace-dir", default="", help="every rank traces (TMM_TRACE=1) into <dir>/trace_rank<r>.txt")
 args = ap.parse_args()
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 if args.trace and rank == 0:
     os.environ["TMM_TRACE"] = "1"
+if args.trace_dir:
+    os.environ["TMM_TRACE"] = "1"
+    os.makedirs(args.trace_dir, exist_ok=True)
+    _fd = os.open(os.path.join(args.trace_dir, f"trace_rank{rank}.txt"), os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+    os.dup2(_fd, 2)
 import tiled_mm_b200 as tmm
 dist = None
 if world > 1:
@@ -29,6 +36,9 @@ br, bc = (k, n) if tb == "N" else (n, k)
 a = tmm.malloc_pinned(dt, ar * ac); b = tmm.malloc_pinned(dt, br * bc); c = tmm.malloc_pinned(dt, m * n)
 rng = np.random.default_rng(rank)
 for arr in (a, b):
+    if args.fill == "const":
+        np.asarray(arr).view(np.float32 if args.dtype in "sc" else np.float64)[:] = 0.5
+        continue
     v = arr.view(np.float32 if args.dtype in "sc" else np.float64)
     for off in range(0, v.size, 1 << 24):
         v[off:off + (1 << 24)] = rng.random(min(1 << 24, v.size - off)) - 0.5
