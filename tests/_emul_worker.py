@@ -523,6 +523,66 @@ def run_ranks(world):
     print(f"EMUL_OK ranks {pr}x{pc}")
 
 
+def run_rank_fails_early(world):
+    """One rank of the grid rejects its arguments BEFORE the agreement round (ld_a too small there only); the others must not wait for it:
+    every rank gets an error for that call, and the next call on the same contexts works (the rounds stayed in step)."""
+    import threading
+    from tiled_mm_b200 import multi_gpu
+    lib.emul_set_device.argtypes = [ctypes.c_int]
+    pr, pc = tmm.grid_shape(world)
+    barrier = threading.Barrier(world)
+    ids, errors, failed_calls = {}, [], []
+
+    def body(rank):
+        try:
+            assert lib.emul_set_device(rank) == 0
+            row, col = rank // pc, rank % pc
+            if pc > 1 and col == 0:
+                ids[("row", row)] = tmm.dist_unique_id()
+            if pr > 1 and row == 0:
+                ids[("col", col)] = tmm.dist_unique_id()
+            barrier.wait()
+            dtype, m, n, k = np.float64, 300, 260, 200
+            ctx = tmm.make_context(dtype, 2, 64, 64, 64)
+            ctx.attach_grid(pr, pc, row, col, ids.get(("row", row)), ids.get(("col", col)))
+            rng = np.random.default_rng(3)
+            a0, b0, c0 = gen(rng, dtype, m * k), gen(rng, dtype, k * n), gen(rng, dtype, m * n)
+            expect = oracle.gemm("N", "N", m, n, k, 1.0, a0, m, b0, k, 0.0, c0.copy(), m).reshape(n, m)
+            i0, i1, j0, j1 = multi_gpu.block_of(rank, world, m, n)
+            ap = tmm.malloc_pinned(dtype, a0.size); ap[:] = a0
+            bp = tmm.malloc_pinned(dtype, b0.size); bp[:] = b0
+            cp = tmm.malloc_pinned(dtype, c0.size); cp[:] = c0
+            for attempt, bad_rank in enumerate([world - 1, 0, None]):
+                lda = (i1 - i0 - 1) if rank == bad_rank else m           # invalid on one rank only: rejected before anything collective
+                try:
+                    tmm.gemm(ctx, "N", "N", i1 - i0, j1 - j0, k, 1.0, ap.ctypes.data + i0 * 8, lda, bp.ctypes.data + j0 * k * 8, k, 0.0,
+                             cp.ctypes.data + (j0 * m + i0) * 8, m, pin_host_buffers=False, copy_c_back=True)
+                    ok = True
+                except (RuntimeError, ValueError, MemoryError) as e:
+                    ok = False
+                    failed_calls.append((attempt, rank, str(e)[:60]))
+                assert ok == (bad_rank is None), f"rank {rank} attempt {attempt}: call {'succeeded' if ok else 'failed'}"
+            got = np.asarray(cp).reshape(n, m)
+            assert np.array_equal(got[j0:j1, i0:i1], expect[j0:j1, i0:i1])
+            barrier.wait()
+            os.environ["TMM_EMUL_ALLOW_FREE_WHILE_IMPORTED"] = "1"
+            barrier.wait()
+            ctx.close()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(f"rank {rank}: {type(e).__name__}: {e}")
+            barrier.abort()
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    assert len(failed_calls) == 2 * world, failed_calls
+    assert lib.emul_violations() == 0, lib.emul_first_violation().decode()
+    print(f"EMUL_OK rank-fails-early world {world}: {len(failed_calls)} calls given up together, next call exact")
+
+
 def run_dry(n_dev):
     """Full-size walk through the real scheduler with address-only memory (TMM_EMUL_DRY=1): BASELINE configs[3] and [4] and a C that
     needs super-blocks.  No arithmetic, no data movement - bounds, 64-bit offsets, ordering, protocol progress and byte counts."""
@@ -568,6 +628,8 @@ if __name__ == "__main__":
     mode = sys.argv[1]
     if mode == "ranks":
         run_ranks(int(sys.argv[2]))
+    elif mode == "rankfails":
+        run_rank_fails_early(int(sys.argv[2]))
     elif mode == "gridfaults":
         run_grid_faults(int(sys.argv[2]))
     elif mode == "faults":

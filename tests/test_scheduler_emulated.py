@@ -147,3 +147,17 @@ def test_one_rank_per_gpu_entry_point_with_emulated_ipc(emul_build, world, extra
     streaming calls on reused contexts, bit-exact per block; through the emulated CUDA IPC calls the import bookkeeping is checked
     (re-import when a peer's buffer changed, outgrown buffers retired instead of freed while imported, everything closed at teardown)."""
     _worker(emul_build, ["ranks", world], world, extra)
+
+
+@pytest.mark.parametrize("world,extra", [(2, {}), (8, {}), (4, {"TMM_DIST_BOARD": "0"})])
+def test_rank_that_fails_before_the_agreement_round_takes_the_grid_with_it(emul_build, world, extra):
+    """A rank that rejects its arguments before anything collective (here: ld_a too small on one rank only) still plays the call's agreement
+    round and reports the failure: every rank returns an error for that call instead of waiting for the missing rank, and the next call on
+    the same contexts is bit-exact.  Run on the shared-memory control board (default) and on the NCCL control collectives (TMM_DIST_BOARD=0)."""
+    _worker(emul_build, ["rankfails", world], world, extra)
+
+
+@pytest.mark.parametrize("world", [4])
+def test_grid_entry_point_on_nccl_control_collectives(emul_build, world):
+    """the control plane without the shared-memory board (what a box without /dev/shm falls back to)"""
+    _worker(emul_build, ["ranks", world], world, {"TMM_DIST_BOARD": "0", "TMM_DIST_FORCE_IPC": "1"})

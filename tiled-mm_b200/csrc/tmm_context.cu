@@ -724,9 +724,26 @@ int tmm_context_last_stats(tmm_context* ctx, tmm_call_stats* out) {
 int tmm_context_set_profiling(tmm_context* ctx, int on) { if (!ctx) return TMM_ERR_INVALID; ctx->profiling = on != 0; return TMM_OK; }
 int tmm_context_set_device_budget(tmm_context* ctx, size_t bytes) { if (!ctx) return TMM_ERR_INVALID; ctx->budget_override = bytes; return TMM_OK; }
 
+static int gemm_on_context(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t ld_a,
+                           const void* b, int64_t ld_b, const void* beta, void* c, int64_t ld_c, int pin_host_buffers, int copy_c_back);
+
 int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t ld_a,
              const void* b, int64_t ld_b, const void* beta, void* c, int64_t ld_c, int pin_host_buffers, int copy_c_back) {
     if (!ctx) return fail(TMM_ERR_INVALID, "null context");
+    if (ctx->children.empty() && ctx->grid.active()) {
+        // One rank of a GPU grid.  Whatever happens locally, every rank takes part in exactly one agreement round per call: a rank that
+        // fails before it gets there (bad argument, failed page-locking or allocation) still plays the round and reports its failure, so
+        // its peers give the call up with it instead of waiting for panel shares that will never come.
+        ctx->grid_round_entered = false;
+        const int rc = gemm_on_context(ctx, trans_a, trans_b, m, n, k, alpha, a, ld_a, b, ld_b, beta, c, ld_c, pin_host_buffers, copy_c_back);
+        if (rc && !ctx->grid_round_entered) { DeviceGuard guard(ctx->device); tmm::dist_abort(ctx); }
+        return rc;
+    }
+    return gemm_on_context(ctx, trans_a, trans_b, m, n, k, alpha, a, ld_a, b, ld_b, beta, c, ld_c, pin_host_buffers, copy_c_back);
+}
+
+static int gemm_on_context(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t ld_a,
+                           const void* b, int64_t ld_b, const void* beta, void* c, int64_t ld_c, int pin_host_buffers, int copy_c_back) {
     if (!ctx->children.empty())  // single-process multi-GPU: C blocks over the child contexts, one host thread each
         return tmm::multi_gemm(ctx, trans_a, trans_b, m, n, k, alpha, a, ld_a, b, ld_b, beta, c, ld_c, pin_host_buffers, copy_c_back);
     const auto t_begin = std::chrono::steady_clock::now();
@@ -844,6 +861,17 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
             c_bytes = (size_t)ldc_dev * n * cl.es;
         }
         const size_t budget = device_budget(ctx);  // after full C is in place
+        // on a GPU grid all ranks plan for the same (largest) block and the smallest budget, so the exchanges line up; the round also
+        // checks that k, the ops and the modes (beta == 0, copy_c_back, "nothing to multiply") agree, and spreads a local failure
+        int64_t m_plan = m, n_plan = n;
+        size_t plan_budget = budget;
+        int rc_before_agree = TMM_OK;
+        if (ctx->grid.active()) {
+            const int flags = (cl.ta << 16) | (cl.tb << 8) | (need_ab ? 4 : 0) | (cl.beta_nonzero ? 2 : 0) | (cl.copy_c_back ? 1 : 0);
+            const int rc_agree = tmm::dist_agree(ctx, m, n, k, flags, budget, &m_plan, &n_plan, &plan_budget, rc);
+            if (!rc) rc = rc_agree;
+            rc_before_agree = rc;
+        }
         if (!rc) {
             if (!need_ab) {
                 // C = beta * C
@@ -864,16 +892,9 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                     }
                 }
             } else {
-                // on a GPU grid all ranks plan for the same (largest) block and the smallest budget, so the exchanges line up
-                int64_t m_plan = m, n_plan = n;
-                size_t plan_budget = budget;
                 const tmm::Grid& gr = ctx->grid;
                 bool need_stage = false;  // only links that could not map peer memory stage their shares through NCCL
-                int rc_before_agree = TMM_OK;
                 if (gr.active()) {
-                    const int flags = (cl.ta << 16) | (cl.tb << 8) | (cl.beta_nonzero ? 2 : 0) | (cl.copy_c_back ? 1 : 0);
-                    rc = tmm::dist_agree(ctx, m, n, k, flags, budget, &m_plan, &n_plan, &plan_budget);
-                    rc_before_agree = rc;
                     need_stage = (gr.rowl.active() && !gr.rowl.direct) || (gr.coll.active() && !gr.coll.direct);
                     if (!rc && need_stage) {
                         // staging rings for the all-gathers: shares of at most one k-chunk of A / one column block of B
@@ -894,6 +915,7 @@ int tmm_gemm(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n,
                 pin_.n_streams = ctx->n_streams; pin_.tile_m = ctx->tile_m; pin_.tile_n = ctx->tile_n; pin_.tile_k = ctx->tile_k;
                 pin_.sm_count = tmm::sm_count();
                 pin_.parts_a = gr.pc; pin_.parts_b = gr.pr;
+                if (gr.active() && ctx->link_h2d_gbs > 0 && ctx->link_d2h_gbs > 0) { pin_.h2d_bw = ctx->link_h2d_gbs * 1e9; pin_.d2h_bw = ctx->link_d2h_gbs * 1e9; }
                 if (cl.dtype == TMM_C32 && tmm::c32_math_mode() == TMM_CMATH_TC) pin_.flops = 140e12;  // complex<float> on the tcgen05 kernel (8mnk real flops)
                 tmm::Plan pl;
                 if (!rc) pl = tmm::make_plan(pin_);

@@ -12,9 +12,13 @@
 #include "tmm_internal.h"
 
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <chrono>
 #include <cstdlib>
@@ -118,6 +122,113 @@ int write_value(cudaStream_t st, uint32_t* addr, uint32_t value) {
     return r ? fail(TMM_ERR_CUDA, "GPU ERROR: cuStreamWriteValue32 failed (%d)", r) : TMM_OK;
 }
 
+
+// ---- control board (Link::board): per-call rounds through POSIX shared memory ----------------------------------------------------------
+// Every rank of a link - a thread of this process or another process on the box - maps the same small segment.  A round is "publish my
+// payload under the round's number, then read everybody's": an all-gather in a few microseconds of host time, with a deadline, no kernel
+// launch and no stream.  Slots are double-buffered by round parity: a rank can only be one round ahead of the slowest reader, because
+// finishing round r + 1 needs every peer's r + 1 publication, which a peer makes only after it has read round r.
+constexpr int BOARD_MAX_PARTS = 16;
+constexpr size_t BOARD_PAYLOAD = 128;
+struct alignas(64) BoardSlot {
+    std::atomic<uint64_t> seq;
+    unsigned char pad[56];
+    unsigned char payload[BOARD_PAYLOAD];
+};
+struct Board { BoardSlot slot[2][BOARD_MAX_PARTS]; };
+static_assert(std::atomic<uint64_t>::is_always_lock_free, "board sequence numbers must be lock-free to work across processes");
+
+#ifdef TMM_EMULATED
+extern "C" void emul_collective(const void* group, int phase);  // tests/emul: a round orders the host threads of its ranks (race detector)
+#define BOARD_HOOK(link, phase) emul_collective(reinterpret_cast<const void*>(static_cast<uintptr_t>((link).board_key)), phase)
+#else
+#define BOARD_HOOK(link, phase) ((void)0)
+#endif
+
+double dist_timeout_s() {
+    const char* v = getenv("TMM_DIST_TIMEOUT_S");
+    return (v && *v) ? atof(v) : 600.0;
+}
+
+uint64_t fnv1a(const void* data, size_t bytes) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < bytes; ++i) { h ^= static_cast<const unsigned char*>(data)[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+void board_name(const Link& link, char* out, size_t n) { snprintf(out, n, "/tmm_b200_%016llx_%u", (unsigned long long)link.board_key, (unsigned)getuid()); }
+
+bool board_open(Link& link, const nccl::UniqueId& id) {
+    const char* off = getenv("TMM_DIST_BOARD");
+    if (off && off[0] == '0') return false;
+    if (link.parts > BOARD_MAX_PARTS) return false;
+    link.board_key = fnv1a(&id, sizeof id) ^ ((uint64_t)link.parts << 56);
+    char name[64];
+    board_name(link, name, sizeof name);
+    const int fd = shm_open(name, O_CREAT | O_RDWR, 0600);
+    if (fd < 0) return false;
+    bool ok = ftruncate(fd, (off_t)sizeof(Board)) == 0;  // a fresh segment reads as zeros: sequence 0 = nothing published
+    void* p = ok ? mmap(nullptr, sizeof(Board), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0) : MAP_FAILED;
+    close(fd);
+    if (p == MAP_FAILED) return false;
+    link.board = p; link.board_bytes = sizeof(Board); link.board_round = 0;
+    return true;
+}
+
+void board_unlink(const Link& link) {
+    if (!link.board_key) return;
+    char name[64];
+    board_name(link, name, sizeof name);
+    shm_unlink(name);
+}
+void board_close(Link& link) {
+    if (link.board) munmap(link.board, link.board_bytes);
+    link.board = nullptr; link.board_bytes = 0;
+}
+
+// one round: all-gather `bytes` (<= 128) per rank; `all` receives parts x bytes
+int board_round(tmm_context* ctx, Link& link, const void* mine, size_t bytes, void* all) {
+    if (link.broken) return fail(TMM_ERR_CUDA, "GPU ERROR: this GPU grid is out of step after a peer missed an earlier call; destroy the contexts");
+    if (bytes > BOARD_PAYLOAD) return fail(TMM_ERR_INVALID, "internal: board payload too large");
+    Board* b = static_cast<Board*>(link.board);
+    const uint64_t round = ++link.board_round;
+    BoardSlot& me = b->slot[round & 1][link.me];
+    memcpy(me.payload, mine, bytes);
+    BOARD_HOOK(link, 0);
+    me.seq.store(round, std::memory_order_release);
+    const double limit_s = dist_timeout_s();
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int g = 0; g < link.parts; ++g) {
+        BoardSlot& peer = b->slot[round & 1][g];
+        for (uint64_t spins = 0; peer.seq.load(std::memory_order_acquire) < round; ++spins) {
+            if (spins < 4096) continue;
+            std::this_thread::yield();
+            if ((spins & 1023) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit_s) {
+                link.broken = true;
+                return fail(TMM_ERR_CUDA, "GPU ERROR: rank %d of this GPU grid link did not reach the call within %.0f s (device %d gives the call up; the grid is unusable)",
+                            g, limit_s, ctx->device);
+            }
+        }
+        memcpy(static_cast<char*>(all) + (size_t)g * bytes, peer.payload, bytes);
+    }
+    BOARD_HOOK(link, 1);
+    return TMM_OK;
+}
+
+// a stream of the control plane must go idle, but a peer may have died: poll with the grid's deadline instead of blocking forever
+int sync_with_deadline(tmm_context* ctx, cudaStream_t st) {
+    const double limit_s = dist_timeout_s();
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint64_t spins = 0;; ++spins) {
+        cudaError_t e = cudaStreamQuery(st);
+        if (e == cudaSuccess) return TMM_OK;
+        if (e != cudaErrorNotReady) return cuda_fail(e, "cudaStreamQuery");
+        if (spins > 4096) std::this_thread::yield();
+        if ((spins & 1023) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit_s)
+            return fail(TMM_ERR_CUDA, "GPU ERROR: a control collective of the GPU grid did not finish within %.0f s on device %d (a peer rank failed?)", limit_s, ctx->device);
+    }
+}
+
 // what one rank tells the others about a buffer it owns
 struct BufMsg {
     int64_t pid;
@@ -129,6 +240,7 @@ static_assert(sizeof(BufMsg) == 96, "BufMsg layout");
 
 // all-gather one BufMsg per rank over the link (tiny NCCL collective + host sync)
 int gather_msgs(tmm_context* ctx, Link& link, const BufMsg& mine, std::vector<BufMsg>& all) {
+    if (link.board) { all.resize(link.parts); return board_round(ctx, link, &mine, sizeof mine, all.data()); }
     const nccl::Api& nc = nccl::api();
     cudaError_t e;
     if ((e = ctx->dist_scratch.reserve(4096)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(dist scratch)");
@@ -138,8 +250,7 @@ int gather_msgs(tmm_context* ctx, Link& link, const BufMsg& mine, std::vector<Bu
     NC(nc.AllGather(d, d + sizeof(BufMsg), sizeof(BufMsg), nccl::Int8, link.comm, ctx->s_comm));
     all.resize(link.parts);
     TMM_CU(cudaMemcpyAsync(all.data(), d + sizeof(BufMsg), sizeof(BufMsg) * link.parts, cudaMemcpyDeviceToHost, ctx->s_comm));
-    TMM_CU(cudaStreamSynchronize(ctx->s_comm));
-    return TMM_OK;
+    return sync_with_deadline(ctx, ctx->s_comm);
 }
 
 BufMsg describe(tmm_context* ctx, void* p, size_t bytes) {
@@ -176,13 +287,21 @@ std::string key_of(const BufMsg& m) { return std::string(reinterpret_cast<const 
 
 // do all ranks of the link agree that a step worked?  (min-reduce of a flag; keeps the ranks on the same path)
 int all_ok(tmm_context* ctx, Link& link, bool mine, bool* everyone) {
+    if (link.board) {
+        int32_t flag = mine ? 1 : 0, got[BOARD_MAX_PARTS];
+        int rc = board_round(ctx, link, &flag, sizeof flag, got);
+        if (rc) return rc;
+        *everyone = true;
+        for (int g = 0; g < link.parts; ++g) *everyone = *everyone && got[g] == 1;
+        return TMM_OK;
+    }
     const nccl::Api& nc = nccl::api();
     int32_t v = mine ? 1 : 0;
     int32_t* d = static_cast<int32_t*>(ctx->dist_scratch.p);
     TMM_CU(cudaMemcpyAsync(d, &v, sizeof v, cudaMemcpyHostToDevice, ctx->s_comm));
     NC(nc.AllReduce(d, d, 1, nccl::Int32, nccl::Min, link.comm, ctx->s_comm));
     TMM_CU(cudaMemcpyAsync(&v, d, sizeof v, cudaMemcpyDeviceToHost, ctx->s_comm));
-    TMM_CU(cudaStreamSynchronize(ctx->s_comm));
+    { int rc = sync_with_deadline(ctx, ctx->s_comm); if (rc) return rc; }
     *everyone = v == 1;
     return TMM_OK;
 }
@@ -194,10 +313,23 @@ void link_unmap(Link& link) {
 }
 
 // at attach: my flag block, the peers' flag blocks, and the decision DMA push vs NCCL staging
-int link_setup(tmm_context* ctx, Link& link) {
+int link_setup(tmm_context* ctx, Link& link, const nccl::UniqueId& id) {
     if (!link.active()) return TMM_OK;
     cudaError_t e;
     if ((e = ctx->dist_scratch.reserve(4096)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(dist scratch)");
+    {
+        // control board: used only if EVERY rank of the link could map it (that question itself is still settled over NCCL)
+        const bool opened = board_open(link, id);
+        void* mapped = link.board;
+        link.board = nullptr;
+        bool everyone = false;
+        int rc = all_ok(ctx, link, opened, &everyone);
+        link.board = mapped;
+        if (link.me == 0) board_unlink(link);  // every rank that could open the segment has it mapped by now: the name can go
+        if (rc || !everyone) board_close(link);
+        if (rc) return rc;
+        TMM_DBG("dev %d link of %d ranks (me %d): control plane %s", ctx->device, link.parts, link.me, link.board ? "shared-memory board" : "NCCL collectives");
+    }
     const char* force = getenv("TMM_DIST_NCCL");
     bool ok = memops().ok && !(force && force[0] == '1');
     void* fl = nullptr;
@@ -231,9 +363,54 @@ void link_teardown(Link& link) {
         if (g < link.peer_flags_ipc.size() && link.peer_flags_ipc[g] && link.peer_flags[g]) cudaIpcCloseMemHandle(link.peer_flags[g]);
     if (link.flags) cudaFree(link.flags);
     if (link.comm && nc.ok) nc.CommDestroy(link.comm);
+    board_close(link);
     link = Link{};
 }
 }  // namespace
+
+
+// ---- host-link probe ------------------------------------------------------------------------------------------------------------------
+// What a GPU's PCIe link delivers depends on how many of the box's GPUs move data at the same time: on the 8-GPU node of this pool one
+// B200 alone copies 55 GB/s each way, eight at once get 8 - 12 GB/s each way (profiles/r2_probe_8gpu.txt: shared uplinks / host memory).
+// The scheduler's chunk and block sizes are a function of these rates, so a grid measures them once, with all its ranks copying at the
+// same time, instead of assuming the single-GPU figure.
+struct LinkRates { double h2d = 0, d2h = 0; };
+
+// Both directions at once on the current device: `bytes` up and `bytes` down, twice (first pass warms up).  `go` is called right before
+// the timed pass so that the callers' ranks start together.
+template <typename Barrier>
+LinkRates probe_host_link(size_t bytes, Barrier&& go) {
+    LinkRates r;
+    char *h_up = nullptr, *h_down = nullptr, *d_up = nullptr, *d_down = nullptr;
+    cudaStream_t s_up = nullptr, s_down = nullptr;
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ok = cudaHostAlloc((void**)&h_up, bytes, cudaHostAllocDefault) == cudaSuccess && cudaHostAlloc((void**)&h_down, bytes, cudaHostAllocDefault) == cudaSuccess &&
+              cudaMalloc((void**)&d_up, bytes) == cudaSuccess && cudaMalloc((void**)&d_down, bytes) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& ev : e) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+    if (ok) memset(h_up, 0, bytes);
+    for (int pass = 0; pass < 2 && ok; ++pass) {
+        if (pass == 1) go();
+        ok = cudaEventRecord(e[0], s_up) == cudaSuccess && cudaEventRecord(e[2], s_down) == cudaSuccess &&
+             cudaMemcpyAsync(d_up, h_up, bytes, cudaMemcpyHostToDevice, s_up) == cudaSuccess &&
+             cudaMemcpyAsync(h_down, d_down, bytes, cudaMemcpyDeviceToHost, s_down) == cudaSuccess && cudaEventRecord(e[1], s_up) == cudaSuccess &&
+             cudaEventRecord(e[3], s_down) == cudaSuccess && cudaStreamSynchronize(s_up) == cudaSuccess && cudaStreamSynchronize(s_down) == cudaSuccess;
+    }
+    float up_ms = 0, down_ms = 0;
+    if (ok && cudaEventElapsedTime(&up_ms, e[0], e[1]) == cudaSuccess && cudaEventElapsedTime(&down_ms, e[2], e[3]) == cudaSuccess && up_ms > 0 && down_ms > 0) {
+        r.h2d = (double)bytes / up_ms * 1e-6;
+        r.d2h = (double)bytes / down_ms * 1e-6;
+    }
+    cudaGetLastError();
+    for (auto& ev : e) if (ev) cudaEventDestroy(ev);
+    if (s_up) cudaStreamDestroy(s_up);
+    if (s_down) cudaStreamDestroy(s_down);
+    if (d_up) cudaFree(d_up);
+    if (d_down) cudaFree(d_down);
+    if (h_up) cudaFreeHost(h_up);
+    if (h_down) cudaFreeHost(h_down);
+    return r;
+}
 
 // Collective over the link, once per call and on EVERY rank of it, whatever happened locally: `local_ok == false` (an allocation failed
 // here, or another link already reported a failure) is spread to the peers, so that all ranks give the call up together instead of
@@ -302,27 +479,64 @@ int link_ack(tmm_context* ctx, Link& link, cudaStream_t stream) {
     return TMM_OK;
 }
 
-int dist_agree(tmm_context* ctx, int64_t m, int64_t n, int64_t k, int flags, size_t budget, int64_t* m_plan, int64_t* n_plan, size_t* budget_min) {
+static void reduce_max8(int64_t* v, const int64_t* all, int parts) {
+    for (int g = 0; g < parts; ++g)
+        for (int i = 0; i < 8; ++i) v[i] = std::max(v[i], all[g * 8 + i]);
+}
+
+// element-wise maximum of 8 words over the whole grid (columns, then rows: after both every rank holds the grid-wide maxima); a rendezvous
+static int grid_reduce_max8(tmm_context* ctx, int64_t* v) {
     const nccl::Api& nc = nccl::api();
-    if (!nc.ok) return fail(TMM_ERR_CUDA, "GPU ERROR: NCCL unavailable: %s", nc.why);
-    cudaError_t e;
-    if ((e = ctx->dist_scratch.reserve(4096)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(dist scratch)");
-    // max-reduce {m, n, k, -k, flags, -flags, -budget}: maxima give the planning block and the smallest budget, and the
-    // +/- pairs show (on every rank alike, so all ranks fail together instead of hanging) whether k and the flags agree.
-    // Being a blocking collective it is also the barrier that keeps a fast rank from pushing panels of the next call into
-    // a peer that is still computing the previous one.
-    int64_t v[8] = {m, n, k, -k, (int64_t)flags, -(int64_t)flags, -(int64_t)std::min<size_t>(budget, (size_t)INT64_MAX), 0};
-    int64_t* d = static_cast<int64_t*>(ctx->dist_scratch.p);
-    TMM_DBG("dev %d agree: m %lld n %lld k %lld", ctx->device, (long long)m, (long long)n, (long long)k);
-    TMM_CU(cudaMemcpyAsync(d, v, sizeof v, cudaMemcpyHostToDevice, ctx->s_comm));
-    if (ctx->grid.pr > 1) NC(nc.AllReduce(d, d, 8, nccl::Int64, nccl::Max, ctx->grid.coll.comm, ctx->s_comm));
-    if (ctx->grid.pc > 1) NC(nc.AllReduce(d, d, 8, nccl::Int64, nccl::Max, ctx->grid.rowl.comm, ctx->s_comm));
-    TMM_CU(cudaMemcpyAsync(v, d, sizeof v, cudaMemcpyDeviceToHost, ctx->s_comm));
-    TMM_CU(cudaStreamSynchronize(ctx->s_comm));
+    Grid& gr = ctx->grid;
+    for (Link* link : {&gr.coll, &gr.rowl}) {
+        if (!link->active()) continue;
+        if (link->board) {  // (a link's ranks agree on having the board: link_setup)
+            int64_t all[BOARD_MAX_PARTS * 8];
+            int rc = board_round(ctx, *link, v, 8 * sizeof(int64_t), all);
+            if (rc) return rc;
+            reduce_max8(v, all, link->parts);
+            continue;
+        }
+        if (!nc.ok) return fail(TMM_ERR_CUDA, "GPU ERROR: NCCL unavailable: %s", nc.why);
+        cudaError_t e;
+        if ((e = ctx->dist_scratch.reserve(4096)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(dist scratch)");
+        int64_t* d = static_cast<int64_t*>(ctx->dist_scratch.p);
+        TMM_CU(cudaMemcpyAsync(d, v, 8 * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->s_comm));
+        NC(nc.AllReduce(d, d, 8, nccl::Int64, nccl::Max, link->comm, ctx->s_comm));
+        TMM_CU(cudaMemcpyAsync(v, d, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->s_comm));
+        int rc = sync_with_deadline(ctx, ctx->s_comm);
+        if (rc) return rc;
+    }
+    return TMM_OK;
+}
+
+int dist_agree(tmm_context* ctx, int64_t m, int64_t n, int64_t k, int flags, size_t budget, int64_t* m_plan, int64_t* n_plan, size_t* budget_min, int local_rc) {
+    ctx->grid_round_entered = true;
+    // max-reduce {m, n, k, -k, flags, -flags, -budget, failed}: maxima give the planning block and the smallest budget, the +/- pairs show
+    // (on every rank alike, so all ranks fail together instead of hanging) whether k and the flags agree, and the last word spreads a
+    // rank-local failure.  Being a rendezvous it is also the barrier that keeps a fast rank from pushing panels of the next call into a
+    // peer that is still computing the previous one (tmm_gemm is synchronous: a rank that arrives here has finished its previous call).
+    int64_t v[8] = {m, n, k, -k, (int64_t)flags, -(int64_t)flags, -(int64_t)std::min<size_t>(budget, (size_t)INT64_MAX), local_rc ? 1 : 0};
+    TMM_DBG("dev %d agree: m %lld n %lld k %lld status %d", ctx->device, (long long)m, (long long)n, (long long)k, local_rc);
+    {
+        int rc = grid_reduce_max8(ctx, v);
+        if (rc) return rc;
+    }
+    if (local_rc) return local_rc;
+    if (v[7] != 0) return fail(TMM_ERR_CUDA, "GPU grid: another rank could not start this call (bad argument, failed registration or allocation there); the call is given up on every rank");
     if (v[2] != -v[3]) return fail(TMM_ERR_INVALID, "GPU grid: ranks disagree on k (%lld vs %lld)", (long long)v[2], (long long)-v[3]);
-    if (v[4] != -v[5]) return fail(TMM_ERR_INVALID, "GPU grid: ranks disagree on trans / beta==0 / copy_c_back");
+    if (v[4] != -v[5]) return fail(TMM_ERR_INVALID, "GPU grid: ranks disagree on trans / beta==0 / copy_c_back / alpha==0");
     *m_plan = v[0]; *n_plan = v[1]; *budget_min = (size_t)(-v[6]);
     TMM_DBG("dev %d agreed: m_plan %lld n_plan %lld budget %zu", ctx->device, (long long)*m_plan, (long long)*n_plan, *budget_min);
+    return TMM_OK;
+}
+
+int dist_abort(tmm_context* ctx) {
+    int64_t mp, np;
+    size_t b;
+    const std::string keep = last_error_cstr();  // the caller reports ITS error, not the round's
+    dist_agree(ctx, 0, 0, 0, 0, 0, &mp, &np, &b, TMM_ERR_INVALID);
+    fail(TMM_ERR_INVALID, "%s", keep.c_str());
     return TMM_OK;
 }
 
@@ -449,12 +663,30 @@ static int attach(tmm_context* ctx, int pr, int pc, int row, int col, const nccl
     TMM_DBG("dev %d attach %dx%d at (%d,%d)", ctx->device, pr, pc, row, col);
     if (pc > 1) NC(nc.CommInitRank(&g.rowl.comm, pc, *row_id, col));
     if (pr > 1) NC(nc.CommInitRank(&g.coll.comm, pr, *col_id, row));
-    int rc = link_setup(ctx, g.rowl);
-    if (!rc) rc = link_setup(ctx, g.coll);
+    int rc = link_setup(ctx, g.rowl, *row_id);
+    if (!rc) rc = link_setup(ctx, g.coll, *col_id);
     // panel buffers that a peer may have mapped are retired, not freed, when they are outgrown (freed after the next link_bind)
     ctx->buf_a.retire = (g.rowl.active() && g.rowl.direct) ? &ctx->retired : nullptr;
     ctx->buf_b.retire = (g.coll.active() && g.coll.direct) ? &ctx->retired : nullptr;
     ctx->budget_cached = 0;
+    ctx->link_h2d_gbs = ctx->link_d2h_gbs = 0;
+#ifndef TMM_EMULATED
+    {
+        // host-link rates with every rank of the grid copying at once; all ranks then plan with the slowest link's figures (TMM_DIST_PROBE=0: skip)
+        const char* pv = getenv("TMM_DIST_PROBE");
+        if (!rc && !(pv && pv[0] == '0')) {
+            int64_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int rc_go = TMM_OK;
+            const LinkRates lr = probe_host_link((size_t)64 << 20, [&] { rc_go = grid_reduce_max8(ctx, v); });
+            const bool valid = rc_go == TMM_OK && lr.h2d > 0 && lr.d2h > 0;
+            int64_t w[8] = {valid ? -(int64_t)(lr.h2d * 1e3) : 0, valid ? -(int64_t)(lr.d2h * 1e3) : 0, valid ? 0 : 1, 0, 0, 0, 0, 0};
+            rc = rc_go ? rc_go : grid_reduce_max8(ctx, w);
+            if (!rc && w[2] == 0) { ctx->link_h2d_gbs = (double)(-w[0]) * 1e-3; ctx->link_d2h_gbs = (double)(-w[1]) * 1e-3; }
+            TMM_DBG("dev %d host link with the whole grid active: %.1f GB/s up, %.1f GB/s down here; grid minimum %.1f / %.1f", ctx->device, lr.h2d, lr.d2h,
+                    ctx->link_h2d_gbs, ctx->link_d2h_gbs);
+        }
+    }
+#endif
     TMM_DBG("dev %d attached rc %d", ctx->device, rc);
     return rc;
 }

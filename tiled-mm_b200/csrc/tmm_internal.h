@@ -89,6 +89,14 @@ struct Link {
     uint32_t ring_sent = 0, acked = 0;     // streaming ring: exchanges into ring slots / exchanges consumed here
     uint32_t slot_last[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ring exchange number that last filled each ring slot
     cudaEvent_t slot_pushed[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // per call: my push out of each ring slot has finished
+    // Control board: a few KB of POSIX shared memory that all ranks of the link (threads or processes of one box) have mapped.  The per-call
+    // agreement and handle exchange are rounds of "publish my 128 bytes, read everybody's" on it - microseconds of host time, no kernel
+    // launch, no stream - instead of blocking NCCL collectives.  nullptr: the board could not be set up and the rounds go through NCCL.
+    void* board = nullptr;
+    size_t board_bytes = 0;
+    uint64_t board_round = 0;              // rounds played on the board (the same number on all ranks of the link)
+    uint64_t board_key = 0;                // hash of the link's unique id (name of the segment)
+    bool broken = false;                   // a peer missed a round's deadline: the link is out of step for good
     bool active() const { return parts > 1; }
 };
 
@@ -138,6 +146,8 @@ struct tmm_context {
     int stage_next = 0;
     cudaEvent_t stage_send_free[tmm::STAGE_SLOTS] = {nullptr, nullptr, nullptr};
     std::vector<void*> retired;             // outgrown panel buffers that peers may still have mapped (DevBuf::retire)
+    bool grid_round_entered = false;        // this call has taken part in the grid's agreement round (tmm_gemm tells the peers when it fails before)
+    double link_h2d_gbs = 0, link_d2h_gbs = 0;  // host-link rates of THIS GPU while every GPU of the grid moves data (measured at attach; 0 = unknown)
     std::vector<tmm_context*> children;     // single-process multi-GPU: one child context per device, driven by host threads
     tmm_context* solo = nullptr;            // plain context on the first device for shapes too small to split
 
@@ -192,7 +202,11 @@ struct InternalContextScope { InternalContextScope(); ~InternalContextScope(); }
 
 // ---- multi-GPU layer (tmm_dist.cu) ----
 // Agree on the planning inputs across the grid (max block dims, min budget) and check that k / flags match everywhere.
-int dist_agree(tmm_context* ctx, int64_t m, int64_t n, int64_t k, int flags, size_t budget, int64_t* m_plan, int64_t* n_plan, size_t* budget_min);
+// `local_rc` != 0 (this rank cannot run the call: bad argument, failed registration / allocation) is spread to all ranks, which then give
+// the call up together; the call returns non-zero on every rank in that case.
+int dist_agree(tmm_context* ctx, int64_t m, int64_t n, int64_t k, int flags, size_t budget, int64_t* m_plan, int64_t* n_plan, size_t* budget_min, int local_rc = 0);
+// A rank that failed before it reached dist_agree takes part in that round all the same, so that its peers are not left waiting.
+int dist_abort(tmm_context* ctx);
 // Device bytes the staging rings need for shares of at most `share_bytes` gathered from up to `parts` ranks.
 size_t dist_stage_bytes(size_t share_bytes, int parts);
 int dist_reserve_stage(tmm_context* ctx, size_t share_bytes, int parts);

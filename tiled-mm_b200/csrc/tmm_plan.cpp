@@ -16,8 +16,8 @@ size_t elem_size(int dt) { return dt == 0 ? 4 : (dt == 1 ? 8 : (dt == 2 ? 8 : 16
 constexpr double kFlopsF64 = 35e12;   // DGEMM / ZGEMM (8mnk counted for complex): DMMA pipe
 constexpr double kFlopsF32 = 140e12;  // SGEMM, FP32-accurate 3xTF32 on tcgen05 (profiles/r1_tc_sgemm_v2.txt); with the FP64 figure the planner
                                       // chose a first block 2 - 5x too narrow for float and left the SMs idle while A streamed in
-constexpr double kH2D = 52e9;
-constexpr double kD2H = 52e9;
+constexpr double kH2D_alone = 52e9;   // one GPU alone on its link; a GPU grid passes what it measured with all its links busy (PlanInput::h2d_bw)
+constexpr double kD2H_alone = 52e9;
 constexpr int64_t BM = 128, BN = 64;  // CTA tile of the FP64 kernels
 
 // developer knobs for schedule experiments (never needed for correctness)
@@ -73,6 +73,7 @@ Plan make_plan(const PlanInput& in) {
     const size_t full_c = in.copy_c_back ? (size_t)p.pitch_c * n * es : 0;
     const double F = (in.dtype >= 2) ? 8.0 : 2.0;
     const double kFlops = in.flops > 0 ? in.flops : (in.dtype == 0 ? env_or("TMM_PLAN_F32_FLOPS", kFlopsF32) : env_or("TMM_PLAN_F64_FLOPS", kFlopsF64));  // complex<float>: SIMT unless the caller says otherwise
+    const double kH2D = in.h2d_bw > 0 ? in.h2d_bw : kH2D_alone, kD2H = in.d2h_bw > 0 ? in.d2h_bw : kD2H_alone;
     const int64_t kc_cap = std::max<int64_t>(256, std::min<int64_t>(2048, round_up(std::max(64, in.tile_k), 64)));
 
     if (full_a + full_b + full_c <= in.budget) {

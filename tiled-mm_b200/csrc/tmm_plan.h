@@ -21,6 +21,7 @@ struct PlanInput {
     int n_streams = 2, tile_m = 5000, tile_n = 5000, tile_k = 5000;  // user hints
     int sm_count = 148;
     double flops = 0;  // GEMM rate the schedule is sized for (flop/s; 0 = the default of the element type) - timing model only
+    double h2d_bw = 0, d2h_bw = 0;  // host-link rates in bytes/s the schedule is sized for (0 = one GPU alone on its link: 52 GB/s) - timing model only
     int parts_a = 1, parts_b = 1;  // GPU grid: this rank uploads 1/parts_a of every A panel and 1/parts_b of every B panel (timing model only)
 };
 
