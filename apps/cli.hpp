@@ -110,6 +110,7 @@ inline bool parse_transpose(std::string s, char* ta, char* tb) {
 
 struct Problem {
     long long m, n, k, tile_m, tile_n, tile_k, n_streams, ld_a, ld_b, ld_c, gpus;
+    long long warm_size = 0;
     long long a_rows, a_cols, b_rows, b_cols;
     char trans_a, trans_b, type;
     double alpha, beta;

@@ -41,6 +41,121 @@ void parallel_fill(T* ptr, size_t count, bool random, unsigned seed) {
     for (auto& th : pool) th.join();
 }
 
+// --scaling "8,1": the copy-back call at several GPU counts on ONE set of pinned host buffers (allocating and filling hundreds of GB
+// dominates an out-of-core run), each checked by the linearity property C x = A (B x) on sampled rows, with the speed-up over the last
+// count (strong scaling: the problem is fixed).  This is how BASELINE configs[3] / [4] are measured (tools/r2_c5.sh).
+template <typename T>
+double linearity_defect(const cli::Problem& p, const T* a, const T* b, const T* c, int rows_sampled) {
+    // x = ones: (B x)[l] = sum_j op(B)[l, j];  then for sampled rows i: |sum_j C[i, j] - sum_l op(A)[i, l] (B x)[l]| / (k * n)
+    const bool ta = p.trans_a != 'N' && p.trans_a != 'n', tb = p.trans_b != 'N' && p.trans_b != 'n';
+    const bool ca = p.trans_a == 'C' || p.trans_a == 'c', cb = p.trans_b == 'C' || p.trans_b == 'c';
+    // B x with x = ones: sums over the columns of op(B).  Walk the STORED matrix column by column (contiguous), whatever the op:
+    //   op(B) = N: stored k x n, (B x)[l] = row sums  -> threads split the stored columns and keep a private accumulator vector
+    //   op(B) = T/C: stored n x k, (B x)[l] = sum of stored column l -> threads split the stored columns, one scalar each
+    std::vector<std::complex<double>> bx((size_t)p.k);
+    const unsigned n_threads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    std::vector<std::thread> pool;
+    if (!tb) {
+        std::vector<std::vector<std::complex<double>>> part(n_threads);
+        for (unsigned t = 0; t < n_threads; ++t)
+            pool.emplace_back([&, t] {
+                part[t].assign((size_t)p.k, 0.0);
+                for (long long j = p.n * t / n_threads; j < p.n * (t + 1) / n_threads; ++j) {
+                    const T* col = b + (size_t)j * p.ld_b;
+                    for (long long l = 0; l < p.k; ++l) part[t][(size_t)l] += std::complex<double>(col[l]);
+                }
+            });
+        for (auto& th : pool) th.join();
+        for (long long l = 0; l < p.k; ++l) {
+            std::complex<double> sum = 0;
+            for (unsigned t = 0; t < n_threads; ++t) sum += part[t][(size_t)l];
+            bx[(size_t)l] = sum;
+        }
+    } else {
+        for (unsigned t = 0; t < n_threads; ++t)
+            pool.emplace_back([&, t] {
+                for (long long l = p.k * t / n_threads; l < p.k * (t + 1) / n_threads; ++l) {
+                    const T* col = b + (size_t)l * p.ld_b;
+                    std::complex<double> sum = 0;
+                    for (long long j = 0; j < p.n; ++j) sum += std::complex<double>(col[j]);
+                    bx[(size_t)l] = cb ? std::conj(sum) : sum;
+                }
+            });
+        for (auto& th : pool) th.join();
+    }
+    double worst = 0;
+    for (int r = 0; r < rows_sampled; ++r) {
+        const long long i = (long long)((double)r / rows_sampled * (double)p.m) + (r * 7) % std::max<long long>(1, p.m / rows_sampled);
+        if (i >= p.m) continue;
+        std::complex<double> lhs = 0, rhs = 0;
+        for (long long j = 0; j < p.n; ++j) lhs += std::complex<double>(c[(size_t)j * p.ld_c + i]);
+        for (long long l = 0; l < p.k; ++l) {
+            std::complex<double> v = ta ? std::complex<double>(a[(size_t)i * p.ld_a + l]) : std::complex<double>(a[(size_t)l * p.ld_a + i]);
+            rhs += (ca ? std::conj(v) : v) * bx[(size_t)l];
+        }
+        worst = std::max(worst, std::abs(lhs - std::complex<double>(p.alpha) * rhs) / ((double)p.k * (double)p.n));
+    }
+    return worst;
+}
+
+template <typename T>
+int run_scaling(const cli::Problem& p, bool random, const std::string& counts) {
+    const double flops_per_mul = flops_per_fma<T>::value * (double)p.m * (double)p.n * (double)p.k;
+    const size_t na = (size_t)p.ld_a * p.a_cols, nb = (size_t)p.ld_b * p.b_cols, nc = (size_t)p.ld_c * p.n;
+    void *pa = nullptr, *pb = nullptr, *pc = nullptr;
+    auto t_alloc = std::chrono::steady_clock::now();
+    {   // page-locking runs at a few GB/s per call: the three allocations go in parallel
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int rcs[3] = {0, 0, 0};
+        std::thread ta([&] { cudaSetDevice(dev); rcs[0] = tmm_malloc_pinned(na * sizeof(T), &pa); });
+        std::thread tb([&] { cudaSetDevice(dev); rcs[1] = tmm_malloc_pinned(nb * sizeof(T), &pb); });
+        std::thread tc([&] { cudaSetDevice(dev); rcs[2] = tmm_malloc_pinned(nc * sizeof(T), &pc); });
+        ta.join(); tb.join(); tc.join();
+        for (int rc : rcs) gpu::check_tmm_status(rc);
+    }
+    T *a_host = static_cast<T*>(pa), *b_host = static_cast<T*>(pb), *c_host = static_cast<T*>(pc);
+    const double alloc_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_alloc).count();
+    auto t_fill = std::chrono::steady_clock::now();
+    parallel_fill(a_host, na, random, 1);
+    parallel_fill(b_host, nb, random, 2);
+    const double fill_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_fill).count();
+    std::printf("host buffers: %.1f GB pinned in %.1f s, filled in %.1f s\n", (double)(na + nb + nc) * sizeof(T) / 1e9, alloc_s, fill_s);
+    auto ctx = gpu::make_context<T>((int)p.n_streams, (int)p.tile_m, (int)p.tile_n, (int)p.tile_k);
+    const T alpha = make_scalar<T>(p.alpha), beta = make_scalar<T>(0.0);
+    std::vector<std::pair<int, double>> results;
+    size_t pos = 0;
+    while (pos < counts.size()) {
+        const size_t comma = counts.find(',', pos);
+        const int g = std::atoi(counts.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos).c_str());
+        pos = comma == std::string::npos ? counts.size() : comma + 1;
+        if (g < 1) continue;
+        parallel_fill(c_host, nc, false, 0);  // (ones: beta = 0 must overwrite them)
+        gpu::check_tmm_status(tmm_context_set_devices(ctx->native(), g, nullptr));
+        if (p.warm_size > 0) {  // first-use costs (stream / event creation, NCCL and peer mappings, the first cudaMalloc) on a small product
+            const long long w = std::min<long long>(p.warm_size, std::min(p.m, std::min(p.n, p.k)));
+            gpu::gemm64<T>(*ctx, p.trans_a, p.trans_b, w, w, w, alpha, a_host, p.ld_a, b_host, p.ld_b, beta, c_host, p.ld_c, false, true);
+            parallel_fill(c_host, (size_t)p.ld_c * w, false, 0);
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        gpu::gemm64<T>(*ctx, p.trans_a, p.trans_b, p.m, p.n, p.k, alpha, a_host, p.ld_a, b_host, p.ld_b, beta, c_host, p.ld_c, false, true);
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        tmm_call_stats st{};
+        tmm_context_last_stats(ctx->native(), &st);
+        const double defect = linearity_defect(p, a_host, b_host, c_host, 16);
+        std::printf("SCALING gpus %d: %.1f ms = %.2f TFLOP/s | H2D %.1f GB, D2H %.1f GB, NVLink %.1f GB, %llu launches, %s | linearity defect %.2e %s\n", g, ms,
+                    flops_per_mul / ms * 1e-9, st.h2d_bytes / 1e9, st.d2h_bytes / 1e9, st.peer_bytes / 1e9, (unsigned long long)st.kernel_launches,
+                    st.regime == 0 ? "resident" : "streaming", defect, defect <= 1e-14 * std::max(1.0, std::abs(p.alpha)) ? "OK" : "FAIL");
+        std::fflush(stdout);
+        results.push_back({g, ms});
+    }
+    if (results.size() > 1)
+        for (size_t i = 0; i + 1 < results.size(); ++i)
+            std::printf("SPEEDUP %d GPUs over %d: %.2fx\n", results[i].first, results.back().first, results.back().second / results[i].second);
+    tmm_free_pinned(a_host); tmm_free_pinned(b_host); tmm_free_pinned(c_host);
+    return 0;
+}
+
 template <typename T>
 int run(const cli::Problem& p, long long repetitions, bool random, const std::string& variants, long long warmup) {
     const double flops_per_mul = flops_per_fma<T>::value * (double)p.m * (double)p.n * (double)p.k;
@@ -92,6 +207,8 @@ int main(int argc, char** argv) {
     table.push_back({"", "variants", "both", "both | back | device: run the copy-C-back variant, the device-resident-C variant, or both (the reference runs both)."});
     table.push_back({"", "warmup", "1", "Untimed runs before the timed ones (the reference does one); 0 for runs that take minutes."});
     table.push_back({"", "random", "0", "1: fill A and B with uniform(-1,1) values instead of ones (realistic power draw)."});
+    table.push_back({"", "scaling", "", "Comma-separated GPU counts, e.g. 8,1: one timed copy-back call per count on the same host buffers, with a result check and the speed-up."});
+    table.push_back({"", "warm_size", "2048", "--scaling: size of the small warm-up product run before each timed call (0: none)."});
     cli::Args args(table);
     if (!args.read(argc, argv)) return 2;
     if (args.help_requested) { args.usage("multiply", "Benchmarking Tiled-MM: measures the runtime of the tiled out-of-core GEMM."); return 0; }
@@ -102,8 +219,18 @@ int main(int argc, char** argv) {
     const bool random = args.integer("random") != 0;
     const std::string variants = args.text("variants");
     const long long warmup = std::max<long long>(0, args.integer("warmup"));
+    const std::string scaling = args.text("scaling");
+    p.warm_size = args.integer("warm_size");
     cli::print_banner(p, repetitions);
     try {
+        if (!scaling.empty()) {
+            switch (p.type) {
+            case 's': return run_scaling<float>(p, random, scaling);
+            case 'c': return run_scaling<std::complex<float>>(p, random, scaling);
+            case 'z': return run_scaling<std::complex<double>>(p, random, scaling);
+            default: return run_scaling<double>(p, random, scaling);
+            }
+        }
         switch (p.type) {
         case 's': return run<float>(p, repetitions, random, variants, warmup);
         case 'c': return run<std::complex<float>>(p, repetitions, random, variants, warmup);

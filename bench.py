@@ -1,17 +1,16 @@
 #!/usr/bin/env python
-"""bench.py - headline benchmark of the hot path gpu::make_context -> gpu::gemm.
+"""bench.py - headline benchmark of the hot path gpu::make_context -> gpu::gemm (host pointers in, host pointers out).
 
-Workload (BASELINE.json configs[1], the README miniapp): dgemm m=n=k=10000, NN, alpha=1, beta=0, pinned host buffers,
-tile hints 5000^3, 2 streams.  A "step" is one gemm.
+A "step" is one host-to-host gemm call.  N = 1: BASELINE.json configs[1], the README miniapp - dgemm m=n=k=10000, NN, alpha=1, beta=0,
+pinned host buffers, tile hints 5000^3, 2 streams.  N > 1 (torchrun, one rank per GPU): the same square dgemm weak-scaled by work -
+n = 10000 * N^(1/3) (12600 / 15872 / 20000: 2e12 flop per GPU, the sizes of the reference's published sweep, README n = 4000 ... 32000) -
+with C cut into a p_r x p_c grid of blocks: every rank holds its A row-panel, its B column-panel and its C block in pinned host memory,
+uploads only a 1/p_c (1/p_r) share of each shared panel over its own PCIe link and receives the rest from its peers over NVLink.
 
-  value   device-resident DGEMM throughput (operands already in HBM, one kernel launch per step, CUDA events)
-  e2e     the same GEMM through the public call with HOST buffers (H2D of A,B and D2H of C inside the timed region) -
-          this is the library's actual product and the headline against the reference arm
-  roofline  FP64 tensor (DMMA) bound for the dominant kernel;  cpu_baseline  host BLAS dgemm on the box's cores
-
-N > 1 (torchrun, one rank per GPU): weak scaling - rank (i,j) of a p_r x p_c grid owns one 10000 x 10000 block of C of the
-global (p_r*10000) x (p_c*10000) x 10000 product; each rank uploads only its 1/p_c slice of the A row-panel and 1/p_r
-slice of the B column-panel over its own PCIe link and the slices are all-gathered over NVLink (NCCL) before the local GEMM.
+  value / e2e   whole-job TFLOP/s of the host-to-host call (H2D of A, B and D2H of C inside the timed region, every step) - what `metric` names
+  roofline      the dominant kernel (DMMA DGEMM) timed device-resident, against the FP64 tensor issue rate measured live on this GPU
+  host_roofline min(N x FP64 peak, AI x aggregate host-link bandwidth), the host links measured live with all N GPUs copying at once
+  cpu_baseline  host BLAS dgemm on the box's cores (N = 1)
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size S]
 """
@@ -32,8 +31,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-FP64_PEAK_TFLOPS = 36.9  # DMMA.8x8x4 issue microbenchmark on this pool's B200 (profiles/r1_probe_b200.txt); 148 SM x 64 FMA/clk x 1.965 GHz = 37.2
-PCIE_H2D_GBS, PCIE_D2H_GBS = 55.6, 57.0  # pinned cudaMemcpyAsync 1 GiB, same probe
+# Fallbacks, used only if the live probes fail (MEASURED_PEAKS.json carries HBM and bf16 figures, neither of which bounds this path):
+FP64_PEAK_FALLBACK = 36.9                         # DMMA.8x8x4 issue microbenchmark on this pool's B200 (profiles/r1_probe_b200.txt)
+PCIE_H2D_FALLBACK, PCIE_D2H_FALLBACK = 55.6, 57.0  # one GPU alone, pinned 1 GiB copies, same probe
 
 
 class ClockSampler:
@@ -167,52 +167,120 @@ class NumaLocal:
                 pass
 
 
-def workload_name(size: int, streams: int = 2) -> str:
-    """One name for the workload, used by both arms (the driver compares the arms on `config`)."""
-    return (f"README miniapp (BASELINE configs[1]): dgemm m=n=k={size} NN alpha=1 beta=0, pinned host buffers, tile 5000^3, {streams} streams, "
-            "pin_host_buffers=false, copy_c_back=true")
+def global_size(world: int, size: int) -> int:
+    """Square problem size at `world` GPUs: the N = 1 size scaled by world^(1/3) (constant flops per GPU), rounded to a multiple of 128."""
+    if world == 1:
+        return size
+    if size == 10000 and world in (2, 4, 8):
+        return {2: 12600, 4: 15872, 8: 20000}[world]
+    return int(round(size * world ** (1.0 / 3.0) / 128.0)) * 128
+
+
+def workload_config(size_global: int, world: int, streams: int = 2) -> dict:
+    """One description of the workload, identical in both arms (the driver compares the arms on `config`)."""
+    if world == 1:
+        w = (f"README miniapp (BASELINE configs[1]): dgemm m=n=k={size_global} NN alpha=1 beta=0, pinned host buffers, tile 5000^3, {streams} streams, "
+             "pin_host_buffers=false, copy_c_back=true")
+    else:
+        w = (f"square dgemm m=n=k={size_global} NN alpha=1 beta=0 (the README experiment's shape; 10000^3 weak-scaled to 2e12 flop per GPU), pinned host buffers, "
+             f"tile 5000^3, {streams} streams, pin_host_buffers=false, copy_c_back=true")
+    return {"workload": w, "l2": "inputs (>= 800 MB per operand) larger than the 126 MB L2; no flush needed"}
 
 
 def grid_shape(n: int):
     return {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}.get(n, (1, n))
 
 
+def share(extent: int, parts: int, g: int):
+    base, rem = divmod(extent, parts)
+    lo = g * base + min(g, rem)
+    return lo, lo + base + (1 if g < rem else 0)
+
+
+# reference settings timed next to the README one (BASELINE.md section 5: "and its best tile/stream setting"): (tile_m, tile_n, tile_k, streams)
+REFERENCE_SWEEP = [(5000, 5000, 5000, 2), (5000, 5000, 5000, 4), (10000, 5000, 2500, 2), (10000, 2500, 2500, 4), (5000, 5000, 2500, 4), (10000, 10000, 2500, 2)]
+
+
 def run_reference(args, rank: int, world: int) -> None:
     """Reference arm: the UNMODIFIED reference library + cuBLAS (oracle/_ref/libtiledmm_ref.so, built from /root/reference by
-    oracle/Makefile) on ONE B200, same buffers / config, through its own public API gpu::gemm."""
+    oracle/Makefile) on ONE B200, through its own public API gpu::gemm, on this arm's workload.  Nothing of the product is loaded:
+    buffers come from the reference's own gpu::malloc_pinned (ref_shim)."""
     if rank != 0:
         return
     import _util
-    size = args.size
+    size = global_size(world, args.size)
     base = {"impl": "reference", "metric": "host-to-host dgemm TFLOP/s", "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(size),
-                       "l2": "inputs (2 x 800 MB) larger than L2", "note": "reference is single-GPU: at N>1 rank 0 runs it on one GPU"}}
+            "config": workload_config(size, world, args.streams)}
     try:
-        import tiled_mm_b200 as tmm
         ref = _util.Reference(cpu=False)
+        ref.lib.ref_malloc_pinned.restype = ctypes.c_void_p
+        ref.lib.ref_malloc_pinned.argtypes = [ctypes.c_size_t]
+        ref.lib.ref_free_pinned.argtypes = [ctypes.c_void_p]
+
+        def pinned(count):
+            p = ref.lib.ref_malloc_pinned(count * 8)
+            assert p, "reference malloc_pinned failed"
+            return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_double)), shape=(count,)), p
+
         with NumaLocal(0):  # same placement policy as our arm
-            a = tmm.malloc_pinned(np.float64, size * size); b = tmm.malloc_pinned(np.float64, size * size); c = tmm.malloc_pinned(np.float64, size * size)
-            fill_uniform(a, 1); fill_uniform(b, 2)
-            np.asarray(c)[:] = 0.0
-        ctx = ref.context(np.float64, 2, 5000, 5000, 5000)
-        for _ in range(args.warmup):
-            ctx.gemm("N", "N", size, size, size, 1.0, a, size, b, size, 0.0, c, size, pin=False, copy_c_back=True)
-        with ClockSampler(0) as cs:
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
+            (a, pa), (b, pb), (c, pc) = pinned(size * size), pinned(size * size), pinned(size * size)
+            fill_uniform(a, 100); fill_uniform(b, 200)
+            c[:] = 0.0
+
+        def timed(tm, tn, tk, streams, warmup, steps, sampler=None):
+            ctx = ref.context(np.float64, streams, tm, tn, tk)
+            for _ in range(warmup):
                 ctx.gemm("N", "N", size, size, size, 1.0, a, size, b, size, 0.0, c, size, pin=False, copy_c_back=True)
-            dt = (time.perf_counter() - t0) / args.steps
-        ctx.close()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                ctx.gemm("N", "N", size, size, size, 1.0, a, size, b, size, 0.0, c, size, pin=False, copy_c_back=True)
+            dt = (time.perf_counter() - t0) / steps
+            ctx.close()
+            return dt
+
+        with ClockSampler(0) as cs:
+            dt = timed(5000, 5000, 5000, args.streams, args.warmup, args.steps)
         tf = 2.0 * size**3 / dt * 1e-12
+        # the reference's best setting among a few (short runs; the README setting above stays the figure of record)
+        best = {"tile": [5000, 5000, 5000], "streams": args.streams, "tflops": round(tf, 3)}
+        sweep = []
+        if not args.no_reference_sweep:
+            for tm, tn, tk, st in REFERENCE_SWEEP:
+                try:
+                    d = timed(tm, tn, tk, st, 1, 3)
+                except AssertionError:
+                    continue
+                t = 2.0 * size**3 / d * 1e-12
+                sweep.append({"tile": [tm, tn, tk], "streams": st, "tflops": round(t, 3)})
+                if t > best["tflops"]:
+                    best = sweep[-1]
         base.update({"value": round(tf, 3), "ms_per_step": round(dt * 1e3, 3), "clocks": cs.summary(),
+                     "reference_best_setting": best, "reference_settings_tried": sweep,
                      "cpu_baseline": {"value": round(tf, 3), "unit": "TFLOP/s", "cores": 1, "kind": "reference",
-                                      "sample": "unmodified reference Tiled-MM (g++ from /root/reference/src) + cuBLAS 12.9 on one B200; 1 host enqueue thread; "
-                                                "the reference has no CPU implementation of this path"},
-                     "e2e": {"value": round(tf, 3), "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+                                      "sample": "unmodified reference Tiled-MM (g++ from /root/reference/src) + cuBLAS 12.9 on one B200, README setting "
+                                                "(tile 5000^3, 2 streams); 1 host enqueue thread; the reference has no CPU implementation of this path"},
+                     "e2e": {"value": round(tf, 3), "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "note": "the reference is single-GPU software: at N > 1 rank 0 runs the same global problem on one GPU"})
+        for p in (pa, pb, pc):
+            ref.lib.ref_free_pinned(p)
     except Exception as e:  # the reference .so did not travel / cannot load
         base = {"impl": "reference", "unavailable": f"oracle/_ref/libtiledmm_ref.so not usable: {type(e).__name__}: {e}"[:300]}
     print(json.dumps(base), flush=True)
+
+
+def ncu_traffic_of_this_build():
+    """DRAM bytes per DGEMM launch from an `ncu --set full` capture, if one was taken for THIS library build (profiles/ncu_dgemm_traffic.json
+    records the sha256 of the .so it profiled); otherwise None - a number from another build is not printed."""
+    try:
+        import hashlib
+        rec = json.loads((ROOT / "profiles" / "ncu_dgemm_traffic.json").read_text())
+        so = (ROOT / "tiled-mm_b200" / "csrc" / "gemm_f64.cu").read_bytes()
+        if rec.get("gemm_f64_cu_sha256") == hashlib.sha256(so).hexdigest():
+            return float(rec["dram_bytes_per_launch"]), rec.get("source", "")
+    except Exception:
+        pass
+    return None, ""
 
 
 def main():
@@ -224,6 +292,7 @@ def main():
     ap.add_argument("--size", type=int, default=10000)
     ap.add_argument("--streams", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-sweep", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl != "reference" else 1)
 
@@ -243,14 +312,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        os.environ.setdefault("TMM_DIST_TIMEOUT_S", "60")  # a grid call here takes ~60 ms: if a peer dies, give up after a minute instead of the library's 10
+        os.environ.setdefault("TMM_DIST_TIMEOUT_S", "60")  # a grid call here takes well under a second: if a peer dies, give up after a minute instead of the library's 10
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    size = args.size
-    m = n = k = size
-    flops = 2.0 * m * n * k
 
     def barrier():
         if dist is not None:
@@ -264,60 +329,48 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ------------------------------------------------------------------ host buffers (pinned, like gpu::malloc_pinned)
+    def sum_over_ranks(xs):
+        if dist is None:
+            return list(xs)
+        t = torch.tensor(list(xs), dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    # ------------------------------------------------------------------ the workload and this rank's part of it
+    S = global_size(world, args.size)   # global m = n = k
     pr, pc = grid_shape(world)
     gi, gj = rank // pc, rank % pc
+    (i0, i1), (j0, j1) = share(S, pr, gi), share(S, pc, gj)
+    m, n, k = i1 - i0, j1 - j0, S       # this rank's C block and the full contraction
+    flops_total = 2.0 * S * S * S
+    flops_rank = 2.0 * m * n * k
+
+    # host buffers (pinned, like gpu::malloc_pinned): this rank's rows of A (m x k, ld = m), its columns of B (k x n), its block of C
     with NumaLocal(local_rank) as numa:  # pinned pages on the NUMA node of this rank's GPU
         a = tmm.malloc_pinned(np.float64, m * k); b = tmm.malloc_pinned(np.float64, k * n); c = tmm.malloc_pinned(np.float64, m * n)
-        fill_uniform(a, 100 + gi); fill_uniform(b, 200 + gj)
+        fill_uniform(a, 100 + gi); fill_uniform(b, 200 + gj)   # ranks of a grid row hold the same A panel, ranks of a grid column the same B panel
         np.asarray(c)[:] = 0.0
     ctx = tmm.make_context(np.float64, args.streams, 5000, 5000, 5000)
 
-    # ------------------------------------------------------------------ (1) device-resident kernel throughput -> value, roofline
-    st = torch.cuda.current_stream()
-    dA = torch.empty(m * k, dtype=torch.float64, device="cuda"); dB = torch.empty(k * n, dtype=torch.float64, device="cuda")
-    dC = torch.empty(m * n, dtype=torch.float64, device="cuda")
-    dA.copy_(torch.from_numpy(np.asarray(a))); dB.copy_(torch.from_numpy(np.asarray(b)))
-
-    def dev_step():
-        tmm.device_gemm(np.float64, "N", "N", m, n, k, 1.0, dA.data_ptr(), m, dB.data_ptr(), k, 0.0, dC.data_ptr(), m, stream=st.cuda_stream)
-
-    for _ in range(args.warmup):
-        dev_step()
+    # ------------------------------------------------------------------ box figures measured live: FP64 tensor issue rate, host links with all N GPUs busy
+    try:
+        fp64_peak, fp64_src = tmm.probe_fp64_peak(), "live DMMA.8x8x4 issue microbenchmark on this GPU (tmm_probe_fp64_peak); MEASURED_PEAKS.json has no FP64 figure"
+    except Exception:
+        fp64_peak, fp64_src = FP64_PEAK_FALLBACK, "fallback: profiles/r1_probe_b200.txt (the live probe failed)"
+    fp64_peak = max_over_ranks(fp64_peak)
     barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as cs_dev:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(st)
-        for s0, s1 in evs:
-            s0.record(st); dev_step(); s1.record(st)
-        e1.record(st)
-        barrier()
-    dev_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    launch_ms = sum(s0.elapsed_time(s1) for s0, s1 in evs) / args.steps
-    value_tf = world * flops / (dev_ms * 1e-3) * 1e-12
-    kernel_tf = flops / (launch_ms * 1e-3) * 1e-12
-
-    # cuBLAS FP64 on the same resident operands (comparator only; never on the product path)
-    A2, B2 = dA.view(k, m).t(), dB.view(n, k).t()
-    for _ in range(2):
-        torch.matmul(A2, B2)
+    try:
+        (up, down), = tmm.probe_host_links([local_rank], nbytes=128 << 20)   # every rank probes its own link; the barrier above starts them together
+    except Exception:
+        up, down = PCIE_H2D_FALLBACK, PCIE_D2H_FALLBACK
+    agg_up, agg_down = sum_over_ranks([up, down])
     barrier()
-    e0.record(st)
-    for _ in range(3):
-        torch.matmul(A2, B2)
-    e1.record(st); barrier()
-    cublas_tf = flops / (e0.elapsed_time(e1) / 3 * 1e-3) * 1e-12
-    del A2, B2, dA, dB, dC
-    torch.cuda.empty_cache()
 
-    # ------------------------------------------------------------------ (2) end to end through the public call -> e2e
+    # ------------------------------------------------------------------ (1) the product: host to host through the public call
     def e2e_step():
         tmm.gemm(ctx, "N", "N", m, n, k, 1.0, a, m, b, k, 0.0, c, m, pin_host_buffers=False, copy_c_back=True)
 
     if world > 1:
-        # rank (gi, gj) owns C block (gi, gj) of the global (pr*m) x (pc*n) x k product: `a` is its A row-panel, `b` its B column-panel.
-        # It uploads 1/pc of a and 1/pr of b over its own PCIe link; NCCL all-gathers the shares over NVLink (csrc/tmm_dist.cu).
         from tiled_mm_b200 import multi_gpu
         grid = multi_gpu.GridGemm(ctx, dist)
 
@@ -326,74 +379,120 @@ def main():
     for _ in range(args.warmup):
         e2e_step()
     barrier()
+    st = torch.cuda.current_stream()
+
     def timed_e2e():
         launches_before = tmm.total_kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local_rank) as sampler:
+            e0.record(st)
             t0 = time.perf_counter()
             for _ in range(args.steps):
-                e2e_step()
+                e2e_step()          # synchronous: returns when every stream of the call is idle and host C is complete
+            e1.record(st)
             barrier()
-            ms = (time.perf_counter() - t0) / args.steps * 1e3
-        return max_over_ranks(ms), sampler, tmm.total_kernel_launches() - launches_before
+            host_ms = (time.perf_counter() - t0) / args.steps * 1e3
+        ev_ms = e0.elapsed_time(e1) / args.steps
+        return max_over_ranks(ev_ms), max_over_ranks(host_ms), sampler, tmm.total_kernel_launches() - launches_before
 
-    e2e_ms, cs_e2e, launches = timed_e2e()
+    e2e_ms, host_ms, cs_e2e, launches = timed_e2e()
     # a timed region that saw a hardware / thermal slowdown on any rank is measured again, once (all ranks decide together)
     remeasured = False
     slow = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     if max_over_ranks(1.0 if slow & set(cs_e2e.summary()["reasons"]) else 0.0) > 0.0:
         time.sleep(5.0)
         barrier()
-        e2e_ms, cs_e2e, launches = timed_e2e()
+        e2e_ms, host_ms, cs_e2e, launches = timed_e2e()
         remeasured = True
-    e2e_tf = world * flops / (e2e_ms * 1e-3) * 1e-12
+    e2e_tf = flops_total / (e2e_ms * 1e-3) * 1e-12
     stt = ctx.last_stats()
-    h2d, d2h, peer = int(stt.h2d_bytes), int(stt.d2h_bytes), int(stt.peer_bytes)
-    if world > 1:  # whole-job bytes per step, summed over ranks
-        t = torch.tensor([h2d, d2h, peer], dtype=torch.int64, device="cuda")
-        dist.all_reduce(t)
-        h2d, d2h, peer = (int(x) for x in t.tolist())
-    # sanity: the timed result is a real product (C x = A (B x) on rank 0 at N = 1)
-    if True:  # every rank checks its own block (its A row-panel and B column-panel are local)
-        x = np.random.default_rng(5).random(n) - 0.5
-        lhs = np.asarray(c).reshape(n, m).T @ x
-        rhs = np.asarray(a).reshape(k, m).T @ (np.asarray(b).reshape(n, k).T @ x)
-        assert np.max(np.abs(lhs - rhs)) <= 1e-15 * k * np.abs(x).sum() + 1e-9, "bench result failed the linearity check"
+    h2d, d2h, peer = (int(v) for v in sum_over_ranks([int(stt.h2d_bytes), int(stt.d2h_bytes), int(stt.peer_bytes)]))
+    launches_total = int(sum_over_ranks([launches])[0])
+    # the timed result is a real product: C x = A (B x) on every rank's block (its A row-panel and B column-panel are local); a rank that
+    # cannot confirm it fails the whole run
+    x = np.random.default_rng(5).random(n) - 0.5
+    lhs = np.asarray(c).reshape(n, m).T @ x
+    rhs = np.asarray(a).reshape(k, m).T @ (np.asarray(b).reshape(n, k).T @ x)
+    ok_here = bool(np.max(np.abs(lhs - rhs)) <= 1e-15 * k * np.abs(x).sum() + 1e-9)
+    checked = int(sum_over_ranks([1.0 if ok_here else 0.0])[0])
+    if checked != world:
+        raise SystemExit(f"bench result failed the linearity check on {world - checked} of {world} ranks")
+
+    # ------------------------------------------------------------------ (2) the dominant kernel alone, operands resident in HBM -> roofline
+    dA = torch.empty(m * k, dtype=torch.float64, device="cuda"); dB = torch.empty(k * n, dtype=torch.float64, device="cuda")
+    dC = torch.empty(m * n, dtype=torch.float64, device="cuda")
+    dA.copy_(torch.from_numpy(np.asarray(a))); dB.copy_(torch.from_numpy(np.asarray(b)))
+
+    def dev_step():
+        tmm.device_gemm(np.float64, "N", "N", m, n, k, 1.0, dA.data_ptr(), m, dB.data_ptr(), k, 0.0, dC.data_ptr(), m, stream=st.cuda_stream)
+
+    for _ in range(3):
+        dev_step()
+    barrier()
+    ksteps = max(3, min(args.steps, 10))
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ksteps)]
+    for s0, s1 in evs:
+        s0.record(st); dev_step(); s1.record(st)
+    barrier()
+    launch_ms = sum(s0.elapsed_time(s1) for s0, s1 in evs) / ksteps
+    kernel_tf = flops_rank / (launch_ms * 1e-3) * 1e-12
+    # cuBLAS FP64 on the same resident operands (comparator only; never on the product path)
+    A2, B2 = dA.view(k, m).t(), dB.view(n, k).t()
+    for _ in range(2):
+        torch.matmul(A2, B2)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(st)
+    for _ in range(3):
+        torch.matmul(A2, B2)
+    c1.record(st); barrier()
+    cublas_tf = flops_rank / (c0.elapsed_time(c1) / 3 * 1e-3) * 1e-12
+    del A2, B2, dA, dB, dC
+    torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_dgemm(size)
+        cpu = cpu_baseline_dgemm(S)
 
     if rank == 0:
-        # rooflines for the host-to-host call: min(FP64 peak, AI x PCIe) and the full-duplex variant
-        pcie_bytes = 8.0 * (m * k / pc + k * n / pr + m * n)  # per GPU: its upload shares of the shared panels + its C block
-        ai = flops / pcie_bytes
-        roof_simple = min(FP64_PEAK_TFLOPS, ai * PCIE_H2D_GBS * 1e-3)
-        t_duplex = max(flops / (FP64_PEAK_TFLOPS * 1e12), 8.0 * (m * k / pc + k * n / pr) / (PCIE_H2D_GBS * 1e9), 8.0 * m * n / (PCIE_D2H_GBS * 1e9))
+        # host-to-host roofline: min(N x FP64 peak, AI x aggregate host-link bandwidth), both measured on this box just now
+        pcie_bytes = 8.0 * 3.0 * S * S  # every element of A, B crosses PCIe once over the whole grid, C goes back once
+        ai = flops_total / pcie_bytes
+        roof_fp64 = world * fp64_peak
+        # duplex links: uploads and downloads overlap; the slower direction bounds the call
+        t_links = max(8.0 * 2.0 * S * S / (agg_up * 1e9), 8.0 * S * S / (agg_down * 1e9))
+        roof_links = flops_total / t_links * 1e-12
+        roof = min(roof_fp64, roof_links)
         clocks = cs_e2e.summary()
         clocks["remeasured_after_slowdown"] = remeasured
+        traffic, traffic_src = ncu_traffic_of_this_build()
+        e2e = {"value": round(e2e_tf, 3), "unit": "TFLOP/s", "ms_per_step": round(e2e_ms, 3), "ms_per_step_host_clock": round(host_ms, 3),
+               "timing": "CUDA events around K synchronous calls (each returns only when every stream of the call is idle and host C is complete), bracketed by "
+                         "barrier + cudaDeviceSynchronize, max over ranks; host clock alongside",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "nvlink_bytes_per_step": peer,
+               "frac_of_host_roofline": round(e2e_tf / roof, 4),
+               "host_roofline": {"formula": "min(N x FP64 tensor peak, flops / max(H2D bytes / aggregate H2D BW, D2H bytes / aggregate D2H BW))", "tflops": round(roof, 2),
+                                 "fp64_bound_tflops": round(roof_fp64, 2), "host_link_bound_tflops": round(roof_links, 2), "ai_flop_per_byte": round(ai, 1),
+                                 "active_bound": "fp64" if roof_fp64 <= roof_links else "host links",
+                                 "aggregate_h2d_gbs": round(agg_up, 1), "aggregate_d2h_gbs": round(agg_down, 1),
+                                 "links_measured": f"live, all {world} GPU(s) copying both ways at once (tmm_probe_host_links, 128 MiB per direction)"}}
         out = {
-            "metric": "host-to-host dgemm TFLOP/s", "value": round(value_tf, 3), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(dev_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": "host-to-host dgemm TFLOP/s", "value": round(e2e_tf, 3), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(e2e_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(size, args.streams) + (f"; weak-scaled over a {pr}x{pc} C-block grid, global {pr*m}x{pc*n}x{k}, A/B panel shares pushed peer-to-peer over NVLink" if world > 1 else ""),
-                       "l2": "inputs (A, B = 800 MB each) larger than the 126 MB L2; no flush needed",
-                       "host_buffers": f"cudaHostAlloc, first touched on the GPU-local NUMA node ({numa.bound} CPUs)" if numa.bound else "cudaHostAlloc (no NUMA binding applied)",
-                       "value_is": "device-resident DGEMM (tmm_device_gemm, operands in HBM)", "e2e_is": "tmm_gemm with host pointers (H2D + GEMM + D2H)"},
-            "e2e": {"value": round(e2e_tf, 3), "unit": "TFLOP/s", "ms_per_step": round(e2e_ms, 3),
-                    "timing": "host clock around K synchronous calls (each returns only when every stream of the call is idle and host C is complete), "
-                              "bracketed by barrier + cudaDeviceSynchronize, max over ranks", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "nvlink_bytes_per_step": peer,
-                    "frac_of_host_roofline": round(e2e_tf / world / roof_simple, 4),
-                    "host_roofline": {"formula": "min(FP64 peak, AI x PCIe H2D BW)", "tflops": round(roof_simple, 2), "ai_flop_per_byte": round(ai, 1),
-                                      "duplex_tflops": round(flops / t_duplex * 1e-12, 2), "active_bound": "fp64" if roof_simple >= FP64_PEAK_TFLOPS - 1e-9 else "pcie",
-                                      "pcie_h2d_gbs": PCIE_H2D_GBS, "pcie_d2h_gbs": PCIE_D2H_GBS}},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": round(kernel_tf, 3), "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": round(kernel_tf / FP64_PEAK_TFLOPS, 4),
-                         "traffic": 13.2e9, "traffic_note": "dram__bytes_read+write per launch from profiles/r1_ncu_dgemm.md (ncu --set full); algorithmic 2.4e9 B; DRAM at 2.9 % of peak, not the bound",
-                         "kernel": "tmm::f64::dgemm_kernel<false,false> (DMMA.8x8x4 fed by TMA)",
-                         "peak_source": "FP64 tensor (DMMA) issue peak measured by tools/probe.cu on this pool (profiles/r1_probe_b200.txt); MEASURED_PEAKS.json "
-                                        "holds only HBM and bf16 figures, which do not bound an FP64 GEMM",
-                         "cublas_dgemm_same_operands_tflops": round(cublas_tf, 3), "algorithmic_flops_per_launch": flops},
-            "clocks": clocks, "clocks_device_resident": cs_dev.summary(),
+            "config": workload_config(S, world, args.streams),
+            "decomposition": {"grid": f"{pr}x{pc}", "rank_block": [m, n, k], "flop_per_gpu": flops_rank,
+                              "host_buffers": f"cudaHostAlloc, first touched on the GPU-local NUMA node ({numa.bound} CPUs)" if numa.bound else "cudaHostAlloc (single NUMA node / no binding applied)",
+                              "exchange": "A / B panel shares pushed peer-to-peer by the copy engines over NVLink" if world > 1 else "none (one GPU)"},
+            "e2e": e2e,
+            "gpu_launches": launches_total,
+            "roofline": {"bound": "tensor", "achieved": round(kernel_tf, 3), "peak": round(fp64_peak, 2), "unit": "TFLOP/s", "frac": round(kernel_tf / fp64_peak, 4),
+                         "traffic": traffic, "traffic_note": traffic_src or "no ncu --set full capture of this build's DGEMM kernel: not printed",
+                         "kernel": "tmm::f64::dgemm_kernel<false,false> (DMMA.8x8x4 fed by TMA), one device-resident launch on this rank's block "
+                                   f"{m}x{n}x{k}, CUDA events on the launching stream",
+                         "ms_per_launch": round(launch_ms, 3), "peak_source": fp64_src,
+                         "cublas_dgemm_same_operands_tflops": round(cublas_tf, 3), "algorithmic_flops_per_launch": flops_rank},
+            "clocks": clocks,
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu

@@ -151,6 +151,13 @@ TMM_API tmm_context* tmm_context_child(tmm_context* ctx, int index);
  * (tiled_mm.cpp:45-123) reduce to; lets a binding stage strided panels without a CUDA runtime binding of its own. */
 TMM_API int tmm_memcpy_2d_async(void* dst, size_t dpitch_bytes, const void* src, size_t spitch_bytes, size_t width_bytes, size_t height, int kind, void* stream);
 
+/* Box probes (no counterpart in the reference): the roofline denominators of this path measured where the code runs.
+ *   tmm_probe_fp64_peak   FP64 tensor (DMMA.8x8x4) issue rate of the current device in TFLOP/s - the ceiling of the DGEMM / ZGEMM kernels
+ *   tmm_probe_host_links  pinned H2D and D2H GB/s of each listed device (NULL: 0..n-1) with ALL of them copying both ways at once -
+ *                         on a multi-GPU box the links share uplinks / host memory, so the figure per GPU falls with the GPU count */
+TMM_API int tmm_probe_fp64_peak(double* tflops);
+TMM_API int tmm_probe_host_links(int n_devices, const int* device_ids, size_t bytes_per_direction, double* h2d_gbs, double* d2h_gbs);
+
 /* Introspection for tests and bench.py */
 typedef struct tmm_call_stats {
     uint64_t h2d_bytes;      /* bytes moved host->device by the last tmm_gemm */

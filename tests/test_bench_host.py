@@ -17,10 +17,18 @@ def _bench():
 
 def test_workload_name_and_grid_shapes():
     b = _bench()
-    name = b.workload_name(10000)
-    assert "dgemm m=n=k=10000" in name and "configs[1]" in name and "2 streams" in name
+    cfg = b.workload_config(10000, 1)
+    assert "dgemm m=n=k=10000" in cfg["workload"] and "configs[1]" in cfg["workload"] and "2 streams" in cfg["workload"]
     assert [b.grid_shape(n) for n in (1, 2, 4, 8)] == [(1, 1), (1, 2), (2, 2), (2, 4)]
     assert b.host_cores() >= 1
+    # N > 1: the square problem weak-scaled by work: 2e12 flop per GPU within 0.1 %
+    for world in (1, 2, 4, 8):
+        S = b.global_size(world, 10000)
+        assert abs(2.0 * S**3 / world - 2e12) <= 2e9, (world, S)
+        assert f"m=n=k={S} " in b.workload_config(S, world)["workload"]
+        pr, pc = b.grid_shape(world)
+        rows = [b.share(S, pr, g) for g in range(pr)]
+        assert rows[0][0] == 0 and rows[-1][1] == S and all(rows[g][1] == rows[g + 1][0] for g in range(pr - 1))
 
 
 def test_clock_sampler_summary_without_nvml():
@@ -91,6 +99,8 @@ tmm.make_context = lambda *a, **k: _Ctx()
 tmm.gemm = gemm
 tmm.device_gemm = device_gemm
 tmm.total_kernel_launches = lambda: state["launches"]
+tmm.probe_fp64_peak = lambda: 37.0
+tmm.probe_host_links = lambda ids=None, n_devices=None, nbytes=0: [(50.0, 50.0) for _ in (ids or [0])]
 sys.modules["tiled_mm_b200"] = tmm
 
 sys.argv = ["bench.py", "--size", "64", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"]
@@ -111,6 +121,8 @@ def test_bench_main_flow_on_stand_ins(tmp_path):
                 "gpu_launches", "roofline", "clocks"):
         assert key in line, key
     assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3 and line["dtype"] == "f64" and line["gpu_launches"] == 14
+    assert line["value"] == line["e2e"]["value"] and line["ms_per_step"] == line["e2e"]["ms_per_step"], "value must be the host-to-host measurement the metric names"
+    assert line["roofline"]["peak"] == 37.0 and line["e2e"]["host_roofline"]["aggregate_h2d_gbs"] == 50.0
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert line["clocks"]["remeasured_after_slowdown"] is False and "workload" in line["config"]

@@ -120,6 +120,9 @@ def load_library() -> ctypes.CDLL:
     lib.tmm_context_child.argtypes = [vp, ci]
     lib.tmm_context_child.restype = vp
     lib.tmm_memcpy_2d_async.argtypes = [vp, sz, vp, sz, sz, sz, ci, vp]
+    if hasattr(lib, "tmm_probe_fp64_peak"):  # (the emulated-runtime build of tests/emul has no device code)
+        lib.tmm_probe_fp64_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
+        lib.tmm_probe_host_links.argtypes = [ci, ctypes.POINTER(ci), sz, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib
 
@@ -402,6 +405,24 @@ def dist_unique_id() -> bytes:
 
 def device_count() -> int:
     return load_library().tmm_device_count()
+
+
+def probe_fp64_peak() -> float:
+    """FP64 tensor (DMMA.8x8x4) issue rate of the current device in TFLOP/s: the ceiling the DGEMM / ZGEMM kernels are measured against."""
+    v = ctypes.c_double(0.0)
+    _check(load_library().tmm_probe_fp64_peak(ctypes.byref(v)))
+    return float(v.value)
+
+
+def probe_host_links(device_ids=None, n_devices: int | None = None, nbytes: int = 64 << 20):
+    """[(h2d GB/s, d2h GB/s)] per device with ALL listed devices copying both ways at once (default: every device of the box)."""
+    lib = load_library()
+    ids = list(device_ids) if device_ids is not None else list(range(n_devices if n_devices is not None else device_count()))
+    arr = (ctypes.c_int * len(ids))(*ids)
+    up = (ctypes.c_double * len(ids))()
+    down = (ctypes.c_double * len(ids))()
+    _check(lib.tmm_probe_host_links(len(ids), arr, nbytes, up, down))
+    return [(float(up[i]), float(down[i])) for i in range(len(ids))]
 
 
 def total_kernel_launches() -> int:

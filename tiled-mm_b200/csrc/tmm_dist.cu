@@ -23,6 +23,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <thread>
 
@@ -374,44 +375,6 @@ void link_teardown(Link& link) {
 // B200 alone copies 55 GB/s each way, eight at once get 8 - 12 GB/s each way (profiles/r2_probe_8gpu.txt: shared uplinks / host memory).
 // The scheduler's chunk and block sizes are a function of these rates, so a grid measures them once, with all its ranks copying at the
 // same time, instead of assuming the single-GPU figure.
-struct LinkRates { double h2d = 0, d2h = 0; };
-
-// Both directions at once on the current device: `bytes` up and `bytes` down, twice (first pass warms up).  `go` is called right before
-// the timed pass so that the callers' ranks start together.
-template <typename Barrier>
-LinkRates probe_host_link(size_t bytes, Barrier&& go) {
-    LinkRates r;
-    char *h_up = nullptr, *h_down = nullptr, *d_up = nullptr, *d_down = nullptr;
-    cudaStream_t s_up = nullptr, s_down = nullptr;
-    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool ok = cudaHostAlloc((void**)&h_up, bytes, cudaHostAllocDefault) == cudaSuccess && cudaHostAlloc((void**)&h_down, bytes, cudaHostAllocDefault) == cudaSuccess &&
-              cudaMalloc((void**)&d_up, bytes) == cudaSuccess && cudaMalloc((void**)&d_down, bytes) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking) == cudaSuccess;
-    for (auto& ev : e) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
-    if (ok) memset(h_up, 0, bytes);
-    for (int pass = 0; pass < 2 && ok; ++pass) {
-        if (pass == 1) go();
-        ok = cudaEventRecord(e[0], s_up) == cudaSuccess && cudaEventRecord(e[2], s_down) == cudaSuccess &&
-             cudaMemcpyAsync(d_up, h_up, bytes, cudaMemcpyHostToDevice, s_up) == cudaSuccess &&
-             cudaMemcpyAsync(h_down, d_down, bytes, cudaMemcpyDeviceToHost, s_down) == cudaSuccess && cudaEventRecord(e[1], s_up) == cudaSuccess &&
-             cudaEventRecord(e[3], s_down) == cudaSuccess && cudaStreamSynchronize(s_up) == cudaSuccess && cudaStreamSynchronize(s_down) == cudaSuccess;
-    }
-    float up_ms = 0, down_ms = 0;
-    if (ok && cudaEventElapsedTime(&up_ms, e[0], e[1]) == cudaSuccess && cudaEventElapsedTime(&down_ms, e[2], e[3]) == cudaSuccess && up_ms > 0 && down_ms > 0) {
-        r.h2d = (double)bytes / up_ms * 1e-6;
-        r.d2h = (double)bytes / down_ms * 1e-6;
-    }
-    cudaGetLastError();
-    for (auto& ev : e) if (ev) cudaEventDestroy(ev);
-    if (s_up) cudaStreamDestroy(s_up);
-    if (s_down) cudaStreamDestroy(s_down);
-    if (d_up) cudaFree(d_up);
-    if (d_down) cudaFree(d_down);
-    if (h_up) cudaFreeHost(h_up);
-    if (h_down) cudaFreeHost(h_down);
-    return r;
-}
-
 // Collective over the link, once per call and on EVERY rank of it, whatever happened locally: `local_ok == false` (an allocation failed
 // here, or another link already reported a failure) is spread to the peers, so that all ranks give the call up together instead of
 // some of them enqueueing work that waits for shares which will never come.

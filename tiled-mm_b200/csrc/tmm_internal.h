@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <map>
 #include <string>
 #include <array>
@@ -226,6 +227,10 @@ int link_wait(tmm_context* ctx, Link& link, cudaStream_t stream);
 // dist_exchange(ring_slot >= 0) waits for the peers' acknowledgement of the exchange that last filled that slot.
 int link_ack(tmm_context* ctx, Link& link, cudaStream_t stream);
 void dist_release(tmm_context* ctx);
+// Host-link probe (tmm_probe.cu): `bytes` up and `bytes` down at the same time on the current device, twice (the first pass warms up);
+// `go` is called right before the timed pass so that several callers (ranks / devices) start together.  GB/s, 0 = failed.
+struct LinkRates { double h2d = 0, d2h = 0; };
+LinkRates probe_host_link(size_t bytes, const std::function<void()>& go);
 // share g of `parts` over an extent: balanced split, [lo, hi)
 inline void share_range(int64_t extent, int parts, int g, int64_t* lo, int64_t* hi) {
     const int64_t base = extent / parts, rem = extent % parts;
