@@ -86,6 +86,10 @@ TMM_API int tmm_context_dtype(tmm_context* ctx);
 /* gpu::malloc_pinned<T>(N, value) minus the fill  — util.hpp:65-72 (cudaHostAlloc, flags 0). The reference
  * has no matching free helper (its apps leak); tmm_free_pinned is cudaFreeHost. */
 TMM_API int tmm_malloc_pinned(size_t bytes, void** out);
+/* Additive: large pinned allocations (out-of-core matrices of hundreds of GB) an order of magnitude faster than cudaHostAlloc - anonymous
+ * memory on 2 MiB pages, first touched by all cores, one cudaHostRegister (portable).  Zero-filled.  Release with tmm_free_pinned ONLY
+ * (not cudaFreeHost); gpu::malloc_pinned keeps the reference's cudaHostAlloc semantics (util.hpp:65-72). */
+TMM_API int tmm_malloc_pinned_large(size_t bytes, void** out);
 TMM_API int tmm_free_pinned(void* p);
 /* gpu::malloc_device / copy_to_device / copy_to_host  — util.hpp:57-63,79-88 */
 TMM_API int tmm_malloc_device(size_t bytes, void** out);
@@ -116,10 +120,10 @@ TMM_API int tmm_device_gemm_bf16(char trans_a, char trans_b, int64_t m, int64_t 
 #define TMM_MATH_FP32 3
 TMM_API int tmm_set_f32_math(int mode);
 TMM_API int tmm_get_f32_math(void);
-/* Math mode of the complex<float> (TMM_C32) GEMM, process-wide.  TMM_CMATH_SIMT (default): complex FMA kernel, true FP32 arithmetic.
- * TMM_CMATH_TC: the complex product as a real product of twice the size, (2m x n) = (2m x 2k)(2k x n) over the (re, im) float view
- * of the operands, on the FP32-accurate tcgen05 kernel (3xTF32; same accuracy class, integer data stays exact).  Opt-in until it has
- * been validated on hardware.  Environment: TMM_C32_MATH = simt | tc. */
+/* Math mode of the complex<float> (TMM_C32) GEMM, process-wide.  TMM_CMATH_TC (default): the complex product as a real product of
+ * twice the size, (2m x n) = (2m x 2k)(2k x n) over the (re, im) float view of the operands, on the FP32-accurate tcgen05 kernel
+ * (3xTF32; FP32 accuracy class, integer data stays exact; 1.8x cuBLAS CGEMM on B200).  TMM_CMATH_SIMT: the complex FMA kernel, true FP32
+ * arithmetic in every product.  Environment: TMM_C32_MATH = tc | simt. */
 #define TMM_CMATH_SIMT 0
 #define TMM_CMATH_TC 3
 TMM_API int tmm_set_c32_math(int mode);

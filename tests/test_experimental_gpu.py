@@ -1,9 +1,8 @@
-"""GPU tests of code paths that were written after the round's GPU budget was spent and have therefore never run on hardware.
-They are opt-in in the product (environment / math-mode switches, defaults untouched) and opt-in here:
-
-    TMM_EXPERIMENTAL=1 python -m pytest tests/test_experimental_gpu.py -m gpu -q
-
-Round 2 runs this first; what passes gets promoted to the default path and into test_gemm_gpu.py."""
+"""GPU tests of the paths that were written after round 1's GPU budget was spent.  Round 2 ran them first thing (profiles/r2_experimental_first_run.txt,
+r2_f64_i8_first_run.txt): all passed, so they are regular GPU tests now.  What became of the paths: the tcgen05 CGEMM embedding is the default
+complex<float> kernel; BF16 inputs and device-pointer operands are additive entry points; the FP64 emulation on the integer tensor cores stays an
+opt-in math mode (TMM_F64_MATH=i8[:S]; north_star names DMMA for FP64).  The SGEMM variants with A through tensor memory / CTA pairs and the
+CTA-pair int8 kernel were slower than the kernels they were meant to replace and were removed (profiles/r2_tc_variants.txt)."""
 import itertools
 import os
 
@@ -12,16 +11,16 @@ import pytest
 
 from test_gemm_gpu import run_case
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("TMM_EXPERIMENTAL") != "1", reason="paths not yet validated on hardware; set TMM_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 ALL_TT = ["".join(p) for p in itertools.product("NTC", "NTC")]
 
 
-@pytest.fixture()
-def c32_tc(gpu_tmm):
-    gpu_tmm.set_c32_math(gpu_tmm.CMATH_TC)
+@pytest.fixture(params=["tc", "simt"])
+def c32_tc(gpu_tmm, request):
+    """both complex<float> kernels: the tcgen05 embedding (default) and the complex-FMA kernel"""
+    gpu_tmm.set_c32_math(gpu_tmm.CMATH_TC if request.param == "tc" else gpu_tmm.CMATH_SIMT)
     yield gpu_tmm
-    gpu_tmm.set_c32_math(gpu_tmm.CMATH_SIMT)
+    gpu_tmm.set_c32_math(gpu_tmm.CMATH_TC)
 
 
 @pytest.mark.parametrize("tt", ALL_TT)
@@ -85,8 +84,9 @@ def test_bf16_input_gemm(gpu_tmm, oracle, tt):
             assert float(np.max(np.abs(got - want))) / (k * 0.25) <= 2e-6, tt
 
 
-@pytest.mark.skipif(os.environ.get("TMM_BF16_NATIVE") != "1", reason="run with TMM_BF16_NATIVE=1: native kind::f16 path for k-contiguous bf16 operands")
-def test_bf16_native_kind_f16_tn(gpu_tmm, oracle):
+def test_bf16_native_kind_f16_tn(gpu_tmm, oracle, monkeypatch):
+    """TMM_BF16_NATIVE=1 (read per call): k-contiguous bf16 operands straight through kind::f16 MMAs, no widening pass"""
+    monkeypatch.setenv("TMM_BF16_NATIVE", "1")
     tmm = gpu_tmm
     to_bf16 = lambda x: (x.view(np.uint32) >> 16).astype(np.uint16)
     rng = np.random.default_rng(22)
@@ -142,31 +142,9 @@ def test_device_pointer_operands(gpu_tmm, oracle, dtype):
         tmm.free_device(p)
 
 
-@pytest.fixture(params=["1", "2"], ids=["one-cta", "cta-pair"])
-def a_via_tmem(request):
-    """TMM_TC_ATMEM=1: the FP32-accurate SGEMM takes its A operand from tensor memory (sgemm_tc_ts_kernel<false>);
-    =2: additionally CTA pairs sharing 256 x 128 tiles through cta_group::2 MMAs (sgemm_tc_ts_kernel<true>).  Read per launch."""
-    os.environ["TMM_TC_ATMEM"] = request.param
-    yield
-    os.environ.pop("TMM_TC_ATMEM", None)
-
-
-@pytest.mark.parametrize("tt", ALL_TT)
-def test_sgemm_a_through_tmem_exact_on_integers(gpu_tmm, oracle, a_via_tmem, tt):
-    """All op pairs (k- and m-contiguous A tiles, both B orientations), ragged edges in m, n and k, beta != 0 and beta = 0."""
-    run_case(gpu_tmm, oracle, np.float32, tt, 130, 67, 95, 2.0, -1.0, pad=(0, 0, 3), ints=True)      # ld multiples of 4 floats: the TMA contract
-    run_case(gpu_tmm, oracle, np.float32, tt, 1000, 520, 1100, 1.0, 0.0, pad=(4, 8, 0), ints=True)   # several tiles, 35 k-blocks, 9 windows
-
-
-@pytest.mark.parametrize("tt", ["NN", "TN", "NT", "TT"])
-def test_sgemm_a_through_tmem_random(gpu_tmm, oracle, a_via_tmem, tt):
-    run_case(gpu_tmm, oracle, np.float32, tt, 777, 530, 4100, 1.5, 0.25, pad=(3, 2, 9), tiles=(256, 300, 500))
-
-
-@pytest.fixture(params=["i8", "i8:7", "i8p", "i8p:7"], ids=["8-slices", "7-slices", "pairs-8-slices", "pairs-7-slices"])
+@pytest.fixture(params=["i8", "i8:7"], ids=["8-slices", "7-slices"])
 def f64_on_int8(request):
-    """TMM_F64_MATH=i8[:S]: DGEMM as S (S + 1) / 2 exact int8 slice GEMMs on tcgen05 (gemm_f64_i8.cu); i8p[:S]: the version on CTA pairs with
-    256 x 256 tiles, one launch per group.  Read per launch."""
+    """TMM_F64_MATH=i8[:S]: DGEMM as S (S + 1) / 2 exact int8 slice GEMMs on tcgen05 (gemm_f64_i8.cu).  Read per launch."""
     os.environ["TMM_F64_MATH"] = request.param
     yield
     os.environ.pop("TMM_F64_MATH", None)

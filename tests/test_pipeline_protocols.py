@@ -303,15 +303,6 @@ def build_i8(sim, pair, tiles, kblocks, slices, max_window):
     sim.add("mma", mma())
 
 
-@pytest.mark.parametrize("pair", [False, True], ids=["one-cta", "cta-pair"])
-@pytest.mark.parametrize("tiles,kblocks,window", [(1, 1, 4), (3, 5, 4), (2, 9, 4), (4, 3, 1), (2, 17, 8)])
-def test_sgemm_a_through_tmem_protocol(pair, tiles, kblocks, window):
-    for seed in range(12):
-        sim = Sim(seed)
-        build_ts(sim, pair, tiles, kblocks, window)
-        sim.run()
-
-
 @pytest.mark.parametrize("tiles,kblocks,window", [(1, 1, 4), (3, 5, 4), (2, 9, 4), (4, 3, 1)])
 def test_default_sgemm_kernel_protocol(tiles, kblocks, window):
     """sgemm_tc_kernel (the hardware-validated default): the same roles with a 3-stage ring and four window accumulators; the split stage of
@@ -322,7 +313,7 @@ def test_default_sgemm_kernel_protocol(tiles, kblocks, window):
         sim.run()
 
 
-@pytest.mark.parametrize("pair", [False, True], ids=["one-cta", "cta-pair"])
+@pytest.mark.parametrize("pair", [False], ids=["one-cta"])
 @pytest.mark.parametrize("tiles,kblocks,slices,max_window", [(1, 1, 2, 2048), (2, 3, 4, 2048), (3, 2, 8, 2048), (2, 5, 3, 4)])
 def test_int8_dgemm_protocol(pair, tiles, kblocks, slices, max_window):
     for seed in range(8):

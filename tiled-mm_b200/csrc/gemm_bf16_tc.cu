@@ -31,7 +31,8 @@ cudaError_t bgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
     if (m <= 0 || n <= 0) return cudaSuccess;
     if (k <= 0) return device_scale(F32, m, n, &beta, c, ldc, st);
     {
-        static const bool native = [] { const char* v = getenv("TMM_BF16_NATIVE"); return v && v[0] == '1'; }();
+        const char* nv = getenv("TMM_BF16_NATIVE");  // read per call (tests switch it)
+        const bool native = nv && nv[0] == '1';
         if (native && ta != 'N' && tb == 'N' && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0 && (lda & 7) == 0 && (ldb & 7) == 0)
             return bgemm_tc_native_tn_launch(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, st);
     }

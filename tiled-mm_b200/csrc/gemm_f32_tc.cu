@@ -89,7 +89,8 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
 
 // The kernel body, parameterised by the ring geometry: NSTAGES stages of [A | (A lo) | B | (B lo)] with B at B_OFF bytes from A.
 //   <3, 2 * OPERAND_BYTES>  the FP32-accurate layout (hi | lo twins, 64 KB per stage)                     -> sgemm_tc_kernel
-//   <6, OPERAND_BYTES>      raw tiles only (plain TF32 / native 16-bit: no split stage, 32 KB per stage)  -> sgemm_tc_deep_kernel
+//   (a six-stage ring of raw tiles for the one-term modes and variants taking A from tensor memory / on CTA pairs were measured in round 2 and
+//    removed: 241 vs 243 TF, and 77 - 88 vs 155 TF - profiles/r2_tc_variants.txt)
 template <int NSTAGES, int B_OFF>
 __device__ __forceinline__ void sgemm_tc_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const Params& p) {
     constexpr int STAGES = NSTAGES, STAGE_BYTES = 2 * B_OFF;
@@ -334,337 +335,6 @@ sgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     sgemm_tc_body<STAGES, 2 * OPERAND_BYTES>(tmap_a, tmap_b, p);
 }
 
-// Experimental (TMM_TC_TF32_STAGES=6, not yet run on hardware): the one-term modes (plain TF32, native bf16) leave the lo twins of the
-// ring unused, so the same shared memory holds SIX 32 KB stages instead of three.  Why it should matter: in one-term mode a k-block is
-// only 256 cycles of MMA work, the measured 866 cycles per k-block (352 TF) equal one TMA round trip (~2600 cycles) divided by the
-// three stages in flight - the ring is latency-bound, not bandwidth-bound.
-constexpr int DEEP_STAGES = 6;
-constexpr int DEEP_SMEM_BYTES = DEEP_STAGES * 2 * OPERAND_BYTES + 1024 + 256;
-__global__ void __launch_bounds__(THREADS, 1)
-sgemm_tc_deep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
-    sgemm_tc_body<DEEP_STAGES, OPERAND_BYTES>(tmap_a, tmap_b, p);
-}
-
-// ---- experimental variant: the A operand goes through TENSOR MEMORY (TMM_TC_ATMEM=1; written after the round's GPU time ran out) ----
-// The kernel above is bound by shared-memory bandwidth: per 32-wide k-block a CTA moves 224 KB through the 128 B/clk
-// port - TMA write 32, split read 32, split write 64 (hi in place + lo twin, A and B), MMA operand reads 12 x (4 + 4) = 96 - for
-// 768 cycles of MMA work.  tcgen05.mma can take A from TMEM instead ([a_tmem] form: lane = row, one 32-bit column per k): the A half
-// of the split stage then writes its hi / lo with tcgen05.st, and the twelve MMAs read A without touching shared memory:
-//     TMA write 32 + split read 32 + B hi/lo write 32 + MMA reads of B 12 x 4 = 48   ->  144 KB per k-block (0.64 x)
-// Differences from sgemm_tc_kernel - everything else (roles, barriers, windowed promotion, epilogue) is the same:
-//   * stage = A raw | B hi | B lo (48 KB), 4 stages; TMEM = 2 window accumulators (2 x 128 columns) + 4 A slots (64 columns each:
-//     hi of k 0..31, lo of k 0..31), slot index = stage index, so the stage barriers also order the TMEM slots
-//   * warps 8-11 (TMEM lane quarter = warp % 4 = rows 32q .. 32q+31) split A: thread = row, it reads its 32 k-values from the landed
-//     tile - k-contiguous tile (A^T): 8 x LDS.128 along the 128B-swizzled row (chunk c sits at c ^ (row & 7): conflict-free);
-//     m-contiguous tile (A): 32 x LDS.32, lanes along m (the tile is loaded UNswizzled: the tensor core never reads it);
-//     warps 12-15 split B in shared memory exactly as before
-//   * the instruction descriptor says "A is K-major" for every op(A) (A from TMEM cannot be transposed: it never needs to be)
-constexpr int TS_STAGES = 4;
-constexpr int TS_STAGE_BYTES = 3 * OPERAND_BYTES;  // A raw | B hi | B lo
-constexpr int TS_ACC_BUFS = 2;
-constexpr int TS_A_COL0 = TS_ACC_BUFS * BN;        // first TMEM column of the A slots
-constexpr int TS_A_SLOT_COLS = 2 * BK;             // hi[BK] | lo[BK]
-constexpr int TS_TMEM_COLS = 512;
-constexpr int TS_SMEM_BYTES = TS_STAGES * TS_STAGE_BYTES + 1024 + 256;
-constexpr int TS_WARP_SPLIT_A0 = 8, TS_WARP_SPLIT_B0 = 12;
-constexpr int TS_REGS_SPLIT_A = 120, TS_REGS_SPLIT_B = 88;
-static_assert(TS_A_COL0 + TS_STAGES * TS_A_SLOT_COLS <= TS_TMEM_COLS, "TMEM budget");
-static_assert(TS_SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(REGS_CONTROL + REGS_EPILOGUE + TS_REGS_SPLIT_A + TS_REGS_SPLIT_B <= 4 * 128, "setmaxnreg budget of the 512 x 128 launch allocation");
-
-// PAIR = true (TMM_TC_ATMEM=2): clusters of two CTAs share one 256 x 128 tile through cta_group::2 MMAs.  Each CTA loads and splits ITS
-// 128 rows of A (into its own tensor memory) and only ITS 64-column half of B (shared memory); the CTA of rank 0 issues the MMAs
-// for both (M = 256: rows 0-127 accumulate in its TMEM, rows 128-255 in the peer's), reading each half of B once for both SMs:
-//     per CTA and k-block: TMA write 24 + split read 24 + B hi/lo write 16 + MMA reads of B 12 x 2 = 24  ->  88 KB (0.39 x of 224):
-//     the shared-memory port (~700 cycles) drops below the MMA time (768 cycles).
-// Protocol differences: the split warps and the accumulate warps of BOTH CTAs arrive on rank 0's ready / acc_empty barriers (remote
-// arrive, release / acquire at cluster scope); tcgen05.commit multicasts the stage-free and window-full arrivals to both CTAs;
-// TMEM is allocated / freed with the cta_group::2 forms by the same warp of both CTAs; cluster barriers bracket the kernel.
-template <bool PAIR>
-__global__ void __launch_bounds__(THREADS, 1)
-sgemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
-    constexpr int B_ROWS = PAIR ? BN / 2 : BN;             // columns of the tile whose B this CTA loads and splits
-    constexpr int B_BYTES = B_ROWS * BK * 4;
-    const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;                 // 0 = the CTA that issues the MMAs
-    const int worker = PAIR ? (int)tc::cluster_id_x() : (int)blockIdx.x;     // tile loop: one worker per CTA / per CTA pair
-    const int workers = PAIR ? (int)tc::cluster_count_x() : (int)gridDim.x;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + TS_STAGES * TS_STAGE_BYTES);  // TMA landed                   -> split warps
-    uint64_t* ready_bar = full_bar + TS_STAGES;                                            // A in TMEM, B hi/lo in smem   -> MMA issuer
-    uint64_t* empty_bar = ready_bar + TS_STAGES;                                           // MMAs retired                 -> TMA producer
-    uint64_t* acc_full_bar = empty_bar + TS_STAGES;
-    uint64_t* acc_empty_bar = acc_full_bar + TS_ACC_BUFS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + TS_ACC_BUFS);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < TS_STAGES; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&ready_bar[s], PAIR ? 2 * SPLIT_WARPS : SPLIT_WARPS);
-            ptx::mbar_init(&empty_bar[s], 1);
-        }
-#pragma unroll
-        for (int b = 0; b < TS_ACC_BUFS; ++b) {
-            ptx::mbar_init(&acc_full_bar[b], 1);
-            ptx::mbar_init(&acc_empty_bar[b], PAIR ? 8 : 4);
-        }
-        ptx::fence_mbar_init();
-    }
-    if (warp == WARP_TMEM) {
-        if (PAIR) tc::tmem_alloc_pair(tmem_slot, TS_TMEM_COLS);
-        else tc::tmem_alloc(tmem_slot, TS_TMEM_COLS);
-    }
-    tc::fence_before_thread_sync();
-    __syncthreads();
-    if (PAIR) tc::cluster_sync();  // the peer's barriers are initialised and its tensor memory is allocated before anything arrives there
-    tc::fence_after_thread_sync();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int total_tiles = p.tiles_m * p.tiles_n;
-    const int kblocks = (p.k + BK - 1) / BK;
-
-    if (warp == WARP_TMA) {
-        // ===== TMA producer =====
-        ptx::setmaxnreg_dec<REGS_CONTROL>();
-        if (lane == 0) {
-            ptx::prefetch_tensormap(&tmap_a);
-            ptx::prefetch_tensormap(&tmap_b);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = worker; tile < total_tiles; tile += workers) {
-                int tm, tn;
-                tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    tc::mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], OPERAND_BYTES + B_BYTES);
-                    unsigned char* sa = base + stage * TS_STAGE_BYTES;
-                    unsigned char* sb = sa + OPERAND_BYTES;
-                    if (p.a_mn_major) {
-#pragma unroll
-                        for (int j = 0; j < BM / ATOM_MN; ++j) ptx::tma_load_2d(sa + j * MN_BOX_BYTES, &tmap_a, &full_bar[stage], (tm * (PAIR ? 2 : 1) + (int)rank) * BM + j * ATOM_MN, kb * BK);
-                    } else {
-                        ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, (tm * (PAIR ? 2 : 1) + (int)rank) * BM);
-                    }
-                    if (p.b_mn_major) {
-#pragma unroll
-                        for (int j = 0; j < B_ROWS / ATOM_MN; ++j) ptx::tma_load_2d(sb + j * MN_BOX_BYTES, &tmap_b, &full_bar[stage], tn * BN + (int)rank * B_ROWS + j * ATOM_MN, kb * BK);
-                    } else {
-                        ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, tn * BN + (int)rank * B_ROWS);  // box of B_ROWS rows (host side)
-                    }
-                    if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == WARP_MMA) {
-        // ===== MMA issuer: A from tensor memory, B from shared memory =====
-        ptx::setmaxnreg_dec<REGS_CONTROL>();
-        if (lane == 0 && rank == 0) {
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int tile = worker; tile < total_tiles; tile += workers) {
-                uint32_t d_tmem = 0;
-                for (int kb = 0, wk = 0; kb < kblocks; ++kb) {
-                    if (wk == 0) {
-                        if (PAIR) tc::mbar_wait_cluster_guarded(&acc_empty_bar[acc], acc_phase ^ 1);
-                        else tc::mbar_wait_guarded(&acc_empty_bar[acc], acc_phase ^ 1);
-                        tc::fence_after_thread_sync();
-                        d_tmem = tmem_base + acc * BN;
-                    }
-                    if (PAIR) tc::mbar_wait_cluster_guarded(&ready_bar[stage], phase);
-                    else tc::mbar_wait_guarded(&ready_bar[stage], phase);
-                    tc::fence_after_thread_sync();
-                    const uint32_t b_hi = ptx::smem_u32(base + stage * TS_STAGE_BYTES + OPERAND_BYTES);
-                    const uint32_t b_lo = b_hi + OPERAND_BYTES;
-                    const uint32_t a_slot = tmem_base + TS_A_COL0 + stage * TS_A_SLOT_COLS;  // lane 0; hi at +k, lo at +BK + k
-#pragma unroll
-                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                        const uint32_t ob = ks * p.kstep_b;
-                        const uint32_t first = (wk | ks) ? 1u : 0u;
-                        const uint32_t ta_hi = a_slot + ks * UMMA_K, ta_lo = ta_hi + BK;
-                        const uint64_t db_hi = tc::smem_desc(p.desc_b, b_hi + ob), db_lo = tc::smem_desc(p.desc_b, b_lo + ob);
-                        if (PAIR) {
-                            tc::mma_tf32_ts_pair(d_tmem, ta_lo, db_hi, p.idesc, first);
-                            tc::mma_tf32_ts_pair(d_tmem, ta_hi, db_lo, p.idesc, 1u);
-                            tc::mma_tf32_ts_pair(d_tmem, ta_hi, db_hi, p.idesc, 1u);
-                        } else {
-                            tc::mma_tf32_ts(d_tmem, ta_lo, db_hi, p.idesc, first);  // small terms first
-                            tc::mma_tf32_ts(d_tmem, ta_hi, db_lo, p.idesc, 1u);
-                            tc::mma_tf32_ts(d_tmem, ta_hi, db_hi, p.idesc, 1u);
-                        }
-                    }
-                    if (PAIR) tc::mma_commit_pair(&empty_bar[stage], 3);  // ... in both CTAs
-                    else tc::mma_commit(&empty_bar[stage]);  // shared-memory stage AND TMEM A slot reusable once these MMAs have read them
-                    if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
-                    if (++wk == p.window || kb == kblocks - 1) {
-                        if (PAIR) tc::mma_commit_pair(&acc_full_bar[acc], 3);
-                        else tc::mma_commit(&acc_full_bar[acc]);
-                        if (++acc == TS_ACC_BUFS) { acc = 0; acc_phase ^= 1; }
-                        wk = 0;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp >= WARP_EPI0 && warp < WARP_EPI0 + 4) {
-        // ===== accumulate + epilogue (as in sgemm_tc_kernel, two window accumulators) =====
-        ptx::setmaxnreg_inc<REGS_EPILOGUE>();
-        const int q = warp - WARP_EPI0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        const int windows = (kblocks + p.window - 1) / p.window;
-        for (int tile = worker; tile < total_tiles; tile += workers) {
-            int tm, tn;
-            tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-            float sum[BN];
-#pragma unroll
-            for (int j = 0; j < BN; ++j) sum[j] = 0.f;
-            for (int w = 0; w < windows; ++w) {
-                tc::mbar_wait_guarded(&acc_full_bar[acc], acc_phase);
-                tc::fence_after_thread_sync();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll
-                for (int h = 0; h < BN / 64; ++h) {
-                    uint32_t v0[32], v1[32];
-                    tc::tmem_ld_32x32b_x32(taddr + h * 64, v0);
-                    tc::tmem_ld_32x32b_x32(taddr + h * 64 + 32, v1);
-                    tc::tmem_ld_wait();
-                    if (h == BN / 64 - 1) {
-                        tc::fence_before_thread_sync();
-                        __syncwarp();
-                        if (lane == 0) { if (PAIR) tc::mbar_arrive_cluster(&acc_empty_bar[acc], 0); else ptx::mbar_arrive(&acc_empty_bar[acc]); }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        sum[h * 64 + j] += __uint_as_float(v0[j]);
-                        sum[h * 64 + 32 + j] += __uint_as_float(v1[j]);
-                    }
-                }
-                if (++acc == TS_ACC_BUFS) { acc = 0; acc_phase ^= 1; }
-            }
-            const int row = (tm * (PAIR ? 2 : 1) + (int)rank) * BM + q * 32 + lane;
-            const bool row_ok = row < p.m;
-            const int col0 = tn * BN;
-            float* cp = p.c + (int64_t)col0 * p.ldc + row;
-            if (p.read_c) {
-#pragma unroll
-                for (int cb = 0; cb < BN / 32; ++cb) {
-                    float old[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) old[j] = (row_ok && col0 + cb * 32 + j < p.n) ? __ldcs(cp + (int64_t)(cb * 32 + j) * p.ldc) : 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (row_ok && col0 + cb * 32 + j < p.n) cp[(int64_t)(cb * 32 + j) * p.ldc] = p.alpha * sum[cb * 32 + j] + p.beta * old[j];
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < BN; ++j)
-                    if (row_ok && col0 + j < p.n) cp[(int64_t)j * p.ldc] = p.alpha * sum[j];
-            }
-        }
-    } else if (warp < WARP_EPI0) {
-        ptx::setmaxnreg_dec<REGS_CONTROL>();
-    } else if (warp < TS_WARP_SPLIT_B0) {
-        // ===== A split: shared memory (raw FP32) -> tensor memory (hi | lo), thread = row of the tile =====
-        ptx::setmaxnreg_dec<TS_REGS_SPLIT_A>();
-        const int q = warp - TS_WARP_SPLIT_A0;  // == warp % 4: the TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + TS_A_COL0;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = worker; tile < total_tiles; tile += workers) {
-            for (int kb = 0; kb < kblocks; ++kb) {
-                tc::mbar_wait_guarded(&full_bar[stage], phase);
-                const unsigned char* sa = base + stage * TS_STAGE_BYTES;
-                const uint32_t slot = lane_base + stage * TS_A_SLOT_COLS;
-#pragma unroll
-                for (int h = 0; h < BK / 16; ++h) {  // 16 k-values at a time (register budget)
-                    float x[16];
-                    if (p.a_mn_major) {
-                        // box q of the tile = rows 32q .. 32q+31, unswizzled: [k][32 m]
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) x[j] = *reinterpret_cast<const float*>(sa + ts_a_elem_offset_mnmajor(row, h * 16 + j));
-                    } else {
-                        // row `row` = 128 bytes; 16-byte chunk c is stored at position c ^ (row & 7) (SWIZZLE_128B, tile 1024-B aligned)
-#pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
-                            const int c = h * 4 + c4;
-                            const float4 v = *reinterpret_cast<const float4*>(sa + ts_a_chunk_offset_kmajor(row, c));
-                            x[c4 * 4 + 0] = v.x; x[c4 * 4 + 1] = v.y; x[c4 * 4 + 2] = v.z; x[c4 * 4 + 3] = v.w;
-                        }
-                    }
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float fh, fl;
-                        if (p.split_trunc) { fh = x[j]; fl = lo_of_truncated(x[j]); }
-                        else split_tf32(x[j], fh, fl);
-                        hi[j] = __float_as_uint(fh);
-                        lo[j] = __float_as_uint(fl);
-                    }
-                    tc::tmem_st_32x32b_x16(slot + h * 16, hi);
-                    tc::tmem_st_32x32b_x16(slot + BK + h * 16, lo);
-                }
-                tc::tmem_st_wait();
-                tc::fence_before_thread_sync();
-                __syncwarp();
-                if (lane == 0) { if (PAIR) tc::mbar_arrive_cluster(&ready_bar[stage], 0); else ptx::mbar_arrive(&ready_bar[stage]); }
-                if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else {
-        // ===== B split in shared memory: raw FP32 -> (hi in place, lo in the twin buffer) =====
-        ptx::setmaxnreg_dec<TS_REGS_SPLIT_B>();
-        const int t = threadIdx.x - TS_WARP_SPLIT_B0 * 32;
-        constexpr int CHUNKS = B_BYTES / 16;
-        constexpr int PER_THREAD = CHUNKS / 128;
-        static_assert(CHUNKS % 128 == 0, "chunk split");
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = worker; tile < total_tiles; tile += workers) {
-            for (int kb = 0; kb < kblocks; ++kb) {
-                tc::mbar_wait_guarded(&full_bar[stage], phase);
-                unsigned char* sb = base + stage * TS_STAGE_BYTES + OPERAND_BYTES;
-                float4 x[PER_THREAD];
-#pragma unroll
-                for (int i = 0; i < PER_THREAD; ++i) x[i] = *reinterpret_cast<const float4*>(sb + (t + i * 128) * 16);
-#pragma unroll
-                for (int i = 0; i < PER_THREAD; ++i) {
-                    const int off = (t + i * 128) * 16;
-                    float4 hi, lo;
-                    if (p.split_trunc) {
-                        lo = make_float4(lo_of_truncated(x[i].x), lo_of_truncated(x[i].y), lo_of_truncated(x[i].z), lo_of_truncated(x[i].w));
-                    } else {
-                        split_tf32(x[i].x, hi.x, lo.x);
-                        split_tf32(x[i].y, hi.y, lo.y);
-                        split_tf32(x[i].z, hi.z, lo.z);
-                        split_tf32(x[i].w, hi.w, lo.w);
-                        *reinterpret_cast<float4*>(sb + off) = hi;
-                    }
-                    *reinterpret_cast<float4*>(sb + off + OPERAND_BYTES) = lo;
-                }
-                if (PAIR) tc::fence_proxy_async_all(); else tc::fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) { if (PAIR) tc::mbar_arrive_cluster(&ready_bar[stage], 0); else ptx::mbar_arrive(&ready_bar[stage]); }
-                if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    }
-
-    tc::fence_before_thread_sync();
-    __syncthreads();
-    if (PAIR) tc::cluster_sync();  // no CTA frees its tensor memory or exits while the peer may still read it or arrive on its barriers
-    if (warp == WARP_TMEM) {
-        tc::fence_after_thread_sync();
-        if (PAIR) tc::tmem_dealloc_pair(tmem_base, TS_TMEM_COLS);
-        else tc::tmem_dealloc(tmem_base, TS_TMEM_COLS);
-    }
-}
-
 static CUresult make_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, uint64_t ld_elems, uint32_t box0, uint32_t box1,
                          CUtensorMapSwizzle swizzle) {
     auto encode = reinterpret_cast<CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -701,22 +371,13 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
     CUresult r;
     const CUtensorMapSwizzle swz_k = CU_TENSOR_MAP_SWIZZLE_128B;
     const CUtensorMapSwizzle swz_mn = (CUtensorMapSwizzle)env_u32("TMM_TC_MN_SWIZZLE", (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    // experimental (TMM_TC_ATMEM=1, FP32-accurate mode only): A through tensor memory, sgemm_tc_ts_kernel
-    bool a_via_tmem = false, cta_pairs = false;  // TMM_TC_ATMEM=2: additionally CTA pairs (cta_group::2), sgemm_tc_ts_kernel<true>
-    if (terms != 1) {
-        const char* tv = getenv("TMM_TC_ATMEM");
-        a_via_tmem = tv && (tv[0] == '1' || tv[0] == '2');
-        cta_pairs = tv && tv[0] == '2';
-    }
     // A: op(A) is m x k.  N: stored m x k (m contiguous) -> boxes [32 m x BK];  T/C: stored k x m (k contiguous) -> one box [BK x BM]
-    // (A through TMEM: the m-contiguous boxes are loaded unswizzled - threads read them, not the tensor core)
-    r = a_mn ? make_map(&map_a, a, (uint64_t)m, (uint64_t)k, (uint64_t)lda, ATOM_MN, BK, a_via_tmem ? CU_TENSOR_MAP_SWIZZLE_NONE : swz_mn)
+    r = a_mn ? make_map(&map_a, a, (uint64_t)m, (uint64_t)k, (uint64_t)lda, ATOM_MN, BK, swz_mn)
              : make_map(&map_a, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, BK, BM, swz_k);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "[tiled-mm_b200] cuTensorMapEncodeTiled(A, f32) failed: %d\n", (int)r); return cudaErrorInvalidValue; }
     // B: op(B) is k x n.  N: stored k x n (k contiguous) -> one box [BK x BN];  T/C: stored n x k (n contiguous) -> boxes [32 n x BK]
-    // (CTA pairs: each CTA loads its half of the tile's columns - a k-contiguous box of BN / 2 rows)
     r = b_mn ? make_map(&map_b, b, (uint64_t)n, (uint64_t)k, (uint64_t)ldb, ATOM_MN, BK, swz_mn)
-             : make_map(&map_b, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, BK, cta_pairs ? BN / 2 : BN, swz_k);
+             : make_map(&map_b, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, BK, BN, swz_k);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "[tiled-mm_b200] cuTensorMapEncodeTiled(B, f32) failed: %d\n", (int)r); return cudaErrorInvalidValue; }
 
     Params p;
@@ -739,68 +400,17 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
     p.window = (int)env_u32("TMM_TC_WINDOW", WINDOW_KBLOCKS);
     if (p.window < 1) p.window = 1;
     {
-        const char* sv = getenv("TMM_TC_SPLIT");  // experimental, not validated on hardware: "trunc"
+        const char* sv = getenv("TMM_TC_SPLIT");  // "trunc": hi = the raw bits (the tensor core ignores the low 13 mantissa bits), only lo is written: 171 vs 155 TF at
+                                                  // 8192^3, representation error 2x that of the round-to-nearest split (profiles/r2_tc_variants.txt); opt-in
         p.split_trunc = (sv && sv[0] == 't') ? 1 : 0;
     }
 
     static bool configured[64] = {false};
-    static bool configured_ts[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
     if (tiles > INT32_MAX) return cudaErrorInvalidValue;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    if (a_via_tmem && cta_pairs) {
-        p.tiles_m = (m + 2 * BM - 1) / (2 * BM);  // a pair works on 256 x 128 tiles
-        p.idesc = tc::instr_desc(tc::FMT_TF32, 2 * BM, BN, false, b_mn);
-        static bool configured_pair[64] = {false};
-        if (dev >= 0 && dev < 64 && !configured_pair[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(sgemm_tc_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
-            if (e != cudaSuccess) return e;
-            configured_pair[dev] = true;
-        }
-        const int64_t pair_tiles = (int64_t)p.tiles_m * p.tiles_n;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * (sm_count() / 2)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = TS_SMEM_BYTES; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        // the kernel is persistent: launch no more pairs than can be resident at once (a GPC with an odd number of SMs strands one)
-        static int resident_pairs[64] = {0};
-        if (dev >= 0 && dev < 64 && resident_pairs[dev] == 0) {
-            int nc = 0;
-            if (cudaOccupancyMaxActiveClusters(&nc, sgemm_tc_ts_kernel<true>, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); nc = sm_count() / 2; }
-            resident_pairs[dev] = nc;
-        }
-        const int pairs = (int)std::min<int64_t>(pair_tiles, (dev >= 0 && dev < 64) ? resident_pairs[dev] : sm_count() / 2);
-        cfg.gridDim = dim3(2 * pairs);
-        cudaError_t e = cudaLaunchKernelEx(&cfg, sgemm_tc_ts_kernel<true>, map_a, map_b, p);
-        count_launch();
-        return e != cudaSuccess ? e : cudaGetLastError();
-    }
-    if (a_via_tmem) {
-        p.idesc = tc::instr_desc(tc::FMT_TF32, BM, BN, false, b_mn);  // A in TMEM is K-major whatever op(A) is
-        if (dev >= 0 && dev < 64 && !configured_ts[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(sgemm_tc_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
-            if (e != cudaSuccess) return e;
-            configured_ts[dev] = true;
-        }
-        sgemm_tc_ts_kernel<false><<<grid, THREADS, TS_SMEM_BYTES, stream>>>(map_a, map_b, p);
-        count_launch();
-        return cudaGetLastError();
-    }
-    if (p.terms == 1 && env_u32("TMM_TC_TF32_STAGES", STAGES) == (uint32_t)DEEP_STAGES) {  // experimental: six raw stages for the one-term mode
-        static bool configured_deep[64] = {false};
-        if (dev >= 0 && dev < 64 && !configured_deep[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(sgemm_tc_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEEP_SMEM_BYTES);
-            if (e != cudaSuccess) return e;
-            configured_deep[dev] = true;
-        }
-        sgemm_tc_deep_kernel<<<grid, THREADS, DEEP_SMEM_BYTES, stream>>>(map_a, map_b, p);
-        count_launch();
-        return cudaGetLastError();
-    }
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(sgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;

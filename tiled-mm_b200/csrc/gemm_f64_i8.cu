@@ -272,221 +272,6 @@ static cudaError_t prepare(const double* x, int64_t stride_row, int64_t stride_k
 }
 
 
-// ---- second version (TMM_F64_MATH=i8p[:slices]): 256 x 256 tiles on CTA pairs, one launch per group g ---------------------------------
-// The kernel above fetches 32 KB from L2 per 128 x 128 x 128 k-block (128 op per byte) and is therefore expected to be L2-bandwidth-bound
-// far below the int8 rate.  Here a cluster of two CTAs shares a 256 x 256 tile through cta_group::2 MMAs (M = 256, N = 256):
-// each CTA loads ITS 128 rows of the A slice and ITS 128-column half of the B slice - still 32 KB per k-block, but for 128 x 256 x 128
-// products: 256 op per byte.  A 256-column int32 accumulator leaves no room for per-thread FP64 sums across the groups, so the sum over
-// g moves to global memory: the host launches the kernel once per group (g = S-1 .. 0, smallest terms first), and the epilogue does
-//     C = [first launch: beta * C, else C] + alpha * 2^(ea[i] + eb[j] - 2 P0 - 7 g) * acc          (FP64 read-modify-write, 2 S x |C| bytes of HBM in all)
-// Protocol: TMA lands in each CTA's own ring; a relay lane per CTA forwards "stage landed" to rank 0's ready barrier (remote arrive,
-// release / acquire at cluster scope), rank 0 issues the MMAs for both CTAs, tcgen05.commit multicasts "stage free" / "window full" to
-// both; all eight accumulate warps of both CTAs hand drained windows back to rank 0; cta_group::2 TMEM allocation; cluster barriers
-// bracket the kernel.  Two 256-column accumulators rotate.
-namespace pair {
-constexpr int TILE_M = 256, TILE_N = 256;   // per pair; each CTA: 128 rows x 256 columns of it
-constexpr int ACC_BUFS = 2, ACC_COLS = 256, TMEM_COLS = ACC_BUFS * ACC_COLS;
-constexpr int WARP_RELAY = 3;
-constexpr int REGS_CONTROL = 40, REGS_EPILOGUE = 152;  // 40 + 152 + 152 + 40 <= 512
-
-struct Params {
-    double* c;
-    int64_t ldc;
-    int m, n, k;
-    double alpha, beta;
-    int first;             // 1: this launch applies beta (or overwrites when read_c = 0); 0: accumulates
-    int read_c;
-    int tiles_m, tiles_n;  // pair tiles
-    int g;                 // group: slice pairs with s + t = g
-    int m_pad, n_pad;      // rows between consecutive slices (multiples of 256)
-    const int* ea;
-    const int* eb;
-    uint64_t desc;
-    uint32_t idesc;
-};
-
-__device__ __forceinline__ void mma_i8_pair(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__global__ void __launch_bounds__(THREADS, 1)
-igemm_group_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);  // own TMA landed            -> own relay lane
-    uint64_t* ready_bar = full_bar + STAGES;                                         // (rank 0) both CTAs landed -> MMA issuer
-    uint64_t* empty_bar = ready_bar + STAGES;                                        // MMAs retired (multicast)  -> own TMA producer
-    uint64_t* acc_full_bar = empty_bar + STAGES;                                     // window complete (mcast)   -> own accumulate warps
-    uint64_t* acc_empty_bar = acc_full_bar + ACC_BUFS;                               // (rank 0) drained by all   -> MMA issuer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + ACC_BUFS);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t rank = tc::cluster_ctarank();
-    const int worker = (int)tc::cluster_id_x(), workers = (int)tc::cluster_count_x();
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&ready_bar[s], 2);
-            ptx::mbar_init(&empty_bar[s], 1);
-        }
-#pragma unroll
-        for (int b = 0; b < ACC_BUFS; ++b) {
-            ptx::mbar_init(&acc_full_bar[b], 1);
-            ptx::mbar_init(&acc_empty_bar[b], 2 * EPI_WARPS);
-        }
-        ptx::fence_mbar_init();
-    }
-    if (warp == WARP_TMEM) tc::tmem_alloc_pair(tmem_slot, TMEM_COLS);
-    tc::fence_before_thread_sync();
-    __syncthreads();
-    tc::cluster_sync();
-    tc::fence_after_thread_sync();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int total_tiles = p.tiles_m * p.tiles_n;
-    const int kblocks = (p.k + BKB - 1) / BKB;
-    const int group_kblocks = (p.g + 1) * kblocks;
-
-    if (warp == WARP_TMA) {
-        ptx::setmaxnreg_dec<REGS_CONTROL>();
-        if (lane == 0) {
-            ptx::prefetch_tensormap(&tmap_a);
-            ptx::prefetch_tensormap(&tmap_b);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = worker; tile < total_tiles; tile += workers) {
-                const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
-                for (int s = 0; s <= p.g; ++s) {
-                    const int row_a = s * p.m_pad + tm * TILE_M + (int)rank * BM;          // my 128 rows of the A slice
-                    const int row_b = (p.g - s) * p.n_pad + tn * TILE_N + (int)rank * BN;   // my 128 columns of the B slice
-                    for (int kb = 0; kb < kblocks; ++kb) {
-                        tc::mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
-                        ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                        unsigned char* sa = base + stage * STAGE_BYTES;
-                        ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BKB, row_a);
-                        ptx::tma_load_2d(sa + OPERAND_BYTES, &tmap_b, &full_bar[stage], kb * BKB, row_b);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == WARP_RELAY) {
-        // ===== relay: "my stage has landed" -> rank 0's ready barrier =====
-        ptx::setmaxnreg_dec<REGS_CONTROL>();
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = worker; tile < total_tiles; tile += workers)
-                for (int kb = 0; kb < group_kblocks; ++kb) {
-                    tc::mbar_wait_guarded(&full_bar[stage], phase);
-                    tc::fence_proxy_async_all();
-                    tc::mbar_arrive_cluster(&ready_bar[stage], 0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-        }
-        __syncwarp();
-    } else if (warp == WARP_MMA) {
-        ptx::setmaxnreg_dec<REGS_CONTROL>();
-        if (lane == 0 && rank == 0) {
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int tile = worker; tile < total_tiles; tile += workers) {
-                uint32_t d_tmem = 0;
-                for (int kb = 0, wk = 0; kb < group_kblocks; ++kb) {
-                    if (wk == 0) {
-                        tc::mbar_wait_cluster_guarded(&acc_empty_bar[acc], acc_phase ^ 1);
-                        tc::fence_after_thread_sync();
-                        d_tmem = tmem_base + acc * ACC_COLS;
-                    }
-                    tc::mbar_wait_cluster_guarded(&ready_bar[stage], phase);
-                    tc::fence_after_thread_sync();
-                    const uint32_t sa = ptx::smem_u32(base + stage * STAGE_BYTES), sb = sa + OPERAND_BYTES;
-#pragma unroll
-                    for (int ks = 0; ks < BKB / UMMA_KB; ++ks)
-                        mma_i8_pair(d_tmem, tc::smem_desc(p.desc, sa + ks * UMMA_KB), tc::smem_desc(p.desc, sb + ks * UMMA_KB), p.idesc, (wk | ks) ? 1u : 0u);
-                    tc::mma_commit_pair(&empty_bar[stage], 3);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                    if (++wk == MAX_WINDOW || kb == group_kblocks - 1) {
-                        tc::mma_commit_pair(&acc_full_bar[acc], 3);
-                        if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
-                        wk = 0;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp >= WARP_EPI0 && warp < WARP_EPI0 + EPI_WARPS) {
-        // ===== accumulate into C: warp = 4 + 4 h + q -> TMEM lanes 32q.. (my rows), columns 128 h .. 128 h + 127 of the 256 =====
-        ptx::setmaxnreg_inc<REGS_EPILOGUE>();
-        const int q = (warp - WARP_EPI0) & 3, h = (warp - WARP_EPI0) >> 2;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        const int windows = (group_kblocks + MAX_WINDOW - 1) / MAX_WINDOW;
-        const int shift = -(2 * P0 + SLICE_BITS * p.g);
-        for (int tile = worker; tile < total_tiles; tile += workers) {
-            const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
-            const int row = tm * TILE_M + (int)rank * BM + q * 32 + lane;
-            const bool row_ok = row < p.m;
-            int e_row = row_ok ? p.ea[row] : 0;
-            const bool bad_row = e_row >= NON_FINITE;
-            if (e_row <= NO_DATA || bad_row) e_row = 0;
-            for (int w = 0; w < windows; ++w) {
-                tc::mbar_wait_guarded(&acc_full_bar[acc], acc_phase);
-                tc::fence_after_thread_sync();
-                const bool overwrite = p.first && w == 0;  // the first window of the first launch replaces C (beta applied), all later ones add
-#pragma unroll 1
-                for (int cb = 0; cb < 4; ++cb) {  // 4 x 32 columns of this warp's half
-                    const int col0 = tn * TILE_N + h * 128 + cb * 32;
-                    uint32_t v[32];
-                    tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + h * 128 + cb * 32, v);
-                    tc::tmem_ld_wait();
-                    if (cb == 3) {  // this warp has read its whole share of the window
-                        tc::fence_before_thread_sync();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive_cluster(&acc_empty_bar[acc], 0);
-                    }
-                    double* cp = p.c + (int64_t)col0 * p.ldc + row;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (row_ok && col0 + j < p.n) {
-                            int e_col = p.eb[col0 + j];
-                            const bool bad = bad_row || e_col >= NON_FINITE;
-                            if (e_col <= NO_DATA || bad) e_col = 0;
-                            const double add = bad ? __longlong_as_double(0x7FF8000000000000ll) : p.alpha * scalbn((double)(int)v[j], e_row + e_col + shift);
-                            double* dst = cp + (int64_t)j * p.ldc;
-                            if (overwrite) *dst = p.read_c ? add + p.beta * *dst : add;
-                            else *dst += add;
-                        }
-                    }
-                }
-                if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
-            }
-        }
-    } else {
-        ptx::setmaxnreg_dec<REGS_CONTROL>();
-    }
-
-    tc::fence_before_thread_sync();
-    __syncthreads();
-    tc::cluster_sync();
-    if (warp == WARP_TMEM) {
-        tc::fence_after_thread_sync();
-        tc::tmem_dealloc_pair(tmem_base, TMEM_COLS);
-    }
-}
-}  // namespace pair
-
 }  // namespace f64i8
 
 // process-wide FP64 math mode: 0 = DMMA (default), otherwise the slice count of the int8 emulation (TMM_F64_MATH=i8 -> 8, i8:7 -> 7, ...)
@@ -494,24 +279,17 @@ int f64_i8_slices() {  // read per call (a getenv): tests and A/B scripts switch
     const char* e = getenv("TMM_F64_MATH");
     if (!e || strncmp(e, "i8", 2) != 0) return 0;
     const char* q = e + 2;
-    if (*q == 'p') ++q;  // "i8p": the CTA-pair version (see f64_i8_pairs)
     int s = 8;
     if (q[0] == ':' && q[1]) s = atoi(q + 1);
     return s < 2 ? 2 : (s > f64i8::MAX_SLICES ? f64i8::MAX_SLICES : s);
 }
-static bool f64_i8_pairs() {
-    const char* e = getenv("TMM_F64_MATH");
-    return e && strncmp(e, "i8p", 3) == 0;
-}
-
 // Returns cudaErrorMemoryAllocation when the slice scratch cannot be had (the caller then runs the DMMA kernel); any other error is final.
 cudaError_t dgemm_i8_launch(char ta, char tb, int m, int n, int k, double alpha, const double* a, int64_t lda, const double* b, int64_t ldb, double beta, double* c,
                             int64_t ldc, cudaStream_t st, int slices) {
     using namespace f64i8;
     if (m <= 0 || n <= 0 || k <= 0) return cudaSuccess;
     const int S = slices < 2 ? 2 : (slices > MAX_SLICES ? MAX_SLICES : slices);
-    const bool pairs = f64_i8_pairs();
-    const int64_t m_pad = round_up(m, pairs ? pair::TILE_M : BM), n_pad = round_up(n, pairs ? pair::TILE_N : BN), pitch = round_up(k, 128);
+    const int64_t m_pad = round_up(m, BM), n_pad = round_up(n, BN), pitch = round_up(k, 128);
     if ((int64_t)S * std::max(m_pad, n_pad) > INT32_MAX) return cudaErrorMemoryAllocation;  // TMA coordinates are 32-bit
     const size_t bytes_a = (size_t)S * m_pad * pitch, bytes_b = (size_t)S * n_pad * pitch;
     int8_t *qa = nullptr, *qb = nullptr;
@@ -534,45 +312,7 @@ cudaError_t dgemm_i8_launch(char ta, char tb, int m, int n, int k, double alpha,
     if (e == cudaSuccess && (make_map_i8(&map_a, qa, (uint64_t)k, (uint64_t)S * m_pad, (uint64_t)pitch) != CUDA_SUCCESS ||
                              make_map_i8(&map_b, qb, (uint64_t)k, (uint64_t)S * n_pad, (uint64_t)pitch) != CUDA_SUCCESS))
         e = cudaErrorInvalidValue;
-    if (e == cudaSuccess && pairs) {
-        pair::Params p;
-        p.c = c; p.ldc = ldc; p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta;
-        p.read_c = beta != 0.0;
-        p.tiles_m = (int)(m_pad / pair::TILE_M); p.tiles_n = (int)(n_pad / pair::TILE_N);
-        p.m_pad = (int)m_pad; p.n_pad = (int)n_pad;
-        p.ea = ea; p.eb = eb;
-        p.desc = tc::smem_desc_template(16, 8 * BKB, tc::LAYOUT_SW128);
-        p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pair::TILE_N >> 3) << 17) | ((uint32_t)(pair::TILE_M >> 4) << 24);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        static bool configured_pair[64] = {false};
-        static int resident_pairs[64] = {0};
-        if (dev >= 0 && dev < 64 && !configured_pair[dev]) {
-            e = cudaFuncSetAttribute(pair::igemm_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-            configured_pair[dev] = e == cudaSuccess;
-        }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * (sm_count() / 2)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        if (e == cudaSuccess && dev >= 0 && dev < 64 && resident_pairs[dev] == 0) {  // persistent kernel: no more pairs than can be resident at once
-            int nc = 0;
-            if (cudaOccupancyMaxActiveClusters(&nc, pair::igemm_group_kernel, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); nc = sm_count() / 2; }
-            resident_pairs[dev] = nc;
-        }
-        const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
-        const int npairs = (int)std::min<int64_t>(tiles, (dev >= 0 && dev < 64 && resident_pairs[dev] > 0) ? resident_pairs[dev] : sm_count() / 2);
-        cfg.gridDim = dim3(2 * npairs);
-        for (int g = S - 1; g >= 0 && e == cudaSuccess; --g) {  // smallest terms first; the first launch applies beta
-            p.g = g;
-            p.first = g == S - 1;
-            e = cudaLaunchKernelEx(&cfg, pair::igemm_group_kernel, map_a, map_b, p);
-            count_launch();
-        }
-        if (e == cudaSuccess) e = cudaGetLastError();
-    } else if (e == cudaSuccess) {
+    if (e == cudaSuccess) {
         Params p;
         p.c = c; p.ldc = ldc; p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta;
         p.read_c = beta != 0.0;

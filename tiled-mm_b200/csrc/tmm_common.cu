@@ -68,8 +68,8 @@ static std::atomic<int> g_c32_mode{-1};
 int c32_math_mode() {
     int v = g_c32_mode.load(std::memory_order_relaxed);
     if (v < 0) {
-        const char* e = getenv("TMM_C32_MATH");  // "simt" (default) | "tc"
-        v = (e && (!strcmp(e, "tc") || !strcmp(e, "TC"))) ? 3 : 0;
+        const char* e = getenv("TMM_C32_MATH");  // "tc" (default since round 2: 128 TF vs 45 TF SIMT vs 71 TF cuBLAS CGEMM at 8192^3) | "simt"
+        v = (e && (!strcmp(e, "simt") || !strcmp(e, "SIMT"))) ? 0 : 3;
         g_c32_mode.store(v, std::memory_order_relaxed);
     }
     return v;

@@ -26,8 +26,11 @@
 #include <cstring>
 #include <thread>
 
+#include <sys/mman.h>
 #include <sys/syscall.h>
 #include <unistd.h>
+
+#include <mutex>
 
 namespace tmm {
 
@@ -520,39 +523,8 @@ int pin(tmm_context* ctx, const void* p, size_t bytes, std::vector<const void*>&
         if (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) return TMM_OK;  // nothing to page-lock
     }
     else cudaGetLastError();
-    // Large one-shot registrations dominate a call on pageable memory (page-locking runs at a few GB/s): the range is cut at
-    // 2 MiB boundaries and the pieces are registered from several host threads at once.  Opt-in (TMM_PIN_THREADS=n > 1) until a tile
-    // copy that spans two adjacent registrations has been timed on hardware; the default is one cudaHostRegister, like the reference.
-    static const int pin_threads = [] { const char* v = getenv("TMM_PIN_THREADS"); int t = (v && *v) ? atoi(v) : 1; return t < 1 ? 1 : (t > 16 ? 16 : t); }();
-    if (!ctx->pin_cache && pin_threads > 1 && bytes >= ((size_t)256 << 20)) {
-        const uintptr_t lo = reinterpret_cast<uintptr_t>(p), hi = lo + bytes, huge = (uintptr_t)2 << 20;
-        std::vector<uintptr_t> cut = {lo};
-        for (int t = 1; t < pin_threads; ++t) {
-            const uintptr_t c = (lo + bytes / pin_threads * t + huge - 1) / huge * huge;
-            if (c > cut.back() && c < hi) cut.push_back(c);
-        }
-        cut.push_back(hi);
-        const size_t pieces = cut.size() - 1;
-        std::vector<cudaError_t> res(pieces, cudaSuccess);
-        std::vector<std::thread> pool;
-        for (size_t i = 0; i < pieces; ++i)
-            pool.emplace_back([&, i] {
-                cudaSetDevice(ctx->device);
-                res[i] = cudaHostRegister(reinterpret_cast<void*>(cut[i]), cut[i + 1] - cut[i], cudaHostRegisterDefault);
-            });
-        for (auto& th : pool) th.join();
-        cudaError_t bad = cudaSuccess;
-        for (size_t i = 0; i < pieces; ++i)
-            if (res[i] != cudaSuccess && res[i] != cudaErrorHostMemoryAlreadyRegistered) bad = res[i];
-        for (size_t i = 0; i < pieces; ++i) {
-            if (res[i] != cudaSuccess) continue;
-            if (bad != cudaSuccess) cudaHostUnregister(reinterpret_cast<void*>(cut[i]));
-            else pinned_now.push_back(reinterpret_cast<const void*>(cut[i]));
-        }
-        cudaGetLastError();
-        if (bad != cudaSuccess) return cuda_fail(bad, "cudaHostRegister");
-        return TMM_OK;
-    }
+    // (Registering a large range in several pieces from several threads was tried in round 2 and removed: cudaHostRegister does not get
+    //  faster with threads, and a DMA copy that spans two adjacent registrations fails - profiles/r2_pin_probe.txt.)
     cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
     if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return TMM_OK; }  // already DMA-able: nothing to do, nothing to undo
     if (e != cudaSuccess) return cuda_fail(e, "cudaHostRegister");
@@ -1121,7 +1093,68 @@ int tmm_malloc_pinned(size_t bytes, void** out) {
     CU(cudaHostAlloc(out, bytes ? bytes : 1, 0));  // flags 0, reference util.hpp:67
     return TMM_OK;
 }
-int tmm_free_pinned(void* p) { if (p) CU(cudaFreeHost(p)); return TMM_OK; }
+
+namespace {
+std::mutex g_large_mu;
+std::map<void*, size_t> g_large;  // allocations of tmm_malloc_pinned_large: base -> mapped length
+}  // namespace
+
+// Hundreds of GB of pinned host memory (the out-of-core configs): cudaHostAlloc page-locks at ~2 GB/s on this pool whatever the thread
+// count (240 GB: two minutes), while anonymous memory on 2 MiB pages, first touched by all cores and registered in ONE cudaHostRegister,
+// reaches 26 GB/s and copies at the same 55 GB/s (profiles/r2_pin_probe.txt).  Additive: gpu::malloc_pinned stays cudaHostAlloc, whose
+// result callers may release with cudaFreeHost; memory from here is released with tmm_free_pinned only.
+int tmm_malloc_pinned_large(size_t bytes, void** out) {
+    if (!out) return fail(TMM_ERR_INVALID, "out is null");
+    *out = nullptr;
+#if defined(__linux__) && !defined(TMM_EMULATED)
+    const size_t huge = (size_t)2 << 20;
+    const size_t len = (std::max<size_t>(bytes, 1) + huge - 1) / huge * huge;
+    void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return fail(TMM_ERR_NOMEM, "mmap of %zu bytes of host memory failed", len);
+    madvise(p, len, MADV_HUGEPAGE);  // best effort: with 4 KiB pages the registration is ~3x slower, not wrong
+    {
+        const unsigned n_threads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < n_threads; ++t)
+            pool.emplace_back([=] {
+                char* q = static_cast<char*>(p);
+                const size_t lo = len / huge * t / n_threads * huge, hi = len / huge * (t + 1) / n_threads * huge;
+                for (size_t off = lo; off < hi; off += 4096) q[off] = 0;  // first touch: the kernel zero-fills the page
+            });
+        for (auto& th : pool) th.join();
+    }
+    cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { munmap(p, len); return cuda_fail(e, "cudaHostRegister(large pinned allocation)"); }
+    {
+        std::lock_guard<std::mutex> lk(g_large_mu);
+        g_large[p] = len;
+    }
+    *out = p;
+    return TMM_OK;
+#else
+    return tmm_malloc_pinned(bytes, out);
+#endif
+}
+
+int tmm_free_pinned(void* p) {
+    if (!p) return TMM_OK;
+#if defined(__linux__) && !defined(TMM_EMULATED)
+    size_t len = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_large_mu);
+        auto it = g_large.find(p);
+        if (it != g_large.end()) { len = it->second; g_large.erase(it); }
+    }
+    if (len) {
+        cudaError_t e = cudaHostUnregister(p);
+        munmap(p, len);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaHostUnregister");
+        return TMM_OK;
+    }
+#endif
+    CU(cudaFreeHost(p));
+    return TMM_OK;
+}
 int tmm_malloc_device(size_t bytes, void** out) {
     if (!out) return fail(TMM_ERR_INVALID, "out is null");
     *out = nullptr;
