@@ -16,21 +16,26 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import tiled_mm_b200 as tmm  # noqa: E402
 
-FP64_PEAK, PCIE = 36.9e12, 55.6e9
+try:
+    FP64_PEAK = tmm.probe_fp64_peak() * 1e12
+    PCIE = tmm.probe_host_links([0], nbytes=256 << 20)[0][0] * 1e9
+except Exception:
+    FP64_PEAK, PCIE = 36.9e12, 55.6e9
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--sizes", default="4000,8000,12000,16000,20000,24000,28000,32000")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--beta", type=float, default=1.0)
 ap.add_argument("--no-reference", action="store_true")
+ap.add_argument("--copy-c-back", type=int, default=1, help="0: the miniapp's second variant - C stays on the device (examples/multiply.cpp:196-229)")
 args = ap.parse_args()
 sizes = [int(s) for s in args.sizes.split(",")]
 nmax = max(sizes)
 a = tmm.malloc_pinned(np.float64, nmax * nmax); b = tmm.malloc_pinned(np.float64, nmax * nmax); c = tmm.malloc_pinned(np.float64, nmax * nmax)
-rng = np.random.default_rng(0)
+slab = np.random.default_rng(0).random(1 << 24) - 0.5   # one random slab repeated (the host RNG would take minutes for 25 GB)
 for arr in (a, b, c):
     for off in range(0, arr.size, 1 << 24):
-        arr[off:off + (1 << 24)] = rng.random(min(1 << 24, arr.size - off)) - 0.5
+        arr[off:off + (1 << 24)] = slab[:min(1 << 24, arr.size - off)]
 
 ref = None
 if not args.no_reference:
@@ -42,6 +47,7 @@ if not args.no_reference:
 
 ours = tmm.make_context(np.float64, 2, 5000, 5000, 5000)
 theirs = ref.context(np.float64, 2, 5000, 5000, 5000) if ref else None
+print(f"dgemm n x n x n, alpha = 1, beta = {args.beta}, copy_c_back = {bool(args.copy_c_back)}; FP64 peak {FP64_PEAK * 1e-12:.1f} TF, PCIe {PCIE * 1e-9:.1f} GB/s (both probed live)")
 print(f"{'n':>6} | {'ours ms':>9} {'TF':>6} {'% roof':>6} | {'reference ms':>12} {'TF':>6} | speed-up | PCIe bytes ours / reference")
 for n in sizes:
     flops = 2.0 * n ** 3
@@ -51,13 +57,13 @@ for n in sizes:
         for _ in range(args.reps):
             t0 = time.perf_counter(); fn(); t = min(t, time.perf_counter() - t0)
         return t
-    t_ours = best(lambda: tmm.gemm(ours, "N", "N", n, n, n, 1.0, a, n, b, n, args.beta, c, n, pin_host_buffers=False, copy_c_back=True))
+    t_ours = best(lambda: tmm.gemm(ours, "N", "N", n, n, n, 1.0, a, n, b, n, args.beta, c, n, pin_host_buffers=False, copy_c_back=bool(args.copy_c_back)))
     st = ours.last_stats()
     moved = st.h2d_bytes + st.d2h_bytes
     roof = min(FP64_PEAK, flops / (moved / PCIE))
     row = f"{n:>6} | {t_ours * 1e3:9.2f} {flops / t_ours * 1e-12:6.2f} {100 * flops / t_ours / roof:6.1f} | "
     if theirs:
-        t_ref = best(lambda: theirs.gemm("N", "N", n, n, n, 1.0, a, n, b, n, args.beta, c, n, pin=False, copy_c_back=True))
+        t_ref = best(lambda: theirs.gemm("N", "N", n, n, n, 1.0, a, n, b, n, args.beta, c, n, pin=False, copy_c_back=bool(args.copy_c_back)))
         tile = tmm.optimal_tile_size(n, 5000)
         nt = -(-n // tile)
         ref_bytes = 8 * n * n * (2 * nt + (2 if args.beta else 1))   # n_tiles_n |A| + n_tiles_m |B| + [beta] |C| up, |C| down
