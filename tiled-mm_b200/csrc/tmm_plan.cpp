@@ -128,7 +128,8 @@ Plan make_plan(const PlanInput& in) {
         // GEMM can hide its upload (ratio r of GEMM time to upload time per unit of k), up to the cap
         {
             const double r = (F * (double)m * (double)n1 / kFlops) / ((double)es * (sa * (double)m + sb * (double)n1) / kH2D);
-            const double growth = env_or("TMM_PLAN_GROWTH", std::max(1.25, std::min(2.0, 0.95 * r)));
+            // (round-2 sweep at 10000^3, r = 1.32: growth 1.25 -> 58.57 ms, 1.5 -> 58.16 ms, 2.0 -> 60.08 ms; profiles/r2_sweep_plan.txt)
+            const double growth = env_or("TMM_PLAN_GROWTH", std::max(1.25, std::min(2.0, 1.15 * r)));
             int64_t done = 0;
             int64_t kc = (int64_t)env_or("TMM_PLAN_KC0", 256);
             const int64_t cap = (int64_t)env_or("TMM_PLAN_KCMAX", (double)kc_cap);
