@@ -269,6 +269,45 @@ def run_reference(args, rank: int, world: int) -> None:
     print(json.dumps(base), flush=True)
 
 
+def choose_device(local_rank: int, world: int, ndev: int):
+    """Which GPU does this rank drive?  With fewer ranks than GPUs (N = 2, 4 on an 8-GPU node) the ranks take the GPUs with the best host links:
+    this path is bound by PCIe before anything else, and on this pool's 8-GPU node the links are not alike - with all eight copying both ways,
+    GPUs 4-7 get 11 / 12 GB/s each and GPUs 0-3 8 / 8 (four alone: 23 / 25 vs 13 / 14; profiles/r2_probe_8gpu.txt).  Rank 0 measures every link at
+    once (tmm_probe_host_links, in a child process so that no CUDA context outlives the probe) and publishes the order through a file; the other
+    ranks wait for it.  BENCH_PLACEMENT=0 keeps rank i on GPU i."""
+    if world <= 1 or world >= ndev or os.environ.get("BENCH_PLACEMENT", "1") == "0":
+        return local_rank, "rank i on GPU i"
+    import subprocess
+    import tempfile
+    path = os.path.join(tempfile.gettempdir(), f"tmm_bench_placement_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}.json")
+    order = None
+    if local_rank == 0:
+        try:
+            out = subprocess.run([sys.executable, "-c", "import json, sys; sys.path.insert(0, %r); import tiled_mm_b200 as t; print(json.dumps(t.probe_host_links(nbytes=64 << 20)))" % str(ROOT)],
+                                 capture_output=True, text=True, timeout=120, cwd=str(ROOT))
+            rates = json.loads(out.stdout.strip().splitlines()[-1])
+            ranked = sorted(range(ndev), key=lambda d: -min(rates[d]))
+            order = sorted(ranked[:world])  # the `world` best-connected GPUs, in index order
+        except Exception:
+            order = list(range(world))
+        tmp = path + ".tmp"
+        with open(tmp, "w") as f:
+            json.dump(order, f)
+        os.replace(tmp, path)
+    else:
+        t_end = time.time() + 150.0
+        while time.time() < t_end:
+            try:
+                with open(path) as f:
+                    order = json.load(f)
+                break
+            except Exception:
+                time.sleep(0.05)
+        if order is None:
+            order = list(range(world))
+    return int(order[local_rank]), f"the {world} GPUs with the fastest host links when all {ndev} copy at once: {order}"
+
+
 def ncu_traffic_of_this_build():
     """DRAM bytes per DGEMM launch from an `ncu --set full` capture, if one was taken for THIS library build (profiles/ncu_dgemm_traffic.json
     records the sha256 of the .so it profiled); otherwise None - a number from another build is not printed."""
@@ -309,13 +348,15 @@ def main():
 
     if not torch.cuda.is_available() or tmm.device_count() < 1:
         raise SystemExit("bench.py needs a B200: tiled_mm_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
+    device_index, placement = choose_device(local_rank, world, tmm.device_count())
+    torch.cuda.set_device(device_index)
     dist = None
     if world > 1:
         os.environ.setdefault("TMM_DIST_TIMEOUT_S", "60")  # a grid call here takes well under a second: if a peer dies, give up after a minute instead of the library's 10
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device_index))
+    local_rank = device_index  # from here on "the GPU this rank drives"
 
     def barrier():
         if dist is not None:
@@ -481,7 +522,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": round(e2e_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(S, world, args.streams),
-            "decomposition": {"grid": f"{pr}x{pc}", "rank_block": [m, n, k], "flop_per_gpu": flops_rank,
+            "decomposition": {"grid": f"{pr}x{pc}", "rank_block": [m, n, k], "flop_per_gpu": flops_rank, "gpu_placement": placement,
                               "host_buffers": f"cudaHostAlloc, first touched on the GPU-local NUMA node ({numa.bound} CPUs)" if numa.bound else "cudaHostAlloc (single NUMA node / no binding applied)",
                               "exchange": "A / B panel shares pushed peer-to-peer by the copy engines over NVLink" if world > 1 else "none (one GPU)"},
             "e2e": e2e,

@@ -17,7 +17,6 @@ sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import _util  # noqa: E402
 import tiled_mm_b200 as tmm  # noqa: E402
 
-os.environ.setdefault("TMM_PIN_THREADS", "4")  # opt-in in the product (read once per process): exercised here
 EMUL = Path(os.environ.get("TMM_EMUL_LIB", str(ROOT / "tests" / "emul" / "_build" / "libtiledmm_emul.so")))
 tmm.LIB_PATH = EMUL          # test-only redirection of the ctypes binding; the product never does this
 lib = tmm.load_library()

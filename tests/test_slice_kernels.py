@@ -41,9 +41,14 @@ int no_data() { return NO_DATA; }
 // the launches of gemm_f64_i8.cu prepare(), with the row cap of the slicing grid lowered to exercise its grid-stride loop
 void run_prepare(const double* x, long stride_row, long stride_k, int rows, int k, int slices, int* e, int8_t* out, long pitch, long slice_stride, int row_cap) {
     std::memset(e, 0x88, (size_t)rows * sizeof(int));
-    const int k_per_block = 512;
-    launch(row_exponents, dim3((unsigned)((rows + 255) / 256), (unsigned)((k + k_per_block - 1) / k_per_block)), dim3(256), x, (int64_t)stride_row, (int64_t)stride_k, rows, k,
-           k_per_block, e);
+    if (stride_k == 1) {
+        const int gx = (k + 1023) / 1024 < 8 ? (k + 1023) / 1024 : 8;
+        launch(row_exponents_kmajor, dim3((unsigned)gx, (unsigned)(rows < row_cap ? rows : row_cap)), dim3(256), x, (int64_t)stride_row, rows, k, e);
+    } else {
+        const int k_per_block = 128;
+        launch(row_exponents, dim3((unsigned)((rows + 255) / 256), (unsigned)((k + k_per_block - 1) / k_per_block)), dim3(256), x, (int64_t)stride_row, (int64_t)stride_k, rows, k,
+               k_per_block, e);
+    }
     if (stride_row == 1)   // as in prepare(): the coalesced variant for row-contiguous operands (k-group cap lowered with row_cap to exercise its grid-stride loop)
         launch(slice_rows_contiguous, dim3((unsigned)((rows + 255) / 256), (unsigned)(((k + 15) / 16) < row_cap ? ((k + 15) / 16) : row_cap)), dim3(256), x, (int64_t)stride_k,
                rows, k, (const int*)e, out, (int64_t)pitch, (int64_t)slice_stride, slices);

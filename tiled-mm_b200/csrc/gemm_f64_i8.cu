@@ -1,4 +1,6 @@
-// EXPERIMENTAL, opt-in (TMM_F64_MATH=i8[:slices]) - written after round 1's GPU budget was spent, cross-compiled only, NOT yet run on hardware.
+// Opt-in FP64 math mode (TMM_F64_MATH=i8[:slices]); the default FP64 path is the DMMA kernel of gemm_f64.cu, as north_star specifies.
+// First hardware run in round 2 (profiles/r2_f64_i8_first_run.txt): bit-exact against cuBLAS on integer data for all op pairs, within the FP64 parity
+// bound on random data, 10000^3 device-resident at 47.6 TFLOP/s with 7 slices (1.34 x cuBLAS DGEMM) and 39.0 with 8.
 //
 // FP64-accurate DGEMM on the INTEGER tensor cores (Ozaki-type error-free slicing):  C = alpha * op(A) * op(B) + beta * C.
 // Why: the DMMA kernel of gemm_f64.cu sits at 96 % of the chip's FP64 rate (36.9 TF), and at 10000^3 that rate - not PCIe (46 TF) - bounds
@@ -52,6 +54,7 @@ struct Params {
     int tiles_m, tiles_n;
     int slices;            // S
     int m_pad, n_pad;      // rows between consecutive slices in the A / B slice stacks (multiples of 128)
+    int row0_a, row0_b;    // first row of this product inside the stacks (a stripe of a panel that was sliced once: see i8_gemm_sliced)
     const int* ea;         // [m] row exponents of op(A)
     const int* eb;         // [n] column exponents of op(B)
     uint64_t desc;         // K-major SWIZZLE_128B descriptor template
@@ -128,7 +131,7 @@ dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
                 for (int g = S - 1; g >= 0; --g)
                     for (int s = 0; s <= g; ++s) {
-                        const int row_a = s * p.m_pad + tm * BM, row_b = (g - s) * p.n_pad + tn * BN;
+                        const int row_a = s * p.m_pad + p.row0_a + tm * BM, row_b = (g - s) * p.n_pad + p.row0_b + tn * BN;
                         for (int kb = 0; kb < kblocks; ++kb) {
                             tc::mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
                             ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -239,6 +242,8 @@ dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
 }
 
+static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
 static CUresult make_map_i8(CUtensorMap* map, const void* base, uint64_t k, uint64_t rows, uint64_t pitch_bytes) {
     auto encode = reinterpret_cast<CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill)>(
@@ -252,15 +257,18 @@ static CUresult make_map_i8(CUtensorMap* map, const void* base, uint64_t k, uint
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 
 // exponents + slices of one operand: `rows` rows of k values, element (i, l) at x[i * stride_row + l * stride_k]
 static cudaError_t prepare(const double* x, int64_t stride_row, int64_t stride_k, int rows, int k, int slices, int* e, int8_t* out, int64_t pitch, int64_t slice_stride,
                            cudaStream_t st) {
     cudaError_t err = cudaMemsetAsync(e, 0x88, (size_t)rows * sizeof(int), st);  // every int below NO_DATA
     if (err != cudaSuccess) return err;
-    const int k_per_block = 512;
-    row_exponents<<<dim3((unsigned)((rows + 255) / 256), (unsigned)((k + k_per_block - 1) / k_per_block)), 256, 0, st>>>(x, stride_row, stride_k, rows, k, k_per_block, e);
+    if (stride_k == 1) {  // k contiguous: coalesced along k, one warp-level atomic per 1024 k-values
+        row_exponents_kmajor<<<dim3((unsigned)std::min((k + 1023) / 1024, 8), (unsigned)std::min(rows, 32768)), 256, 0, st>>>(x, stride_row, rows, k, e);
+    } else {
+        const int k_per_block = 128;  // rows contiguous: a thread per row, the k range spread over grid.y for parallelism on narrow chunks
+        row_exponents<<<dim3((unsigned)((rows + 255) / 256), (unsigned)((k + k_per_block - 1) / k_per_block)), 256, 0, st>>>(x, stride_row, stride_k, rows, k, k_per_block, e);
+    }
     count_launch();
     if (stride_row == 1)  // rows contiguous in memory (op(A) = N, op(B) = T): coalesced along the rows
         slice_rows_contiguous<<<dim3((unsigned)((rows + 255) / 256), (unsigned)std::min((k + 15) / 16, 4096)), 256, 0, st>>>(x, stride_k, rows, k, e, out, pitch, slice_stride,
@@ -283,62 +291,81 @@ int f64_i8_slices() {  // read per call (a getenv): tests and A/B scripts switch
     if (q[0] == ':' && q[1]) s = atoi(q + 1);
     return s < 2 ? 2 : (s > f64i8::MAX_SLICES ? f64i8::MAX_SLICES : s);
 }
+size_t i8_slices_layout(int rows, int k, int slices, int64_t* rows_pad, int64_t* pitch) {
+    const int64_t rp = f64i8::round_up(rows, f64i8::BM), pt = f64i8::round_up(k, 128);
+    if (rows_pad) *rows_pad = rp;
+    if (pitch) *pitch = pt;
+    return (size_t)slices * (size_t)rp * (size_t)pt;
+}
+
+cudaError_t i8_slice_operand(const double* x, int64_t stride_row, int64_t stride_k, int rows, int k, const I8Slices& out, cudaStream_t st) {
+    if (rows <= 0 || k <= 0) return cudaSuccess;
+    return f64i8::prepare(x, stride_row, stride_k, rows, k, out.slices, out.e, out.q, out.pitch, out.rows_pad * out.pitch, st);
+}
+
+cudaError_t i8_gemm_sliced(const I8Slices& a, int a_row0, int m, const I8Slices& b, int b_row0, int n, double alpha, double beta, double* c, int64_t ldc, cudaStream_t st) {
+    using namespace f64i8;
+    if (m <= 0 || n <= 0) return cudaSuccess;
+    if (a.k != b.k || a.slices != b.slices || a.pitch != b.pitch || a_row0 < 0 || b_row0 < 0 || a_row0 + m > a.rows || b_row0 + n > b.rows) return cudaErrorInvalidValue;
+    const int S = a.slices, k = a.k;
+    if ((int64_t)S * std::max(a.rows_pad, b.rows_pad) > INT32_MAX) return cudaErrorInvalidValue;  // TMA coordinates are 32-bit
+    CUtensorMap map_a, map_b;
+    if (make_map_i8(&map_a, a.q, (uint64_t)k, (uint64_t)S * a.rows_pad, (uint64_t)a.pitch) != CUDA_SUCCESS ||
+        make_map_i8(&map_b, b.q, (uint64_t)k, (uint64_t)S * b.rows_pad, (uint64_t)b.pitch) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+    Params p;
+    p.c = c; p.ldc = ldc; p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta;
+    p.read_c = beta != 0.0;
+    p.tiles_m = (m + BM - 1) / BM; p.tiles_n = (n + BN - 1) / BN;
+    p.slices = S; p.m_pad = (int)a.rows_pad; p.n_pad = (int)b.rows_pad;
+    p.row0_a = a_row0; p.row0_b = b_row0;
+    p.ea = a.e + a_row0; p.eb = b.e + b_row0;
+    p.desc = tc::smem_desc_template(16, 8 * BKB, tc::LAYOUT_SW128);  // 128-byte rows, 8-row swizzle atoms 1024 B apart
+    //        D = S32 (2)   A, B = signed 8 bit (1)        both K-major        N >> 3                     M >> 4
+    p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(dgemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+    const int grid = (int)std::min<int64_t>(tiles, sm_count());
+    dgemm_i8_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// One self-contained product: slice both operands into stream-ordered scratch, multiply, release.
 // Returns cudaErrorMemoryAllocation when the slice scratch cannot be had (the caller then runs the DMMA kernel); any other error is final.
 cudaError_t dgemm_i8_launch(char ta, char tb, int m, int n, int k, double alpha, const double* a, int64_t lda, const double* b, int64_t ldb, double beta, double* c,
                             int64_t ldc, cudaStream_t st, int slices) {
     using namespace f64i8;
     if (m <= 0 || n <= 0 || k <= 0) return cudaSuccess;
     const int S = slices < 2 ? 2 : (slices > MAX_SLICES ? MAX_SLICES : slices);
-    const int64_t m_pad = round_up(m, BM), n_pad = round_up(n, BN), pitch = round_up(k, 128);
-    if ((int64_t)S * std::max(m_pad, n_pad) > INT32_MAX) return cudaErrorMemoryAllocation;  // TMA coordinates are 32-bit
-    const size_t bytes_a = (size_t)S * m_pad * pitch, bytes_b = (size_t)S * n_pad * pitch;
-    int8_t *qa = nullptr, *qb = nullptr;
+    I8Slices sa, sb;
+    sa.rows = m; sb.rows = n; sa.k = sb.k = k; sa.slices = sb.slices = S;
+    const size_t bytes_a = i8_slices_layout(m, k, S, &sa.rows_pad, &sa.pitch), bytes_b = i8_slices_layout(n, k, S, &sb.rows_pad, &sb.pitch);
+    if ((int64_t)S * std::max(sa.rows_pad, sb.rows_pad) > INT32_MAX) return cudaErrorMemoryAllocation;  // TMA coordinates are 32-bit
     int* ex = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&qa), bytes_a, st);
-    if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&qb), bytes_b, st);
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&sa.q), bytes_a, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&sb.q), bytes_b, st);
     if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&ex), (size_t)(m + n) * sizeof(int), st);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        if (qa) cudaFreeAsync(qa, st);
-        if (qb) cudaFreeAsync(qb, st);
+        if (sa.q) cudaFreeAsync(sa.q, st);
+        if (sb.q) cudaFreeAsync(sb.q, st);
         return cudaErrorMemoryAllocation;
     }
-    int *ea = ex, *eb = ex + m;
+    sa.e = ex; sb.e = ex + m;
     // op(A) row i, k index l:  N: a[l * lda + i]   T/C: a[i * lda + l]        op(B) column j, k index l:  N: b[j * ldb + l]   T/C: b[l * ldb + j]
-    e = prepare(a, ta == 'N' ? 1 : lda, ta == 'N' ? lda : 1, m, k, S, ea, qa, pitch, m_pad * pitch, st);
-    if (e == cudaSuccess) e = prepare(b, tb == 'N' ? ldb : 1, tb == 'N' ? 1 : ldb, n, k, S, eb, qb, pitch, n_pad * pitch, st);
-
-    CUtensorMap map_a, map_b;
-    if (e == cudaSuccess && (make_map_i8(&map_a, qa, (uint64_t)k, (uint64_t)S * m_pad, (uint64_t)pitch) != CUDA_SUCCESS ||
-                             make_map_i8(&map_b, qb, (uint64_t)k, (uint64_t)S * n_pad, (uint64_t)pitch) != CUDA_SUCCESS))
-        e = cudaErrorInvalidValue;
-    if (e == cudaSuccess) {
-        Params p;
-        p.c = c; p.ldc = ldc; p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta;
-        p.read_c = beta != 0.0;
-        p.tiles_m = (int)(m_pad / BM); p.tiles_n = (int)(n_pad / BN);
-        p.slices = S; p.m_pad = (int)m_pad; p.n_pad = (int)n_pad;
-        p.ea = ea; p.eb = eb;
-        p.desc = tc::smem_desc_template(16, 8 * BKB, tc::LAYOUT_SW128);  // 128-byte rows, 8-row swizzle atoms 1024 B apart
-        //        D = S32 (2)   A, B = signed 8 bit (1)        both K-major        N >> 3                     M >> 4
-        p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        static bool configured[64] = {false};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev >= 0 && dev < 64 && !configured[dev]) {
-            e = cudaFuncSetAttribute(dgemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-            configured[dev] = e == cudaSuccess;
-        }
-        if (e == cudaSuccess) {
-            const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
-            const int grid = (int)std::min<int64_t>(tiles, sm_count());
-            dgemm_i8_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
-            count_launch();
-            e = cudaGetLastError();
-        }
-    }
-    cudaFreeAsync(qa, st);
-    cudaFreeAsync(qb, st);
+    e = i8_slice_operand(a, ta == 'N' ? 1 : lda, ta == 'N' ? lda : 1, m, k, sa, st);
+    if (e == cudaSuccess) e = i8_slice_operand(b, tb == 'N' ? ldb : 1, tb == 'N' ? 1 : ldb, n, k, sb, st);
+    if (e == cudaSuccess) e = i8_gemm_sliced(sa, 0, m, sb, 0, n, alpha, beta, c, ldc, st);
+    cudaFreeAsync(sa.q, st);
+    cudaFreeAsync(sb.q, st);
     cudaFreeAsync(ex, st);
     return e;
 }

@@ -63,6 +63,20 @@ void set_c32_math_mode(int mode);
 // experimental FP64 emulation on the int8 tensor cores (gemm_f64_i8.cu; TMM_F64_MATH=i8[:slices], default off): slice count of the process
 // (0 = DMMA), and the launcher - any ld / alignment; cudaErrorMemoryAllocation = no scratch, the caller runs the DMMA kernel instead
 int f64_i8_slices();
+// the two halves of that product, for callers that multiply one sliced panel many times (the scheduler: a k-chunk of A meets several column
+// stripes, the resident A meets every column block): S int8 slices of an operand's `rows` x k values, k contiguous -
+// slice s, row i, k index l at q[(s * rows_pad + i) * pitch + l]; e[i] = power-of-two scale of row i
+struct I8Slices {
+    int8_t* q = nullptr;
+    int* e = nullptr;
+    int rows = 0, k = 0, slices = 0;
+    int64_t rows_pad = 0, pitch = 0;
+};
+size_t i8_slices_layout(int rows, int k, int slices, int64_t* rows_pad, int64_t* pitch);  // bytes of q (e needs `rows` ints)
+// element (row i, k index l) of the operand at x[i * stride_row + l * stride_k]
+cudaError_t i8_slice_operand(const double* x, int64_t stride_row, int64_t stride_k, int rows, int k, const I8Slices& out, cudaStream_t stream);
+// C[m x n] = alpha * A[a_row0 .. a_row0 + m) * B[b_row0 .. b_row0 + n)^T + beta * C on pre-sliced operands (same k, slice count and pitch)
+cudaError_t i8_gemm_sliced(const I8Slices& a, int a_row0, int m, const I8Slices& b, int b_row0, int n, double alpha, double beta, double* c, int64_t ldc, cudaStream_t stream);
 cudaError_t dgemm_i8_launch(char ta, char tb, int m, int n, int k, double alpha, const double* a, int64_t lda, const double* b, int64_t ldb, double beta,
                             double* c, int64_t ldc, cudaStream_t stream, int slices);
 

@@ -207,6 +207,34 @@ size_t device_budget(tmm_context* ctx) {
 
 using tmm::TraceScope;
 
+#ifndef TMM_EMULATED
+// ---- opt-in FP64 emulation on the int8 tensor cores (TMM_F64_MATH=i8[:S], csrc/gemm_f64_i8.cu) inside the resident schedule ------------------
+// Launch by launch the emulation would slice its operands again and again: a k-chunk of A meets up to four column stripes, and the resident
+// A meets every phase-2 column block (9 slicing passes over A at 10000^3; host-to-host 69 ms against 58.6 ms with DMMA, although the kernel
+// itself is 1.34 x faster - profiles/r2_f64_i8_first_run.txt).  Here every panel piece is sliced ONCE, where it lands, and the slice GEMMs
+// run on the cached slices: per k-chunk the A chunk (all stripes share it) and each stripe's B chunk, then - for phase 2 - all of A over the
+// full k (one more pass, its own row scales) and each column block of B.  Slices live in context-owned storage carved per call.
+struct I8Cache {
+    bool on = false;
+    int slices = 0;
+    char* q_base = nullptr; size_t q_off = 0, q_cap = 0;
+    int* e_base = nullptr; size_t e_off = 0, e_cap = 0;
+    std::vector<tmm::I8Slices> a_chunk;               // [chunk]
+    std::vector<std::vector<tmm::I8Slices>> b_chunk;  // [chunk][stripe]
+    tmm::I8Slices a_full;
+    std::vector<tmm::I8Slices> b_block;               // [block]
+    bool carve(tmm::I8Slices* out, int rows, int k) {
+        out->rows = rows; out->k = k; out->slices = slices;
+        const size_t bytes = tmm::i8_slices_layout(rows, k, slices, &out->rows_pad, &out->pitch);
+        const size_t q_at = (q_off + 1023) / 1024 * 1024;
+        if (q_at + bytes > q_cap || e_off + (size_t)rows > e_cap) return false;
+        out->q = reinterpret_cast<int8_t*>(q_base + q_at); q_off = q_at + bytes;
+        out->e = e_base + e_off; e_off += (size_t)rows;
+        return true;
+    }
+};
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // Resident regime: device holds all of A, B and C.
 // ------------------------------------------------------------------------------------------------
@@ -265,6 +293,55 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
             }
         }
     }
+#ifndef TMM_EMULATED
+    I8Cache i8;
+    if (cl.dtype == TMM_F64 && tmm::f64_i8_slices() > 0 && cl.k > 0) {
+        // size the slice storage for this plan; if it cannot be had, every launch slices for itself (the plain path of device_gemm)
+        i8.slices = tmm::f64_i8_slices();
+        const int64_t m_pad = round_up(cl.m, 128);
+        size_t q_need = 0, e_need = 0;
+        int64_t k_pitch_sum = 0, n1_pad = 0;
+        for (int ci = 0; ci < n_chunks; ++ci) k_pitch_sum += round_up(pl.chunks[ci], 128);
+        for (int sidx = 0; sidx < NS; ++sidx) n1_pad += round_up(std::max<int64_t>(0, s_off[sidx + 1] - s_off[sidx]), 128);
+        q_need += (size_t)i8.slices * (size_t)(m_pad + n1_pad) * (size_t)k_pitch_sum + (size_t)(n_chunks * (NS + 1)) * 1024;
+        e_need += (size_t)n_chunks * (size_t)(cl.m + n1);
+        if (!pl.blocks.empty() && n1 < cl.n) {
+            int64_t nb_pad = 0;
+            for (int64_t nb : pl.blocks) nb_pad += round_up(nb, 128);
+            q_need += (size_t)i8.slices * (size_t)(m_pad + nb_pad) * (size_t)round_up(cl.k, 128) + (pl.blocks.size() + 1) * 1024;
+            e_need += (size_t)cl.m + (size_t)(cl.n - n1);
+        }
+        size_t fr = 0, to = 0;
+        const size_t held = ctx->i8_q.cap + ctx->i8_e.cap;
+        if (cudaMemGetInfo(&fr, &to) == cudaSuccess && q_need + e_need * sizeof(int) <= fr + held - std::min<size_t>(fr + held, (size_t)1 << 30) &&
+            ctx->i8_q.reserve(q_need) == cudaSuccess && ctx->i8_e.reserve(e_need * sizeof(int)) == cudaSuccess) {
+            i8.on = true;
+            i8.q_base = static_cast<char*>(ctx->i8_q.p); i8.q_cap = ctx->i8_q.cap;
+            i8.e_base = static_cast<int*>(ctx->i8_e.p); i8.e_cap = ctx->i8_e.cap / sizeof(int);
+            i8.a_chunk.resize(n_chunks);
+            i8.b_chunk.assign(n_chunks, std::vector<tmm::I8Slices>(NS));
+            i8.b_block.resize(pl.blocks.size());
+            for (int ci = 0; ci < n_chunks && i8.on; ++ci) {
+                i8.on = i8.carve(&i8.a_chunk[ci], (int)cl.m, (int)pl.chunks[ci]);
+                for (int sidx = 0; sidx < NS && i8.on; ++sidx)
+                    if (s_off[sidx + 1] > s_off[sidx]) i8.on = i8.carve(&i8.b_chunk[ci][sidx], (int)(s_off[sidx + 1] - s_off[sidx]), (int)pl.chunks[ci]);
+            }
+            if (i8.on && !pl.blocks.empty() && n1 < cl.n) {
+                i8.on = i8.carve(&i8.a_full, (int)cl.m, (int)cl.k);
+                int64_t jb = pl.n1;
+                for (size_t blk = 0; blk < pl.blocks.size() && i8.on; ++blk) {
+                    const int64_t nb = std::min<int64_t>(pl.blocks[blk], cl.n - jb);
+                    if (nb <= 0) break;
+                    i8.on = i8.carve(&i8.b_block[blk], (int)nb, (int)cl.k);
+                    jb += nb;
+                }
+            }
+        } else cudaGetLastError();
+    }
+    const double i8_alpha = *static_cast<const double*>(cl.alpha);
+    // element (row i of op(A), k index l) of a device sub-block of A at base[i * stride_row + l * stride_k]; likewise columns of op(B)
+    const int64_t a_sr = cl.ta == 'N' ? 1 : pa, a_sk = cl.ta == 'N' ? pa : 1, b_sr = cl.tb == 'N' ? pb : 1, b_sk = cl.tb == 'N' ? 1 : pb;
+#endif
     // beta != 0: host C is read (only then, reference tiled_mm.cpp:325).  Uploading the whole C[:, 0:n1] before the first chunk would
     // keep the SMs idle for |C block| / BW_pcie (8 ms at 10000^3); instead stripe s's C travels right before k-chunk s, so the first
     // chain starts after ONE stripe of C and the later stripes join one chunk apart, catching up on the chunks that arrived first.
@@ -280,6 +357,16 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
         const int64_t p0 = chunk_p0[ci], kc = pl.chunks[ci];
         const Sub sa = a_sub(cl, 0, cl.m, p0, kc), sbs = b_sub(cl, p0, kc, js, ws);
         TraceScope ts(ctx, ctx->s_p1[sidx % P1], "gemm1", js, ws, kc);
+#ifndef TMM_EMULATED
+        if (i8.on) {  // this stripe's B chunk is sliced here, once; the A chunk was sliced when it arrived (below)
+            cudaStream_t st = ctx->s_p1[sidx % P1];
+            cudaError_t e8 = tmm::i8_slice_operand(reinterpret_cast<const double*>(dB + ((size_t)sbs.col * pb + sbs.row) * es), b_sr, b_sk, (int)ws, (int)kc, i8.b_chunk[ci][sidx], st);
+            if (e8 == cudaSuccess)
+                e8 = tmm::i8_gemm_sliced(i8.a_chunk[ci], 0, (int)cl.m, i8.b_chunk[ci][sidx], 0, (int)ws, i8_alpha, ci == 0 ? *static_cast<const double*>(cl.beta) : 1.0,
+                                         reinterpret_cast<double*>((char*)dC + (size_t)js * ldc_dev * es), ldc_dev, st);
+            return e8 == cudaSuccess ? TMM_OK : cuda_fail(e8, "int8 slice GEMM (phase 1)");
+        }
+#endif
         return launch_gemm(cl, cl.m, ws, kc, dA + ((size_t)sa.col * pa + sa.row) * es, pa, dB + ((size_t)sbs.col * pb + sbs.row) * es, pb,
                            ci == 0 ? cl.beta : (const void*)cl.one, (char*)dC + (size_t)js * ldc_dev * es, ldc_dev, ctx->s_p1[sidx % P1]);
     };
@@ -298,6 +385,18 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
             int rc = panels_ready(cl, ctx->s_p1, P1);
             if (rc) return rc;
         }
+#ifndef TMM_EMULATED
+        if (i8.on) {  // the chunk of A that just arrived: sliced once on the first stripe's stream, the other stripe streams wait for it
+            TraceScope ts(ctx, ctx->s_p1[0], "sliceA", p0, kc);
+            cudaError_t e8 = tmm::i8_slice_operand(reinterpret_cast<const double*>(dA + ((size_t)sa.col * pa + sa.row) * es), a_sr, a_sk, (int)cl.m, (int)kc, i8.a_chunk[ci], ctx->s_p1[0]);
+            if (e8 != cudaSuccess) return cuda_fail(e8, "int8 slicing of an A chunk");
+            if (P1 > 1) {
+                CU(ctx->get_event(&ev));
+                CU(cudaEventRecord(ev, ctx->s_p1[0]));
+                for (int j = 1; j < P1; ++j) CU(cudaStreamWaitEvent(ctx->s_p1[j], ev, 0));
+            }
+        }
+#endif
         for (int s = 0; s < NS; ++s) {
             if (cl.beta_nonzero && s > ci) continue;                      // this stripe's C has not been sent yet
             if (cl.beta_nonzero && s == ci)                               // it has now: catch up on the chunks that are already here
@@ -332,6 +431,10 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
     }
     // ---- phase 2: A resident; remaining column blocks of B, full k each, C block streams back at once
     int64_t j0 = pl.n1;
+#ifndef TMM_EMULATED
+    bool a_full_sliced = false;
+    cudaEvent_t a_full_ev = nullptr;
+#endif
     for (size_t blk = 0; blk < pl.blocks.size(); ++blk) {
         const int64_t nb = std::min<int64_t>(pl.blocks[blk], cl.n - j0);
         if (nb <= 0) break;  // this rank's block is narrower than the planned one (same for its whole grid column)
@@ -353,6 +456,24 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
             int rc = panels_ready(cl, cs);
             if (rc) return rc;
         }
+#ifndef TMM_EMULATED
+        if (i8.on) {
+            if (!a_full_sliced) {  // all of A is on the device now (the copies this stream just waited for): one slicing pass over the full k
+                TraceScope ts(ctx, cs, "sliceA", 0, cl.k);
+                const Sub sfull = a_sub(cl, 0, cl.m, 0, cl.k);
+                cudaError_t e8 = tmm::i8_slice_operand(reinterpret_cast<const double*>(dA + ((size_t)sfull.col * pa + sfull.row) * es), a_sr, a_sk, (int)cl.m, (int)cl.k, i8.a_full, cs);
+                if (e8 != cudaSuccess) return cuda_fail(e8, "int8 slicing of A");
+                CU(ctx->get_event(&a_full_ev));
+                CU(cudaEventRecord(a_full_ev, cs));
+                a_full_sliced = true;
+            } else CU(cudaStreamWaitEvent(cs, a_full_ev, 0));
+            TraceScope ts(ctx, cs, "gemm2", j0, nb);
+            cudaError_t e8 = tmm::i8_slice_operand(reinterpret_cast<const double*>(db), b_sr, b_sk, (int)nb, (int)cl.k, i8.b_block[blk], cs);
+            if (e8 == cudaSuccess)
+                e8 = tmm::i8_gemm_sliced(i8.a_full, 0, (int)cl.m, i8.b_block[blk], 0, (int)nb, i8_alpha, *static_cast<const double*>(cl.beta), reinterpret_cast<double*>(dcb), ldc_dev, cs);
+            if (e8 != cudaSuccess) return cuda_fail(e8, "int8 slice GEMM (phase 2)");
+        } else
+#endif
         {
             TraceScope ts(ctx, cs, "gemm2", j0, nb);
             int rc = launch_gemm(cl, cl.m, nb, cl.k, dA, pa, db, pb, cl.beta, dcb, ldc_dev, cs);
@@ -619,7 +740,7 @@ void tmm_context_destroy(tmm_context* ctx) {
     for (cudaStream_t s : all) if (s) cudaStreamDestroy(s);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
-    ctx->buf_a.release(); ctx->buf_b.release(); ctx->buf_c.release(); ctx->full_c.release();
+    ctx->buf_a.release(); ctx->buf_b.release(); ctx->buf_c.release(); ctx->full_c.release(); ctx->i8_q.release(); ctx->i8_e.release();
     for (void* old : ctx->retired) cudaFree(old);
     delete ctx;
 }
@@ -889,6 +1010,12 @@ static int gemm_on_context(tmm_context* ctx, char trans_a, char trans_b, int64_t
                 pin_.parts_a = gr.pc; pin_.parts_b = gr.pr;
                 if (gr.active() && ctx->link_h2d_gbs > 0 && ctx->link_d2h_gbs > 0) { pin_.h2d_bw = ctx->link_h2d_gbs * 1e9; pin_.d2h_bw = ctx->link_d2h_gbs * 1e9; }
                 if (cl.dtype == TMM_C32 && tmm::c32_math_mode() == TMM_CMATH_TC) pin_.flops = 140e12;  // complex<float> on the tcgen05 kernel (8mnk real flops)
+#ifndef TMM_EMULATED
+                if (cl.dtype == TMM_F64 && tmm::f64_i8_slices() > 0) {  // opt-in FP64 emulation: a faster GEMM wants a wider first block (the call becomes upload-bound)
+                    const char* fv = getenv("TMM_PLAN_F64_FLOPS");
+                    pin_.flops = (fv && *fv) ? atof(fv) : (tmm::f64_i8_slices() <= 7 ? 55e12 : 42e12);
+                }
+#endif
                 tmm::Plan pl;
                 if (!rc) pl = tmm::make_plan(pin_);
                 ctx->stats.regime = pl.regime;

@@ -44,6 +44,30 @@ static __global__ void __launch_bounds__(256) row_exponents(const double* __rest
     if (best > NO_DATA) atomicMax(&e[i], best);
 }
 
+// The same for operands whose k index is contiguous in memory (stride_k == 1: op(A) = T / C, op(B) = N): the kernel above would read with a
+// stride of one row per lane.  Here blockIdx.y walks the rows (grid-stride) and the threads of a block read 4 consecutive k-values each,
+// 1024 per step - coalesced; one atomicMax per warp (per thread where there are no warps: the CPU build of tests/test_slice_kernels.py).
+static __global__ void __launch_bounds__(256) row_exponents_kmajor(const double* __restrict__ x, int64_t stride_row, int rows, int k, int* __restrict__ e) {
+    for (int i = blockIdx.y; i < rows; i += gridDim.y) {
+        const double* p = x + (int64_t)i * stride_row;
+        int best = NO_DATA;
+        for (int l4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; l4 < k; l4 += gridDim.x * blockDim.x * 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (l4 + j < k) {
+                    const int ex = exponent_above(p[l4 + j]);
+                    best = ex > best ? ex : best;
+                }
+        }
+#ifdef __CUDA_ARCH__
+        best = __reduce_max_sync(0xffffffffu, best);
+        if ((threadIdx.x & 31) == 0 && best > NO_DATA) atomicMax(&e[i], best);
+#else
+        if (best > NO_DATA) atomicMax(&e[i], best);
+#endif
+    }
+}
+
 // q_s[i, l] for s < slices, written as int8 at out[s * slice_stride + i * pitch + l] (bytes); four consecutive l per thread (one 32-bit store
 // per slice); grid.x covers groups of four k-values, grid.y the rows (grid-stride).
 static __global__ void __launch_bounds__(256) slice_rows(const double* __restrict__ x, int64_t stride_row, int64_t stride_k, int rows, int k, const int* __restrict__ e,
@@ -53,16 +77,18 @@ static __global__ void __launch_bounds__(256) slice_rows(const double* __restric
     for (int i = blockIdx.y; i < rows; i += gridDim.y) {
         const bool finite_row = e[i] < NON_FINITE;
         const int ei = (e[i] <= NO_DATA || !finite_row) ? 0 : e[i];
+        // t = x 2^(P0 - e): slice s is q_s = rint(t_s), t_(s+1) = (t_s - q_s) 2^BITS - the same numbers as q_s = rint(r_s 2^(P0 + BITS s)),
+        // r_(s+1) = r_s - q_s 2^-(P0 + BITS s), with one scalbn per element instead of three per slice (t - rint(t) and the scaling by a power
+        // of two are exact); the slicing passes were 11 of the 41 ms of a device-resident 10000^3 call before (profiles/r2_ncu_kernels.md)
         double r[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) r[j] = (finite_row && l4 + j < k) ? scalbn(x[(int64_t)i * stride_row + (int64_t)(l4 + j) * stride_k], -ei) : 0.0;
+        for (int j = 0; j < 4; ++j) r[j] = (finite_row && l4 + j < k) ? scalbn(x[(int64_t)i * stride_row + (int64_t)(l4 + j) * stride_k], P0 - ei) : 0.0;
         for (int s = 0; s < slices; ++s) {
-            const int p = P0 + SLICE_BITS * s;
             uint32_t packed = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const double q = rint(scalbn(r[j], p));
-                r[j] -= scalbn(q, -p);
+                const double q = rint(r[j]);
+                r[j] = (r[j] - q) * (double)(1 << SLICE_BITS);
                 packed |= ((uint32_t)(uint8_t)(int8_t)(int)q) << (8 * j);
             }
             *reinterpret_cast<uint32_t*>(out + (int64_t)s * slice_stride + (int64_t)i * pitch + l4) = packed;
@@ -82,14 +108,13 @@ static __global__ void __launch_bounds__(256) slice_rows_contiguous(const double
     for (int l16 = blockIdx.y * 16; l16 < k; l16 += gridDim.y * 16) {
         double r[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = (finite_row && l16 + j < k) ? scalbn(x[(int64_t)(l16 + j) * stride_k + i], -ei) : 0.0;
+        for (int j = 0; j < 16; ++j) r[j] = (finite_row && l16 + j < k) ? scalbn(x[(int64_t)(l16 + j) * stride_k + i], P0 - ei) : 0.0;
         for (int s = 0; s < slices; ++s) {
-            const int p = P0 + SLICE_BITS * s;
             uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const double q = rint(scalbn(r[j], p));
-                r[j] -= scalbn(q, -p);
+                const double q = rint(r[j]);
+                r[j] = (r[j] - q) * (double)(1 << SLICE_BITS);
                 w[j >> 2] |= ((uint32_t)(uint8_t)(int8_t)(int)q) << (8 * (j & 3));
             }
             uint32_t* dst = reinterpret_cast<uint32_t*>(out + (int64_t)s * slice_stride + (int64_t)i * pitch + l16);
