@@ -1,4 +1,4 @@
-"""The GPU-box scripts under tools/ cost GPU minutes when they are wrong: every one must parse, and the round-2 scripts may only call
+"""The GPU-box scripts under tools/ cost GPU minutes when they are wrong: every one must parse, and the round-2 scripts (tools/r2_*.sh) may only call
 binaries that tools/Makefile / apps/Makefile build, python files that exist, and test files that exist."""
 import re
 import subprocess
@@ -16,7 +16,7 @@ def test_script_parses(script):
     assert r.returncode == 0, r.stderr
 
 
-@pytest.mark.parametrize("script", [s for s in SCRIPTS if s.name.startswith("gpu_round2")], ids=lambda p: p.name)
+@pytest.mark.parametrize("script", [s for s in SCRIPTS if s.name.startswith("r2_")], ids=lambda p: p.name)
 def test_round2_scripts_reference_things_that_exist(script):
     text = script.read_text()
     tools_mk = (ROOT / "tools" / "Makefile").read_text()
@@ -46,7 +46,7 @@ def test_every_switch_the_round2_scripts_set_is_read_somewhere():
                 sources += f.read_text(errors="ignore")
     missing = []
     for script in SCRIPTS:
-        if not script.name.startswith("gpu_round2"):
+        if not script.name.startswith("r2_"):
             continue
         for name in set(re.findall(r"\b(TMM_[A-Z0-9_]+)=", script.read_text())):
             if f'"{name}"' not in sources and f"'{name}'" not in sources:
