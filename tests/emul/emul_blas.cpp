@@ -9,6 +9,7 @@
 #include <cctype>
 #include <cstdio>
 #include <cstring>
+#include <complex>
 #include <vector>
 
 extern "C" int oracle_gemm_ex(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t lda, const void* b,
@@ -50,6 +51,37 @@ cudaError_t device_scale(int dtype, int64_t m, int64_t n, const void* beta, void
     const double one[2] = {0, 0};
     if (emul_dry_run()) return cudaSuccess;
     return oracle_gemm_ex(dtype, 'N', 'N', m, n, 0, one, c, m > 1 ? m : 1, c, 1, beta, c, ldc, 0) == 0 ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+// C += beta * S: element-wise on the host, in the arithmetic of the element type (one multiply, one add - what the device kernel does)
+template <typename T>
+static void add_scaled_host(int64_t m, int64_t n, const void* beta, const void* s, int64_t lds, void* c, int64_t ldc) {
+    const T b = *static_cast<const T*>(beta);
+    const T* sp = static_cast<const T*>(s);
+    T* cp = static_cast<T*>(c);
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t i = 0; i < m; ++i) cp[j * ldc + i] = cp[j * ldc + i] + b * sp[j * lds + i];
+}
+cudaError_t device_add_scaled(int dtype, int64_t m, int64_t n, const void* beta, const void* s, int64_t lds, void* c, int64_t ldc, cudaStream_t st) {
+    if (m <= 0 || n <= 0) return cudaSuccess;
+    const size_t es = dtype_size(dtype);
+    emul_check_device_range(c, ((size_t)(n - 1) * ldc + m) * es);
+    emul_check_device_range(s, ((size_t)(n - 1) * lds + m) * es);
+    {
+        const int sid = emul_op_begin(st);
+        emul_op_access(sid, s, (size_t)lds * es, (size_t)m * es, (size_t)n, 0, "add_scaled S");
+        emul_op_access(sid, c, (size_t)ldc * es, (size_t)m * es, (size_t)n, 1, "add_scaled C");
+    }
+    count_launch();
+    if (emul_dry_run()) return cudaSuccess;
+    switch (dtype) {
+    case F32: add_scaled_host<float>(m, n, beta, s, lds, c, ldc); break;
+    case F64: add_scaled_host<double>(m, n, beta, s, lds, c, ldc); break;
+    case C32: add_scaled_host<std::complex<float>>(m, n, beta, s, lds, c, ldc); break;
+    case C64: add_scaled_host<std::complex<double>>(m, n, beta, s, lds, c, ldc); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t lda, const void* b,

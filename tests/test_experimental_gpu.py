@@ -142,12 +142,14 @@ def test_device_pointer_operands(gpu_tmm, oracle, dtype):
         tmm.free_device(p)
 
 
-@pytest.fixture(params=["i8", "i8:7"], ids=["8-slices", "7-slices"])
+@pytest.fixture(params=[("i8", "1"), ("i8:7", "1"), ("i8:7", "0")], ids=["8-slices", "7-slices", "7-slices-no-clusters"])
 def f64_on_int8(request):
-    """TMM_F64_MATH=i8[:S]: DGEMM as S (S + 1) / 2 exact int8 slice GEMMs on tcgen05 (gemm_f64_i8.cu).  Read per launch."""
-    os.environ["TMM_F64_MATH"] = request.param
+    """TMM_F64_MATH=i8[:S]: DGEMM as S (S + 1) / 2 exact int8 slice GEMMs on tcgen05 (gemm_f64_i8.cu), on 2 x 2 clusters with TMA-multicast operand
+    halves (default) or one CTA per tile (TMM_I8_CLUSTER=0).  Both switches are read per launch."""
+    os.environ["TMM_F64_MATH"], os.environ["TMM_I8_CLUSTER"] = request.param
     yield
     os.environ.pop("TMM_F64_MATH", None)
+    os.environ.pop("TMM_I8_CLUSTER", None)
 
 
 @pytest.mark.parametrize("tt", ALL_TT)
@@ -182,3 +184,11 @@ def test_dgemm_on_int8_non_finite_rows_and_columns(gpu_tmm, f64_on_int8):
     assert np.all(~np.isfinite(out[bad])) and np.all(np.isfinite(out[~bad]))
     a0, b0 = a.copy(), b.copy(); a0[7, 11] = 0; b0[5, 140] = 0
     assert np.array_equal(out[~bad], (a0 @ b0)[~bad])
+
+
+@pytest.mark.parametrize("tt,beta", [("NN", 0.0), ("TN", -1.0), ("NT", 2.0)])
+def test_dgemm_on_int8_through_the_scheduler_with_cached_slices(gpu_tmm, oracle, f64_on_int8, tt, beta):
+    """Host-to-host calls in the opt-in mode: several k-chunks, stripes and phase-2 column blocks, so that the slices cached per call (A chunk once
+    for all stripes, A over the full k once for all blocks) and the row sub-ranges of a slice stack are exercised; exact on integer data."""
+    run_case(gpu_tmm, oracle, np.float64, tt, 1100, 1700, 900, 1.0, beta, pad=(3, 5, 7), ints=True, tiles=(256, 256, 128))
+    run_case(gpu_tmm, oracle, np.float64, tt, 777, 1530, 4100, 1.5, beta, pad=(0, 1, 2), tiles=(256, 300, 500))

@@ -50,7 +50,7 @@ void run_prepare(const double* x, long stride_row, long stride_k, int rows, int 
                k_per_block, e);
     }
     if (stride_row == 1)   // as in prepare(): the coalesced variant for row-contiguous operands (k-group cap lowered with row_cap to exercise its grid-stride loop)
-        launch(slice_rows_contiguous, dim3((unsigned)((rows + 255) / 256), (unsigned)(((k + 15) / 16) < row_cap ? ((k + 15) / 16) : row_cap)), dim3(256), x, (int64_t)stride_k,
+        launch(slice_rows_contiguous, dim3((unsigned)((rows + 255) / 256), (unsigned)(((k + K_PER_THREAD - 1) / K_PER_THREAD) < row_cap ? ((k + K_PER_THREAD - 1) / K_PER_THREAD) : row_cap)), dim3(256), x, (int64_t)stride_k,
                rows, k, (const int*)e, out, (int64_t)pitch, (int64_t)slice_stride, slices);
     else
         launch(slice_rows, dim3((unsigned)((k + 1023) / 1024), (unsigned)(rows < row_cap ? rows : row_cap)), dim3(256), x, (int64_t)stride_row, (int64_t)stride_k, rows, k,

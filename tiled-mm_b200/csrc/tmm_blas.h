@@ -22,6 +22,8 @@ cudaError_t device_gemm(int dtype, char trans_a, char trans_b, int64_t m, int64_
 
 // C = beta * C over an m x n column-major block (beta == 0 writes zeros without reading C).
 cudaError_t device_scale(int dtype, int64_t m, int64_t n, const void* beta, void* c, int64_t ldc, cudaStream_t stream);
+// C += beta * S (m x n, column-major, separate leading dimensions)
+cudaError_t device_add_scaled(int dtype, int64_t m, int64_t n, const void* beta, const void* s, int64_t lds, void* c, int64_t ldc, cudaStream_t stream);
 
 // Number of kernels launched by this layer since process start (bench.py's gpu_launches).
 uint64_t launch_count();

@@ -2,6 +2,8 @@
 // driver entry point lookup.
 #include "tmm_blas.h"
 
+#include <algorithm>
+
 #include <atomic>
 #include <mutex>
 #include <cctype>
@@ -130,6 +132,43 @@ cudaError_t device_scale(int dtype, int64_t m, int64_t n, const void* beta, void
     case F64: { double b = *static_cast<const double*>(beta); return scale_impl<double>(m, n, b, b == 0.0, c, ldc, st); }
     case C32: { const float* b = static_cast<const float*>(beta); return scale_impl<cuFloatComplex>(m, n, make_cuFloatComplex(b[0], b[1]), b[0] == 0.f && b[1] == 0.f, c, ldc, st); }
     case C64: { const double* b = static_cast<const double*>(beta); return scale_impl<cuDoubleComplex>(m, n, make_cuDoubleComplex(b[0], b[1]), b[0] == 0.0 && b[1] == 0.0, c, ldc, st); }
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---- C += beta * S  (the scheduler adds the caller's beta * C at the END of a block's accumulation: its upload then no longer gates the first GEMM)
+template <typename T> struct Fma;
+template <> struct Fma<float> { static __device__ float f(float b, float s, float c) { return c + b * s; } };
+template <> struct Fma<double> { static __device__ double f(double b, double s, double c) { return c + b * s; } };
+template <> struct Fma<cuFloatComplex> { static __device__ cuFloatComplex f(cuFloatComplex b, cuFloatComplex s, cuFloatComplex c) { return cuCaddf(c, cuCmulf(b, s)); } };
+template <> struct Fma<cuDoubleComplex> { static __device__ cuDoubleComplex f(cuDoubleComplex b, cuDoubleComplex s, cuDoubleComplex c) { return cuCadd(c, cuCmul(b, s)); } };
+
+template <typename T>
+__global__ void add_scaled_kernel(T* c, int64_t ldc, const T* __restrict__ s, int64_t lds, int64_t m, int64_t n, T beta) {
+    const int64_t total = m * n;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t col = idx / m, row = idx - col * m;
+        T* p = c + col * ldc + row;
+        *p = Fma<T>::f(beta, s[col * lds + row], *p);
+    }
+}
+
+template <typename T>
+static cudaError_t add_scaled_impl(int64_t m, int64_t n, T beta, const void* s, int64_t lds, void* c, int64_t ldc, cudaStream_t st) {
+    if (m <= 0 || n <= 0) return cudaSuccess;
+    const int64_t total = m * n;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8);
+    add_scaled_kernel<T><<<blocks, 256, 0, st>>>(static_cast<T*>(c), ldc, static_cast<const T*>(s), lds, m, n, beta);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t device_add_scaled(int dtype, int64_t m, int64_t n, const void* beta, const void* s, int64_t lds, void* c, int64_t ldc, cudaStream_t st) {
+    switch (dtype) {
+    case F32: return add_scaled_impl<float>(m, n, *static_cast<const float*>(beta), s, lds, c, ldc, st);
+    case F64: return add_scaled_impl<double>(m, n, *static_cast<const double*>(beta), s, lds, c, ldc, st);
+    case C32: { const float* b = static_cast<const float*>(beta); return add_scaled_impl<cuFloatComplex>(m, n, make_cuFloatComplex(b[0], b[1]), s, lds, c, ldc, st); }
+    case C64: { const double* b = static_cast<const double*>(beta); return add_scaled_impl<cuDoubleComplex>(m, n, make_cuDoubleComplex(b[0], b[1]), s, lds, c, ldc, st); }
     }
     return cudaErrorInvalidValue;
 }

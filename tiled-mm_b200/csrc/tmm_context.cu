@@ -92,6 +92,7 @@ struct Call {
     // stored shapes (reference tiled_mm.cpp:507-514)
     int64_t a_rows, a_cols, b_rows, b_cols;
     unsigned char one[16];  // scalar 1 of the dtype (beta' for k-chunks > 0, tiled_mm.cpp:309)
+    unsigned char zero[16] = {0};  // scalar 0 (first launch of a block whose beta * C is added at the end)
     int64_t m_plan, n_plan;  // dims the schedule was planned for: == m, n on one GPU; the grid-wide maximum block dims on a GPU
                              // grid, where every rank must walk the same schedule so that the panel exchanges line up
 };
@@ -199,7 +200,7 @@ size_t device_budget(tmm_context* ctx) {
     if (ctx->budget_cached) return ctx->budget_cached;  // refreshed whenever an allocation fails or the context grows full C
     size_t fr = 0, to = 0;
     if (cudaMemGetInfo(&fr, &to) != cudaSuccess) return (size_t)8 << 30;
-    size_t held = ctx->buf_a.cap + ctx->buf_b.cap + ctx->buf_c.cap;
+    size_t held = ctx->buf_a.cap + ctx->buf_b.cap + ctx->buf_c.cap + ctx->buf_cs.cap;
     double avail = (double)fr + (double)held;
     ctx->budget_cached = (size_t)(avail * 0.92);
     return ctx->budget_cached;
@@ -238,7 +239,7 @@ struct I8Cache {
 // ------------------------------------------------------------------------------------------------
 // Resident regime: device holds all of A, B and C.
 // ------------------------------------------------------------------------------------------------
-int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
+int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev, void* dCs) {
     tmm_context* ctx = cl.ctx;
     const size_t es = cl.es;
     const int64_t pa = pl.pitch_a, pb = pl.pitch_b;
@@ -258,6 +259,12 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
     const int64_t n1 = std::min<int64_t>(pl.n1, cl.n);  // the plan is for (m_plan, n_plan) >= (m, n): clamp to this rank's block
     ctx->stats.k_chunks = (int)pl.chunks.size();
     ctx->stats.c_blocks = 1 + (int)pl.blocks.size();
+    // beta != 0 with a staging copy: every block starts its accumulation from zero (like beta == 0: no C upload in front of the first GEMM) and
+    // beta * C is added from the staging copy once the block's last launch is done - the C uploads move behind the A / B panels that gate compute.
+    // (Round 1 uploaded C[:, 0:n1] stripe by stripe in front of the first k-chunks: at dgemm 10000^3, beta = 1, the SMs idled ~8 ms early in the
+    //  call and it took 67 ms against 58 ms for beta = 0 although its uploads, 46 ms, fit under the 56 ms of GEMM - profiles/r2_beta1_trace_before.txt.)
+    const bool defer_c = cl.beta_nonzero && dCs != nullptr;
+    const bool c_first = cl.beta_nonzero && !defer_c;
 
     cudaEvent_t ev;
     // ---- phase 1: A streams in as k-chunks with the first column block of B.  The block is cut into P1 column stripes, each a
@@ -277,8 +284,8 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
     int NS = P1;
     int64_t s_off[MAX_STRIPES + 1];
     for (int s = 0; s <= NS; ++s) s_off[s] = s == NS ? n1 : std::min<int64_t>(n1, round_up(n1 * s / NS, 64));
-    if (cl.beta_nonzero) {
-        // Experiment (TMM_PLAN_CSTRIPES=<count> | chunks; not the default until measured): with beta != 0 the work that is unlocked per
+    if (c_first) {
+        // Experiment (TMM_PLAN_CSTRIPES=<count> | chunks; measured in round 2: 71.8 ms against 67.1 ms for the default stripes - not the default): with beta != 0 the work that is unlocked per
         // uploaded byte is largest when the columns of C arrive at the same pace as the k-columns of A, i.e. one stripe per k-chunk
         // with widths in proportion to the chunk widths, instead of a few fat stripes whose C delays the first chunks.
         const char* v = getenv("TMM_PLAN_CSTRIPES");
@@ -362,17 +369,17 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
             cudaStream_t st = ctx->s_p1[sidx % P1];
             cudaError_t e8 = tmm::i8_slice_operand(reinterpret_cast<const double*>(dB + ((size_t)sbs.col * pb + sbs.row) * es), b_sr, b_sk, (int)ws, (int)kc, i8.b_chunk[ci][sidx], st);
             if (e8 == cudaSuccess)
-                e8 = tmm::i8_gemm_sliced(i8.a_chunk[ci], 0, (int)cl.m, i8.b_chunk[ci][sidx], 0, (int)ws, i8_alpha, ci == 0 ? *static_cast<const double*>(cl.beta) : 1.0,
+                e8 = tmm::i8_gemm_sliced(i8.a_chunk[ci], 0, (int)cl.m, i8.b_chunk[ci][sidx], 0, (int)ws, i8_alpha, ci == 0 ? (defer_c ? 0.0 : *static_cast<const double*>(cl.beta)) : 1.0,
                                          reinterpret_cast<double*>((char*)dC + (size_t)js * ldc_dev * es), ldc_dev, st);
             return e8 == cudaSuccess ? TMM_OK : cuda_fail(e8, "int8 slice GEMM (phase 1)");
         }
 #endif
         return launch_gemm(cl, cl.m, ws, kc, dA + ((size_t)sa.col * pa + sa.row) * es, pa, dB + ((size_t)sbs.col * pb + sbs.row) * es, pb,
-                           ci == 0 ? cl.beta : (const void*)cl.one, (char*)dC + (size_t)js * ldc_dev * es, ldc_dev, ctx->s_p1[sidx % P1]);
+                           ci == 0 ? (defer_c ? (const void*)cl.zero : cl.beta) : (const void*)cl.one, (char*)dC + (size_t)js * ldc_dev * es, ldc_dev, ctx->s_p1[sidx % P1]);
     };
     for (int ci = 0; ci < n_chunks; ++ci) {
         const int64_t p0 = chunk_p0[ci], kc = pl.chunks[ci];
-        if (cl.beta_nonzero && ci < NS) { int rc = upload_c_stripe(ci); if (rc) return rc; }
+        if (c_first && ci < NS) { int rc = upload_c_stripe(ci); if (rc) return rc; }
         const Sub sa = a_sub(cl, 0, cl.m, p0, kc), sb = b_sub(cl, p0, kc, 0, n1);
         {
             TraceScope ts(ctx, ctx->s_h2d, "h2dAB", p0, kc);
@@ -398,20 +405,52 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
         }
 #endif
         for (int s = 0; s < NS; ++s) {
-            if (cl.beta_nonzero && s > ci) continue;                      // this stripe's C has not been sent yet
-            if (cl.beta_nonzero && s == ci)                               // it has now: catch up on the chunks that are already here
+            if (c_first && s > ci) continue;                              // this stripe's C has not been sent yet
+            if (c_first && s == ci)                                       // it has now: catch up on the chunks that are already here
                 for (int cj = 0; cj < ci; ++cj) { int rc = launch_stripe_chunk(s, cj); if (rc) return rc; }
             int rc = launch_stripe_chunk(s, ci);
             if (rc) return rc;
         }
     }
-    if (cl.beta_nonzero)
+    if (c_first)
         for (int s = n_chunks; s < NS; ++s) {                             // fewer k-chunks than stripes: the remaining chains start here
             int rc = upload_c_stripe(s);
             if (!rc) rc = panels_ready(cl, &ctx->s_p1[s % P1], 1);
             for (int cj = 0; cj < n_chunks && !rc; ++cj) rc = launch_stripe_chunk(s, cj);
             if (rc) return rc;
         }
+    // phase-2 geometry is needed here already: with deferred C the first column block's B is fetched BEFORE the C stripes of phase 1, so that the
+    // block's GEMM can back-fill the SMs while those stripes travel
+    bool first_block_prefetched = false;
+    if (defer_c) {
+        if (!pl.blocks.empty() && pl.n1 < cl.n) {
+            const int64_t nb0 = std::min<int64_t>(pl.blocks[0], cl.n - pl.n1);
+            if (nb0 > 0) {
+                const Sub sb0 = b_sub(cl, 0, cl.k, pl.n1, nb0);
+                TraceScope ts(ctx, ctx->s_h2d, "h2dB", pl.n1, nb0);
+                int rc = fetch_b(cl, dB + ((size_t)sb0.col * pb + sb0.row) * es, pb, sb0);
+                if (!rc) rc = panels_ready(cl, ctx->s_compute[1]);  // block 0's stream waits for the copies up to HERE, not for the C stripes that follow
+                if (rc) return rc;
+                first_block_prefetched = true;
+            }
+        }
+        for (int sidx = 0; sidx < NS; ++sidx) {
+            const int64_t js = s_off[sidx], ws = s_off[sidx + 1] - js;
+            if (ws <= 0) continue;
+            cudaStream_t st = ctx->s_p1[sidx % P1];
+            {
+                TraceScope ts(ctx, ctx->s_h2d, "h2dC", js, ws);
+                int rc = h2d_2d(cl, (char*)dCs + (size_t)js * ldc_dev * es, ldc_dev, cl.c + (size_t)js * cl.ldc * es, cl.ldc, cl.m, ws, ctx->s_h2d);
+                if (rc) return rc;
+            }
+            CU(ctx->get_event(&ev));
+            CU(cudaEventRecord(ev, ctx->s_h2d));
+            CU(cudaStreamWaitEvent(st, ev, 0));
+            TraceScope ts(ctx, st, "addC", js, ws);
+            cudaError_t e2 = tmm::device_add_scaled(cl.dtype, cl.m, ws, cl.beta, (char*)dCs + (size_t)js * ldc_dev * es, ldc_dev, (char*)dC + (size_t)js * ldc_dev * es, ldc_dev, st);
+            if (e2 != cudaSuccess) return cuda_fail(e2, "C += beta * C_host");
+        }
+    }
     if (cl.copy_c_back) {
         // stripes finish in order; each leaves for the host as soon as its chain is done
         for (int s = 0; s < NS; ++s) {
@@ -439,20 +478,20 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
         const int64_t nb = std::min<int64_t>(pl.blocks[blk], cl.n - j0);
         if (nb <= 0) break;  // this rank's block is narrower than the planned one (same for its whole grid column)
         char* dcb = (char*)dC + (size_t)j0 * ldc_dev * es;
-        if (cl.beta_nonzero) {
+        if (c_first) {
             TraceScope ts(ctx, ctx->s_h2d, "h2dC", j0, nb);
             int rc = h2d_2d(cl, dcb, ldc_dev, cl.c + (size_t)j0 * cl.ldc * es, cl.ldc, cl.m, nb, ctx->s_h2d);
             if (rc) return rc;
         }
         Sub sb = b_sub(cl, 0, cl.k, j0, nb);
         char* db = dB + ((size_t)sb.col * pb + sb.row) * es;
-        {
+        if (!(blk == 0 && first_block_prefetched)) {
             TraceScope ts(ctx, ctx->s_h2d, "h2dB", j0, nb);
             int rc = fetch_b(cl, db, pb, sb);
             if (rc) return rc;
         }
         cudaStream_t cs = ctx->s_compute[1 + blk % (ncs - 1)];
-        {
+        if (!(blk == 0 && first_block_prefetched)) {
             int rc = panels_ready(cl, cs);
             if (rc) return rc;
         }
@@ -470,14 +509,28 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev) {
             TraceScope ts(ctx, cs, "gemm2", j0, nb);
             cudaError_t e8 = tmm::i8_slice_operand(reinterpret_cast<const double*>(db), b_sr, b_sk, (int)nb, (int)cl.k, i8.b_block[blk], cs);
             if (e8 == cudaSuccess)
-                e8 = tmm::i8_gemm_sliced(i8.a_full, 0, (int)cl.m, i8.b_block[blk], 0, (int)nb, i8_alpha, *static_cast<const double*>(cl.beta), reinterpret_cast<double*>(dcb), ldc_dev, cs);
+                e8 = tmm::i8_gemm_sliced(i8.a_full, 0, (int)cl.m, i8.b_block[blk], 0, (int)nb, i8_alpha, defer_c ? 0.0 : *static_cast<const double*>(cl.beta), reinterpret_cast<double*>(dcb), ldc_dev, cs);
             if (e8 != cudaSuccess) return cuda_fail(e8, "int8 slice GEMM (phase 2)");
         } else
 #endif
         {
             TraceScope ts(ctx, cs, "gemm2", j0, nb);
-            int rc = launch_gemm(cl, cl.m, nb, cl.k, dA, pa, db, pb, cl.beta, dcb, ldc_dev, cs);
+            int rc = launch_gemm(cl, cl.m, nb, cl.k, dA, pa, db, pb, defer_c ? (const void*)cl.zero : cl.beta, dcb, ldc_dev, cs);
             if (rc) return rc;
+        }
+        if (defer_c) {  // the block's share of the caller's C travels behind its B; added when both the GEMM and the copy are done
+            char* dsb = (char*)dCs + (size_t)j0 * ldc_dev * es;
+            {
+                TraceScope ts(ctx, ctx->s_h2d, "h2dC", j0, nb);
+                int rc = h2d_2d(cl, dsb, ldc_dev, cl.c + (size_t)j0 * cl.ldc * es, cl.ldc, cl.m, nb, ctx->s_h2d);
+                if (rc) return rc;
+            }
+            CU(ctx->get_event(&ev));
+            CU(cudaEventRecord(ev, ctx->s_h2d));
+            CU(cudaStreamWaitEvent(cs, ev, 0));
+            TraceScope ts(ctx, cs, "addC", j0, nb);
+            cudaError_t e2 = tmm::device_add_scaled(cl.dtype, cl.m, nb, cl.beta, dsb, ldc_dev, dcb, ldc_dev, cs);
+            if (e2 != cudaSuccess) return cuda_fail(e2, "C += beta * C_host");
         }
         if (cl.copy_c_back) {
             CU(ctx->get_event(&ev));
@@ -740,7 +793,7 @@ void tmm_context_destroy(tmm_context* ctx) {
     for (cudaStream_t s : all) if (s) cudaStreamDestroy(s);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
-    ctx->buf_a.release(); ctx->buf_b.release(); ctx->buf_c.release(); ctx->full_c.release(); ctx->i8_q.release(); ctx->i8_e.release();
+    ctx->buf_a.release(); ctx->buf_b.release(); ctx->buf_c.release(); ctx->buf_cs.release(); ctx->full_c.release(); ctx->i8_q.release(); ctx->i8_e.release();
     for (void* old : ctx->retired) cudaFree(old);
     delete ctx;
 }
@@ -1043,7 +1096,13 @@ static int gemm_on_context(tmm_context* ctx, char trans_a, char trans_b, int64_t
                         if ((e = ctx->buf_c.reserve(pl.bytes_c)) != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(C)");
                         dC = ctx->buf_c.p;
                     }
-                    if (!rc) rc = run_resident(cl, pl, dC, cl.copy_c_back ? pl.pitch_c : ldc_dev);
+                    void* dCs = nullptr;  // staging copy of the caller's C (beta != 0): same pitch as dC
+                    if (!rc && pl.bytes_c_stage) {
+                        const size_t need = (size_t)(cl.copy_c_back ? pl.pitch_c : ldc_dev) * n * cl.es;
+                        if ((e = ctx->buf_cs.reserve(need)) != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(C staging)");
+                        dCs = ctx->buf_cs.p;
+                    }
+                    if (!rc) rc = run_resident(cl, pl, dC, cl.copy_c_back ? pl.pitch_c : ldc_dev, dCs);
                     else if (agreed) tmm::grid_bind(ctx, rc);
                 } else {
                     rc = run_streaming(cl, pl, cl.copy_c_back ? nullptr : dC, ldc_dev);
@@ -1053,7 +1112,7 @@ static int gemm_on_context(tmm_context* ctx, char trans_a, char trans_b, int64_t
         const bool nothing_enqueued = ctx->stats.h2d_copies == 0 && ctx->stats.d2h_copies == 0 && tmm::launch_count() == launches_before;
         if (rc == TMM_ERR_NOMEM && attempt == 0 && nothing_enqueued && !ctx->grid.active() && !ctx->budget_override) {
             fprintf(stderr, "tiled_mm_b200: device allocation failed (%s); releasing staging storage and re-planning with the current free memory\n", tmm_last_error());
-            ctx->buf_a.release(); ctx->buf_b.release(); ctx->buf_c.release();
+            ctx->buf_a.release(); ctx->buf_b.release(); ctx->buf_c.release(); ctx->buf_cs.release();
             ctx->budget_cached = 0;
             rc = TMM_OK;
             continue;

@@ -76,10 +76,14 @@ Plan make_plan(const PlanInput& in) {
     const double kH2D = in.h2d_bw > 0 ? in.h2d_bw : kH2D_alone, kD2H = in.d2h_bw > 0 ? in.d2h_bw : kD2H_alone;
     const int64_t kc_cap = std::max<int64_t>(256, std::min<int64_t>(2048, round_up(std::max(64, in.tile_k), 64)));
 
-    if (full_a + full_b + full_c <= in.budget) {
+    // beta != 0 in the resident regime: the caller's C is uploaded into a staging copy and added when a block's accumulation is complete, so
+    // that its upload does not gate the first GEMM (make_plan's consumer: run_resident).  TMM_PLAN_DEFER_C=0: upload it up front as in round 1.
+    const bool defer_c = in.beta_nonzero && env_or("TMM_PLAN_DEFER_C", 1.0) != 0.0;
+    const size_t stage_c = defer_c ? (size_t)p.pitch_c * n * es : 0;
+    if (full_a + full_b + full_c + stage_c <= in.budget) {
         // ---------------- resident ----------------
         p.regime = REGIME_RESIDENT;
-        p.bytes_a = full_a; p.bytes_b = full_b; p.bytes_c = full_c;
+        p.bytes_a = full_a; p.bytes_b = full_b; p.bytes_c = full_c; p.bytes_c_stage = stage_c;
         // phase-1 column block: wide enough that a k-chunk's GEMM outlasts its upload (with 20 % margin)
         // (m too small for that => the call is PCIe-bound whatever we do: bring A in behind a narrow block and let
         //  phase 2 overlap the D2H of finished C blocks with the H2D of later B blocks)
@@ -130,12 +134,23 @@ Plan make_plan(const PlanInput& in) {
             const double r = (F * (double)m * (double)n1 / kFlops) / ((double)es * (sa * (double)m + sb * (double)n1) / kH2D);
             // (round-2 sweep at 10000^3, r = 1.32: growth 1.25 -> 58.57 ms, 1.5 -> 58.16 ms, 2.0 -> 60.08 ms; profiles/r2_sweep_plan.txt)
             const double growth = env_or("TMM_PLAN_GROWTH", std::max(1.25, std::min(2.0, 1.15 * r)));
+            // When phase 1 as a whole is upload-bound (beta != 0 adds the C block to its uploads; narrow m; slow links of a GPU grid), the GEMMs keep
+            // up with the arriving chunks and what remains after the LAST byte has landed is the last chunk's GEMM - exposed in full.  Then the
+            // chunks taper off again: never more than ~1/3 of the k range that is still to come.  (dgemm 10000^3 beta = 1: the 2896-wide last chunk
+            // of the growth-only schedule left 8.9 ms of GEMM behind the last upload, profiles/r2_beta1_trace_before.txt.)
+            const double t_up1 = (double)es * ((double)k * (sa * (double)m + sb * (double)n1) + ((in.beta_nonzero && !defer_c) ? (double)m * (double)n1 : 0.0)) / kH2D;
+            const double t_gemm1 = F * (double)m * (double)n1 * (double)k / kFlops;
+            const bool taper = env_or("TMM_PLAN_TAPER", t_gemm1 < 1.15 * t_up1 ? 1.0 : 0.0) != 0.0;
             int64_t done = 0;
             int64_t kc = (int64_t)env_or("TMM_PLAN_KC0", 256);
             const int64_t cap = (int64_t)env_or("TMM_PLAN_KCMAX", (double)kc_cap);
             while (done < k) {
                 int64_t c = std::min(kc, k - done);
-                if (k - done - c < kc / 2) c = k - done;  // fold a small remainder into this chunk
+                if (taper) {
+                    const int64_t third = std::max<int64_t>(512, (int64_t)(0.35 * (double)(k - done)) / 64 * 64);
+                    c = std::min(c, third);
+                    if (k - done - c < 384) c = k - done;
+                } else if (k - done - c < kc / 2) c = k - done;  // fold a small remainder into this chunk
                 p.chunks.push_back(c);
                 done += c;
                 kc = std::min<int64_t>(cap, std::max<int64_t>(kc + 64, (int64_t)((double)kc * growth) / 64 * 64));

@@ -33,6 +33,7 @@ struct Plan {
     int64_t a_rows = 0, a_cols = 0, b_rows = 0, b_cols = 0;  // stored shapes (reference tiled_mm.cpp:507-514)
     int64_t pitch_a = 0, pitch_b = 0, pitch_c = 0;           // device pitches in elements (128-byte multiples)
     size_t bytes_a = 0, bytes_b = 0, bytes_c = 0;            // device bytes (bytes_c = 0 when C lives in the context's full C)
+    size_t bytes_c_stage = 0;                                // resident regime, beta != 0: staging copy of the caller's C (added at the end of each block's accumulation)
     // resident regime
     int64_t n1 = 0;                  // phase-1 column block [0, n1)
     std::vector<int64_t> chunks;     // phase-1 k-chunk widths, sum = k

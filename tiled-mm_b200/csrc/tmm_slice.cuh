@@ -97,28 +97,35 @@ static __global__ void __launch_bounds__(256) slice_rows(const double* __restric
 }
 
 // The same for operands whose ROWS are contiguous in memory (stride_row == 1: op(A) = N, op(B) = T): consecutive threads take consecutive
-// rows, so every read is a coalesced run along the rows; a thread handles sixteen k-values and stores them as one 16-byte vector per slice.
-// grid.x covers the rows, grid.y groups of sixteen k-values (grid-stride).  pitch and slice_stride are multiples of 16.
+// rows, so every read is a coalesced run along the rows; a thread handles K_PER_THREAD = 32 k-values and stores them as two 16-byte vectors
+// per slice = one full 32-byte sector (the first version stored four separate words per 16 k-values: every warp store touched 32 sectors for
+// 4 useful bytes each, and this pass was most of the 10 ms the passes took at 10000^3).  grid.x covers the rows, grid.y groups of 32 k-values
+// (grid-stride).  pitch and slice_stride are multiples of 32.
+constexpr int K_PER_THREAD = 32;
+struct alignas(16) Q16 { uint32_t w[4]; };
 static __global__ void __launch_bounds__(256) slice_rows_contiguous(const double* __restrict__ x, int64_t stride_k, int rows, int k, const int* __restrict__ e,
                                                                     int8_t* __restrict__ out, int64_t pitch, int64_t slice_stride, int slices) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     const bool finite_row = e[i] < NON_FINITE;
     const int ei = (e[i] <= NO_DATA || !finite_row) ? 0 : e[i];
-    for (int l16 = blockIdx.y * 16; l16 < k; l16 += gridDim.y * 16) {
-        double r[16];
+    for (int l0 = blockIdx.y * K_PER_THREAD; l0 < k; l0 += gridDim.y * K_PER_THREAD) {
+        double r[K_PER_THREAD];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = (finite_row && l16 + j < k) ? scalbn(x[(int64_t)(l16 + j) * stride_k + i], P0 - ei) : 0.0;
+        for (int j = 0; j < K_PER_THREAD; ++j) r[j] = (finite_row && l0 + j < k) ? scalbn(x[(int64_t)(l0 + j) * stride_k + i], P0 - ei) : 0.0;
         for (int s = 0; s < slices; ++s) {
-            uint32_t w[4] = {0, 0, 0, 0};
+            Q16 q[K_PER_THREAD / 16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const double q = rint(r[j]);
-                r[j] = (r[j] - q) * (double)(1 << SLICE_BITS);
-                w[j >> 2] |= ((uint32_t)(uint8_t)(int8_t)(int)q) << (8 * (j & 3));
+            for (int v = 0; v < K_PER_THREAD / 16; ++v) q[v].w[0] = q[v].w[1] = q[v].w[2] = q[v].w[3] = 0;
+#pragma unroll
+            for (int j = 0; j < K_PER_THREAD; ++j) {
+                const double t = rint(r[j]);
+                r[j] = (r[j] - t) * (double)(1 << SLICE_BITS);
+                q[j >> 4].w[(j >> 2) & 3] |= ((uint32_t)(uint8_t)(int8_t)(int)t) << (8 * (j & 3));
             }
-            uint32_t* dst = reinterpret_cast<uint32_t*>(out + (int64_t)s * slice_stride + (int64_t)i * pitch + l16);
-            dst[0] = w[0]; dst[1] = w[1]; dst[2] = w[2]; dst[3] = w[3];
+            Q16* dst = reinterpret_cast<Q16*>(out + (int64_t)s * slice_stride + (int64_t)i * pitch + l0);
+#pragma unroll
+            for (int v = 0; v < K_PER_THREAD / 16; ++v) dst[v] = q[v];
         }
     }
 }
