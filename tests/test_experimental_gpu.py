@@ -142,14 +142,12 @@ def test_device_pointer_operands(gpu_tmm, oracle, dtype):
         tmm.free_device(p)
 
 
-@pytest.fixture(params=[("i8", "1"), ("i8:7", "1"), ("i8:7", "0")], ids=["8-slices", "7-slices", "7-slices-no-clusters"])
+@pytest.fixture(params=["i8", "i8:7"], ids=["8-slices", "7-slices"])
 def f64_on_int8(request):
-    """TMM_F64_MATH=i8[:S]: DGEMM as S (S + 1) / 2 exact int8 slice GEMMs on tcgen05 (gemm_f64_i8.cu), on 2 x 2 clusters with TMA-multicast operand
-    halves (default) or one CTA per tile (TMM_I8_CLUSTER=0).  Both switches are read per launch."""
-    os.environ["TMM_F64_MATH"], os.environ["TMM_I8_CLUSTER"] = request.param
+    """TMM_F64_MATH=i8[:S]: DGEMM as S (S + 1) / 2 exact int8 slice GEMMs on tcgen05 (gemm_f64_i8.cu).  Read per launch."""
+    os.environ["TMM_F64_MATH"] = request.param
     yield
     os.environ.pop("TMM_F64_MATH", None)
-    os.environ.pop("TMM_I8_CLUSTER", None)
 
 
 @pytest.mark.parametrize("tt", ALL_TT)

@@ -19,6 +19,10 @@
 //   * TWO accumulate/epilogue warpgroups (warps 4-7: columns 0-63, warps 8-11: columns 64-127): int32 -> double, scaled by the group's power
 //     of two (exact), added into 64 FP64 registers per thread; tile end: scalbn by ea[i] + eb[j], alpha / beta, plain stores (any ldc)
 //   * int32 never overflows: |q| <= 64, so a window of W k-blocks adds at most W * 128 * 4096 < 2^31 for W <= 4095; longer groups are cut
+// What bounds it (round 2): 627 cycles per k-block against 271 of integer MMA work - the six 32 KB stages in flight per SM over a ~1.9 us load
+// latency are exactly the measured 15 TB/s of L2 -> SM traffic.  A variant on 2 x 2 clusters that TMA-multicasts operand halves (half the L2
+// requests, same bytes landing per SM) ran at the same pace per CTA with fewer CTAs resident (33 clusters) and was removed
+// (profiles/r2_i8_cluster_experiment.txt); more MACs per landed byte needs 256-wide tiles, i.e. another home for the FP64 sums.
 #include "tmm_blas.h"
 #include "tmm_tc.cuh"
 #include "tmm_slice.cuh"
@@ -39,7 +43,7 @@ constexpr int ACC_BUFS = 4, TMEM_COLS = ACC_BUFS * BN;
 constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_TMEM = 2, WARP_EPI0 = 4, EPI_WARPS = 8;
 constexpr int THREADS = 512;
 constexpr int REGS_CONTROL = 40, REGS_EPILOGUE = 208;  // 40 + 208 + 208 + 40 <= 512
-constexpr int GROUP_COLS = 16;
+constexpr int GROUP_COLS = 8;                    // raster width (measured 2 / 4 / 8 / 16: 41.3 / 40.6 / 40.4 / 41.3 ms at 10000^3, profiles/r2_i8_cluster_experiment.txt)
 constexpr int MAX_WINDOW = 2048;                 // k-blocks per int32 accumulation window (overflow bound: 4095)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -82,14 +86,6 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t desc_a, uint64_
         : "memory");
 }
 
-// CL = 1: one CTA per tile, every CTA loads its own 16 KB + 16 KB per k-block (128 MAC per byte from L2: the kernel is L2-bandwidth-bound,
-//         15 TB/s L2 -> SM with the integer pipe 44 % active - profiles/r2_ncu_kernels.md).
-// CL = 2: clusters of 2 x 2 CTAs on 2 x 2 neighbouring tiles.  The two CTAs of a cluster row need the same A tile, those of a cluster column the
-//         same B tile: every CTA loads HALF of its A tile and HALF of its B tile (64 rows = 8 swizzle atoms each) and TMA-multicasts each half to
-//         itself and the partner that needs it - 16 KB instead of 32 KB per CTA and k-block.  MMAs, TMEM and epilogue stay per CTA (cta_group::1).
-//         A stage is refilled by three producers (own halves, the A partner's half, the B partner's half), so its empty barrier collects the MMA
-//         commits of all three CTAs (multicast commit); cluster barriers bracket the kernel.
-template <int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
     extern __shared__ unsigned char smem_raw[];
@@ -107,7 +103,7 @@ dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], CL == 2 ? 3 : 1);
+            ptx::mbar_init(&empty_bar[s], 1);
         }
 #pragma unroll
         for (int b = 0; b < ACC_BUFS; ++b) {
@@ -119,24 +115,12 @@ dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (warp == WARP_TMEM) tc::tmem_alloc(tmem_slot, TMEM_COLS);
     tc::fence_before_thread_sync();
     __syncthreads();
-    if (CL == 2) tc::cluster_sync();  // the partners' barriers exist before anything is multicast at them
     tc::fence_after_thread_sync();
     const uint32_t tmem_base = *tmem_slot;
 
+    const int total_tiles = p.tiles_m * p.tiles_n;
     const int kblocks = (p.k + BKB - 1) / BKB;
     const int S = p.slices;
-    // work units: tiles (CL = 1) or 2 x 2 super-tiles (CL = 2), walked by CTAs / clusters in the same column-group raster
-    const uint32_t crank = CL == 2 ? tc::cluster_ctarank() : 0u;
-    const int rm = (int)(crank & 1u), rn = (int)(crank >> 1);
-    const uint16_t mask_a = (uint16_t)((1u << crank) | (1u << (crank ^ 2u)));  // same cluster row (same A tile)
-    const uint16_t mask_b = (uint16_t)((1u << crank) | (1u << (crank ^ 1u)));  // same cluster column (same B tile)
-    const int units_m = CL == 2 ? (p.tiles_m + 1) / 2 : p.tiles_m, units_n = CL == 2 ? (p.tiles_n + 1) / 2 : p.tiles_n;
-    const int total_tiles = units_m * units_n;
-    const int unit0 = CL == 2 ? (int)tc::cluster_id_x() : (int)blockIdx.x, unit_step = CL == 2 ? (int)tc::cluster_count_x() : (int)gridDim.x;
-    auto coords = [&](int unit, int& tm, int& tn) {
-        tile_coords(unit, units_m, units_n, tm, tn);
-        if (CL == 2) { tm = 2 * tm + rm; tn = 2 * tn + rn; }  // (a CTA beyond the matrix edge still loads and multiplies: its partners need its halves and its commits; stores are masked)
-    };
 
     if (warp == WARP_TMA) {
         // ===== TMA producer: for g = S-1 .. 0, for s = 0 .. g: A slice s against B slice g - s =====
@@ -146,9 +130,9 @@ dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             ptx::prefetch_tensormap(&tmap_b);
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int tm, tn;
-                coords(tile, tm, tn);
+                tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
                 for (int g = S - 1; g >= 0; --g)
                     for (int s = 0; s <= g; ++s) {
                         const int row_a = s * p.m_pad + p.row0_a + tm * BM, row_b = (g - s) * p.n_pad + p.row0_b + tn * BN;
@@ -156,13 +140,8 @@ dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                             tc::mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
                             ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
                             unsigned char* sa = base + stage * STAGE_BYTES;
-                            if (CL == 2) {  // my half of the A tile to my cluster row, my half of the B tile to my cluster column
-                                ptx::tma_load_2d_multicast(sa + rn * (OPERAND_BYTES / 2), &tmap_a, &full_bar[stage], kb * BKB, row_a + rn * (BM / 2), mask_a);
-                                ptx::tma_load_2d_multicast(sa + OPERAND_BYTES + rm * (OPERAND_BYTES / 2), &tmap_b, &full_bar[stage], kb * BKB, row_b + rm * (BN / 2), mask_b);
-                            } else {
-                                ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BKB, row_a);
-                                ptx::tma_load_2d(sa + OPERAND_BYTES, &tmap_b, &full_bar[stage], kb * BKB, row_b);
-                            }
+                            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BKB, row_a);
+                            ptx::tma_load_2d(sa + OPERAND_BYTES, &tmap_b, &full_bar[stage], kb * BKB, row_b);
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -175,7 +154,7 @@ dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (lane == 0) {
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 for (int g = S - 1; g >= 0; --g) {
                     const int group_kblocks = (g + 1) * kblocks;
                     uint32_t d_tmem = 0;
@@ -191,8 +170,7 @@ dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
                         for (int ks = 0; ks < BKB / UMMA_KB; ++ks)
                             mma_i8(d_tmem, tc::smem_desc(p.desc, sa + ks * UMMA_KB), tc::smem_desc(p.desc, sb + ks * UMMA_KB), p.idesc, (wk | ks) ? 1u : 0u);
-                        if (CL == 2) tc::mma_commit_multicast(&empty_bar[stage], (uint16_t)(mask_a | mask_b));
-                        else tc::mma_commit(&empty_bar[stage]);
+                        tc::mma_commit(&empty_bar[stage]);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         if (++wk == MAX_WINDOW || kb == group_kblocks - 1) {
                             tc::mma_commit(&acc_full_bar[acc]);
@@ -210,9 +188,9 @@ dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int q = (warp - WARP_EPI0) & 3, h = (warp - WARP_EPI0) >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int tm, tn;
-            coords(tile, tm, tn);
+            tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
             double sum[64];
 #pragma unroll
             for (int j = 0; j < 64; ++j) sum[j] = 0.0;
@@ -262,7 +240,6 @@ dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
     tc::fence_before_thread_sync();
     __syncthreads();
-    if (CL == 2) tc::cluster_sync();  // no CTA leaves while a partner may still multicast into its stages or arrive on its barriers
     if (warp == WARP_TMEM) {
         tc::fence_after_thread_sync();
         tc::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -271,14 +248,14 @@ dgemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
 static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 
-static CUresult make_map_i8(CUtensorMap* map, const void* base, uint64_t k, uint64_t rows, uint64_t pitch_bytes, uint32_t box_rows = BM) {
+static CUresult make_map_i8(CUtensorMap* map, const void* base, uint64_t k, uint64_t rows, uint64_t pitch_bytes) {
     auto encode = reinterpret_cast<CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill)>(
         tensormap_encode_fn());
     if (!encode) return CUDA_ERROR_NOT_SUPPORTED;
     cuuint64_t dims[2] = {k, rows};
     cuuint64_t strides[1] = {pitch_bytes};
-    cuuint32_t box[2] = {BKB, box_rows};
+    cuuint32_t box[2] = {BKB, BM};
     cuuint32_t estr[2] = {1, 1};
     return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -336,18 +313,14 @@ cudaError_t i8_gemm_sliced(const I8Slices& a, int a_row0, int m, const I8Slices&
     if (a.k != b.k || a.slices != b.slices || a.pitch != b.pitch || a_row0 < 0 || b_row0 < 0 || a_row0 + m > a.rows || b_row0 + n > b.rows) return cudaErrorInvalidValue;
     const int S = a.slices, k = a.k;
     if ((int64_t)S * std::max(a.rows_pad, b.rows_pad) > INT32_MAX) return cudaErrorInvalidValue;  // TMA coordinates are 32-bit
-    const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
-    // 2 x 2 clusters with multicast halves (TMM_I8_CLUSTER=0: one CTA per tile) when there are at least 2 x 2 tiles
-    const char* clv = getenv("TMM_I8_CLUSTER");
-    const bool clusters = !(clv && clv[0] == '0') && tiles_m >= 2 && tiles_n >= 2;
     CUtensorMap map_a, map_b;
-    if (make_map_i8(&map_a, a.q, (uint64_t)k, (uint64_t)S * a.rows_pad, (uint64_t)a.pitch, clusters ? BM / 2 : BM) != CUDA_SUCCESS ||
-        make_map_i8(&map_b, b.q, (uint64_t)k, (uint64_t)S * b.rows_pad, (uint64_t)b.pitch, clusters ? BN / 2 : BN) != CUDA_SUCCESS)
+    if (make_map_i8(&map_a, a.q, (uint64_t)k, (uint64_t)S * a.rows_pad, (uint64_t)a.pitch) != CUDA_SUCCESS ||
+        make_map_i8(&map_b, b.q, (uint64_t)k, (uint64_t)S * b.rows_pad, (uint64_t)b.pitch) != CUDA_SUCCESS)
         return cudaErrorInvalidValue;
     Params p;
     p.c = c; p.ldc = ldc; p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta;
     p.read_c = beta != 0.0;
-    p.tiles_m = tiles_m; p.tiles_n = tiles_n;
+    p.tiles_m = (m + BM - 1) / BM; p.tiles_n = (n + BN - 1) / BN;
     p.slices = S; p.m_pad = (int)a.rows_pad; p.n_pad = (int)b.rows_pad;
     p.row0_a = a_row0; p.row0_b = b_row0;
     p.ea = a.e + a_row0; p.eb = b.e + b_row0;
@@ -355,37 +328,16 @@ cudaError_t i8_gemm_sliced(const I8Slices& a, int a_row0, int m, const I8Slices&
     //        D = S32 (2)   A, B = signed 8 bit (1)        both K-major        N >> 3                     M >> 4
     p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     static bool configured[64] = {false};
-    static int resident_clusters[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(dgemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(dgemm_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(dgemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    if (clusters) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(4 * (sm_count() / 4)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        if (dev >= 0 && dev < 64 && resident_clusters[dev] == 0) {  // persistent kernel: no more clusters than can be resident at once
-            int nc = 0;
-            if (cudaOccupancyMaxActiveClusters(&nc, dgemm_i8_kernel<2>, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); nc = sm_count() / 4 - 2; }
-            resident_clusters[dev] = nc;
-        }
-        const int64_t units = (int64_t)((tiles_m + 1) / 2) * ((tiles_n + 1) / 2);
-        const int ncl = (int)std::min<int64_t>(units, (dev >= 0 && dev < 64 && resident_clusters[dev] > 0) ? resident_clusters[dev] : sm_count() / 4 - 2);
-        cfg.gridDim = dim3(4 * ncl);
-        cudaError_t e = cudaLaunchKernelEx(&cfg, dgemm_i8_kernel<2>, map_a, map_b, p);
-        count_launch();
-        return e != cudaSuccess ? e : cudaGetLastError();
-    }
     const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
     const int grid = (int)std::min<int64_t>(tiles, sm_count());
-    dgemm_i8_kernel<1><<<grid, THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
+    dgemm_i8_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
     count_launch();
     return cudaGetLastError();
 }

@@ -54,16 +54,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
-// The same load delivered to the same shared-memory offset of every CTA in `cta_mask` of this cluster; each destination's mbarrier (same offset)
-// is credited with the bytes that land there.
-__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-        : "memory");
-}
-
 // Warpgroup register reallocation (all 4 warps of a warpgroup must execute it).
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {

@@ -90,13 +90,6 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
 }
 
-// ... and on the barrier at the same offset in every CTA of `cta_mask` (a cluster whose CTAs multicast operand halves into each other's stages:
-// a stage may be refilled only when every CTA that receives a share of the refill has retired its MMAs on it)
-__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(ptx::smem_u32(bar)), "h"(cta_mask)
-                 : "memory");
-}
-
 // TMEM -> registers: lane i of the warp reads TMEM lane (base lane + i), 32 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -136,9 +129,8 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity
 }
 
 
-// ---- clusters ------------------------------------------------------------------------------------------------------------------------
-// (the cta_group::2 helpers below were validated by tools/tc_probe2.cu and the round-2 variants that used them; the kernels that remain use
-//  clusters for TMA multicast only)
+// ---- CTA pairs (cta_group::2): the two CTAs of a cluster share one 256-row MMA issued by the CTA of rank 0 ------------------------
+// (experimental - gemm_f32_tc.cu sgemm_tc_ts_kernel<true>, TMM_TC_ATMEM=2; not yet run on hardware)
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
