@@ -16,8 +16,13 @@ for n in $G $((G/2)); do
   echo "##### bench.py --gpus $n"
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) bench.py --gpus $n --steps 5 --warmup 3 2>&1 | grep -E '^\{|Error|error|Traceback' | tail -3
 done
+if [ "$MODE" = "bench" ]; then
+  echo "##### bench.py --impl reference --gpus $G (rank 0 runs the same global problem on one GPU)"
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29650 bench.py --impl reference --gpus $G --steps 3 --warmup 1 2>&1 | grep -E '^\{|Error|error|Traceback' | tail -2
+else
 echo "##### strong scaling through the drop-in C++ path (one process, a host thread per GPU): dgemm 20000^3"
 timeout 300 bin/multiply -m 20000 -n 20000 -k 20000 --scaling $G,$G,1 --random 1 2>&1 | grep -E "SCALING|SPEEDUP|host buffers|rror"
+fi
 if [ "$MODE" = "c5" ]; then
   echo "##### BASELINE configs[4]: dgemm 100000^3 (240 GB, out of core on one GPU)"
   TMM_DIST_TIMEOUT_S=120 timeout 900 bin/multiply -m 100000 -n 100000 -k 100000 --scaling $G,$G,1 --random 1 2>&1 | grep -E "SCALING|SPEEDUP|host buffers|rror"
