@@ -855,7 +855,9 @@ int tmm_context_reserve_device_c(tmm_context* ctx, int64_t m, int64_t n) {
 void* tmm_context_stream(tmm_context* ctx, int kind, int index) {
     if (!ctx) return nullptr;
     switch (kind) {
-    case TMM_STREAM_COMPUTE: return (index >= 0 && index < ctx->n_compute()) ? (void*)ctx->s_compute[index] : nullptr;
+    // the reference serves stream ids [0, n_streams) (gpu_context.cpp:26-33); this context has at most four compute streams whatever the hint, so
+    // larger ids wrap around instead of failing
+    case TMM_STREAM_COMPUTE: return (index >= 0 && index < std::max(ctx->n_streams, ctx->n_compute())) ? (void*)ctx->s_compute[index % ctx->n_compute()] : nullptr;
     case TMM_STREAM_H2D: return index == 0 ? (void*)ctx->s_h2d : nullptr;
     case TMM_STREAM_D2H: return index == 0 ? (void*)ctx->s_d2h : nullptr;
     default: return nullptr;
@@ -867,8 +869,21 @@ int tmm_context_last_stats(tmm_context* ctx, tmm_call_stats* out) {
     *out = ctx->stats;
     return TMM_OK;
 }
-int tmm_context_set_profiling(tmm_context* ctx, int on) { if (!ctx) return TMM_ERR_INVALID; ctx->profiling = on != 0; return TMM_OK; }
-int tmm_context_set_device_budget(tmm_context* ctx, size_t bytes) { if (!ctx) return TMM_ERR_INVALID; ctx->budget_override = bytes; return TMM_OK; }
+// (both setters reach the child contexts of a multi-device parent and its single-device stand-in as well, whenever they are called - ADVICE r1)
+int tmm_context_set_profiling(tmm_context* ctx, int on) {
+    if (!ctx) return TMM_ERR_INVALID;
+    ctx->profiling = on != 0;
+    for (tmm_context* ch : ctx->children) ch->profiling = ctx->profiling;
+    if (ctx->solo) ctx->solo->profiling = ctx->profiling;
+    return TMM_OK;
+}
+int tmm_context_set_device_budget(tmm_context* ctx, size_t bytes) {
+    if (!ctx) return TMM_ERR_INVALID;
+    ctx->budget_override = bytes;
+    for (tmm_context* ch : ctx->children) ch->budget_override = bytes;
+    if (ctx->solo) ctx->solo->budget_override = bytes;
+    return TMM_OK;
+}
 
 static int gemm_on_context(tmm_context* ctx, char trans_a, char trans_b, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t ld_a,
                            const void* b, int64_t ld_b, const void* beta, void* c, int64_t ld_c, int pin_host_buffers, int copy_c_back);

@@ -833,6 +833,7 @@ int tmm_context_set_devices(tmm_context* ctx, int n_devices, const int* device_i
         if (!rc) {  // shapes too small for the grid fall back to one plain context on the first device
             cudaSetDevice(ids[0]);
             rc = tmm_context_create(ctx->dtype, ctx->n_streams, ctx->max_tile_m, ctx->max_tile_n, ctx->max_tile_k, &ctx->solo);
+            if (!rc && ctx->solo) { ctx->solo->budget_override = ctx->budget_override; ctx->solo->profiling = ctx->profiling; }
         }
     }
     cudaSetDevice(prev);

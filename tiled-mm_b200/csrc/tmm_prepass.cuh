@@ -65,7 +65,10 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     uint32_t h = (u + 0x1000u) & 0xFFFFE000u;
     float r = x - __uint_as_float(h);
     if ((u & 0x7F800000u) == 0x7F800000u) { h = (u & 0x007FFFFFu) ? 0x7FC00000u : u; r = 0.f; }
-    else if ((h & 0x7F800000u) == 0x7F800000u) r = 0.f;  // rounded up to Inf
+    else if ((h & 0x7F800000u) == 0x7F800000u) {  // a finite x within 2^-12 of FLT_MAX would round UP to Inf: take the largest finite TF32 instead, lo carries the rest
+        h = (u & 0x80000000u) | 0x7F7FE000u;
+        r = x - __uint_as_float(h);
+    }
     hi = __uint_as_float(h);
     lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
 }
@@ -78,14 +81,6 @@ __device__ __forceinline__ float lo_of_truncated(float x) {
     const float r = x - __uint_as_float(u & 0xFFFFE000u);
     return __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
 }
-
-// sgemm_tc_ts_kernel (A operand through tensor memory): where element (row, k) of the landed 128 x 32 FP32 A tile sits in shared
-// memory, as a byte offset from the (1024-byte aligned) start of the tile.
-//   k-contiguous tile: ONE TMA box [32 k x 128 rows] with SWIZZLE_128B - row r is 128 bytes, its 16-byte chunk c is stored at chunk
-//   position c ^ (r & 7) (address bits [4,7) xor-ed with bits [7,10))
-__device__ __forceinline__ int ts_a_chunk_offset_kmajor(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
-//   m-contiguous tile: FOUR unswizzled TMA boxes [32 m x 32 k], box = row / 32, inside a box [k][32 m]
-__device__ __forceinline__ int ts_a_elem_offset_mnmajor(int row, int k) { return (row >> 5) * 4096 + k * 128 + (row & 31) * 4; }
 
 }  // namespace f32tc
 }  // namespace tmm
