@@ -121,7 +121,9 @@ def test_own_test_multiply_types_and_transposes(gpu_apps, args):
 @pytest.mark.parametrize("case", CTEST_CASES)
 def test_reference_test_app_passes_on_this_library(gpu_apps, case):
     """The reference's tests/test-multiply.cpp, compiled unchanged, run against this library (binary built where the reference
-    sources exist; it travels with the repository)."""
+    sources exist; it travels with the repository).  NOT a parity test: the app's own oracle, compute_reference, calls blas_api::dgemm,
+    which here is this library's device GEMM - so this checks that the drop-in headers and the scheduler agree with the one-shot device
+    kernel on the reference's ctest cases; parity against cuBLAS / the oracle is what tests/test_gemm_gpu.py establishes."""
     exe = BIN / "ref-test-multiply"
     if not exe.exists():
         pytest.skip("bin/ref-test-multiply was not built (reference sources absent at build time)")

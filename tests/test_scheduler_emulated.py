@@ -84,14 +84,22 @@ def test_replan_when_free_memory_shrinks_between_calls(emul_build):
 @pytest.mark.parametrize("stripes,devices", [(2, 1), (3, 1), (4, 1), (4, 4)])
 def test_phase1_column_stripes_with_staggered_c_upload(emul_build, stripes, devices):
     """Phase 1 cut into several column stripes (forced with TMM_PLAN_P1SPLIT; the shapes of this suite are too small to get them
-    by themselves): with beta != 0 stripe s's share of C is uploaded right before k-chunk s and the stripe catches up on the chunks
-    that arrived earlier - including the case of fewer chunks than stripes."""
-    _worker(emul_build, ["sweep", devices, 400 if devices == 1 else 100, 40 + stripes], devices, {"TMM_PLAN_P1SPLIT": str(stripes)})
+    by themselves), in round 1's C-first order (TMM_PLAN_DEFER_C=0, kept as a switch): with beta != 0 stripe s's share of C is uploaded
+    right before k-chunk s and the stripe catches up on the chunks that arrived earlier - including the case of fewer chunks than stripes."""
+    _worker(emul_build, ["sweep", devices, 400 if devices == 1 else 100, 40 + stripes], devices, {"TMM_PLAN_P1SPLIT": str(stripes), "TMM_PLAN_DEFER_C": "0"})
+
+
+@pytest.mark.parametrize("stripes,devices", [(1, 1), (3, 1), (4, 4), (4, 8)])
+def test_beta_times_c_added_after_the_accumulation(emul_build, stripes, devices):
+    """The default order for beta != 0 (round 2): every block accumulates from zero, the caller's C travels behind the A / B panels into a staging
+    copy and C += beta * C_host runs when the block's last launch and its share of the copy are both done; the first phase-2 block's B is
+    fetched ahead of the C stripes.  Bit-exact against the oracle on integer data, race detector and bounds checks on, one GPU and grids."""
+    _worker(emul_build, ["sweep", devices, 400 if devices == 1 else 100, 70 + stripes], devices, {"TMM_PLAN_P1SPLIT": str(stripes)})
 
 
 def test_one_c_stripe_per_k_chunk_experiment(emul_build):
-    """TMM_PLAN_CSTRIPES=chunks (opt-in schedule experiment for beta != 0: as many column stripes as k-chunks, more stripes than streams)"""
-    _worker(emul_build, ["sweep", 1, 500, 61], 1, {"TMM_PLAN_CSTRIPES": "chunks"})
+    """TMM_PLAN_CSTRIPES=chunks (schedule experiment of the C-first order: as many column stripes as k-chunks, more stripes than streams)"""
+    _worker(emul_build, ["sweep", 1, 500, 61], 1, {"TMM_PLAN_CSTRIPES": "chunks", "TMM_PLAN_DEFER_C": "0"})
 
 
 def test_scheduler_under_address_and_ub_sanitizers():
