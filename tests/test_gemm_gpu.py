@@ -262,6 +262,25 @@ def test_device_gemm_boundary(gpu_tmm, oracle):
         tmm.free_device(p)
 
 
+def test_device_sgemm_outside_the_tma_contract(gpu_tmm, oracle):
+    """blas_api::sgemm on device pointers with an odd ld or a base at 4 mod 16: re-pitched by the copy engine and run on the tcgen05 kernel
+    (round 1 dropped these to the SIMT kernel); exact on integer data like every other path, and the launch count shows which kernel ran."""
+    tmm = gpu_tmm
+    m, n, k = 300, 200, 100
+    a0, b0, c0 = oracle.fixture_abc(np.float32, 305 * k + 8, 203 * n + 8, m * n)
+    da, db, dc = (tmm.malloc_device(x.nbytes) for x in (a0, b0, c0))
+    tmm.copy_to_device(a0, da); tmm.copy_to_device(b0, db)
+    out = np.empty_like(c0)
+    for tt, oa, lda, ob, ldb in [("NN", 0, 301, 0, 103), ("NN", 1, 304, 0, 104), ("TT", 1, 101, 3, 201), ("TN", 0, 103, 1, 101), ("NT", 2, 303, 0, 202)]:
+        expect = oracle.gemm(tt[0], tt[1], m, n, k, 2.0, a0[oa:], lda, b0[ob:], ldb, -1.0, c0.copy(), m)
+        tmm.copy_to_device(c0, dc)
+        tmm.device_gemm(np.float32, tt[0], tt[1], m, n, k, 2.0, da + 4 * oa, lda, db + 4 * ob, ldb, -1.0, dc, m)
+        tmm.copy_to_host(dc, out)
+        assert np.array_equal(out, expect), (tt, oa, lda, ob, ldb)
+    for p in (da, db, dc):
+        tmm.free_device(p)
+
+
 # ---- golden vectors and the real reference ------------------------------------------------------------------------
 def test_golden_vectors(gpu_tmm, oracle):
     tmm = gpu_tmm

@@ -58,10 +58,20 @@ int f32_math_mode() {
 }
 void set_f32_math_mode(int mode) { g_f32_mode.store(mode == 1 ? 1 : (mode == 0 ? 0 : 3), std::memory_order_relaxed); }
 
+static cudaError_t sgemm_repitched(char ta, char tb, int m, int n, int k, float alpha, const float* a, int64_t lda, const float* b, int64_t ldb, float beta,
+                                   float* c, int64_t ldc, cudaStream_t st, int mode);
+
 cudaError_t sgemm_launch(char ta, char tb, int m, int n, int k, float alpha, const float* a, int64_t lda, const float* b, int64_t ldb, float beta,
                          float* c, int64_t ldc, cudaStream_t st) {
     const int mode = f32_math_mode();
     if (mode != 0 && sgemm_tc_eligible(a, lda, b, ldb)) return sgemm_tc_launch(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, st, mode);
+    if (mode != 0) {
+        // outside the TMA contract (base not 16-byte aligned, ld not a multiple of 4 floats): re-pitch once with the copy engine and stay on the
+        // tensor cores, as the FP64 path does (the SIMT kernel is ~4x slower than what the reference's cuBLAS call delivers here)
+        cudaError_t e = sgemm_repitched(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, st, mode);
+        if (e != cudaErrorMemoryAllocation) return e;
+        cudaGetLastError();
+    }
     return sgemm_simt_launch(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, st);
 }
 
@@ -198,6 +208,18 @@ cudaError_t repitch(Operand& op, int64_t rows, int64_t cols, size_t es, cudaStre
     return cudaSuccess;
 }
 }  // namespace
+
+static cudaError_t sgemm_repitched(char ta, char tb, int m, int n, int k, float alpha, const float* a, int64_t lda, const float* b, int64_t ldb, float beta,
+                                   float* c, int64_t ldc, cudaStream_t st, int mode) {
+    Operand A{a, lda}, B{b, ldb};
+    cudaError_t e = repitch(A, ta == 'N' ? m : k, ta == 'N' ? k : m, sizeof(float), st);
+    if (e == cudaSuccess) e = repitch(B, tb == 'N' ? k : n, tb == 'N' ? n : k, sizeof(float), st);
+    if (e == cudaSuccess) e = sgemm_tc_launch(ta, tb, m, n, k, alpha, static_cast<const float*>(A.p), A.ld, static_cast<const float*>(B.p), B.ld, beta, c, ldc, st, mode);
+    else e = cudaErrorMemoryAllocation;  // no scratch: the caller falls back to the SIMT kernel on the operands as they are
+    if (A.scratch) cudaFreeAsync(A.scratch, st);
+    if (B.scratch) cudaFreeAsync(B.scratch, st);
+    return e;
+}
 
 static cudaError_t fp64_gemm(int dtype, char ta, char tb, int m, int n, int k, const void* alpha, const void* a, int64_t lda, const void* b, int64_t ldb,
                              const void* beta, void* c, int64_t ldc, cudaStream_t st) {
