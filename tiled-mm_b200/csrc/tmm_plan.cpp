@@ -162,6 +162,8 @@ Plan make_plan(const PlanInput& in) {
         while (j0 < n) {
             const int64_t remaining = n - j0;
             int64_t nb;
+            // (carving a final 128- or 64-column block off the last one, so that the exposed last D2H is shorter, was measured in round 2: 58.18 vs
+            //  58.20 ms at 10000^3 - nothing, profiles/r2_final_single_gpu.txt)
             if (remaining <= 512) nb = remaining;
             else if (remaining <= target + 512) nb = std::max<int64_t>(BN, std::min((remaining - 256) / BN * BN, pick_block_cols(m, target, remaining, in.sm_count)));
             else nb = pick_block_cols(m, target, remaining, in.sm_count);
