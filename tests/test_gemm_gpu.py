@@ -282,6 +282,28 @@ def test_device_sgemm_outside_the_tma_contract(gpu_tmm, oracle):
         tmm.free_device(p)
 
 
+def test_large_pinned_allocation_and_box_probes(gpu_tmm, oracle):
+    """The additive entry points of round 2: tmm_malloc_pinned_large (2 MiB pages + one cudaHostRegister; zero-filled; DMA-able like
+    cudaHostAlloc memory - the gemm below runs with pin_host_buffers = false) and the probes behind the bench's roofline denominators."""
+    tmm = gpu_tmm
+    m, n, k = 700, 500, 300
+    a0, b0, c0 = oracle.fixture_abc(np.float64, m * k, k * n, m * n)
+    expect = oracle.gemm("N", "N", m, n, k, 1.0, a0, m, b0, k, 1.0, c0.copy(), m)
+    a, b, c = (tmm.malloc_pinned_large(np.float64, x.size) for x in (a0, b0, c0))
+    assert not np.asarray(a).any() and not np.asarray(c).any(), "fresh large pinned memory must read as zeros"
+    a[:] = a0; b[:] = b0; c[:] = c0
+    with tmm.make_context(np.float64) as ctx:
+        tmm.gemm(ctx, "N", "N", m, n, k, 1.0, a, m, b, k, 1.0, c, m, pin_host_buffers=False, copy_c_back=True)
+        st = ctx.last_stats()
+    assert np.array_equal(np.asarray(c), expect)
+    assert st.h2d_bytes == 8 * (m * k + k * n + m * n) and st.d2h_bytes == 8 * m * n
+    del a, b, c                                            # tmm_free_pinned: cudaHostUnregister + munmap for this kind
+    peak = tmm.probe_fp64_peak()
+    assert 25.0 < peak < 60.0, peak                        # B200: 148 SMs x 64 FMA/clk x 2 x ~1.9 GHz = 37 TF
+    (up, down), = tmm.probe_host_links([0], nbytes=32 << 20)
+    assert 5.0 < up < 80.0 and 5.0 < down < 80.0, (up, down)   # PCIe Gen5 x16: ~55 GB/s each way alone
+
+
 # ---- golden vectors and the real reference ------------------------------------------------------------------------
 def test_golden_vectors(gpu_tmm, oracle):
     tmm = gpu_tmm

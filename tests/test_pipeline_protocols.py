@@ -1,5 +1,7 @@
-"""Executable model of the mbarrier protocols of the experimental tcgen05 kernels that have never run on hardware
-(csrc/gemm_f32_tc.cu sgemm_tc_ts_kernel<false|true>, csrc/gemm_f64_i8.cu dgemm_i8_kernel and pair::igemm_group_kernel).
+"""Executable model of the mbarrier protocols of the tcgen05 kernels (csrc/gemm_f32_tc.cu sgemm_tc_kernel, csrc/gemm_f64_i8.cu dgemm_i8_kernel).
+Written in round 1 for kernels that had not yet run; both run on hardware since round 2 (bit-exact parity tests), so this is now a cheap pre-flight
+check for changes to their pipelines - it is not evidence that a kernel works, the GPU tests are.  (The model also still knows the roles of the
+A-through-TMEM and CTA-pair variants that were measured slower and removed; only the one-CTA configurations are exercised.)
 
 Every role of a kernel (TMA producer, split warps, relay lane, MMA issuer, accumulate warps) is a generator transcribed from the kernel's
 loops - same barriers, same arrival counts, same parity bookkeeping, same order of waits / arrives / commits; a tiny scheduler interleaves

@@ -94,6 +94,8 @@ def load_library() -> ctypes.CDLL:
     lib.tmm_context_dtype.argtypes = [vp]
     lib.tmm_malloc_pinned.argtypes = [sz, ctypes.POINTER(vp)]
     lib.tmm_free_pinned.argtypes = [vp]
+    if hasattr(lib, "tmm_malloc_pinned_large"):
+        lib.tmm_malloc_pinned_large.argtypes = [sz, ctypes.POINTER(vp)]
     lib.tmm_malloc_device.argtypes = [sz, ctypes.POINTER(vp)]
     lib.tmm_free_device.argtypes = [vp]
     lib.tmm_copy_to_device.argtypes = [vp, vp, sz]
@@ -323,6 +325,22 @@ def malloc_pinned(dtype, count: int, value=0) -> np.ndarray:
     arr = np.frombuffer(buf, dtype=dt, count=count).view(_PinnedArray)
     arr._owner = owner
     arr.fill(value)
+    return arr
+
+
+def malloc_pinned_large(dtype, count: int) -> np.ndarray:
+    """tmm_malloc_pinned_large: zero-filled pinned memory on 2 MiB pages, first touched by all cores and registered in one cudaHostRegister -
+    an order of magnitude faster than cudaHostAlloc for the hundreds of GB the out-of-core configs need.  Same array type and lifetime rules
+    as malloc_pinned (tmm_free_pinned knows both kinds)."""
+    lib = load_library()
+    dt = np.dtype(dtype)
+    p = ctypes.c_void_p()
+    nbytes = max(1, count) * dt.itemsize
+    _check(lib.tmm_malloc_pinned_large(nbytes, ctypes.byref(p)))
+    owner = _PinnedOwner(p.value)
+    buf = (ctypes.c_byte * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=count).view(_PinnedArray)
+    arr._owner = owner
     return arr
 
 

@@ -421,7 +421,7 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
     return cudaGetLastError();
 }
 
-// Experimental (TMM_BF16_NATIVE=1, not yet run on hardware): bf16 operands straight through kind::f16 MMAs for the "TN" case, where both
+// Opt-in (TMM_BF16_NATIVE=1; green on hardware since round 2, tests/test_experimental_gpu.py::test_bf16_native_kind_f16_tn): bf16 operands straight through kind::f16 MMAs for the "TN" case, where both
 // operands are k-contiguous.  A 128 x 64 bf16 tile has exactly the byte geometry of the 128 x 32 FP32 K-major tile above (128-byte rows,
 // SWIZZLE_128B, 32 bytes per UMMA_K slice - 16 bf16 instead of 8 tf32), so the same kernel runs it with a BF16 tensor map, bk = 64 and
 // the f16 instruction kind; no widening pass, twice the MMA rate.  Other op pairs keep the widening path of gemm_bf16_tc.cu.

@@ -63,7 +63,7 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t desc_a, uint64
 }
 // D[tmem] (+)= A[tmem] * B[smem]^T : the A operand is read from tensor memory (lane = row, one 32-bit column per k), so it costs
 // no shared-memory bandwidth.  A in TMEM is always K-major: the instruction descriptor's "A is MN-major" bit must be 0.
-// (experimental - gemm_f32_tc.cu sgemm_tc_ts_kernel, TMM_TC_ATMEM=1; not yet run on hardware)
+// (validated on hardware by tools/tc_probe2.cu probe 3; the SGEMM variant that used it measured slower and was removed in round 2 - the probe keeps the helper)
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -130,7 +130,7 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity
 
 
 // ---- CTA pairs (cta_group::2): the two CTAs of a cluster share one 256-row MMA issued by the CTA of rank 0 ------------------------
-// (experimental - gemm_f32_tc.cu sgemm_tc_ts_kernel<true>, TMM_TC_ATMEM=2; not yet run on hardware)
+// (the cta_group::2 helpers below are validated on hardware by tools/tc_probe2.cu probes 5 - 7; the kernels that used them measured slower and were removed in round 2)
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
