@@ -169,3 +169,17 @@ def test_rank_that_fails_before_the_agreement_round_takes_the_grid_with_it(emul_
 def test_grid_entry_point_on_nccl_control_collectives(emul_build, world):
     """the control plane without the shared-memory board (what a box without /dev/shm falls back to)"""
     _worker(emul_build, ["ranks", world], world, {"TMM_DIST_BOARD": "0", "TMM_DIST_FORCE_IPC": "1"})
+
+
+@pytest.mark.parametrize("devices,mode", [(2, "grid"), (4, "sweep"), (8, "sweep"), (8, "ranks")])
+def test_upload_shares_follow_the_measured_link_rates(emul_build, devices, mode):
+    """The ranks of a link do not sit behind equally fast host links; with measured rates (made up per device on the emulated runtime,
+    TMM_EMUL_LINK_RATES=1) the shares of a shared panel are unequal - boundaries agreed by integer arithmetic on every rank, every element
+    still uploaded exactly once (the byte accounting of the workers checks it), results bit-exact, no race, on resident and streaming calls."""
+    env = {"TMM_EMUL_LINK_RATES": "1", "TMM_DEBUG": "0"}
+    if mode == "grid":
+        _worker(emul_build, ["grid", devices, "direct"], devices, env)
+    elif mode == "ranks":
+        _worker(emul_build, ["ranks", devices], devices, dict(env, TMM_DIST_FORCE_IPC="1"))
+    else:
+        _worker(emul_build, ["sweep", devices, 120, 90 + devices], devices, env)

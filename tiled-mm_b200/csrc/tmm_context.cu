@@ -1032,6 +1032,7 @@ static int gemm_on_context(tmm_context* ctx, char trans_a, char trans_b, int64_t
             const int rc_agree = tmm::dist_agree(ctx, m, n, k, flags, budget, &m_plan, &n_plan, &plan_budget, rc);
             if (!rc) rc = rc_agree;
             rc_before_agree = rc;
+            if (!rc) tmm::dist_set_shares(ctx, m_plan, n_plan, k, cl.es, cl.beta_nonzero, cl.copy_c_back);  // who uploads how much of a shared panel
         }
         if (!rc) {
             if (!need_ab) {

@@ -508,7 +508,7 @@ static int dist_push(tmm_context* ctx, Link& link, size_t es, const char* src, i
                      int ring_slot) {
     const int parts = link.parts, me = link.me;
     int64_t lo, hi;
-    share_range(cols, parts, me, &lo, &hi);
+    upload_share(link, cols, me, &lo, &hi);
     if (ring_slot >= 0) {
         // the peers must have consumed the exchange that last filled this ring slot before it is overwritten
         const uint32_t last = link.slot_last[ring_slot & 7];
@@ -606,6 +606,71 @@ int dist_exchange(tmm_context* ctx, Link& link, size_t es, const char* src, int6
     return TMM_OK;
 }
 
+// all-gather four words per rank over a link (attach time only)
+static int link_gather4(tmm_context* ctx, Link& link, const int64_t* mine, std::vector<int64_t>& all) {
+    all.assign((size_t)link.parts * 4, 0);
+    if (!link.active()) return TMM_OK;
+    if (link.board) return board_round(ctx, link, mine, 4 * sizeof(int64_t), all.data());
+    const nccl::Api& nc = nccl::api();
+    char* d = static_cast<char*>(ctx->dist_scratch.p) + 256;
+    TMM_CU(cudaMemcpyAsync(d, mine, 32, cudaMemcpyHostToDevice, ctx->s_comm));
+    NC(nc.AllGather(d, d + 32, 32, nccl::Int8, link.comm, ctx->s_comm));
+    TMM_CU(cudaMemcpyAsync(all.data(), d + 32, (size_t)32 * link.parts, cudaMemcpyDeviceToHost, ctx->s_comm));
+    return sync_with_deadline(ctx, ctx->s_comm);
+}
+
+// Shares that equalise the ranks' host-link time for this call.  Rank g of a link carries, besides its share f_g of this link's panel (P bytes),
+// a fixed load: its (roughly equal) share of the other link's panel and its C block, up and / or down.  With measured rates u_g (up) and d_g (down),
+//     T = (fixed_up_g + f_g P) / u_g + fixed_down_g / d_g   for all g,   sum f_g = 1
+// has the closed form below; shares are floored at 5 % (every rank keeps a part in the exchange) and renormalised.  Millionths, integer inputs.
+static void balance_link(Link& link, double panel_bytes, double other_up_bytes, double c_up_bytes, double c_down_bytes) {
+    link.cut.clear();
+    const int parts = link.parts;
+    if (!link.active() || !link.direct || (int)link.rate_up.size() != parts || (int)link.rate_down.size() != parts || panel_bytes <= 0) return;
+    for (int g = 0; g < parts; ++g)
+        if (link.rate_up[g] <= 0 || link.rate_down[g] <= 0) return;
+    double sum_u = 0, sum_fixed = 0;
+    for (int g = 0; g < parts; ++g) {
+        const double u = link.rate_up[g], d = link.rate_down[g];
+        sum_u += u;
+        sum_fixed += (other_up_bytes + c_up_bytes) + u * c_down_bytes / d;
+    }
+    const double T = (panel_bytes + sum_fixed) / sum_u;  // (bytes per MB/s: the unit cancels in f)
+    std::vector<double> f(parts);
+    double total = 0;
+    for (int g = 0; g < parts; ++g) {
+        const double u = link.rate_up[g], d = link.rate_down[g];
+        f[g] = ((T - c_down_bytes / d) * u - (other_up_bytes + c_up_bytes)) / panel_bytes;
+        if (!(f[g] > 0.05)) f[g] = 0.05;
+        total += f[g];
+    }
+    link.cut.assign(parts + 1, 0);
+    double acc = 0;
+    for (int g = 0; g < parts; ++g) {
+        acc += f[g] / total;
+        link.cut[g + 1] = g == parts - 1 ? 1000000 : std::min<int64_t>(1000000, (int64_t)(acc * 1e6 + 0.5));
+    }
+}
+
+void dist_set_shares(tmm_context* ctx, int64_t m_plan, int64_t n_plan, int64_t k, size_t es, bool c_up, bool c_down) {
+    Grid& g = ctx->grid;
+    g.rowl.cut.clear(); g.coll.cut.clear();
+    static const bool off = [] { const char* v = getenv("TMM_DIST_BALANCE"); return v && v[0] == '0'; }();
+    if (off || !g.active()) return;
+    const double pa = (double)m_plan * (double)k * (double)es, pb = (double)k * (double)n_plan * (double)es, pc = (double)m_plan * (double)n_plan * (double)es;
+    // the row link shares the A panel (its ranks also upload ~1/p_r of their B panel), the column link the B panel (~1/p_c of their A panel)
+    balance_link(g.rowl, pa, pb / std::max(1, g.pr), c_up ? pc : 0.0, c_down ? pc : 0.0);
+    balance_link(g.coll, pb, pa / std::max(1, g.pc), c_up ? pc : 0.0, c_down ? pc : 0.0);
+    if (debug_on()) {
+        for (Link* l : {&g.rowl, &g.coll})
+            if (!l->cut.empty()) {
+                std::string sline;
+                for (int i = 0; i < l->parts; ++i) sline += " " + std::to_string((l->cut[i + 1] - l->cut[i]) / 10000) + "%";
+                TMM_DBG("dev %d %s link upload shares:%s", ctx->device, l == &g.rowl ? "row (A)" : "column (B)", sline.c_str());
+            }
+    }
+}
+
 void dist_release(tmm_context* ctx) {
     ctx->buf_a.retire = ctx->buf_b.retire = nullptr;
     link_teardown(ctx->grid.rowl);
@@ -633,8 +698,10 @@ static int attach(tmm_context* ctx, int pr, int pc, int row, int col, const nccl
     ctx->buf_b.retire = (g.coll.active() && g.coll.direct) ? &ctx->retired : nullptr;
     ctx->budget_cached = 0;
     ctx->link_h2d_gbs = ctx->link_d2h_gbs = 0;
-#ifndef TMM_EMULATED
     {
+        int64_t mine[4] = {0, 0, 0, 0};  // this rank's own link figures in MB/s (0 = unknown)
+        bool have = false;
+#ifndef TMM_EMULATED
         // host-link rates with every rank of the grid copying at once; all ranks then plan with the slowest link's figures (TMM_DIST_PROBE=0: skip)
         const char* pv = getenv("TMM_DIST_PROBE");
         if (!rc && !(pv && pv[0] == '0')) {
@@ -645,11 +712,27 @@ static int attach(tmm_context* ctx, int pr, int pc, int row, int col, const nccl
             int64_t w[8] = {valid ? -(int64_t)(lr.h2d * 1e3) : 0, valid ? -(int64_t)(lr.d2h * 1e3) : 0, valid ? 0 : 1, 0, 0, 0, 0, 0};
             rc = rc_go ? rc_go : grid_reduce_max8(ctx, w);
             if (!rc && w[2] == 0) { ctx->link_h2d_gbs = (double)(-w[0]) * 1e-3; ctx->link_d2h_gbs = (double)(-w[1]) * 1e-3; }
+            if (valid) { mine[0] = (int64_t)(lr.h2d * 1e3); mine[1] = (int64_t)(lr.d2h * 1e3); }
+            have = true;
             TMM_DBG("dev %d host link with the whole grid active: %.1f GB/s up, %.1f GB/s down here; grid minimum %.1f / %.1f", ctx->device, lr.h2d, lr.d2h,
                     ctx->link_h2d_gbs, ctx->link_d2h_gbs);
         }
-    }
+#else
+        // the emulated runtime has no links to measure; TMM_EMUL_LINK_RATES=1 gives every device a different made-up figure so that the
+        // rate-balanced upload shares are exercised by the CPU suite
+        const char* fv = getenv("TMM_EMUL_LINK_RATES");
+        if (!rc && fv && fv[0] == '1') { mine[0] = 8000 + 5000 * (ctx->device % 3); mine[1] = 9000 + 2500 * ((ctx->device + 1) % 4); have = true; }
 #endif
+        // every rank's own figures, per link: the upload shares of a call follow them (dist_set_shares)
+        for (Link* l : {&g.rowl, &g.coll}) {
+            l->rate_up.clear(); l->rate_down.clear(); l->cut.clear();
+            if (rc || !have || !l->active()) continue;
+            std::vector<int64_t> all;
+            rc = link_gather4(ctx, *l, mine, all);
+            if (!rc)
+                for (int i = 0; i < l->parts; ++i) { l->rate_up.push_back((int32_t)all[(size_t)i * 4]); l->rate_down.push_back((int32_t)all[(size_t)i * 4 + 1]); }
+        }
+    }
     TMM_DBG("dev %d attached rc %d", ctx->device, rc);
     return rc;
 }

@@ -98,6 +98,10 @@ struct Link {
     uint64_t board_round = 0;              // rounds played on the board (the same number on all ranks of the link)
     uint64_t board_key = 0;                // hash of the link's unique id (name of the segment)
     bool broken = false;                   // a peer missed a round's deadline: the link is out of step for good
+    // Upload shares by link speed (DMA-push plane): the ranks of a link do not sit behind equally fast host links (8-GPU node of this pool: 8 vs
+    // 11 GB/s each way with all links busy), so the rank behind the slower link uploads the smaller part of a shared panel.
+    std::vector<int32_t> rate_up, rate_down;  // MB/s of every rank of the link, measured at attach with the whole grid copying (empty: unknown)
+    std::vector<int64_t> cut;                 // per call: share boundaries in millionths, cut[0] = 0 .. cut[parts] = 1000000 (empty: equal shares)
     bool active() const { return parts > 1; }
 };
 
@@ -239,6 +243,15 @@ inline void share_range(int64_t extent, int parts, int g, int64_t* lo, int64_t* 
     *lo = g * base + (g < rem ? g : rem);
     *hi = *lo + base + (g < rem ? 1 : 0);
 }
+// upload share of rank g of a link over `cols` stored columns: by the link's per-call boundaries if it has any, else the balanced split
+inline void upload_share(const Link& link, int64_t cols, int g, int64_t* lo, int64_t* hi) {
+    if ((int)link.cut.size() != link.parts + 1) { share_range(cols, link.parts, g, lo, hi); return; }
+    *lo = (int64_t)((__int128)cols * link.cut[g] / 1000000);
+    *hi = (int64_t)((__int128)cols * link.cut[g + 1] / 1000000);
+}
+// Per call, after the grid has agreed on (m_plan, n_plan, k): set both links' share boundaries from the measured link rates (identical on all
+// ranks of a link: integer arithmetic on agreed inputs).
+void dist_set_shares(tmm_context* ctx, int64_t m_plan, int64_t n_plan, int64_t k, size_t es, bool c_up, bool c_down);
 // single-process multi-GPU: run one call over the children of a parent context
 int multi_gemm(tmm_context* parent, char ta, char tb, int64_t m, int64_t n, int64_t k, const void* alpha, const void* a, int64_t lda, const void* b,
                int64_t ldb, const void* beta, void* c, int64_t ldc, int pin, int copy_c_back);
