@@ -71,11 +71,12 @@ def test_out_of_core_configs_stream(tmm):
 
 
 def test_headline_plan_is_the_measured_one(tmm):
-    """The plan of BASELINE configs[1] is pinned to the one that was measured on hardware (profiles/r2_sweep_plan.txt: chunk growth 1.5,
-    8 chunks, 58.16 ms against 58.57 ms for round 1's 12-chunk plan): planner changes made without a GPU must not move it."""
+    """The plan of BASELINE configs[1] is pinned to the one that was measured on hardware (profiles/r2_sweep_plan.txt, r2_sweep_plan_fine2.txt:
+    chunk growth 1.52 from a 192-wide first chunk, 9 chunks, 58.02 - 58.06 ms against 58.57 ms for round 1's 12-chunk plan): planner changes
+    made without a GPU must not move it."""
     p = tmm.plan_describe(np.float64, "N", "N", 10000, 10000, 10000, False, True, int(0.92 * 178e9))
     assert p["regime"] == 0 and p["n1"] == 5504
-    assert p["chunks"] == [256, 384, 576, 832, 1216, 1792, 2048, 2896]
+    assert p["chunks"] == [192, 256, 384, 576, 832, 1216, 1792, 2048, 2704]
     assert p["blocks"] == [1664, 1664, 896, 272]
 
 

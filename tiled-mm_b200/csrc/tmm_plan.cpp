@@ -142,7 +142,7 @@ Plan make_plan(const PlanInput& in) {
             const double t_gemm1 = F * (double)m * (double)n1 * (double)k / kFlops;
             const bool taper = env_or("TMM_PLAN_TAPER", t_gemm1 < 1.15 * t_up1 ? 1.0 : 0.0) != 0.0;
             int64_t done = 0;
-            int64_t kc = (int64_t)env_or("TMM_PLAN_KC0", 256);
+            int64_t kc = (int64_t)env_or("TMM_PLAN_KC0", 192);  // (first chunk 64 ... 512 swept in round 2: 192 is the shortest call by 0.14 ms, profiles/r2_sweep_plan_fine*.txt)
             const int64_t cap = (int64_t)env_or("TMM_PLAN_KCMAX", (double)kc_cap);
             while (done < k) {
                 int64_t c = std::min(kc, k - done);

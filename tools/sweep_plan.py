@@ -37,6 +37,17 @@ def run(cfg):
 run({})
 base = run({})
 print(f"default: best {base[0]:.2f} median {base[1]:.2f} ms  chunks {base[2]} blocks {base[3]}", flush=True)
+if os.environ.get("SWEEP_FINE") == "1":   # second pass of round 2: around the adopted growth (1.15 r = 1.52 at 10000^3)
+    fine = [{"TMM_PLAN_KC0": k0} for k0 in (64, 96, 128, 160, 192, 224)] + [{"TMM_PLAN_GROWTH": 1.45, "TMM_PLAN_KC0": k0} for k0 in (128, 192)] + \
+           [{"TMM_PLAN_GROWTH": g} for g in (1.3, 1.38, 1.45, 1.6, 1.7)] + [{"TMM_PLAN_GROWTH": 1.52, "TMM_PLAN_KC0": k0} for k0 in (192, 320, 384, 512)] + \
+           [{"TMM_PLAN_GROWTH": 1.4, "TMM_PLAN_KC0": 384}, {"TMM_PLAN_GROWTH": 1.4, "TMM_PLAN_KC0": 512}, {"TMM_PLAN_KCMAX": 3072, "TMM_PLAN_GROWTH": 1.52}, {"TMM_PLAN_P1SPLIT": 3}, {"TMM_PLAN_P1SPLIT": 2}]
+    for cfg in fine:
+        r = run(cfg)
+        print(f"{cfg}: best {r[0]:.2f} median {r[1]:.2f} ms  chunks {r[2]} blocks {r[3]}", flush=True)
+    r = run({})
+    print(f"default again: best {r[0]:.2f} median {r[1]:.2f} ms", flush=True)
+    ctx.close()
+    sys.exit(0)
 one_at_a_time = [{"TMM_PLAN_KC0": v} for v in (128, 192, 384)] + [{"TMM_PLAN_GROWTH": v} for v in (1.25, 1.5, 2.0)] + \
                 [{"TMM_PLAN_KCMAX": v} for v in (1024, 3072, 4096)] + [{"TMM_PLAN_P1SPLIT": v} for v in (1, 2, 3)] + \
                 [{"TMM_PLAN_NB": v} for v in (1024, 1536, 3072)] + [{"TMM_PLAN_MARGIN": v} for v in (1.1, 1.2, 1.5)]
