@@ -2,9 +2,12 @@
 // single-GPU, tiled_mm.cpp never selects a device).  Nothing is reduced across GPUs: k is never split, so the
 // summation structure of every C element is the one-GPU one.  The only exchange is of read-only panels:
 //   * the p_c GPUs of a grid row need the same A row-panel, the p_r GPUs of a grid column the same B column-panel;
-//   * each GPU uploads a distinct 1/p share of every shared panel chunk over its OWN PCIe link (so aggregate host-link
-//     bandwidth scales with the GPU count) and the shares are all-gathered over NVLink 5 / NVSwitch with NCCL,
-//     chunk by chunk, on a dedicated high-priority stream that overlaps the DMMA kernels of the previous chunk.
+//   * each GPU uploads a distinct share of every shared panel chunk over its OWN PCIe link (so aggregate host-link bandwidth scales with the
+//     GPU count) and DMA-pushes it with the copy engines into the same place of every peer's panel over NVLink 5 / NVSwitch (mapped peer
+//     memory: peer access inside a process, CUDA IPC across processes); arrival and acknowledgement counters are stream memory operations -
+//     no SMs, no staging, no host on the data path.  Fallback data plane: ncclAllGather through a staging ring.
+//   * control plane per call: a few rounds on a shared-memory board (microseconds of host time, with a deadline); NCCL at attach and as fallback.
+//   * the shares follow the link rates measured at attach with every rank copying at once (a box's host links are neither independent nor alike).
 // Two ways in:
 //   (1) one process per GPU (torchrun): tmm_context_attach_grid() on each rank's context; tmm_gemm() then means "my block";
 //   (2) one process, many GPUs: tmm_context_set_devices() turns a context into a parent whose tmm_gemm() partitions C
