@@ -32,6 +32,8 @@ if os.environ.get("TMM_NCCL_LIB"):  # let the race detector see that a blocking 
     _stub = ctypes.CDLL(os.environ["TMM_NCCL_LIB"], mode=ctypes.RTLD_GLOBAL)
     _stub.nccl_stub_set_sync_hook(ctypes.cast(lib.emul_collective, ctypes.c_void_p))
     _stub.nccl_stub_set_stream_hook(ctypes.cast(lib.emul_collective_stream, ctypes.c_void_p))
+if os.environ.get("TMM_EMUL_C32_TC") == "1":   # complex<float> takes the scheduler's prepared-operand path (stand-ins in tests/emul/emul_blas.cpp)
+    tmm.set_c32_math(3)
 oracle = _util.Oracle()
 ALL_TT = ["".join(p) for p in itertools.product("NTC", "NTC")]
 
@@ -223,6 +225,8 @@ def run_sweep(n_dev, n_cases, seed):
     streams, both copy modes, tight device budgets (streaming regime with C super-blocks), contexts REUSED across calls."""
     rng = np.random.default_rng(seed)
     dtypes = [np.float64, np.complex128, np.float32, np.complex64]
+    if os.environ.get("TMM_EMUL_DTYPES"):   # e.g. "c": complex<float> only
+        dtypes = [{"d": np.float64, "z": np.complex128, "s": np.float32, "c": np.complex64}[ch] for ch in os.environ["TMM_EMUL_DTYPES"]] * 4
     done = 0
     while done < n_cases:
         dtype = dtypes[int(rng.integers(0, 4))]
@@ -255,6 +259,11 @@ def run_sweep(n_dev, n_cases, seed):
         check_clean(f"sweep seed {seed} after {done} cases ({np.dtype(dtype)}, {n_dev} devices)")
     for d in range(n_dev):
         assert lib.emul_live_device_bytes(d) == 0
+    if os.environ.get("TMM_EMUL_C32_TC") == "1":
+        lib.emul_prepared_cgemm_launches.restype = ctypes.c_uint64
+        launches = lib.emul_prepared_cgemm_launches()
+        assert launches > done, f"the prepared-operand path took only {launches} launches in {done} complex<float> calls"
+        print(f"prepared-operand launches: {launches}")
     print(f"EMUL_OK sweep {n_dev} devices, {done} cases")
 
 
@@ -320,6 +329,8 @@ def run_drysweep(n_dev, n_cases, seed):
     pr, pc = tmm.grid_shape(n_dev)
     A, B, C = 0x200000000000, 0x300000000000, 0x400000000000
     dtypes = [np.float64, np.complex128, np.float32, np.complex64]
+    if os.environ.get("TMM_EMUL_DTYPES"):   # e.g. "c": complex<float> only
+        dtypes = [{"d": np.float64, "z": np.complex128, "s": np.float32, "c": np.complex64}[ch] for ch in os.environ["TMM_EMUL_DTYPES"]] * 4
     done = 0
     while done < n_cases:
         dtype = dtypes[int(rng.integers(0, 4))]

@@ -282,6 +282,39 @@ def test_device_sgemm_outside_the_tma_contract(gpu_tmm, oracle):
         tmm.free_device(p)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64])
+def test_float_non_finite_and_huge_operands(gpu_tmm, dtype):
+    """FP32-accurate tensor-core path (3xTF32 split, csrc/tmm_prepass.cuh split_tf32_x4): an Inf / NaN in row i of A or column j of B makes
+    row i / column j of C non-finite (the split sends Inf through hi alone, so Inf times an exactly representable value comes out as NaN
+    where FP32 arithmetic gives Inf - the documented deviation); a finite operand next to FLT_MAX stays finite; every other
+    element is exact on integer data."""
+    tmm = gpu_tmm
+    m, n, k = 200, 150, 300
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 10, (k, m)).astype(dtype).T.copy(order="F")   # column-major m x k
+    b = rng.integers(0, 10, (n, k)).astype(dtype).T.copy(order="F")   # column-major k x n
+    a[7, 11] = np.inf; b[5, 140] = np.nan
+    huge = np.float32(3.4028235e38)                                    # FLT_MAX: rounding it to TF32 must not produce Inf
+    a[20, :] = 0; a[20, 3] = huge; b[3, :] = 0; b[3, 9] = np.float32(0.25); b[5, 140] = np.nan
+    c = np.zeros((m, n), dtype, order="F")
+    da, db, dc = (tmm.malloc_device(x.nbytes) for x in (a, b, c))
+    tmm.copy_to_device(a.reshape(-1, order="F"), da); tmm.copy_to_device(b.reshape(-1, order="F"), db); tmm.copy_to_device(c.reshape(-1, order="F"), dc)
+    tmm.device_gemm(dtype, "N", "N", m, n, k, 1.0, da, m, db, k, 0.0, dc, m)
+    out = np.empty(m * n, dtype); tmm.copy_to_host(dc, out)
+    out = out.reshape(n, m).T
+    for p in (da, db, dc):
+        tmm.free_device(p)
+    bad = np.zeros((m, n), bool); bad[7, :] = True; bad[:, 140] = True
+    assert np.all(~np.isfinite(out[bad])) and np.all(np.isfinite(out[~bad]))
+    a0, b0 = a.astype(np.complex128 if dtype == np.complex64 else np.float64), b.astype(np.complex128 if dtype == np.complex64 else np.float64)
+    a0[7, 11] = 0; b0[5, 140] = 0
+    want = a0 @ b0
+    ok = ~bad
+    ok[20, 9] = False
+    assert np.array_equal(out[ok], want[ok].astype(dtype))
+    assert np.isfinite(out[20, 9]) and abs(out[20, 9] - want[20, 9]) <= 2.0 ** -21 * abs(want[20, 9])   # FLT_MAX / 4, from hi + lo
+
+
 def test_large_pinned_allocation_and_box_probes(gpu_tmm, oracle):
     """The additive entry points of round 2: tmm_malloc_pinned_large (2 MiB pages + one cudaHostRegister; zero-filled; DMA-able like
     cudaHostAlloc memory - the gemm below runs with pin_host_buffers = false) and the probes behind the bench's roofline denominators."""

@@ -315,6 +315,175 @@ def test_default_sgemm_kernel_protocol(tiles, kblocks, window):
         sim.run()
 
 
+# ------------------------------------------------------------------------------------------------------------------------------------------
+# sgemm_tc_kernel with the dynamic tile feed (round 2): the producer draws tile numbers from a counter shared by all CTAs of the launch and passes
+# them on through a TILE_RING-entry ring (tile_full count 1; tile_empty count 1 MMA lane + 4 accumulate warps + 8 split warps); one packed
+# counter per thread gives slot and parity; -1 ends every role; the CTA that reports its past-the-end draw last zeroes the counter pair.
+def build_dynamic(sim, ctas, total_tiles, kblocks, window, stages=3, accs=4, ring=4):
+    STAGES, ACCS, SPLIT_WARPS, RING = stages, accs, 8, ring
+    sched = [0, 0]
+    seen = {role: [] for role in ("tma", "mma", "acc", "split")}
+
+    def cta(c):
+        full = [Barrier(1) for _ in range(STAGES)]
+        ready = [Barrier(SPLIT_WARPS) for _ in range(STAGES)]
+        empty = [Barrier(1) for _ in range(STAGES)]
+        acc_full = [Barrier(1) for _ in range(ACCS)]
+        acc_empty = [Barrier(4) for _ in range(ACCS)]
+        tile_full = [Barrier(1) for _ in range(RING)]
+        tile_empty = [Barrier(1 + 4 + SPLIT_WARPS) for _ in range(RING)]
+        tile_ring = [None] * RING
+        pipe = Pipe(STAGES, ACCS)
+        split_left = [0] * STAGES
+
+        def next_tile(state):  # consumer side: state = [tr_count]
+            slot = state[0] % RING
+            yield ("wait", tile_full[slot], (state[0] // RING) & 1)
+            t = tile_ring[slot]
+            assert t is not None
+            tile_empty[slot].arrive()
+            state[0] += 1
+            state.append(t)
+
+        def producer():
+            stage, phase, tr = 0, 0, 0
+
+            def draw():
+                t = sched[0]
+                sched[0] += 1
+                return t if t < total_tiles else -1
+            tile = draw()
+            while True:
+                slot = tr % RING
+                yield ("wait", tile_empty[slot], ((tr // RING) & 1) ^ 1)
+                tile_ring[slot] = tile
+                tile_full[slot].arrive()
+                tr += 1
+                if tile < 0:
+                    break
+                seen["tma"].append(tile)
+                yield ("sleep", sim.rng.randint(1, 20))  # the atomic's round trip
+                nxt = draw()
+                for _ in range(kblocks):
+                    yield ("wait", empty[stage], phase ^ 1)
+                    assert pipe.stage[stage] == "free", f"TMA overwrites stage {stage} in state {pipe.stage[stage]}"
+                    pipe.stage[stage] = "loading"
+
+                    def landed(s=stage):
+                        pipe.stage[s] = "landed"
+                        split_left[s] = SPLIT_WARPS
+                        full[s].arrive()
+                    sim.later(20, 200, landed)
+                    stage += 1
+                    if stage == STAGES:
+                        stage, phase = 0, phase ^ 1
+                tile = nxt
+            sched[1] += 1
+            if sched[1] == ctas:
+                sched[0] = sched[1] = 0
+
+        def split_warp(w):
+            stage, phase, st = 0, 0, [0]
+            while True:
+                yield from next_tile(st)
+                if st.pop() < 0:
+                    break
+                for _ in range(kblocks):
+                    yield ("wait", full[stage], phase)
+                    assert pipe.stage[stage] == "landed", f"split reads stage {stage} in state {pipe.stage[stage]}"
+                    yield ("sleep", sim.rng.randint(1, 30))
+                    split_left[stage] -= 1
+                    if split_left[stage] == 0:
+                        pipe.stage[stage] = "ready"
+                    ready[stage].arrive()
+                    stage += 1
+                    if stage == STAGES:
+                        stage, phase = 0, phase ^ 1
+
+        def mma():
+            stage, acc, phase, acc_phase, st = 0, 0, 0, 0, [0]
+            while True:
+                yield from next_tile(st)
+                t = st.pop()
+                if t < 0:
+                    break
+                seen["mma"].append(t)
+                wk = 0
+                for kb in range(kblocks):
+                    if wk == 0:
+                        yield ("wait", acc_empty[acc], acc_phase ^ 1)
+                        assert pipe.acc[acc] == "free", f"window {acc} reopened in state {pipe.acc[acc]}"
+                        pipe.acc[acc] = "accumulating"
+                    yield ("wait", ready[stage], phase)
+                    last = (wk + 1 == window) or (kb == kblocks - 1)
+
+                    def close(a=acc):
+                        pipe.acc[a] = "full"
+                        pipe.acc_drains[a] = 4
+                        acc_full[a].arrive()
+                    mma_async(sim, [pipe], stage, [empty[stage]], on_done=close if last else None)
+                    stage += 1
+                    if stage == STAGES:
+                        stage, phase = 0, phase ^ 1
+                    wk += 1
+                    if last:
+                        acc += 1
+                        if acc == ACCS:
+                            acc, acc_phase = 0, acc_phase ^ 1
+                        wk = 0
+
+        def accumulate_warp(w):
+            acc_count, st = 0, [0]
+            windows = (kblocks + window - 1) // window
+            while True:
+                yield from next_tile(st)
+                t = st.pop()
+                if t < 0:
+                    break
+                if w == 0:
+                    seen["acc"].append(t)
+                for _ in range(windows):
+                    acc = acc_count % ACCS
+                    yield ("wait", acc_full[acc], (acc_count // ACCS) & 1)
+                    assert pipe.acc[acc] == "full", f"window {acc} drained in state {pipe.acc[acc]}"
+                    yield ("sleep", sim.rng.randint(1, 40))
+                    pipe.acc_drains[acc] -= 1
+                    if pipe.acc_drains[acc] == 0:
+                        pipe.acc[acc] = "free"
+                    acc_empty[acc].arrive()
+                    acc_count += 1
+                yield ("sleep", sim.rng.randint(1, 300))  # the tile's global-memory epilogue
+
+        def late(gen, delay):  # a CTA that gets its SM late (another launch held it)
+            yield ("sleep", delay)
+            yield from gen
+
+        delay = sim.rng.choice([1, 1, 500, 3000])
+        sim.add(f"tma{c}", late(producer(), delay))
+        for w in range(SPLIT_WARPS):
+            sim.add(f"split{c}.{w}", late(split_warp(w), delay))
+        for w in range(4):
+            sim.add(f"acc{c}.{w}", late(accumulate_warp(w), delay))
+        sim.add(f"mma{c}", late(mma(), delay))
+
+    for c in range(ctas):
+        cta(c)
+    return sched, seen
+
+
+@pytest.mark.parametrize("ctas,tiles,kblocks,window", [(1, 1, 1, 4), (1, 6, 5, 4), (3, 10, 3, 4), (4, 3, 9, 4), (2, 7, 2, 1)])
+def test_dynamic_tile_feed_protocol(ctas, tiles, kblocks, window):
+    """Every tile is loaded, multiplied and written back exactly once, by the roles of one and the same CTA, whichever CTAs start late; every role
+    ends; the counter pair is back at zero for the launch that takes the slot next."""
+    for seed in range(8):
+        sim = Sim(seed)
+        sched, seen = build_dynamic(sim, ctas, tiles, kblocks, window)
+        sim.run()
+        assert sched == [0, 0]
+        for role in ("tma", "mma", "acc"):
+            assert sorted(seen[role]) == list(range(tiles)), (role, seen[role])
+
+
 @pytest.mark.parametrize("pair", [False], ids=["one-cta"])
 @pytest.mark.parametrize("tiles,kblocks,slices,max_window", [(1, 1, 2, 2048), (2, 3, 4, 2048), (3, 2, 8, 2048), (2, 5, 3, 4)])
 def test_int8_dgemm_protocol(pair, tiles, kblocks, slices, max_window):

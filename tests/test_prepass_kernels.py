@@ -14,6 +14,7 @@ from test_c32_embedding import embed_a, embed_b
 ROOT = Path(__file__).resolve().parent.parent
 
 HARNESS = r'''
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
@@ -50,6 +51,15 @@ void run_split_b_t(const float* b, long ldb, int n, int k, int conj, float* out,
 }
 void run_split(const float* x, long count, float* hi, float* lo, float* lo_trunc) {
     for (long i = 0; i < count; ++i) { tmm::f32tc::split_tf32(x[i], hi[i], lo[i]); lo_trunc[i] = tmm::f32tc::lo_of_truncated(x[i]); }
+}
+// the split as the kernel's split warps apply it: 16-byte chunks of four elements (count is a multiple of 4)
+void run_split_x4(const float* x, long count, float* hi, float* lo) {
+    for (long i = 0; i + 4 <= count; i += 4) {
+        const float v[4] = {x[i], x[i + 1], x[i + 2], x[i + 3]};
+        float h[4], l[4];
+        tmm::f32tc::split_tf32_x4(v, h, l);
+        for (int j = 0; j < 4; ++j) { hi[i + j] = h[j]; lo[i + j] = l[j]; }
+    }
 }
 // the A-split reads of sgemm_tc_ts_kernel, thread by thread: lane-quarter q, lane l -> row 32q + l, two halves of 16 k-values
 void run_widen(const uint16_t* in, long ld, int rows, int cols, float* out, long pitch, int cap) {
@@ -139,6 +149,11 @@ def test_tf32_operand_splits(kernels):
     special = ~np.isfinite(x)
     assert np.all(lo[special] == 0) and np.all(lot[special] == 0) and np.array_equal(np.isnan(hi[special]), np.isnan(x[special]))
     assert np.array_equal(hi[np.isinf(x)], x[np.isinf(x)])
+    # the chunked form the kernel uses (short path for chunks of plain values, split_tf32 for a chunk with an Inf / NaN / huge value): identical
+    n4 = x.size // 4 * 4
+    hi4, lo4 = np.zeros(n4, np.float32), np.zeros(n4, np.float32)
+    kernels.run_split_x4(_fp(x), ctypes.c_long(n4), _fp(hi4), _fp(lo4))
+    assert np.array_equal(hi4.view(np.uint32), hi[:n4].view(np.uint32)) and np.array_equal(lo4.view(np.uint32), lo[:n4].view(np.uint32))
     near_max = np.isfinite(x) & (np.abs(x) > 3.4e38)                                                  # finite inputs never turn into Inf: hi is clamped
     assert near_max.any() and np.all(np.isfinite(hi[near_max])) and np.all(np.abs(hi[near_max].astype(np.float64) + lo[near_max] - x[near_max]) <= 2.0 ** -21 * np.abs(x[near_max].astype(np.float64)))
 

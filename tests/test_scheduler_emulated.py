@@ -97,6 +97,24 @@ def test_beta_times_c_added_after_the_accumulation(emul_build, stripes, devices)
     _worker(emul_build, ["sweep", devices, 400 if devices == 1 else 100, 70 + stripes], devices, {"TMM_PLAN_P1SPLIT": str(stripes)})
 
 
+@pytest.mark.parametrize("stripes,devices,c_first", [(1, 1, False), (3, 1, False), (4, 1, True), (2, 4, False), (4, 8, False)])
+def test_complex_float_operands_prepared_once(emul_build, stripes, devices, c_first):
+    """complex<float> on the tensor-core embedding (round 2): the scheduler embeds every k-chunk of A once into the context's A' buffer (one
+    stream, the stripe streams wait on its event), phase 2 multiplies the A' the chunks add up to, op(B) = T / C pieces are split by the launch
+    that consumes them; a sub-block off the 16-byte grid falls back to a self-contained launch.  Stand-ins with the device passes' layouts and
+    declared accesses (tests/emul/emul_blas.cpp): bit-exact against the oracle's complex GEMM on integer data, range checker and race detector on."""
+    env = {"TMM_PLAN_P1SPLIT": str(stripes), "TMM_EMUL_C32_TC": "1", "TMM_EMUL_DTYPES": "c"}
+    if c_first:
+        env["TMM_PLAN_DEFER_C"] = "0"
+    _worker(emul_build, ["sweep", devices, 300 if devices == 1 else 80, 90 + stripes], devices, env)
+
+
+def test_race_detector_sees_the_prepared_operands(emul_build):
+    """Mutation check for the test above: with the event waits dropped, a stripe stream multiplies a chunk of A' that another stream is still writing."""
+    _worker(emul_build, ["sweep", 1, 60, 93], 1, {"TMM_PLAN_P1SPLIT": "3", "TMM_EMUL_C32_TC": "1", "TMM_EMUL_DTYPES": "c", "TMM_EMUL_DROP_WAITS": "1"},
+            expect_failure="unordered conflicting accesses")
+
+
 def test_one_c_stripe_per_k_chunk_experiment(emul_build):
     """TMM_PLAN_CSTRIPES=chunks (schedule experiment of the C-first order: as many column stripes as k-chunks, more stripes than streams)"""
     _worker(emul_build, ["sweep", 1, 500, 61], 1, {"TMM_PLAN_CSTRIPES": "chunks", "TMM_PLAN_DEFER_C": "0"})

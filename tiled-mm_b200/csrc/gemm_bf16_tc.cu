@@ -39,18 +39,18 @@ cudaError_t bgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
     const int ar = ta == 'N' ? m : k, ac = ta == 'N' ? k : m, br = tb == 'N' ? k : n, bc = tb == 'N' ? n : k;
     const int64_t pa = round_up(ar, 32), pb = round_up(br, 32);  // 128-byte columns: TMA-legal for any input ld
     float *a32 = nullptr, *b32 = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&a32), (size_t)pa * ac * sizeof(float), st);
+    cudaError_t e = scratch_alloc(reinterpret_cast<void**>(&a32), (size_t)pa * ac * sizeof(float), st);
     if (e != cudaSuccess) return e;
-    e = cudaMallocAsync(reinterpret_cast<void**>(&b32), (size_t)pb * bc * sizeof(float), st);
-    if (e != cudaSuccess) { cudaFreeAsync(a32, st); return e; }
+    e = scratch_alloc(reinterpret_cast<void**>(&b32), (size_t)pb * bc * sizeof(float), st);
+    if (e != cudaSuccess) { scratch_free(a32, st); return e; }
     auto grid = [](int rows, int cols) { return dim3((unsigned)((rows + 255) / 256), (unsigned)(cols > 32768 ? 32768 : cols)); };
     widen<<<grid(ar, ac), 256, 0, st>>>(static_cast<const uint16_t*>(a), lda, ar, ac, a32, pa);
     widen<<<grid(br, bc), 256, 0, st>>>(static_cast<const uint16_t*>(b), ldb, br, bc, b32, pb);
     count_launch(); count_launch();
     e = cudaGetLastError();
     if (e == cudaSuccess) e = sgemm_tc_launch(ta == 'N' ? 'N' : 'T', tb == 'N' ? 'N' : 'T', m, n, k, alpha, a32, pa, b32, pb, beta, c, ldc, st, /*terms=*/1);
-    cudaFreeAsync(a32, st);
-    cudaFreeAsync(b32, st);
+    scratch_free(a32, st);
+    scratch_free(b32, st);
     return e;
 }
 

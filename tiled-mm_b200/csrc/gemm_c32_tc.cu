@@ -10,7 +10,8 @@
 // because  w * b = w * re(b) + (i w) * im(b).  The real product has 2 * (2m) * n * (2k) = 8mnk flops - exactly the complex flop
 // count - and runs on the FP32-accurate 3xTF32 kernel of gemm_f32_tc.cu unchanged (same TMA / TMEM / windowed-promotion
 // pipeline, same accuracy: small integers stay exact).  What this file adds is the operand preparation, one elementwise pass
-// per launch into stream-ordered scratch (cudaMallocAsync):
+// per operand - into buffers of the caller (the scheduler prepares every piece of a panel once, see below) or, for a self-contained call,
+// into stream-ordered scratch of the library's pool:
 //   A  always (it has to be duplicated as w and i*w; alpha and the conjugation of op 'C' are folded in for free):
 //        2 x |A| bytes written; k-contiguous for op T/C, m-contiguous for op N - the SGEMM kernel takes either orientation
 //   B  op N: nothing - the stored matrix read as floats IS B' (zero copy) when its base and pitch meet the TMA contract
@@ -37,24 +38,64 @@ static inline dim3 pass_grid(int contiguous, int columns) {
 
 }  // namespace c32tc
 
+// ---- the three steps, for callers that prepare an operand once and multiply it many times (the scheduler: a k-chunk of A meets every column
+// stripe, the resident A meets every phase-2 column block - csrc/tmm_context.cu run_resident) ----------------------------------------------
+
+// A' of alpha * op(A) for an m x k block of op(A).  ta == 'N': a2 is (2m x 2k), m-contiguous, pitch_a2 floats per column (even);
+// otherwise a2 holds A'^T = (2k x 2m), k-contiguous.  A k sub-range [p0, p0 + kc) of a larger A' starts at a2 + 2 * p0 * pitch_a2 ('N') or
+// a2 + 2 * p0 (otherwise): chunks embedded one by one into the same buffer add up to the A' of the whole panel.
+cudaError_t cgemm_tc_embed_a(char ta, int m, int k, const float* al, const void* a, int64_t lda, float* a2, int64_t pitch_a2, cudaStream_t st) {
+    using namespace c32tc;
+    if (m <= 0 || k <= 0) return cudaSuccess;
+    const float2 alpha = make_float2(al[0], al[1]);
+    if (ta == 'N') embed_a_n<<<pass_grid(m, k), 256, 0, st>>>(static_cast<const float2*>(a), lda, m, k, alpha, reinterpret_cast<float2*>(a2), pitch_a2 / 2);
+    else embed_a_t<<<pass_grid(k, m), 256, 0, st>>>(static_cast<const float2*>(a), lda, k, m, alpha, ta == 'C' ? 1 : 0, reinterpret_cast<float2*>(a2), pitch_a2 / 2);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// B'^T of op(B) for tb == 'T' / 'C': stored n x k complex (n contiguous) -> (n x 2k) floats, n-contiguous, pitch_b2 floats per column.
+// (tb == 'N' needs no pass: the stored matrix read as floats is B', pitch 2 * ldb.)
+cudaError_t cgemm_tc_split_b(char tb, int n, int k, const void* b, int64_t ldb, float* b2, int64_t pitch_b2, cudaStream_t st) {
+    using namespace c32tc;
+    if (n <= 0 || k <= 0) return cudaSuccess;
+    split_b_t<<<pass_grid(n, k), 256, 0, st>>>(static_cast<const float2*>(b), ldb, n, k, tb == 'C' ? 1 : 0, b2, pitch_b2);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// C = A' B' + beta * C on prepared operands: the real (2m x n) = (2m x 2k)(2k x n) product on the FP32-accurate 3xTF32 kernel.
+// cudaErrorInvalidValue when a2 / b2 do not meet the TMA contract (16-byte aligned base, pitch a multiple of 4 floats).
+cudaError_t cgemm_tc_prepared(char ta, char tb, int m, int n, int k, const float* a2, int64_t pitch_a2, const float* b2, int64_t pitch_b2,
+                              const float* be, void* c, int64_t ldc, cudaStream_t st) {
+    if (m <= 0 || n <= 0 || k <= 0) return cudaSuccess;
+    if (!sgemm_tc_eligible(a2, pitch_a2, b2, pitch_b2)) return cudaErrorInvalidValue;
+    float beta_r = be[0];
+    cudaError_t e = cudaSuccess;
+    if (be[1] != 0.f) {  // complex beta: C <- beta * C first, then accumulate with 1
+        e = device_scale(C32, m, n, be, c, ldc, st);
+        beta_r = 1.f;
+    }
+    if (e == cudaSuccess) e = sgemm_tc_launch(ta == 'N' ? 'N' : 'T', tb == 'N' ? 'N' : 'T', 2 * m, n, 2 * k, 1.f, a2, pitch_a2, b2, pitch_b2, beta_r, static_cast<float*>(c), 2 * ldc, st, 3);
+    return e;
+}
+
+// One self-contained call (blas_api::cgemm, device-pointer operands): the passes write into stream-ordered scratch.
 // Returns cudaErrorMemoryAllocation when the scratch cannot be had (caller falls back to SIMT); any other error is final.
 cudaError_t cgemm_tc_launch(char ta, char tb, int m, int n, int k, const float* al, const void* a, int64_t lda, const void* b, int64_t ldb,
                             const float* be, void* c, int64_t ldc, cudaStream_t st) {
     using namespace c32tc;
     if (m <= 0 || n <= 0 || k <= 0) return cudaSuccess;
     if (m > INT32_MAX / 2 || k > INT32_MAX / 2) return cudaErrorMemoryAllocation;  // the doubled extents must fit the SGEMM's int sizes
-    const float2 alpha = make_float2(al[0], al[1]);
     const bool a_n = ta == 'N', b_n = tb == 'N';
 
     // ---- A' ----
     const int64_t pitch_a = a_n ? round_up(2 * (int64_t)m, 32) : round_up(2 * (int64_t)k, 32);  // floats; 128-byte columns
     const int64_t cols_a = a_n ? 2 * (int64_t)k : 2 * (int64_t)m;
     float* a2 = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&a2), (size_t)pitch_a * (size_t)cols_a * sizeof(float), st);
+    cudaError_t e = scratch_alloc(reinterpret_cast<void**>(&a2), (size_t)pitch_a * (size_t)cols_a * sizeof(float), st);
     if (e != cudaSuccess) { cudaGetLastError(); return cudaErrorMemoryAllocation; }
-    if (a_n) embed_a_n<<<pass_grid(m, k), 256, 0, st>>>(static_cast<const float2*>(a), lda, m, k, alpha, reinterpret_cast<float2*>(a2), pitch_a / 2);
-    else embed_a_t<<<pass_grid(k, m), 256, 0, st>>>(static_cast<const float2*>(a), lda, k, m, alpha, ta == 'C' ? 1 : 0, reinterpret_cast<float2*>(a2), pitch_a / 2);
-    count_launch();
+    e = cgemm_tc_embed_a(ta, m, k, al, a, lda, a2, pitch_a, st);
 
     // ---- B' ----
     const float* b2 = nullptr;
@@ -63,35 +104,21 @@ cudaError_t cgemm_tc_launch(char ta, char tb, int m, int n, int k, const float* 
     if (b_n && (reinterpret_cast<uintptr_t>(b) & 15) == 0 && (ldb & 1) == 0) {
         b2 = static_cast<const float*>(b);  // zero copy: (2k x n) floats with pitch 2 * ldb
         ldb2 = 2 * ldb;
-    } else {
+    } else if (e == cudaSuccess) {
         const int64_t pitch_b = b_n ? round_up(2 * (int64_t)k, 32) : round_up((int64_t)n, 32);
         const int64_t cols_b = b_n ? (int64_t)n : 2 * (int64_t)k;
-        e = cudaMallocAsync(reinterpret_cast<void**>(&b_scratch), (size_t)pitch_b * (size_t)cols_b * sizeof(float), st);
-        if (e != cudaSuccess) { cudaGetLastError(); cudaFreeAsync(a2, st); return cudaErrorMemoryAllocation; }
-        if (b_n) {  // same values, legal pitch: the copy engine re-pitches
+        e = scratch_alloc(reinterpret_cast<void**>(&b_scratch), (size_t)pitch_b * (size_t)cols_b * sizeof(float), st);
+        if (e != cudaSuccess) { cudaGetLastError(); scratch_free(a2, st); return cudaErrorMemoryAllocation; }
+        if (b_n)  // same values, legal pitch: the copy engine re-pitches
             e = cudaMemcpy2DAsync(b_scratch, (size_t)pitch_b * sizeof(float), b, (size_t)ldb * sizeof(float2), (size_t)k * sizeof(float2), (size_t)n,
                                   cudaMemcpyDeviceToDevice, st);
-            if (e != cudaSuccess) { cudaFreeAsync(a2, st); cudaFreeAsync(b_scratch, st); return e; }
-        } else {
-            split_b_t<<<pass_grid(n, k), 256, 0, st>>>(static_cast<const float2*>(b), ldb, n, k, tb == 'C' ? 1 : 0, b_scratch, pitch_b);
-            count_launch();
-        }
+        else e = cgemm_tc_split_b(tb, n, k, b, ldb, b_scratch, pitch_b, st);
         b2 = b_scratch;
         ldb2 = pitch_b;
     }
-
-    // ---- beta ----
-    float beta_r = be[0];
-    if (be[1] != 0.f) {  // complex beta: C <- beta * C first, then accumulate with 1
-        e = device_scale(C32, m, n, be, c, ldc, st);
-        beta_r = 1.f;
-    }
-    if (e == cudaSuccess) e = cudaGetLastError();
-    // ---- the real product on tcgen05: (2m x n) = (2m x 2k) (2k x n), FP32-accurate 3xTF32 ----
-    if (e == cudaSuccess)
-        e = sgemm_tc_launch(a_n ? 'N' : 'T', b_n ? 'N' : 'T', 2 * m, n, 2 * k, 1.f, a2, pitch_a, b2, ldb2, beta_r, static_cast<float*>(c), 2 * ldc, st, 3);
-    cudaFreeAsync(a2, st);
-    if (b_scratch) cudaFreeAsync(b_scratch, st);
+    if (e == cudaSuccess) e = cgemm_tc_prepared(ta, tb, m, n, k, a2, pitch_a, b2, ldb2, be, c, ldc, st);
+    scratch_free(a2, st);
+    scratch_free(b_scratch, st);
     return e;
 }
 

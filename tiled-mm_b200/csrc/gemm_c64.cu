@@ -18,6 +18,7 @@
 #include "tmm_ptx.cuh"
 
 #include <cstdio>
+#include <type_traits>
 
 namespace tmm {
 namespace c64 {
@@ -79,7 +80,9 @@ zgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + STAGES * C::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
 
-    const int warp = threadIdx.x >> 5;
+    // read through a shuffle so that the compiler knows the warp index (and every branch taken on it: the roles, the edge path of the main
+    // loop) to be warp-uniform and keeps the pipeline bookkeeping inside those branches on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -136,51 +139,64 @@ zgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < NJ; ++j) { acr[i][j][0] = acr[i][j][1] = 0.0; aci[i][j][0] = aci[i][j][1] = 0.0; }
 
-    int stage = 0;
-    uint32_t phase = 0;
-    const int prefetch_kb = p.read_c ? max(0, kblocks - 12) : -1;
-    for (int kb = 0; kb < kblocks; ++kb) {
-        if (kb == prefetch_kb) {
-            // lane l covers column wn + l of this warp's 32 x 32 block of C: 32 rows = 512 B = 4 (5 if unaligned) lines
-            const int col = tn * BN + wn + lane;
-            if (col < p.n) {
-                const char* cp = reinterpret_cast<const char*>(p.c + (int64_t)col * p.ldc + tm * BM + wm);
-                const int rows = min(WM, p.m - (tm * BM + wm));
+    // edge tiles: DMMA tiles that lie entirely past m / n are skipped (warp-uniform counts; see gemm_f64.cu)
+    const int mi_valid = min(MI, max(0, (p.m - (tm * BM + wm) + 7) >> 3));
+    const int nj_valid = min(NJ, max(0, (p.n - (tn * BN + wn) + 7) >> 3));
+
+    auto main_loop = [&](auto edge_tag) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
+        int stage = 0;
+        uint32_t phase = 0;
+        const int prefetch_kb = p.read_c ? max(0, kblocks - 12) : -1;
+        for (int kb = 0; kb < kblocks; ++kb) {
+            if (kb == prefetch_kb) {
+                // lane l covers column wn + l of this warp's 32 x 32 block of C: 32 rows = 512 B = 4 (5 if unaligned) lines
+                const int col = tn * BN + wn + lane;
+                if (col < p.n) {
+                    const char* cp = reinterpret_cast<const char*>(p.c + (int64_t)col * p.ldc + tm * BM + wm);
+                    const int rows = min(WM, p.m - (tm * BM + wm));
 #pragma unroll
-                for (int o = 0; o < 5; ++o)
-                    if (o * 128 < rows * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + o * 128));
-            }
-        }
-        ptx::mbar_wait(&full_bar[stage], phase);
-        const double2* st = reinterpret_cast<const double2*>(base + stage * C::STAGE_BYTES);
-        const double2* as = st + a_off;
-        const double2* bs = st + b_off;
-#pragma unroll
-        for (int ks = 0; ks < BK / 4; ++ks) {
-            double br[NJ], bi[NJ];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const double2 v = bs[ks * B_K_STRIDE + j * B_J_STRIDE];
-                br[j] = v.x; bi[j] = v.y;
-            }
-#pragma unroll
-            for (int i = 0; i < MI; ++i) {
-                const double2 v = as[ks * A_K_STRIDE + i * A_I_STRIDE];
-                // all sign handling sits on the A fragment (4 values) so the B fragments stay untouched
-                const double ar = v.x, az = flip(v.x, p.mask_z), ax = flip(v.y, p.mask_x), ay = flip(v.y, p.mask_y);
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    ptx::dmma_884(acr[i][j][0], acr[i][j][1], ar, br[j]);
-                    ptx::dmma_884(aci[i][j][0], aci[i][j][1], az, bi[j]);
-                    ptx::dmma_884(acr[i][j][0], acr[i][j][1], ax, bi[j]);
-                    ptx::dmma_884(aci[i][j][0], aci[i][j][1], ay, br[j]);
+                    for (int o = 0; o < 5; ++o)
+                        if (o * 128 < rows * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + o * 128));
                 }
             }
+            ptx::mbar_wait(&full_bar[stage], phase);
+            const double2* st = reinterpret_cast<const double2*>(base + stage * C::STAGE_BYTES);
+            const double2* as = st + a_off;
+            const double2* bs = st + b_off;
+            if (!EDGE || (mi_valid > 0 && nj_valid > 0)) {
+#pragma unroll
+                for (int ks = 0; ks < BK / 4; ++ks) {
+                    double br[NJ], bi[NJ];
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const double2 v = bs[ks * B_K_STRIDE + j * B_J_STRIDE];
+                        br[j] = v.x; bi[j] = v.y;
+                    }
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) {
+                        if (EDGE && i >= mi_valid) continue;
+                        const double2 v = as[ks * A_K_STRIDE + i * A_I_STRIDE];
+                        // all sign handling sits on the A fragment (4 values) so the B fragments stay untouched
+                        const double ar = v.x, az = flip(v.x, p.mask_z), ax = flip(v.y, p.mask_x), ay = flip(v.y, p.mask_y);
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            if (EDGE && j >= nj_valid) continue;
+                            ptx::dmma_884(acr[i][j][0], acr[i][j][1], ar, br[j]);
+                            ptx::dmma_884(aci[i][j][0], aci[i][j][1], az, bi[j]);
+                            ptx::dmma_884(acr[i][j][0], acr[i][j][1], ax, bi[j]);
+                            ptx::dmma_884(aci[i][j][0], aci[i][j][1], ay, br[j]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-    }
+    };
+    if (mi_valid == MI && nj_valid == NJ) main_loop(std::false_type{});
+    else main_loop(std::true_type{});
 
     // epilogue: lane (g,t) owns rows 8i+g, columns 8j+2t, 8j+2t+1 of its warp tile; one 16-byte access per element
     const int row0 = tm * BM + wm + g;

@@ -30,6 +30,13 @@
 //               Tile end: alpha/beta and plain coalesced global stores (any ldc; the device-resident C of
 //               copy_c_back=false has ld = m, reference tiled_mm.cpp:446)
 //   warp 2      TMEM allocation / release
+// Tiles are handed out DYNAMICALLY: the producer draws tile numbers from a per-launch counter in global memory (atomicAdd) and passes them to the
+// other roles through a four-entry ring in shared memory (tile_full / tile_empty mbarriers; -1 ends the kernel).  The scheduler runs several of
+// these launches at once on different streams (column stripes of phase 1, column blocks of phase 2); a persistent CTA keeps its SM until its
+// launch has no tiles left, so with the static stride (tile += gridDim.x) a CTA that got its SM late finished late and the launch ended with
+// most SMs idle (cgemm 8000^3 host-to-host: the last phase-2 block, 1 ms of work, took 6.2 ms - profiles/r2_cgemm_diag.txt).  With the
+// counter a late CTA simply finds fewer tiles.  The last CTA to leave zeroes the counter pair for the launch that takes the slot next.
+// TMM_TC_SCHED=static selects the fixed stride.
 // All m / n / k edges are handled by TMA zero fill plus masked stores.
 #include "tmm_blas.h"
 #include "tmm_tc.cuh"
@@ -38,6 +45,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 namespace tmm {
 namespace f32tc {
@@ -53,8 +61,10 @@ constexpr int TMEM_COLS = ACC_BUFS * BN;
 constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_TMEM = 2, WARP_EPI0 = 4, WARP_SPLIT0 = 8, SPLIT_WARPS = 8;
 constexpr int THREADS = (WARP_SPLIT0 + SPLIT_WARPS) * 32;
 constexpr int GROUP_COLS = 16;
-constexpr int REGS_CONTROL = 40, REGS_SPLIT = 88, REGS_EPILOGUE = 232;  // setmaxnreg split of the 512 x 128 launch allocation
+constexpr int REGS_CONTROL = 56, REGS_SPLIT = 88, REGS_EPILOGUE = 232;  // setmaxnreg split of the 512 x 128 launch allocation
 constexpr int WINDOW_KBLOCKS = 4;  // k-blocks summed in TMEM before promotion to the FP32 register accumulators
+constexpr int TILE_RING = 4;       // tile numbers in flight between the producer and the other roles
+constexpr int SCHED_SLOTS = 4096;  // counter pairs in global memory, one per launch in flight (taken round robin)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 static_assert(BM == BN, "operand tiles share one size");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -74,6 +84,7 @@ struct Params {
     int window;  // k-blocks per TMEM accumulation window
     int bk;          // operand elements per k-block: 32 FP32 (= 128 B); 64 for the 16-bit variant below - the byte geometry is the same
     int f16_kind;    // experimental: operands are bf16, K-major, multiplied by kind::f16 MMAs (one term); see bgemm_tc_native_launch
+    int* sched;       // [0] next tile, [1] CTAs that have drawn their last number; nullptr: static stride
     int split_trunc;  // experimental (TMM_TC_SPLIT=trunc): hi = the raw FP32 bits (the tensor core ignores the low 13 mantissa bits), only lo is written
 };
 
@@ -102,7 +113,11 @@ __device__ __forceinline__ void sgemm_tc_body(const CUtensorMap& tmap_a, const C
     uint64_t* empty_bar = ready_bar + STAGES;                                        // MMAs retired        -> TMA producer
     uint64_t* acc_full_bar = empty_bar + STAGES;                                     // accumulator final   -> epilogue
     uint64_t* acc_empty_bar = acc_full_bar + ACC_BUFS;                               // accumulator drained -> MMA issuer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + ACC_BUFS);
+    uint64_t* tile_full_bar = acc_empty_bar + ACC_BUFS;                              // tile number written -> MMA issuer, accumulate and split warps
+    uint64_t* tile_empty_bar = tile_full_bar + TILE_RING;                            // ... read by all of them -> producer
+    int* tile_ring = reinterpret_cast<int*>(tile_empty_bar + TILE_RING);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_ring + TILE_RING);
+    static_assert((3 * NSTAGES + 2 * ACC_BUFS + 2 * TILE_RING) * 8 + TILE_RING * 4 + 4 <= 256, "barrier block");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -119,6 +134,11 @@ __device__ __forceinline__ void sgemm_tc_body(const CUtensorMap& tmap_a, const C
             ptx::mbar_init(&acc_full_bar[b], 1);
             ptx::mbar_init(&acc_empty_bar[b], 4);
         }
+#pragma unroll
+        for (int r = 0; r < TILE_RING; ++r) {
+            ptx::mbar_init(&tile_full_bar[r], 1);
+            ptx::mbar_init(&tile_empty_bar[r], 1 + 4 + (p.terms == 3 ? SPLIT_WARPS : 0));  // MMA lane + accumulate warps + split warps
+        }
         ptx::fence_mbar_init();
     }
     if (warp == WARP_TMEM) tc::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -128,7 +148,29 @@ __device__ __forceinline__ void sgemm_tc_body(const CUtensorMap& tmap_a, const C
     const uint32_t tmem_base = *tmem_slot;
 
     const int total_tiles = p.tiles_m * p.tiles_n;
-    const int kblocks = (p.k + p.bk - 1) / p.bk;
+    const int kblocks = (p.k + p.bk - 1) >> (p.bk == 64 ? 6 : 5);  // bk is 32 (FP32 operands) or 64 (the 16-bit variant); a shift is cheap enough to recompute per role
+    // consumer side of the tile ring: every role but the producer reads the same sequence of tile numbers, -1 last.  One counter per thread
+    // carries both the slot (low bits) and the phase (next bit): the accumulate warps have no register to spare.
+    static_assert((TILE_RING & (TILE_RING - 1)) == 0 && (ACC_BUFS & (ACC_BUFS - 1)) == 0, "ring sizes are powers of two");
+    uint32_t tr_count = 0;
+    auto next_tile_warp = [&]() -> int {  // whole warp, converged
+        const uint32_t slot = tr_count & (TILE_RING - 1);
+        tc::mbar_wait_guarded(&tile_full_bar[slot], (tr_count / TILE_RING) & 1);
+        // (the shuffles here and below tell the compiler that the tile number - and with it every loop that runs on it - is warp-uniform:
+        //  without them the pipeline bookkeeping of all roles leaves the uniform datapath; measured 92 instead of 155 TF at 8192^3)
+        const int t = __shfl_sync(0xffffffffu, tile_ring[slot], 0);
+        if (lane == 0) ptx::mbar_arrive(&tile_empty_bar[slot]);
+        ++tr_count;
+        return t;
+    };
+    auto next_tile_lane = [&]() -> int {  // a single lane
+        const uint32_t slot = tr_count & (TILE_RING - 1);
+        tc::mbar_wait_guarded(&tile_full_bar[slot], (tr_count / TILE_RING) & 1);
+        const int t = __shfl_sync(0x1u, tile_ring[slot], 0);
+        ptx::mbar_arrive(&tile_empty_bar[slot]);
+        ++tr_count;
+        return t;
+    };
 
     // Every role starts with its share of the warpgroup-wide register reallocation (setmaxnreg): the control and split
     // warpgroups hand registers to the accumulate/epilogue warpgroup.
@@ -140,9 +182,22 @@ __device__ __forceinline__ void sgemm_tc_body(const CUtensorMap& tmap_a, const C
             ptx::prefetch_tensormap(&tmap_b);
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            auto draw = [&](int after) -> int {  // the next tile of this CTA, -1 when the launch has none left
+                const int t = p.sched ? atomicAdd(&p.sched[0], 1) : (after < 0 ? (int)blockIdx.x : after + (int)gridDim.x);
+                return __shfl_sync(0x1u, t < total_tiles ? t : -1, 0);
+            };
+            int tile = draw(-1);
+            for (;;) {
+                const uint32_t slot = tr_count & (TILE_RING - 1);
+                tc::mbar_wait_guarded(&tile_empty_bar[slot], ((tr_count / TILE_RING) & 1) ^ 1);
+                tile_ring[slot] = tile;
+                ptx::mbar_arrive(&tile_full_bar[slot]);
+                ++tr_count;
+                if (tile < 0) break;
+                const int next = draw(tile);  // issued ahead of this tile's loads: the atomic's round trip hides behind them
                 int tm, tn;
                 tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+                tile = next;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait_guarded(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * OPERAND_BYTES);
@@ -163,6 +218,10 @@ __device__ __forceinline__ void sgemm_tc_body(const CUtensorMap& tmap_a, const C
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (p.sched) {
+                // every CTA draws exactly one number past the end; the CTA that reports it last knows that nobody will touch the pair again
+                if (atomicAdd(&p.sched[1], 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; }
+            }
         }
         __syncwarp();
     } else if (warp == WARP_MMA) {
@@ -172,7 +231,7 @@ __device__ __forceinline__ void sgemm_tc_body(const CUtensorMap& tmap_a, const C
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             const bool split = p.terms == 3;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            while (next_tile_lane() >= 0) {
                 uint32_t d_tmem = 0;
                 for (int kb = 0, wk = 0; kb < kblocks; ++kb) {
                     if (wk == 0) {  // open a window: its TMEM accumulator must have been drained
@@ -216,17 +275,17 @@ __device__ __forceinline__ void sgemm_tc_body(const CUtensorMap& tmap_a, const C
         // ===== accumulate + epilogue: warp q owns TMEM lanes 32q .. 32q+31 = rows 32q + lane of the tile =====
         ptx::setmaxnreg_inc<REGS_EPILOGUE>();
         const int q = warp - WARP_EPI0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
+        uint32_t acc_count = 0;  // window accumulator = low bits, phase = the next bit
         const int windows = (kblocks + p.window - 1) / p.window;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = next_tile_warp(); tile >= 0; tile = next_tile_warp()) {
             int tm, tn;
             tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
             float sum[BN];
 #pragma unroll
             for (int j = 0; j < BN; ++j) sum[j] = 0.f;
             for (int w = 0; w < windows; ++w) {
-                tc::mbar_wait_guarded(&acc_full_bar[acc], acc_phase);
+                const uint32_t acc = acc_count & (ACC_BUFS - 1);
+                tc::mbar_wait_guarded(&acc_full_bar[acc], (acc_count / ACC_BUFS) & 1);
                 tc::fence_after_thread_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll
@@ -246,7 +305,7 @@ __device__ __forceinline__ void sgemm_tc_body(const CUtensorMap& tmap_a, const C
                         sum[h * 64 + 32 + j] += __uint_as_float(v1[j]);
                     }
                 }
-                if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+                ++acc_count;
             }
             const int row = tm * BM + q * 32 + lane;
             const bool row_ok = row < p.m;
@@ -281,7 +340,7 @@ __device__ __forceinline__ void sgemm_tc_body(const CUtensorMap& tmap_a, const C
         static_assert(CHUNKS % (SPLIT_WARPS * 32) == 0, "chunk split");
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        while (next_tile_warp() >= 0) {
             for (int kb = 0; kb < kblocks; ++kb) {
                 tc::mbar_wait_guarded(&full_bar[stage], phase);
                 unsigned char* st = base + stage * STAGE_BYTES;
@@ -305,13 +364,11 @@ __device__ __forceinline__ void sgemm_tc_body(const CUtensorMap& tmap_a, const C
                 for (int i = 0; i < PER_THREAD; ++i) {
                     const int idx = t + i * (SPLIT_WARPS * 32);
                     const int off = idx * 16 + (idx >= OPERAND_BYTES / 16 ? OPERAND_BYTES : 0);
-                    float4 hi, lo;
-                    split_tf32(x[i].x, hi.x, lo.x);
-                    split_tf32(x[i].y, hi.y, lo.y);
-                    split_tf32(x[i].z, hi.z, lo.z);
-                    split_tf32(x[i].w, hi.w, lo.w);
-                    *reinterpret_cast<float4*>(st + off) = hi;
-                    *reinterpret_cast<float4*>(st + off + OPERAND_BYTES) = lo;
+                    const float v[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+                    float hi[4], lo[4];
+                    split_tf32_x4(v, hi, lo);
+                    *reinterpret_cast<float4*>(st + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(st + off + OPERAND_BYTES) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
                 tc::fence_proxy_async_smem();
                 __syncwarp();
@@ -347,6 +404,27 @@ static CUresult make_map(CUtensorMap* map, const float* base, uint64_t dim0, uin
     cuuint32_t estr[2] = {1, 1};
     return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+// One counter pair per launch in flight, from a zeroed per-device array taken round robin (the kernel's last CTA zeroes its pair again).
+// nullptr (static stride) when TMM_TC_SCHED=static or the array cannot be had.
+static int* sched_slot() {
+    static std::mutex mu;
+    static int* base[64] = {};
+    static bool tried[64] = {};
+    static unsigned next[64] = {};
+    static const bool is_static = [] { const char* v = getenv("TMM_TC_SCHED"); return v && v[0] == 's'; }();
+    if (is_static) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!tried[dev]) {
+        tried[dev] = true;
+        void* q = nullptr;
+        if (cudaMalloc(&q, SCHED_SLOTS * 2 * sizeof(int)) == cudaSuccess && cudaMemset(q, 0, SCHED_SLOTS * 2 * sizeof(int)) == cudaSuccess) base[dev] = static_cast<int*>(q);
+        else cudaGetLastError();
+    }
+    return base[dev] ? base[dev] + 2 * (next[dev]++ % SCHED_SLOTS) : nullptr;
 }
 
 // developer override of the MN-major descriptor fields (tools/tc_test.cu sweeps them on a new driver / chip)
@@ -416,6 +494,7 @@ cudaError_t sgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
+    p.sched = sched_slot();
     sgemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(map_a, map_b, p);
     count_launch();
     return cudaGetLastError();
@@ -467,6 +546,7 @@ cudaError_t bgemm_tc_native_tn_launch(int m, int n, int k, float alpha, const vo
     const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
     if (tiles > INT32_MAX) return cudaErrorInvalidValue;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    p.sched = sched_slot();
     sgemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(map_a, map_b, p);
     count_launch();
     return cudaGetLastError();

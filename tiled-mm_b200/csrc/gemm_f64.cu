@@ -26,6 +26,7 @@
 #include "tmm_ptx.cuh"
 
 #include <cstdio>
+#include <type_traits>
 
 namespace tmm {
 namespace f64 {
@@ -84,7 +85,9 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + STAGES * C::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
 
-    const int warp = threadIdx.x >> 5;
+    // read through a shuffle so that the compiler knows the warp index (and every branch taken on it: the roles, the edge path of the main
+    // loop) to be warp-uniform and keeps the pipeline bookkeeping inside those branches on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -143,43 +146,62 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < NJ; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    int stage = 0;
-    uint32_t phase = 0;
-    // read-modify-write launches pull this warp's 64 x 32 block of C towards L2 a few k-blocks before the epilogue
-    // needs it (early enough to cover the HBM latency, late enough not to be evicted again by the A/B stream)
-    const int prefetch_kb = p.read_c ? max(0, kblocks - 12) : -1;
-    for (int kb = 0; kb < kblocks; ++kb) {
-        if (kb == prefetch_kb) {
-            // lane l covers column wn + l: 64 rows = 512 B = 4 (5 when unaligned) 128-byte lines
-            const int col = tn * BN + wn + lane;
-            if (col < p.n) {
-                const char* cp = reinterpret_cast<const char*>(p.c + (int64_t)col * p.ldc + tm * BM + wm);
-                const int rows = min(WM, p.m - (tm * BM + wm));
+    // Edge tiles: TMA zero-fills what lies past m / n, and a warp would multiply those zeros at full price (dgemm 10000^3: 79 x 157 tiles cover
+    // 10112 x 10048, 1.6 % of all DMMAs).  The count of 8-row / 8-column DMMA tiles that hold at least one element of C is warp-uniform, so an
+    // edge warp predicates its DMMAs on it (a warp entirely outside C issues none and only keeps the pipeline's barriers moving); interior warps
+    // run the unpredicated loop.
+    const int mi_valid = min(MI, max(0, (p.m - (tm * BM + wm) + 7) >> 3));
+    const int nj_valid = min(NJ, max(0, (p.n - (tn * BN + wn) + 7) >> 3));
+
+    auto main_loop = [&](auto edge_tag) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
+        int stage = 0;
+        uint32_t phase = 0;
+        // read-modify-write launches pull this warp's 64 x 32 block of C towards L2 a few k-blocks before the epilogue
+        // needs it (early enough to cover the HBM latency, late enough not to be evicted again by the A/B stream)
+        const int prefetch_kb = p.read_c ? max(0, kblocks - 12) : -1;
+        for (int kb = 0; kb < kblocks; ++kb) {
+            if (kb == prefetch_kb) {
+                // lane l covers column wn + l: 64 rows = 512 B = 4 (5 when unaligned) 128-byte lines
+                const int col = tn * BN + wn + lane;
+                if (col < p.n) {
+                    const char* cp = reinterpret_cast<const char*>(p.c + (int64_t)col * p.ldc + tm * BM + wm);
+                    const int rows = min(WM, p.m - (tm * BM + wm));
 #pragma unroll
-                for (int o = 0; o < 5; ++o)
-                    if (o * 128 < rows * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + o * 128));
+                    for (int o = 0; o < 5; ++o)
+                        if (o * 128 < rows * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + o * 128));
+                }
             }
+            ptx::mbar_wait(&full_bar[stage], phase);
+            const double* st = reinterpret_cast<const double*>(base + stage * C::STAGE_BYTES);
+            const double* as = st + a_off;
+            const double* bs = st + b_off;
+            if (!EDGE || (mi_valid > 0 && nj_valid > 0)) {
+#pragma unroll
+                for (int ks = 0; ks < BK / 4; ++ks) {
+                    double af[MI], bf[NJ];
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) af[i] = as[ks * A_K_STRIDE + i * A_I_STRIDE];
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) bf[j] = bs[ks * B_K_STRIDE + j * B_J_STRIDE];
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) {
+                        if (EDGE && i >= mi_valid) continue;
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            if (EDGE && j >= nj_valid) continue;
+                            ptx::dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::mbar_wait(&full_bar[stage], phase);
-        const double* st = reinterpret_cast<const double*>(base + stage * C::STAGE_BYTES);
-        const double* as = st + a_off;
-        const double* bs = st + b_off;
-#pragma unroll
-        for (int ks = 0; ks < BK / 4; ++ks) {
-            double af[MI], bf[NJ];
-#pragma unroll
-            for (int i = 0; i < MI; ++i) af[i] = as[ks * A_K_STRIDE + i * A_I_STRIDE];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) bf[j] = bs[ks * B_K_STRIDE + j * B_J_STRIDE];
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) ptx::dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-    }
+    };
+    if (mi_valid == MI && nj_valid == NJ) main_loop(std::false_type{});
+    else main_loop(std::true_type{});
 
     // epilogue: lane (g,t) owns rows 8i+g, columns 8j+2t, 8j+2t+1 of its warp tile
     const int row0 = tm * BM + wm + g;

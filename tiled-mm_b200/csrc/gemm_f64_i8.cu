@@ -354,13 +354,13 @@ cudaError_t dgemm_i8_launch(char ta, char tb, int m, int n, int k, double alpha,
     const size_t bytes_a = i8_slices_layout(m, k, S, &sa.rows_pad, &sa.pitch), bytes_b = i8_slices_layout(n, k, S, &sb.rows_pad, &sb.pitch);
     if ((int64_t)S * std::max(sa.rows_pad, sb.rows_pad) > INT32_MAX) return cudaErrorMemoryAllocation;  // TMA coordinates are 32-bit
     int* ex = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&sa.q), bytes_a, st);
-    if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&sb.q), bytes_b, st);
-    if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&ex), (size_t)(m + n) * sizeof(int), st);
+    cudaError_t e = scratch_alloc(reinterpret_cast<void**>(&sa.q), bytes_a, st);
+    if (e == cudaSuccess) e = scratch_alloc(reinterpret_cast<void**>(&sb.q), bytes_b, st);
+    if (e == cudaSuccess) e = scratch_alloc(reinterpret_cast<void**>(&ex), (size_t)(m + n) * sizeof(int), st);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        if (sa.q) cudaFreeAsync(sa.q, st);
-        if (sb.q) cudaFreeAsync(sb.q, st);
+        scratch_free(sa.q, st);
+        scratch_free(sb.q, st);
         return cudaErrorMemoryAllocation;
     }
     sa.e = ex; sb.e = ex + m;
@@ -368,9 +368,9 @@ cudaError_t dgemm_i8_launch(char ta, char tb, int m, int n, int k, double alpha,
     e = i8_slice_operand(a, ta == 'N' ? 1 : lda, ta == 'N' ? lda : 1, m, k, sa, st);
     if (e == cudaSuccess) e = i8_slice_operand(b, tb == 'N' ? ldb : 1, tb == 'N' ? 1 : ldb, n, k, sb, st);
     if (e == cudaSuccess) e = i8_gemm_sliced(sa, 0, m, sb, 0, n, alpha, beta, c, ldc, st);
-    cudaFreeAsync(sa.q, st);
-    cudaFreeAsync(sb.q, st);
-    cudaFreeAsync(ex, st);
+    scratch_free(sa.q, st);
+    scratch_free(sb.q, st);
+    scratch_free(ex, st);
     return e;
 }
 

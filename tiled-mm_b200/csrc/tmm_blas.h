@@ -52,6 +52,11 @@ cudaError_t cgemm_simt_launch(char ta, char tb, int m, int n, int k, const float
                               const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
 cudaError_t cgemm_tc_launch(char ta, char tb, int m, int n, int k, const float* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
                             const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
+// the three steps of cgemm_tc_launch for callers that prepare an operand once and multiply it many times (gemm_c32_tc.cu has the layouts)
+cudaError_t cgemm_tc_embed_a(char ta, int m, int k, const float* alpha2, const void* a, int64_t lda, float* a2, int64_t pitch_a2, cudaStream_t stream);
+cudaError_t cgemm_tc_split_b(char tb, int n, int k, const void* b, int64_t ldb, float* b2, int64_t pitch_b2, cudaStream_t stream);
+cudaError_t cgemm_tc_prepared(char ta, char tb, int m, int n, int k, const float* a2, int64_t pitch_a2, const float* b2, int64_t pitch_b2,
+                              const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
 // BF16 inputs, FP32 output / accumulation, on the tcgen05 TF32 path (bf16 is a subset of tf32: identical products) - gemm_bf16_tc.cu
 cudaError_t bgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb,
                             float beta, float* c, int64_t ldc, cudaStream_t stream);
@@ -90,6 +95,10 @@ cudaError_t zgemm_simt_launch(char ta, char tb, int m, int n, int k, const doubl
 
 void count_launch();
 int sm_count();
+// stream-ordered scratch from the library's own per-device pool (keeps what it has grown to across calls; tmm_common.cu)
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t stream);
+void scratch_free(void* p, cudaStream_t stream);  // nullptr is fine
+void scratch_trim();                              // free blocks of the current device's pool go back to the driver
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency)
 void* tensormap_encode_fn();
 

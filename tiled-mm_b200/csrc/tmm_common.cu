@@ -43,6 +43,60 @@ void* tensormap_encode_fn() {
     return fn;
 }
 
+// ---- stream-ordered scratch ----------------------------------------------------------------------
+// Operand preparation (complex embedding, BF16 widening, re-pitching, int8 slices) works in stream-ordered scratch.  The device's DEFAULT pool
+// releases its free blocks to the driver at every synchronisation (release threshold 0): each host-to-host call ends in one, so the next call's
+// first launches would pay a physical allocation of up to a few GB again, and the pool's attributes belong to the application anyway.  The
+// library therefore keeps one pool of its own per device that holds on to what it has grown to; scratch_trim() hands the free blocks back
+// (the scheduler calls it when it re-reads the free device memory, so cached scratch never shrinks an out-of-core plan).
+// TMM_POOL_KEEP=0: the default pool with its default behaviour (A/B switch).
+namespace {
+struct ScratchPools {
+    std::mutex mu;
+    cudaMemPool_t pool[64] = {};
+    bool tried[64] = {};
+};
+ScratchPools& pools() { static ScratchPools* p = new ScratchPools; return *p; }  // leaked on purpose: no teardown order problem at exit
+cudaMemPool_t scratch_pool() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    ScratchPools& sp = pools();
+    std::lock_guard<std::mutex> lk(sp.mu);
+    if (!sp.tried[dev]) {
+        sp.tried[dev] = true;
+        const char* v = getenv("TMM_POOL_KEEP");
+        if (!(v && v[0] == '0')) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaMemPool_t mp = nullptr;
+            if (cudaMemPoolCreate(&mp, &props) == cudaSuccess) {
+                uint64_t keep = UINT64_MAX;
+                cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+                sp.pool[dev] = mp;
+            }
+            cudaGetLastError();
+        }
+    }
+    return sp.pool[dev];
+}
+}  // namespace
+
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+    cudaMemPool_t mp = scratch_pool();
+    return mp ? cudaMallocFromPoolAsync(p, bytes, mp, st) : cudaMallocAsync(p, bytes, st);
+}
+void scratch_free(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+void scratch_trim() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    ScratchPools& sp = pools();
+    std::lock_guard<std::mutex> lk(sp.mu);
+    if (sp.pool[dev]) cudaMemPoolTrimTo(sp.pool[dev], 0);
+}
+
 // ---- float GEMM math mode and dispatch ---------------------------------------------------------
 static std::atomic<int> g_f32_mode{-1};
 int f32_math_mode() {
@@ -200,10 +254,10 @@ cudaError_t repitch(Operand& op, int64_t rows, int64_t cols, size_t es, cudaStre
     if (tma_ok(op.p, op.ld, es) || rows <= 0 || cols <= 0) return cudaSuccess;
     const int64_t q = 128 / (int64_t)es, pitch = (rows + q - 1) / q * q;
     void* buf = nullptr;
-    cudaError_t e = cudaMallocAsync(&buf, (size_t)pitch * (size_t)cols * es, st);
+    cudaError_t e = scratch_alloc(&buf, (size_t)pitch * (size_t)cols * es, st);
     if (e != cudaSuccess) return e;
     e = cudaMemcpy2DAsync(buf, (size_t)pitch * es, op.p, (size_t)op.ld * es, (size_t)rows * es, (size_t)cols, cudaMemcpyDeviceToDevice, st);
-    if (e != cudaSuccess) { cudaFreeAsync(buf, st); return e; }
+    if (e != cudaSuccess) { scratch_free(buf, st); return e; }
     op.p = buf; op.ld = pitch; op.scratch = buf;
     return cudaSuccess;
 }
@@ -216,8 +270,8 @@ static cudaError_t sgemm_repitched(char ta, char tb, int m, int n, int k, float 
     if (e == cudaSuccess) e = repitch(B, tb == 'N' ? k : n, tb == 'N' ? n : k, sizeof(float), st);
     if (e == cudaSuccess) e = sgemm_tc_launch(ta, tb, m, n, k, alpha, static_cast<const float*>(A.p), A.ld, static_cast<const float*>(B.p), B.ld, beta, c, ldc, st, mode);
     else e = cudaErrorMemoryAllocation;  // no scratch: the caller falls back to the SIMT kernel on the operands as they are
-    if (A.scratch) cudaFreeAsync(A.scratch, st);
-    if (B.scratch) cudaFreeAsync(B.scratch, st);
+    scratch_free(A.scratch, st);
+    scratch_free(B.scratch, st);
     return e;
 }
 
@@ -242,8 +296,8 @@ static cudaError_t fp64_gemm(int dtype, char ta, char tb, int m, int n, int k, c
                                              static_cast<const double*>(b), ldb, *static_cast<const double*>(beta), static_cast<double*>(c), ldc, st)
                          : zgemm_simt_launch(ta, tb, m, n, k, static_cast<const double*>(alpha), a, lda, b, ldb, static_cast<const double*>(beta), c, ldc, st);
     }
-    if (A.scratch) cudaFreeAsync(A.scratch, st);
-    if (B.scratch) cudaFreeAsync(B.scratch, st);
+    scratch_free(A.scratch, st);
+    scratch_free(B.scratch, st);
     return e;
 }
 

@@ -199,6 +199,9 @@ size_t device_budget(tmm_context* ctx) {
     if (ctx->budget_override) return ctx->budget_override;
     if (ctx->budget_cached) return ctx->budget_cached;  // refreshed whenever an allocation fails or the context grows full C
     size_t fr = 0, to = 0;
+#ifndef TMM_EMULATED
+    tmm::scratch_trim();  // cached operand-preparation scratch goes back to the driver before the free memory is read
+#endif
     if (cudaMemGetInfo(&fr, &to) != cudaSuccess) return (size_t)8 << 30;
     size_t held = ctx->buf_a.cap + ctx->buf_b.cap + ctx->buf_c.cap + ctx->buf_cs.cap;
     double avail = (double)fr + (double)held;
@@ -349,6 +352,53 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev, void*
     // element (row i of op(A), k index l) of a device sub-block of A at base[i * stride_row + l * stride_k]; likewise columns of op(B)
     const int64_t a_sr = cl.ta == 'N' ? 1 : pa, a_sk = cl.ta == 'N' ? pa : 1, b_sr = cl.tb == 'N' ? pb : 1, b_sk = cl.tb == 'N' ? 1 : pb;
 #endif
+    // ---- complex<float> on the tcgen05 kernel (csrc/gemm_c32_tc.cu): operands prepared ONCE, where they land ---------------------------------
+    // The kernel multiplies the real embedding A' (2m x 2k floats, alpha folded in) with B' (the stored B read as floats for op N, a split
+    // copy for op T / C).  Launch by launch that meant a stream-ordered allocation and a pass over A for every stripe of every k-chunk and over
+    // all of A for every phase-2 block; the allocations could block the enqueueing host thread for tens of milliseconds when the pool had to
+    // wait for a block to come back (profiles/r2_split_fix.txt: cgemm 8000^3 30 ms in one process, 89 ms after other sizes had shaped the pool).
+    // Here A' of the whole panel lives in a context buffer: each k-chunk is embedded once when it arrives (on the first stripe's stream, the
+    // other stripe streams wait for it) and the chunks add up to the A' of the resident A that phase 2 multiplies; B pieces are split by the
+    // launch that consumes them, into the matching position of a second context buffer.  No allocation on the launch path.
+    struct C32Prep {
+        bool on = false;
+        float* a2 = nullptr; int64_t pitch_a2 = 0;
+        float* b2 = nullptr; int64_t pitch_b2 = 0;
+        cudaEvent_t last_embed = nullptr;
+    } c32;
+    if (cl.dtype == TMM_C32 && tmm::c32_math_mode() == TMM_CMATH_TC && tmm::f32_math_mode() != 0 && cl.k > 0 && cl.m > 0 && cl.n > 0 &&
+        cl.m <= INT32_MAX / 2 && cl.k <= INT32_MAX / 2) {
+        c32.pitch_a2 = cl.ta == 'N' ? round_up(2 * cl.m, 32) : round_up(2 * cl.k, 32);
+        const size_t a2_bytes = (size_t)c32.pitch_a2 * (size_t)(2 * (cl.ta == 'N' ? cl.k : cl.m)) * sizeof(float);
+        c32.pitch_b2 = cl.tb == 'N' ? 2 * pb : round_up(cl.n, 32);
+        const size_t b2_bytes = cl.tb == 'N' ? 0 : (size_t)c32.pitch_b2 * (size_t)(2 * cl.k) * sizeof(float);
+        if (ctx->c32_a2.reserve(a2_bytes) == cudaSuccess && (b2_bytes == 0 || ctx->c32_b2.reserve(b2_bytes) == cudaSuccess)) {
+            c32.on = true;
+            c32.a2 = static_cast<float*>(ctx->c32_a2.p);
+            c32.b2 = static_cast<float*>(ctx->c32_b2.p);
+        } else cudaGetLastError();  // no room: every launch prepares its own operands (device_gemm)
+    }
+    // the launch of one block on prepared operands: rows [0, m) of op(A), columns [j0, j0 + nj) of op(B), k range [p0, p0 + kc)
+    auto c32_gemm = [&](int64_t j0, int64_t nj, int64_t p0, int64_t kc, const void* beta, void* dc, cudaStream_t st) -> int {
+        const float* a2 = cl.ta == 'N' ? c32.a2 + (size_t)(2 * p0) * c32.pitch_a2 : c32.a2 + 2 * p0;
+        const Sub sbs = b_sub(cl, p0, kc, j0, nj);
+        const char* db = dB + ((size_t)sbs.col * pb + sbs.row) * es;
+        const float* b2;
+        if (cl.tb == 'N') b2 = reinterpret_cast<const float*>(db);  // zero copy: the stored k x n block read as (2k x n) floats
+        else {
+            float* out = c32.b2 + (size_t)(2 * p0) * c32.pitch_b2 + j0;
+            cudaError_t e1 = tmm::cgemm_tc_split_b(cl.tb, (int)nj, (int)kc, db, pb, out, c32.pitch_b2, st);
+            if (e1 != cudaSuccess) return cuda_fail(e1, "complex<float> operand split (B)");
+            b2 = out;
+        }
+        cudaError_t e1 = tmm::cgemm_tc_prepared(cl.ta, cl.tb, (int)cl.m, (int)nj, (int)kc, a2, c32.pitch_a2, b2, c32.pitch_b2, static_cast<const float*>(beta), dc, ldc_dev, st);
+        if (e1 == cudaErrorInvalidValue) {  // a sub-block off the 16-byte grid (odd chunk start): this launch prepares its own operands
+            cudaGetLastError();
+            const Sub sa = a_sub(cl, 0, cl.m, p0, kc);
+            return launch_gemm(cl, cl.m, nj, kc, dA + ((size_t)sa.col * pa + sa.row) * es, pa, db, pb, beta, dc, ldc_dev, st);
+        }
+        return e1 == cudaSuccess ? TMM_OK : cuda_fail(e1, "complex<float> GEMM on prepared operands");
+    };
     // beta != 0: host C is read (only then, reference tiled_mm.cpp:325).  Uploading the whole C[:, 0:n1] before the first chunk would
     // keep the SMs idle for |C block| / BW_pcie (8 ms at 10000^3); instead stripe s's C travels right before k-chunk s, so the first
     // chain starts after ONE stripe of C and the later stripes join one chunk apart, catching up on the chunks that arrived first.
@@ -374,8 +424,10 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev, void*
             return e8 == cudaSuccess ? TMM_OK : cuda_fail(e8, "int8 slice GEMM (phase 1)");
         }
 #endif
+        const void* beta1 = ci == 0 ? (defer_c ? (const void*)cl.zero : cl.beta) : (const void*)cl.one;
+        if (c32.on) return c32_gemm(js, ws, p0, kc, beta1, (char*)dC + (size_t)js * ldc_dev * es, ctx->s_p1[sidx % P1]);
         return launch_gemm(cl, cl.m, ws, kc, dA + ((size_t)sa.col * pa + sa.row) * es, pa, dB + ((size_t)sbs.col * pb + sbs.row) * es, pb,
-                           ci == 0 ? (defer_c ? (const void*)cl.zero : cl.beta) : (const void*)cl.one, (char*)dC + (size_t)js * ldc_dev * es, ldc_dev, ctx->s_p1[sidx % P1]);
+                           beta1, (char*)dC + (size_t)js * ldc_dev * es, ldc_dev, ctx->s_p1[sidx % P1]);
     };
     for (int ci = 0; ci < n_chunks; ++ci) {
         const int64_t p0 = chunk_p0[ci], kc = pl.chunks[ci];
@@ -391,6 +443,15 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev, void*
         {
             int rc = panels_ready(cl, ctx->s_p1, P1);
             if (rc) return rc;
+        }
+        if (c32.on) {  // the chunk of A that just arrived: embedded once on the first stripe's stream, the other stripe streams wait for it
+            TraceScope ts(ctx, ctx->s_p1[0], "embedA", p0, kc);
+            float* out = cl.ta == 'N' ? c32.a2 + (size_t)(2 * p0) * c32.pitch_a2 : c32.a2 + 2 * p0;
+            cudaError_t e1 = tmm::cgemm_tc_embed_a(cl.ta, (int)cl.m, (int)kc, static_cast<const float*>(cl.alpha), dA + ((size_t)sa.col * pa + sa.row) * es, pa, out, c32.pitch_a2, ctx->s_p1[0]);
+            if (e1 != cudaSuccess) return cuda_fail(e1, "complex<float> operand embedding (A chunk)");
+            CU(ctx->get_event(&c32.last_embed));
+            CU(cudaEventRecord(c32.last_embed, ctx->s_p1[0]));
+            for (int j = 1; j < P1; ++j) CU(cudaStreamWaitEvent(ctx->s_p1[j], c32.last_embed, 0));
         }
 #ifndef TMM_EMULATED
         if (i8.on) {  // the chunk of A that just arrived: sliced once on the first stripe's stream, the other stripe streams wait for it
@@ -513,7 +574,12 @@ int run_resident(Call& cl, const tmm::Plan& pl, void* dC, int64_t ldc_dev, void*
             if (e8 != cudaSuccess) return cuda_fail(e8, "int8 slice GEMM (phase 2)");
         } else
 #endif
-        {
+        if (c32.on) {  // the chunks embedded in phase 1 are the A' of the whole panel: wait for the last of them, then multiply on full k
+            if (c32.last_embed) CU(cudaStreamWaitEvent(cs, c32.last_embed, 0));
+            TraceScope ts(ctx, cs, "gemm2", j0, nb);
+            int rc = c32_gemm(j0, nb, 0, cl.k, defer_c ? (const void*)cl.zero : cl.beta, dcb, cs);
+            if (rc) return rc;
+        } else {
             TraceScope ts(ctx, cs, "gemm2", j0, nb);
             int rc = launch_gemm(cl, cl.m, nb, cl.k, dA, pa, db, pb, defer_c ? (const void*)cl.zero : cl.beta, dcb, ldc_dev, cs);
             if (rc) return rc;
@@ -567,6 +633,21 @@ int run_streaming(Call& cl, const tmm::Plan& pl, void* dC_full, int64_t ldc_full
         ctx->retired.clear();
     } else if (alloc_rc) return alloc_rc;
     cudaStream_t cs = ctx->s_compute[0];
+    // complex<float> on the tcgen05 kernel: every ring slot gets a twin for its prepared operands (A' = 2 x the A slot, B'^T = the B slot for
+    // op(B) = T / C), filled on the compute stream right before the launch that reads it - no allocation on the launch path (see run_resident)
+    struct { bool on = false; float* a2 = nullptr; float* b2 = nullptr; int64_t pitch_a2 = 0, pitch_b2 = 0; size_t a2_slot = 0, b2_slot = 0; } c32;
+    if (cl.dtype == TMM_C32 && tmm::c32_math_mode() == TMM_CMATH_TC && tmm::f32_math_mode() != 0 && cl.k > 0 && MB <= INT32_MAX / 2 && kc <= INT32_MAX / 2) {
+        c32.pitch_a2 = cl.ta == 'N' ? round_up(2 * MB, 32) : round_up(2 * kc, 32);
+        c32.a2_slot = (size_t)c32.pitch_a2 * (size_t)(2 * (cl.ta == 'N' ? kc : MB));   // floats
+        c32.pitch_b2 = cl.tb == 'N' ? 2 * pl.pb_slot : round_up(NB, 32);
+        c32.b2_slot = cl.tb == 'N' ? 0 : (size_t)c32.pitch_b2 * (size_t)(2 * kc);
+        if (ctx->c32_a2.reserve(c32.a2_slot * SLOTS * sizeof(float)) == cudaSuccess &&
+            (c32.b2_slot == 0 || ctx->c32_b2.reserve(c32.b2_slot * SLOTS * sizeof(float)) == cudaSuccess)) {
+            c32.on = true;
+            c32.a2 = static_cast<float*>(ctx->c32_a2.p);
+            c32.b2 = static_cast<float*>(ctx->c32_b2.p);
+        } else cudaGetLastError();
+    }
     std::vector<cudaEvent_t> slot_free(SLOTS, nullptr);
     cudaEvent_t cbuf_free[2] = {nullptr, nullptr};
     int slot = 0, cbuf = 0, nblocks = 0;
@@ -618,7 +699,25 @@ int run_streaming(Call& cl, const tmm::Plan& pl, void* dC_full, int64_t ldc_full
                     int rc = panels_ready(cl, cs);
                     if (rc) return rc;
                 }
-                if (mine) {
+                if (mine && c32.on) {
+                    TraceScope ts(ctx, cs, "gemmS", i0, j0, p0);
+                    float* a2 = c32.a2 + (size_t)slot * c32.a2_slot;
+                    const float* b2 = reinterpret_cast<const float*>(db);  // op N: the slot read as floats
+                    cudaError_t e1 = tmm::cgemm_tc_embed_a(cl.ta, (int)mi, (int)kcc, static_cast<const float*>(cl.alpha), da, pl.pa_slot, a2, c32.pitch_a2, cs);
+                    if (e1 == cudaSuccess && cl.tb != 'N') {
+                        float* out = c32.b2 + (size_t)slot * c32.b2_slot;
+                        e1 = tmm::cgemm_tc_split_b(cl.tb, (int)nj, (int)kcc, db, pl.pb_slot, out, c32.pitch_b2, cs);
+                        b2 = out;
+                    }
+                    if (e1 == cudaSuccess)
+                        e1 = tmm::cgemm_tc_prepared(cl.ta, cl.tb, (int)mi, (int)nj, (int)kcc, a2, c32.pitch_a2, b2, c32.pitch_b2,
+                                                    static_cast<const float*>(ci == 0 ? cl.beta : (const void*)cl.one), dcb, ldcb, cs);
+                    if (e1 == cudaErrorInvalidValue) {  // a slot off the 16-byte grid: this launch prepares its own operands
+                        cudaGetLastError();
+                        int rc = launch_gemm(cl, mi, nj, kcc, da, pl.pa_slot, db, pl.pb_slot, ci == 0 ? cl.beta : (const void*)cl.one, dcb, ldcb, cs);
+                        if (rc) return rc;
+                    } else if (e1 != cudaSuccess) return cuda_fail(e1, "complex<float> GEMM on prepared operands (streaming)");
+                } else if (mine) {
                     TraceScope ts(ctx, cs, "gemmS", i0, j0, p0);
                     int rc = launch_gemm(cl, mi, nj, kcc, da, pl.pa_slot, db, pl.pb_slot, ci == 0 ? cl.beta : (const void*)cl.one, dcb, ldcb, cs);
                     if (rc) return rc;
@@ -793,7 +892,7 @@ void tmm_context_destroy(tmm_context* ctx) {
     for (cudaStream_t s : all) if (s) cudaStreamDestroy(s);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
-    ctx->buf_a.release(); ctx->buf_b.release(); ctx->buf_c.release(); ctx->buf_cs.release(); ctx->full_c.release(); ctx->i8_q.release(); ctx->i8_e.release();
+    ctx->buf_a.release(); ctx->buf_b.release(); ctx->buf_c.release(); ctx->buf_cs.release(); ctx->full_c.release(); ctx->c32_a2.release(); ctx->c32_b2.release(); ctx->i8_q.release(); ctx->i8_e.release();
     for (void* old : ctx->retired) cudaFree(old);
     delete ctx;
 }

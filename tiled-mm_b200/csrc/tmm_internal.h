@@ -128,6 +128,7 @@ struct tmm_context {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comm = nullptr, s_compute[MAX_COMPUTE] = {nullptr, nullptr, nullptr, nullptr};
     tmm::DevBuf buf_a, buf_b, buf_c;  // panel / ring / staged-C storage (grow-only, reused across calls)
     tmm::DevBuf buf_cs;               // beta != 0, resident regime: staging copy of the caller's C (same pitch as the device C of the call)
+    tmm::DevBuf c32_a2, c32_b2;       // complex<float> on the tcgen05 kernel: the real embedding A' of the resident A panel (2 x |A|) and, for op(B) = T / C, B'^T (|B|)
     tmm::DevBuf i8_q, i8_e;           // opt-in FP64 emulation (TMM_F64_MATH=i8): int8 slices and row scales of the panels, carved per call
     tmm::DevBuf full_c;               // API-visible device C (copy_c_back = false), column-major ld = m
     size_t full_c_elems = 0;

@@ -73,6 +73,28 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
 }
 
+// The same split without the special cases: exact for every x with |x| < 2^127 (rounding to TF32 then stays finite).
+__device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
+}
+
+// Four neighbouring elements, as the split warps of sgemm_tc_kernel take them (one 16-byte chunk): one comparison per element decides whether
+// the chunk takes the five-instruction path; a chunk holding an Inf, a NaN or a value of 2^127 or more goes through split_tf32.  (The split
+// warps sit between TMA and the tensor core on a three-stage ring: with the special cases applied to every element - ~19 instructions - the
+// FP32-accurate mode ran at 96 TF instead of 155 TF at 8192^3, profiles/r2_bisect_tc.txt.)
+__device__ __forceinline__ void split_tf32_x4(const float (&x)[4], float (&hi)[4], float (&lo)[4]) {
+    constexpr float LIM = 1.7014118e38f;  // 2^127; a NaN compares false
+    const bool plain = (fabsf(x[0]) < LIM) & (fabsf(x[1]) < LIM) & (fabsf(x[2]) < LIM) & (fabsf(x[3]) < LIM);
+    if (plain) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32_fast(x[i], hi[i], lo[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(x[i], hi[i], lo[i]);
+    }
+}
+
 // Variant for hi = raw bits: the hardware reads trunc(x) (top 19 bits), so lo = x - trunc(x) (exact), rounded to TF32.
 // |lo| < 2^-10 |x| instead of 2^-11 |x| (one bit less accurate than the round-to-nearest split) but the tile is not rewritten.
 __device__ __forceinline__ float lo_of_truncated(float x) {
