@@ -46,8 +46,8 @@ int f32_math_mode();
 void set_f32_math_mode(int mode);
 cudaError_t cgemm_launch(char ta, char tb, int m, int n, int k, const float* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
                          const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
-// complex<float> back ends: SIMT complex FMA kernel (default) and the real embedding on the tcgen05 3xTF32 kernel (gemm_c32_tc.cu;
-// returns cudaErrorMemoryAllocation when its scratch cannot be allocated, and the dispatcher then falls back to SIMT)
+// complex<float> back ends: the real embedding on the tcgen05 3xTF32 kernel (default; gemm_c32_tc.cu; returns cudaErrorMemoryAllocation when its
+// scratch cannot be allocated, and the dispatcher then falls back) and the SIMT complex FMA kernel
 cudaError_t cgemm_simt_launch(char ta, char tb, int m, int n, int k, const float* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
                               const float* beta2, void* c, int64_t ldc, cudaStream_t stream);
 cudaError_t cgemm_tc_launch(char ta, char tb, int m, int n, int k, const float* alpha2, const void* a, int64_t lda, const void* b, int64_t ldb,
@@ -63,7 +63,7 @@ cudaError_t bgemm_tc_launch(char ta, char tb, int m, int n, int k, float alpha, 
 // experimental native kind::f16 variant for k-contiguous operands (op(A) = T, op(B) = N); TMM_BF16_NATIVE=1
 cudaError_t bgemm_tc_native_tn_launch(int m, int n, int k, float alpha, const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, float beta, float* c,
                                       int64_t ldc, cudaStream_t stream);
-// process-wide math mode of the complex<float> GEMM: 0 = SIMT (default), 3 = FP32-accurate on tensor cores
+// process-wide math mode of the complex<float> GEMM: 3 = FP32-accurate on tensor cores (default), 0 = SIMT
 int c32_math_mode();
 void set_c32_math_mode(int mode);
 
