@@ -158,3 +158,20 @@ def test_tf32_operand_splits(kernels):
     assert near_max.any() and np.all(np.isfinite(hi[near_max])) and np.all(np.abs(hi[near_max].astype(np.float64) + lo[near_max] - x[near_max]) <= 2.0 ** -21 * np.abs(x[near_max].astype(np.float64)))
 
 
+
+
+def test_chunked_split_equals_the_per_element_split_on_random_bit_patterns(kernels):
+    """split_tf32_x4 (what the split warps run: the short path for chunks of plain values, split_tf32 for a chunk holding an Inf / NaN / value of
+    2^127 or more) against split_tf32 element by element, over two million uniformly random 32-bit patterns - every exponent, denormals, both
+    zeros, NaN payloads - and over chunks that mix one special value with plain ones: bit-identical hi and lo."""
+    rng = np.random.default_rng(11)
+    bits = rng.integers(0, 1 << 32, 1 << 21, dtype=np.uint64).astype(np.uint32)
+    bits[::64] = rng.choice(np.array([0x7F800000, 0xFF800000, 0x7FC00000, 0x7F7FFFFF, 0xFF7FFFFF, 0x7F000000, 0x7EFFFFFF, 0x00000001, 0x80000000], np.uint32), bits[::64].size)
+    x = bits.view(np.float32)
+    hi, lo, lot, hi4, lo4 = (np.zeros_like(x) for _ in range(5))
+    kernels.run_split(_fp(x), ctypes.c_long(x.size), _fp(hi), _fp(lo), _fp(lot))
+    kernels.run_split_x4(_fp(x), ctypes.c_long(x.size), _fp(hi4), _fp(lo4))
+    assert np.array_equal(hi4.view(np.uint32), hi.view(np.uint32)) and np.array_equal(lo4.view(np.uint32), lo.view(np.uint32))
+    fin = np.isfinite(x)
+    assert np.all(np.isfinite(hi[fin])) and np.all(np.isfinite(lo[fin])), "a finite operand must never split into a non-finite part"
+    assert np.all((hi.view(np.uint32) & np.uint32(0x1FFF)) == 0) and np.all((lo.view(np.uint32) & np.uint32(0x1FFF)) == 0)
